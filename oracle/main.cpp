@@ -1,0 +1,225 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Never linked into or called from the product path.
+//
+// `modkit_oracle pileup [flags] <in.bam> <out.bed>`: CPU restatement of `modkit pileup`
+// (reference v0.4.4, src/pileup/subcommand.rs:381-817) used (a) as the parity checker in tests/
+// and (b) as the `cpu_baseline` / `--impl reference` arm of bench.py (the Rust reference cannot be
+// built in this image: no cargo/rustc). Parallelised like the reference: one worker per genomic
+// interval (src/pileup/mod.rs:696-715), results written in feeder order.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+
+#include "driver.hpp"
+
+using namespace orc;
+
+static void die(const std::string& m) { fprintf(stderr, "> Error! %s\n", m.c_str()); exit(1); }
+
+int main(int argc, char** argv) {
+    try {
+        if (argc < 2 || std::string(argv[1]) != "pileup") die("usage: modkit_oracle pileup [flags] <in.bam> <out.bed>");
+        std::vector<std::string> pos;
+        int threads = 4;
+        uint32_t interval_size = 100000, sampling_interval_size = 1000000;
+        size_t num_reads = 10042;
+        bool have_frac = false; double frac = 0;
+        bool no_filtering = false, include_unmapped = false, force_allow = false, cpg = false, mask = false;
+        bool traditional = false, combine_mods = false, combine_strands = false, mixed = false, header = false, invert_edge = false;
+        float percentile = 0.1f;
+        std::vector<std::string> filter_thresholds, mod_thresholds, motif_parts;
+        std::string region_s, sample_region_s, ignore_s, ref_fp, edge_s, timing_fp;
+        for (int i = 2; i < argc; i++) {
+            std::string a = argv[i];
+            auto val = [&]() -> std::string { if (i + 1 >= argc) die("missing value for " + a); return argv[++i]; };
+            if (a == "-t" || a == "--threads") threads = std::stoi(val());
+            else if (a == "-i" || a == "--interval-size") interval_size = (uint32_t)std::stoul(val());
+            else if (a == "--region") region_s = val();
+            else if (a == "--sample-region") sample_region_s = val();
+            else if (a == "--sampling-interval-size") sampling_interval_size = (uint32_t)std::stoul(val());
+            else if (a == "-n" || a == "--num-reads") num_reads = std::stoul(val());
+            else if (a == "-f" || a == "--sampling-frac") { have_frac = true; frac = std::stod(val()); }
+            else if (a == "--seed" || a == "--max-depth" || a == "--queue-size" || a == "--chunk-size" || a == "--log-filepath" || a == "--log") val();
+            else if (a == "--no-filtering") no_filtering = true;
+            else if (a == "-p" || a == "--filter-percentile") percentile = std::stof(val());
+            else if (a == "--filter-threshold" || a == "--pass_threshold") filter_thresholds.push_back(val());
+            else if (a == "--mod-thresholds" || a == "--mod-threshold") mod_thresholds.push_back(val());
+            else if (a == "--include-unmapped") include_unmapped = true;
+            else if (a == "--ignore") ignore_s = val();
+            else if (a == "--force-allow-implicit") force_allow = true;
+            else if (a == "--motif") { motif_parts.push_back(val()); motif_parts.push_back(val()); }
+            else if (a == "--cpg") cpg = true;
+            else if (a == "-r" || a == "--ref" || a == "--reference") ref_fp = val();
+            else if (a == "-k" || a == "--mask") mask = true;
+            else if (a == "--preset") { if (val() != "traditional") die("unknown preset"); traditional = true; }
+            else if (a == "--combine-mods") combine_mods = true;
+            else if (a == "--combine-strands") combine_strands = true;
+            else if (a == "--edge-filter") edge_s = val();
+            else if (a == "--invert-edge-filter") invert_edge = true;
+            else if (a == "--only-tabs" || a == "--suppress-progress") {}
+            else if (a == "--mixed-delim" || a == "--mixed-delimiters") mixed = true;
+            else if (a == "--header" || a == "--with-header" || a == "--include_header") header = true;
+            else if (a == "--timing-json") timing_fp = val();
+            else if (a.size() > 1 && a[0] == '-' && a != "-") die("unsupported flag " + a);
+            else pos.push_back(a);
+        }
+        if (pos.size() != 2) die("expected <in.bam> <out.bed>");
+        auto t0 = std::chrono::steady_clock::now();
+        BamFile bam;
+        bam.load(pos[0], threads);
+        auto t_load = std::chrono::steady_clock::now();
+
+        Region region, sample_region;
+        const Region* rp = nullptr; const Region* srp = nullptr;
+        if (!region_s.empty()) { region = parse_region(region_s, bam); rp = &region; }
+        if (!sample_region_s.empty()) { sample_region = parse_region(sample_region_s, bam); srp = &sample_region; }
+        std::vector<RefRecord> targets = get_targets(bam, rp);
+        {
+            uint64_t mapped = 0;
+            for (auto& t : targets) mapped += bam.n_mapped[t.tid];
+            if (!mapped) die("did not find any mapped reads, perform alignment first or use modkit extract and/or modkit summary to inspect unaligned modBAMs");
+        }
+        if (percentile > 1.0f) die("filter percentile must be <= 1.0");
+        if (combine_strands && !(cpg || !motif_parts.empty())) die("need to specify either --motif or --cpg to combine strands");
+
+        PileupParams P;
+        P.force_allow_implicit = force_allow;
+        bool threshold_collapse = false;
+        if (traditional) {
+            P.numeric = COLLAPSE; P.collapse_code = 'h'; combine_strands = true; threshold_collapse = true;
+        } else if (combine_mods) {
+            P.numeric = COMBINE;
+        } else if (!ignore_s.empty()) {
+            ModCode c;
+            if (!parse_mod_code(ignore_s, &c)) die("failed to parse mod code " + ignore_s);
+            P.numeric = COLLAPSE; P.collapse_code = c; threshold_collapse = true;
+        }
+        P.combine_strands = combine_strands;
+        if (!edge_s.empty()) {
+            P.edge.on = true; P.edge.inverted = invert_edge;
+            auto c = edge_s.find(',');
+            if (c == std::string::npos) P.edge.start = P.edge.end = std::stoul(edge_s);
+            else { P.edge.start = std::stoul(edge_s.substr(0, c)); P.edge.end = std::stoul(edge_s.substr(c + 1)); }
+        }
+        // motifs
+        std::vector<Motif> motifs;
+        bool have_motifs = false;
+        if (!motif_parts.empty()) {
+            if (traditional) die("cannot use presets and motifs together");
+            for (size_t i = 0; i + 1 < motif_parts.size(); i += 2)
+                for (size_t j = i + 2; j + 1 < motif_parts.size(); j += 2)
+                    if (motif_parts[i] == motif_parts[j] && motif_parts[i + 1] == motif_parts[j + 1]) die("cannot have the same motif more than once");
+            bool has_cg0 = false;
+            for (size_t i = 0; i + 1 < motif_parts.size(); i += 2) if (motif_parts[i] == "CG" && motif_parts[i + 1] == "0") has_cg0 = true;
+            if (cpg && !has_cg0) { motif_parts.push_back("CG"); motif_parts.push_back("0"); }
+            for (size_t i = 0; i + 1 < motif_parts.size(); i += 2) motifs.push_back(Motif::parse(motif_parts[i], std::stoi(motif_parts[i + 1])));
+            have_motifs = true;
+        } else if (traditional || cpg) {
+            motifs.push_back(Motif::parse("CG", 0));
+            have_motifs = true;
+        }
+        std::vector<std::string> motif_labels;
+        for (auto& m : motifs) motif_labels.push_back(m.label());
+        MotifLookup lookup;
+        if (have_motifs) {
+            if (ref_fp.empty()) die("reference fasta is required for using --motif or --cpg options");
+            if (combine_strands) for (auto& m : motifs) if (!m.palindrome) die("cannot combine strands with a motif that is not a palindrome");
+            lookup.fa.open(ref_fp);
+            lookup.motifs = motifs;
+            lookup.mask = mask;
+            for (auto& m : motifs) lookup.longest = std::max<uint64_t>(lookup.longest, m.length);
+        }
+        // thresholds
+        auto parse_base_thr = [&](const std::string& raw) {
+            auto c = raw.find(':');
+            if (c == std::string::npos) { P.caller.default_thr = std::stof(raw); return; }
+            int b = base_idx(raw[0]);
+            if (b < 0) die("failed to parse base " + raw);
+            P.caller.base_set[b] = true;
+            P.caller.base_thr[b] = std::stof(raw.substr(c + 1));
+        };
+        for (auto& raw : mod_thresholds) {
+            auto c = raw.find(':');
+            ModCode code;
+            if (c == std::string::npos || !parse_mod_code(raw.substr(0, c), &code)) die("illegal per-mod threshold " + raw);
+            P.caller.mod_thr.push_back({code, std::stof(raw.substr(c + 1))});
+        }
+        if (!filter_thresholds.empty()) {
+            for (auto& raw : filter_thresholds) parse_base_thr(raw);
+        } else if (!no_filtering) {
+            SampleOptions so;
+            so.threads = threads;
+            so.sampling_interval_size = sampling_interval_size;
+            if (have_frac) { if (frac != 1.0) die("oracle supports only -f 1.0 (Rust StdRng sampling is not reproducible)"); so.frac_all = true; }
+            so.num_reads = num_reads;
+            so.region = srp ? srp : rp;
+            so.include_unmapped = include_unmapped;
+            so.collapse = threshold_collapse;
+            so.collapse_code = P.collapse_code;
+            so.edge = P.edge;
+            estimate_thresholds(bam, so, percentile, &P.caller);
+            for (int b = 0; b < 4; b++) if (P.caller.base_set[b]) fprintf(stderr, "> Using filter threshold %.9g for %c.\n", P.caller.base_thr[b], BASES[b]);
+        }
+        auto t_thr = std::chrono::steady_clock::now();
+
+        std::vector<Interval> ivs = make_intervals(targets, interval_size, combine_strands, have_motifs ? &lookup : nullptr);
+        uint64_t total_positions = 0;
+        for (auto& iv : ivs) total_positions += iv.end - iv.start;
+        auto t_ivs = std::chrono::steady_clock::now();
+
+        FILE* out = (pos[1] == "-" || pos[1] == "stdout") ? stdout : fopen(pos[1].c_str(), "w");
+        if (!out) die("failed to make output file");
+        if (header) fputs(bedmethyl_header(), out);
+
+        StateTable st;
+        std::vector<std::string> results(ivs.size());
+        std::vector<char> done(ivs.size(), 0);
+        std::atomic<size_t> next{0};
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t n_rows = 0;
+        auto worker = [&]() {
+            while (true) {
+                size_t i = next.fetch_add(1);
+                if (i >= ivs.size()) break;
+                std::vector<Row> rows;
+                process_interval(bam, ivs[i], P, st, have_motifs ? &motifs : nullptr, &rows);
+                std::string text;
+                const std::string& chrom = bam.ref_names[ivs[i].tid];
+                for (auto& R : rows) format_row(R, chrom, motif_labels, mixed, &text);
+                std::lock_guard<std::mutex> g(mu);
+                results[i].swap(text);
+                done[i] = 1;
+                n_rows += rows.size();
+                cv.notify_all();
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < std::max(1, threads); t++) pool.emplace_back(worker);
+        for (size_t i = 0; i < ivs.size(); i++) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return done[i] != 0; });
+            std::string text;
+            text.swap(results[i]);
+            lk.unlock();
+            fwrite(text.data(), 1, text.size(), out);
+        }
+        for (auto& t : pool) t.join();
+        if (out != stdout) fclose(out); else fflush(out);
+        auto t1 = std::chrono::steady_clock::now();
+        auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+        fprintf(stderr, "> Done, processed %zu rows. positions=%llu load=%.3fs thresholds=%.3fs intervals=%.3fs pileup=%.3fs total=%.3fs\n",
+                n_rows, (unsigned long long)total_positions, sec(t0, t_load), sec(t_load, t_thr), sec(t_thr, t_ivs), sec(t_ivs, t1), sec(t0, t1));
+        if (!timing_fp.empty()) {
+            FILE* tf = fopen(timing_fp.c_str(), "w");
+            if (tf) {
+                fprintf(tf, "{\"positions\": %llu, \"rows\": %zu, \"threads\": %d, \"load_s\": %.6f, \"thresholds_s\": %.6f, \"intervals_s\": %.6f, \"pileup_s\": %.6f, \"total_s\": %.6f}\n",
+                        (unsigned long long)total_positions, n_rows, threads, sec(t0, t_load), sec(t_load, t_thr), sec(t_thr, t_ivs), sec(t_ivs, t1), sec(t0, t1));
+                fclose(tf);
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        die(e.what());
+    }
+    return 1;
+}
