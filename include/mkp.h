@@ -1,0 +1,144 @@
+/* mkp.h — C ABI of the B200-native `modkit pileup` hot path (device side).
+ *
+ * The reference (nanoporetech/modkit v0.4.4) has no FFI for this path; the seam this library
+ * replaces is
+ *     pub fn process_region_batch(&MultiChromCoordinates, bam_fp, &MultipleThresholdModCaller,
+ *                                 &PileupNumericOptions, force_allow, combine_strands, max_depth,
+ *                                 Option<&EdgeFilter>, Option<&Vec<SamTag>>)
+ *         -> Vec<Result<ModBasePileup, String>>            (src/pileup/mod.rs:684-716)
+ * called from src/pileup/subcommand.rs:739 and consumed by PileupWriter::write
+ * (src/writers.rs:35-37, 159-183).  A Rust host binds these entry points with `extern "C"`
+ * (see INTEGRATION.md); this repository's own host (C++/Python) uses the same entry points.
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross the boundary; every function
+ * returns 0 on success and a negative code on failure (mkp_last_error gives the text); one
+ * context per GPU / host thread; buffers are caller-owned unless stated.
+ */
+#ifndef MKP_H
+#define MKP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mkp_ctx mkp_ctx;
+
+/* ---- packed read blocks (what the host slices out of BAM records) -------------------------
+ * One 32-byte header per read + one byte heap.  A read's heap block starts at `off`
+ * (16-byte aligned) and holds, back to back:
+ *     CIGAR   u32[n_cigar]          (BAM encoding: len<<4 | op, ops MIDNSHP=X)
+ *     SEQ     u8[(l_seq+1)/2]       (BAM 4-bit encoding, "=ACMGRSVTWYHKDBN")
+ *     ML      u8[len_ml]            (ML/Ml B:C array)
+ *     MM      u8[len_mm]            (MM/Mm Z string without the NUL)
+ * QNAME, QUAL and all other aux tags are not needed by the path and are not shipped.
+ * Reads are in BAM (coordinate-sorted) order.
+ */
+typedef struct {
+    int32_t  ref_start;   /* 0-based leftmost reference position (BAM pos)              */
+    uint32_t l_seq;
+    uint32_t n_cigar;
+    uint32_t flags;       /* low 16 bits: BAM flag; high bits: MKP_RF_*                 */
+    uint64_t off;         /* byte offset of the read's block in the heap                */
+    uint32_t len_ml;
+    uint32_t len_mm;
+} mkp_read_hdr;
+
+/* host-side tag lookup outcome (src/mod_bam.rs:1388-1470): MM/ML missing or of the wrong aux
+ * type, or MN present and != l_seq  =>  the read yields no mod calls but still counts as a base */
+#define MKP_RF_TAGS_INVALID (1u << 16)
+
+/* ---- parameters: MultipleThresholdModCaller (src/threshold_mod_caller.rs:7-13) +
+ *      PileupNumericOptions (src/pileup/mod.rs:667-671) + EdgeFilter (src/mod_bam.rs:1634-1639) */
+#define MKP_MAX_MOD_THRESHOLDS 16
+typedef struct {
+    float    default_threshold;
+    float    base_threshold[4];          /* A C G T */
+    uint8_t  base_threshold_set[4];
+    uint32_t n_mod_thresholds;
+    uint32_t mod_code[MKP_MAX_MOD_THRESHOLDS];   /* char code point, or 0x80000000|ChEBI */
+    float    mod_threshold[MKP_MAX_MOD_THRESHOLDS];
+    uint8_t  numeric_mode;               /* 0 passthrough, 1 combine (--combine-mods), 2 collapse ReDistribute */
+    uint32_t collapse_code;
+    uint8_t  force_allow_implicit;
+    uint8_t  edge_filter_on, edge_filter_inverted;
+    uint32_t edge_filter_start, edge_filter_end;
+} mkp_params;
+
+/* ---- one chunk of work: reads overlapping [start,end) of one contig -------------------------
+ * focus_pos / focus_neg: optional bitmaps over [start,end) (bit i of word i/32 = position
+ * start+i) holding the positions whose StrandRule admits the + / - tally
+ * (FocusPositions::check_position, src/interval_chunks.rs:352-374).  NULL = AllPositions. */
+typedef struct {
+    uint32_t start, end;
+    const mkp_read_hdr* hdrs;
+    uint32_t n_reads;
+    const uint8_t* heap;
+    uint64_t heap_bytes;
+    const uint32_t* focus_pos;
+    const uint32_t* focus_neg;
+} mkp_chunk;
+
+/* ---- output row == PileupFeatureCounts (src/pileup/mod.rs:54-68), integers only ------------
+ * valid_coverage = n_mod + n_canon + n_other; fraction_modified is formatted by the host. */
+typedef struct {
+    uint32_t pos;
+    uint32_t code;        /* char code point, or 0x80000000|ChEBI                             */
+    uint8_t  strand;      /* '+' or '-'                                                        */
+    uint8_t  primary_base;/* 0..3 = A C G T                                                    */
+    uint16_t reserved;
+    uint32_t n_mod, n_canon, n_other, n_delete, n_filtered, n_diff, n_nocall;
+} mkp_row;                /* 40 bytes */
+
+typedef struct {          /* per-chunk counters, filled by mkp_pileup_* */
+    uint64_t n_rows;
+    uint64_t n_hot;           /* positions that received a counter slot            */
+    uint64_t n_calls;         /* projected base-mod calls                           */
+    uint32_t n_reads_used;    /* reads that produced mod calls (ReadCache "used")   */
+    uint32_t n_reads_skipped; /* admitted reads without usable mod info (skip_set)  */
+    uint32_t n_states;        /* distinct (primary base, mod code) pairs seen       */
+    uint32_t device_error;    /* 0, or MKP_DERR_* bits (also turned into an error)  */
+    float    kernel_ms[8];    /* CUDA-event times of the pipeline stages            */
+} mkp_stats;
+
+#define MKP_DERR_TOO_MANY_STATES   1u   /* > 32 distinct (base,code) states                      */
+#define MKP_DERR_TOO_MANY_LISTS    2u   /* > 16 MM lists in one read                             */
+#define MKP_DERR_TOO_MANY_CODES    4u   /* > 4 codes at one read position                        */
+#define MKP_DERR_IMPLICIT_MODE     8u   /* '.'/default-mode list needing implicit fill (not yet on device) */
+
+int  mkp_create(int device, mkp_ctx** out);
+void mkp_destroy(mkp_ctx* ctx);
+const char* mkp_last_error(const mkp_ctx* ctx);   /* valid until the next call on ctx */
+int  mkp_set_params(mkp_ctx* ctx, const mkp_params* params);
+
+/* Copy a host chunk to the device (pinned or pageable host memory). The chunk stays resident
+ * until the next mkp_upload_chunk / mkp_destroy. */
+int  mkp_upload_chunk(mkp_ctx* ctx, const mkp_chunk* host_chunk);
+
+/* Run the pileup kernels on the resident chunk. Rows stay on the device. */
+int  mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats);
+
+/* Copy the rows of the last mkp_pileup_resident to host memory owned by ctx
+ * (sorted by position, then strand '+' < '-', then code). */
+int  mkp_fetch_rows(mkp_ctx* ctx, const mkp_row** rows, size_t* n_rows);
+
+/* upload + pileup + fetch in one call: the drop-in for process_region_batch on host buffers. */
+int  mkp_pileup_chunk(mkp_ctx* ctx, const mkp_chunk* host_chunk, const mkp_row** rows, size_t* n_rows,
+                      mkp_stats* stats);
+
+/* Threshold estimation support (src/thresholds.rs:118-156, src/mod_bam.rs:489-505): for the
+ * resident chunk, histogram of the argmax probability of every call of the reads selected by
+ * `take` (n_reads flags, host memory; NULL = all), per canonical base, bin = round(p*1024).
+ * `contributes[i]` (optional, host memory, n_reads bytes) receives 1 when read i yielded >= 1
+ * value.  hist is u64[4][1025]; `inexact` counts values that are not multiples of 1/1024. */
+int  mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* take,
+                          uint64_t* hist, uint8_t* contributes, uint64_t* inexact);
+
+/* Device pointers of the resident histogram for an NCCL all-reduce by the caller. */
+size_t mkp_algorithmic_bytes(const mkp_chunk* chunk, size_t n_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MKP_H */

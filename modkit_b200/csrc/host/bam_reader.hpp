@@ -1,0 +1,330 @@
+// Host-side BGZF/BAM/BAI access for the B200 pileup path (no htslib in this image: from scratch on zlib).
+// Replaces what the reference gets from rust-htslib: IndexedReader::{from_path, fetch, index_stats}
+// (src/pileup/mod.rs:732-743, src/reads_sampler/sampling_schedule.rs:683-722) and aux lookup
+// (src/mod_bam.rs:1388-1470).  Records are sliced straight into the device layout of include/mkp.h.
+#pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/mkp.h"
+
+namespace mkh {
+
+template <class T> inline T load_le(const uint8_t* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
+
+struct MappedFile {
+    const uint8_t* data = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    void open(const std::string& path) {
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot open " + path);
+        struct stat st;
+        if (fstat(fd, &st) != 0) throw std::runtime_error("cannot stat " + path);
+        size = (size_t)st.st_size;
+        if (size) {
+            void* p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p == MAP_FAILED) throw std::runtime_error("mmap failed for " + path);
+            data = (const uint8_t*)p;
+        }
+    }
+    ~MappedFile() { if (data) munmap((void*)data, size); if (fd >= 0) ::close(fd); }
+};
+
+// One alignment record, as offsets into the inflated stream
+struct RecRef {
+    uint64_t off;        // offset of refID field
+    uint32_t size;       // block_size
+    int32_t pos;
+    int32_t end;         // htslib bam_endpos
+};
+
+struct BamIndexStats { std::vector<uint64_t> n_mapped, n_unmapped; uint64_t n_no_coor = 0; bool from_bai = false; };
+
+class BamReader {
+public:
+    std::vector<uint8_t> raw;                 // inflated stream (whole file; v1 keeps it resident)
+    std::vector<std::string> ref_names;
+    std::vector<uint32_t> ref_lens;
+    std::vector<std::vector<RecRef>> by_tid;  // coordinate order
+    std::vector<std::vector<int32_t>> run_max_end;
+    std::vector<RecRef> unplaced;
+    BamIndexStats stats;
+
+    void open(const std::string& path, int threads) {
+        MappedFile mf;
+        mf.open(path);
+        struct Member { size_t in_off, in_len, out_off; uint32_t out_len; };
+        std::vector<Member> members;
+        size_t off = 0, total = 0;
+        while (off + 28 <= mf.size) {
+            const uint8_t* p = mf.data + off;
+            if (p[0] != 0x1f || p[1] != 0x8b || !(p[3] & 4)) throw std::runtime_error(path + ": not a BGZF file");
+            const uint16_t xlen = load_le<uint16_t>(p + 10);
+            int bsize = -1;
+            for (size_t x = 12; x + 4 <= 12u + xlen;) {
+                const uint16_t sl = load_le<uint16_t>(p + x + 2);
+                if (p[x] == 'B' && p[x + 1] == 'C' && sl == 2) bsize = load_le<uint16_t>(p + x + 4);
+                x += 4 + sl;
+            }
+            if (bsize < 0) throw std::runtime_error(path + ": BGZF member without BSIZE");
+            const size_t mlen = (size_t)bsize + 1;
+            if (off + mlen > mf.size) throw std::runtime_error(path + ": truncated BGZF member");
+            const uint32_t isize = load_le<uint32_t>(p + mlen - 4);
+            members.push_back({off + 12 + xlen, mlen - 20 - xlen, total, isize});
+            total += isize;
+            off += mlen;
+        }
+        raw.resize(total + 16);
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        auto work = [&]() {
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+            for (;;) {
+                size_t b = next.fetch_add(16);
+                if (b >= members.size()) break;
+                for (size_t k = b; k < std::min(members.size(), b + 16); k++) {
+                    const Member& m = members[k];
+                    if (!m.out_len) continue;
+                    inflateReset(&zs);
+                    zs.next_in = (Bytef*)(mf.data + m.in_off); zs.avail_in = (uInt)m.in_len;
+                    zs.next_out = raw.data() + m.out_off; zs.avail_out = m.out_len;
+                    if (inflate(&zs, Z_FINISH) != Z_STREAM_END) bad = true;
+                }
+            }
+            inflateEnd(&zs);
+        };
+        int nt = std::max(1, threads);
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        if (bad) throw std::runtime_error(path + ": inflate failed");
+        index_records(total);
+        load_bai(path);
+    }
+
+    // reads overlapping [beg,end) on tid in file order: half-open record span [pos, endpos)
+    template <class F> void for_overlapping(uint32_t tid, int64_t beg, int64_t end, F&& f) const {
+        const auto& v = by_tid[tid];
+        const auto& rm = run_max_end[tid];
+        size_t i = std::upper_bound(rm.begin(), rm.end(), (int32_t)std::min<int64_t>(beg, INT32_MAX)) - rm.begin();
+        for (; i < v.size() && v[i].pos < end; i++) if (v[i].end > beg) f(v[i]);
+    }
+    const uint8_t* rec(const RecRef& r) const { return raw.data() + r.off; }
+
+private:
+    void index_records(size_t total) {
+        const uint8_t* p = raw.data();
+        if (total < 12 || memcmp(p, "BAM\1", 4) != 0) throw std::runtime_error("not a BAM stream");
+        size_t o = 8 + load_le<uint32_t>(p + 4);
+        const uint32_t n_ref = load_le<uint32_t>(p + o);
+        o += 4;
+        for (uint32_t i = 0; i < n_ref; i++) {
+            const uint32_t ln = load_le<uint32_t>(p + o);
+            ref_names.emplace_back((const char*)p + o + 4, ln ? ln - 1 : 0);
+            ref_lens.push_back(load_le<uint32_t>(p + o + 4 + ln));
+            o += 8 + ln;
+        }
+        by_tid.assign(n_ref, {});
+        run_max_end.assign(n_ref, {});
+        stats.n_mapped.assign(n_ref, 0);
+        stats.n_unmapped.assign(n_ref, 0);
+        while (o + 4 <= total) {
+            const uint32_t bs = load_le<uint32_t>(p + o);
+            if (o + 4 + bs > total || bs < 32) throw std::runtime_error("corrupt BAM record");
+            const uint8_t* r = p + o + 4;
+            RecRef ref;
+            ref.off = o + 4; ref.size = bs;
+            const int32_t tid = load_le<int32_t>(r);
+            ref.pos = load_le<int32_t>(r + 4);
+            const uint16_t flag = load_le<uint16_t>(r + 14);
+            const uint16_t n_cig = load_le<uint16_t>(r + 12);
+            int64_t span = 0;
+            if (!(flag & 4) && n_cig) {
+                const uint8_t* c = r + 32 + r[8];
+                for (uint16_t k = 0; k < n_cig; k++) {
+                    const uint32_t v = load_le<uint32_t>(c + 4 * k);
+                    const uint32_t op = v & 15;
+                    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += v >> 4;
+                }
+            }
+            ref.end = (int32_t)(ref.pos + (span ? span : 1));
+            if (tid >= 0 && (uint32_t)tid < n_ref) {
+                by_tid[tid].push_back(ref);
+                if (flag & 4) stats.n_unmapped[tid]++; else stats.n_mapped[tid]++;
+            } else {
+                unplaced.push_back(ref);
+                stats.n_no_coor++;
+            }
+            o += 4 + bs;
+        }
+        for (uint32_t t = 0; t < n_ref; t++) {
+            int32_t m = INT32_MIN;
+            run_max_end[t].reserve(by_tid[t].size());
+            for (auto& r : by_tid[t]) { m = std::max(m, r.end); run_max_end[t].push_back(m); }
+        }
+    }
+
+    // BAI pseudo-bin 37450 (SAMv1 5.2): per-reference mapped/unmapped counts == hts_idx_get_stat
+    void load_bai(const std::string& bam_path) {
+        std::string cand[2] = {bam_path + ".bai", bam_path.size() > 4 ? bam_path.substr(0, bam_path.size() - 4) + ".bai" : std::string()};
+        for (auto& path : cand) {
+            if (path.empty()) continue;
+            FILE* f = fopen(path.c_str(), "rb");
+            if (!f) continue;
+            std::vector<uint8_t> b;
+            uint8_t buf[65536];
+            size_t n;
+            while ((n = fread(buf, 1, sizeof buf, f)) > 0) b.insert(b.end(), buf, buf + n);
+            fclose(f);
+            if (b.size() < 8 || memcmp(b.data(), "BAI\1", 4) != 0) continue;
+            size_t o = 4;
+            const uint32_t n_ref = load_le<uint32_t>(b.data() + o);
+            o += 4;
+            if (n_ref != ref_names.size()) continue;
+            BamIndexStats s;
+            s.n_mapped.assign(n_ref, 0); s.n_unmapped.assign(n_ref, 0);
+            bool ok = true;
+            for (uint32_t r = 0; r < n_ref && ok; r++) {
+                if (o + 4 > b.size()) { ok = false; break; }
+                const uint32_t n_bin = load_le<uint32_t>(b.data() + o);
+                o += 4;
+                for (uint32_t k = 0; k < n_bin; k++) {
+                    if (o + 8 > b.size()) { ok = false; break; }
+                    const uint32_t bin = load_le<uint32_t>(b.data() + o), n_chunk = load_le<uint32_t>(b.data() + o + 4);
+                    o += 8;
+                    if (o + 16ull * n_chunk > b.size()) { ok = false; break; }
+                    if (bin == 37450 && n_chunk == 2) {
+                        s.n_mapped[r] = load_le<uint64_t>(b.data() + o + 16);
+                        s.n_unmapped[r] = load_le<uint64_t>(b.data() + o + 24);
+                    }
+                    o += 16ull * n_chunk;
+                }
+                if (!ok || o + 4 > b.size()) { ok = false; break; }
+                const uint32_t n_intv = load_le<uint32_t>(b.data() + o);
+                o += 4 + 8ull * n_intv;
+            }
+            if (!ok) continue;
+            if (o + 8 <= b.size()) s.n_no_coor = load_le<uint64_t>(b.data() + o);
+            s.from_bai = true;
+            stats = s;
+            return;
+        }
+        // no usable index: keep the counts taken while scanning the records (identical for a consistent index)
+    }
+};
+
+// ---- slicing BAM records into packed read blocks (include/mkp.h) --------------------------------
+struct AuxHit { char type = 0, sub = 0; const uint8_t* p = nullptr; uint32_t n = 0; };
+
+inline bool aux_find(const uint8_t* aux, const uint8_t* end, char a, char b, AuxHit* out) {
+    const uint8_t* p = aux;
+    while (p + 3 <= end) {
+        const char t0 = (char)p[0], t1 = (char)p[1], ty = (char)p[2];
+        p += 3;
+        AuxHit h;
+        h.type = ty;
+        size_t sz;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; h.p = p; break;
+            case 's': case 'S': sz = 2; h.p = p; break;
+            case 'i': case 'I': case 'f': sz = 4; h.p = p; break;
+            case 'Z': case 'H': { const uint8_t* q = (const uint8_t*)memchr(p, 0, end - p); if (!q) return false; h.p = p; h.n = (uint32_t)(q - p); sz = h.n + 1; break; }
+            case 'B': {
+                if (p + 5 > end) return false;
+                h.sub = (char)p[0];
+                h.n = load_le<uint32_t>(p + 1);
+                const size_t es = (h.sub == 'c' || h.sub == 'C') ? 1 : (h.sub == 's' || h.sub == 'S') ? 2 : 4;
+                h.p = p + 5;
+                sz = 5 + es * (size_t)h.n;
+                break;
+            }
+            default: return false;
+        }
+        if (p + sz > end) return false;
+        if (t0 == a && t1 == b) { *out = h; return true; }
+        p += sz;
+    }
+    return false;
+}
+
+struct PackedChunk {
+    std::vector<mkp_read_hdr> hdrs;
+    std::vector<uint8_t> heap;
+    std::vector<RecRef> recs;      // provenance of each packed read
+    void clear() { hdrs.clear(); heap.clear(); recs.clear(); }
+    size_t algorithmic_bytes() const {
+        size_t b = 0;
+        for (auto& h : hdrs) b += 32 + 4ull * h.n_cigar + (h.l_seq + 1) / 2 + h.len_mm + h.len_ml;
+        return b;
+    }
+};
+
+// Append one BAM record. Resolves MM/Mm, ML/Ml, MN exactly like parse_raw_mod_tags (src/mod_bam.rs:1457-1470).
+inline void pack_record(const uint8_t* r, uint32_t size, PackedChunk* out) {
+    mkp_read_hdr h;
+    memset(&h, 0, sizeof h);
+    h.ref_start = load_le<int32_t>(r + 4);
+    const uint32_t l_name = r[8];
+    uint32_t n_cigar = load_le<uint16_t>(r + 12);
+    const uint32_t flag = load_le<uint16_t>(r + 14);
+    h.l_seq = (uint32_t)std::max(0, load_le<int32_t>(r + 16));
+    const uint8_t* cigar = r + 32 + l_name;
+    const uint8_t* seq = cigar + 4ull * n_cigar;
+    const uint8_t* qual = seq + (h.l_seq + 1) / 2;
+    const uint8_t* aux = qual + h.l_seq;
+    const uint8_t* end = r + size;
+    // long CIGARs (> 65535 ops) live in the CG:B,I tag (SAMv1 4.2.2)
+    AuxHit cg;
+    if (n_cigar == 2 && aux_find(aux, end, 'C', 'G', &cg) && cg.type == 'B' && cg.sub == 'I') {
+        const uint32_t c0 = load_le<uint32_t>(cigar);
+        if ((c0 & 15) == 4 && (c0 >> 4) == h.l_seq) { cigar = cg.p; n_cigar = cg.n; }
+    }
+    AuxHit mm, ml, mn;
+    bool ok = (aux_find(aux, end, 'M', 'M', &mm) || aux_find(aux, end, 'M', 'm', &mm)) && mm.type == 'Z';
+    ok = ok && (aux_find(aux, end, 'M', 'L', &ml) || aux_find(aux, end, 'M', 'l', &ml)) && ml.type == 'B' && ml.sub == 'C';
+    if (ok && aux_find(aux, end, 'M', 'N', &mn)) {
+        int64_t v = -1;
+        switch (mn.type) {
+            case 'c': v = (int8_t)mn.p[0]; break; case 'C': v = mn.p[0]; break;
+            case 's': v = load_le<int16_t>(mn.p); break; case 'S': v = load_le<uint16_t>(mn.p); break;
+            case 'i': v = load_le<int32_t>(mn.p); break; case 'I': v = load_le<uint32_t>(mn.p); break;
+            default: ok = false;
+        }
+        if (ok && (uint64_t)v != (uint64_t)h.l_seq) ok = false;
+    }
+    h.n_cigar = n_cigar;
+    h.flags = flag | (ok ? 0u : MKP_RF_TAGS_INVALID);
+    h.len_ml = ok ? ml.n : 0;
+    h.len_mm = ok ? mm.n : 0;
+    size_t o = (out->heap.size() + 15) & ~(size_t)15;
+    h.off = o;
+    const size_t need = 4ull * n_cigar + (h.l_seq + 1) / 2 + h.len_ml + h.len_mm;
+    out->heap.resize(o + need);
+    uint8_t* d = out->heap.data() + o;
+    memcpy(d, cigar, 4ull * n_cigar); d += 4ull * n_cigar;
+    memcpy(d, seq, (h.l_seq + 1) / 2); d += (h.l_seq + 1) / 2;
+    if (ok) { memcpy(d, ml.p, ml.n); d += ml.n; memcpy(d, mm.p, mm.n); }
+    out->hdrs.push_back(h);
+}
+
+inline void pack_region(const BamReader& bam, uint32_t tid, uint32_t start, uint32_t end, PackedChunk* out) {
+    bam.for_overlapping(tid, start, end, [&](const RecRef& r) { pack_record(bam.rec(r), r.size, out); out->recs.push_back(r); });
+}
+
+}  // namespace mkh

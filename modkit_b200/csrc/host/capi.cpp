@@ -1,0 +1,53 @@
+// Host C API used by the Python mirror (modkit_b200/__init__.py), tests and bench.py.
+#include "pileup_run.hpp"
+
+using namespace mkh;
+
+struct mkh_bam { BamReader reader; };
+struct mkh_packed { PackedChunk pc; };
+
+extern "C" {
+
+// In-process `modkit pileup`: returns the process exit code the reference would (0 ok, 1 error -> "> Error! ...").
+int mkh_pileup_main(int argc, const char* const* argv) {
+    PileupOptions o;
+    std::string err;
+    if (!parse_pileup_args(argc, argv, &o, &err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 2; }
+    RunSummary s;
+    if (run_pileup(o, &s, &err)) { fprintf(stderr, "> Error! %s\n", err.c_str()); return 1; }
+    return 0;
+}
+
+int mkh_bam_open(const char* path, int threads, mkh_bam** out) {
+    try { mkh_bam* b = new mkh_bam(); b->reader.open(path, threads); *out = b; return 0; }
+    catch (const std::exception& e) { fprintf(stderr, "mkh_bam_open: %s\n", e.what()); return -1; }
+}
+void mkh_bam_close(mkh_bam* b) { delete b; }
+uint32_t mkh_bam_n_refs(const mkh_bam* b) { return (uint32_t)b->reader.ref_names.size(); }
+const char* mkh_bam_ref_name(const mkh_bam* b, uint32_t tid) { return b->reader.ref_names[tid].c_str(); }
+uint32_t mkh_bam_ref_len(const mkh_bam* b, uint32_t tid) { return b->reader.ref_lens[tid]; }
+uint64_t mkh_bam_n_mapped(const mkh_bam* b, uint32_t tid) { return b->reader.stats.n_mapped[tid]; }
+uint64_t mkh_bam_n_records(const mkh_bam* b, uint32_t tid) { return b->reader.by_tid[tid].size(); }
+
+int mkh_pack_region(const mkh_bam* b, uint32_t tid, uint32_t start, uint32_t end, mkh_packed** out) {
+    try { mkh_packed* p = new mkh_packed(); pack_region(b->reader, tid, start, end, &p->pc); *out = p; return 0; }
+    catch (const std::exception& e) { fprintf(stderr, "mkh_pack_region: %s\n", e.what()); return -1; }
+}
+void mkh_packed_free(mkh_packed* p) { delete p; }
+uint32_t mkh_packed_n_reads(const mkh_packed* p) { return (uint32_t)p->pc.hdrs.size(); }
+const mkp_read_hdr* mkh_packed_hdrs(const mkh_packed* p) { return p->pc.hdrs.data(); }
+const uint8_t* mkh_packed_heap(const mkh_packed* p) { return p->pc.heap.data(); }
+uint64_t mkh_packed_heap_bytes(const mkh_packed* p) { return p->pc.heap.size(); }
+uint64_t mkh_packed_algorithmic_bytes(const mkh_packed* p) { return p->pc.algorithmic_bytes(); }
+
+// bedMethyl text of device rows for an all-positions run (bench: rows -> text, writers.rs:87-156)
+uint64_t mkh_format_rows(const mkp_row* rows, uint64_t n, const char* chrom, int mixed_delim, char* out, uint64_t cap) {
+    BedFormat fmt; fmt.mixed_delim = mixed_delim != 0;
+    std::string text;
+    const std::string c = chrom;
+    for (uint64_t i = 0; i < n; i++) { OutRow o{rows[i], -1, (char)rows[i].strand}; format_bed_row(o, c, fmt, &text); }
+    if (out && text.size() <= cap) memcpy(out, text.data(), text.size());
+    return text.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,373 @@
+// Host side of the B200 `modkit pileup` path: everything the reference does around
+// process_region_batch (src/pileup/subcommand.rs:381-817) that is not the hot loop itself:
+//   reference intervals + focus positions   src/interval_chunks.rs:61-297, 563-643; src/fasta.rs:92-226
+//   motif search                            src/find_motifs/motif_bed.rs:21-330
+//   strand combining / motif labelling      src/pileup/mod.rs:331-363, 469-561
+//   bedMethyl text                          src/writers.rs:87-156
+// The per-read work (MM/ML decode, CIGAR projection, thresholding, counting) runs on the GPU behind
+// include/mkp.h; nothing here computes calls or counts.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+#include "bam_reader.hpp"
+
+namespace mkh {
+
+// ---------------------------------------------------------------- FASTA (.fai) -------------------
+class IndexedFasta {
+    struct Ent { uint64_t len, off, bases, width; };
+    std::map<std::string, Ent> ents_;
+    FILE* fh_ = nullptr;
+public:
+    ~IndexedFasta() { if (fh_) fclose(fh_); }
+    void open(const std::string& fa) {
+        std::ifstream f(fa + ".fai");
+        if (!f) throw std::runtime_error("failed to open FASTA index " + fa + ".fai (a .fai is required)");
+        std::string name;
+        Ent e;
+        std::string line;
+        while (std::getline(f, line)) { std::istringstream ss(line); if (ss >> name >> e.len >> e.off >> e.bases >> e.width) ents_[name] = e; }
+        fh_ = fopen(fa.c_str(), "rb");
+        if (!fh_) throw std::runtime_error("failed to open FASTA " + fa);
+    }
+    uint64_t length(const std::string& contig) const { auto it = ents_.find(contig); return it == ents_.end() ? 0 : it->second.len; }
+    // upper-cased (unless keep_case) bases [b,e)
+    void slice(const std::string& contig, uint64_t b, uint64_t e, bool keep_case, std::string* out) {
+        out->clear();
+        auto it = ents_.find(contig);
+        if (it == ents_.end()) throw std::runtime_error("contig " + contig + " missing from FASTA index");
+        const Ent& en = it->second;
+        e = std::min(e, en.len);
+        if (b >= e) return;
+        const uint64_t first = en.off + (b / en.bases) * en.width + b % en.bases;
+        const uint64_t last = en.off + ((e - 1) / en.bases) * en.width + (e - 1) % en.bases;
+        std::string buf(last - first + 1, '\0');
+        fseeko(fh_, (off_t)first, SEEK_SET);
+        const size_t got = fread(&buf[0], 1, buf.size(), fh_);
+        out->reserve(e - b);
+        for (size_t i = 0; i < got; i++) { char c = buf[i]; if (c == '\n' || c == '\r') continue; out->push_back(keep_case ? c : (char)toupper((unsigned char)c)); }
+    }
+};
+
+// ---------------------------------------------------------------- motifs -------------------------
+struct MotifSpec {
+    std::string raw;
+    int offset = 0, rc_offset = 0, len = 0;
+    bool palindromic = false;
+    std::vector<uint8_t> fwd, rev;   // per position: allowed-base bit set A1 C2 G4 T8
+    std::string label() const { return raw + "," + std::to_string(offset); }
+};
+
+inline uint8_t iupac_bits(char c) {
+    switch (c) {
+        case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8; case 'U': return 0;
+        case 'M': return 3; case 'R': return 5; case 'W': return 9; case 'S': return 6; case 'Y': return 10; case 'K': return 12;
+        case 'V': return 7; case 'H': return 11; case 'D': return 13; case 'B': return 14; case 'X': case 'N': return 15;
+        default: return 0xff;
+    }
+}
+inline uint8_t comp_bits(uint8_t m) { return (uint8_t)(((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3)); }
+
+inline MotifSpec parse_motif(const std::string& raw, int offset) {
+    MotifSpec m;
+    m.raw = raw; m.len = (int)raw.size(); m.offset = offset;
+    if (m.len == 1 && std::string("ACGT").find(raw[0]) == std::string::npos)
+        throw std::runtime_error("degenerate bases are not supported as single base motifs, must be 'A', 'C', 'G', or 'T'.");
+    if (offset + 1 > m.len) throw std::runtime_error("motif not long enough for offset " + std::to_string(offset));
+    m.rc_offset = m.len - (offset + 1);
+    for (char c : raw) { uint8_t b = iupac_bits(c); if (b == 0xff) throw std::runtime_error(std::string("Invalid IUPAC code: ") + c); m.fwd.push_back(b); }
+    for (int i = m.len - 1; i >= 0; i--) m.rev.push_back(raw[i] == 'U' ? 1 : comp_bits(m.fwd[i]));
+    // The reference compares the forward regex text with its reverse complement (motif_bed.rs:217-222). The text of
+    // a class such as "[AC]" reverse-complements to "[GT]" with the letters in reversed order, so the texts are equal
+    // exactly when the class sets are equal position by position and every class reads the same after that reversal,
+    // which holds for all IUPAC classes the reference emits except none: set equality is the criterion.
+    m.palindromic = (m.fwd == m.rev);
+    for (char c : raw) if (c == 'U') m.palindromic = false;
+    return m;
+}
+
+inline uint8_t base_bit(char c) { return c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 4 : c == 'T' ? 8 : 0; }
+
+typedef std::map<uint32_t, uint8_t> SiteRules;   // position -> StrandRule bits (1 '+', 2 '-', 3 both)
+
+inline void add_site(SiteRules* s, uint32_t p, uint8_t strand_bit) {
+    auto it = s->find(p);
+    if (it == s->end()) (*s)[p] = strand_bit; else if (it->second != strand_bit) it->second = 3;
+}
+
+// all hits of one motif inside seq (which starts at reference coordinate `origin`)
+inline void motif_sites(const std::string& seq, uint64_t origin, const MotifSpec& m, SiteRules* out) {
+    const size_t n = seq.size();
+    auto hit = [&](size_t i, const std::vector<uint8_t>& cls) {
+        if (i + cls.size() > n) return false;
+        for (size_t k = 0; k < cls.size(); k++) if (!(base_bit(seq[i + k]) & cls[k])) return false;
+        return true;
+    };
+    if (m.palindromic) {
+        for (size_t i = 0; i < n; i++) if (hit(i, m.fwd)) { add_site(out, (uint32_t)(origin + i + m.offset), 1); add_site(out, (uint32_t)(origin + i + m.rc_offset), 2); }
+    } else if (m.len == 1) {
+        const char fw = m.raw[0], rv = fw == 'A' ? 'T' : fw == 'C' ? 'G' : fw == 'G' ? 'C' : 'A';
+        for (size_t i = 0; i < n; i++) { if (seq[i] == fw) add_site(out, (uint32_t)(origin + i), 1); else if (seq[i] == rv) add_site(out, (uint32_t)(origin + i), 2); }
+    } else {
+        for (size_t i = 0; i < n; i++) {
+            if (hit(i, m.fwd)) add_site(out, (uint32_t)(origin + i + m.offset), 1);
+            if (hit(i, m.rev)) add_site(out, (uint32_t)(origin + i + m.rc_offset), 2);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- intervals ----------------------
+struct RefTarget { uint32_t tid, start, length; std::string name; uint32_t end() const { return start + length; } };
+
+struct RefInterval {
+    uint32_t tid = 0, start = 0, end = 0;
+    bool all_positions = true;
+    SiteRules rule;                                      // focus positions
+    std::map<uint32_t, std::vector<int>> plus_ids, minus_ids;   // motif ids per strand
+};
+
+struct MotifContext {
+    IndexedFasta fasta;
+    std::vector<MotifSpec> motifs;
+    bool keep_case = false;   // --mask
+    uint64_t longest = 0;
+};
+
+inline void fill_focus(RefInterval* iv, const std::vector<SiteRules>& sites, const std::vector<MotifSpec>& motifs, bool combine) {
+    iv->all_positions = false;
+    auto inside = [&](uint32_t p) { return p >= iv->start && p < iv->end; };
+    if (combine) {   // FocusPositions::new_motif_combine_strands
+        for (size_t id = 0; id < sites.size(); id++) for (auto& kv : sites[id]) {
+            if (!inside(kv.first)) continue;
+            auto it = iv->rule.find(kv.first);
+            if (it == iv->rule.end()) iv->rule[kv.first] = kv.second; else if (it->second != kv.second) it->second = 3;
+            if (kv.second & 1) iv->plus_ids[kv.first].push_back((int)id); else iv->minus_ids[kv.first].push_back((int)id);
+        }
+        return;
+    }
+    bool all_single = true;
+    for (auto& m : motifs) all_single = all_single && m.len == 1;
+    if (sites.size() == 1) {
+        for (auto& kv : sites[0]) {
+            if (!inside(kv.first)) continue;
+            iv->rule[kv.first] = kv.second;
+            if (kv.second & 1) iv->plus_ids[kv.first] = {0};
+            if (kv.second & 2) iv->minus_ids[kv.first] = {0};
+        }
+    } else if (all_single) {
+        auto id_of = [&](const char* b) { for (size_t i = 0; i < motifs.size(); i++) if (motifs[i].raw == b) return (int)i; return -1; };
+        const char* pairs[2][2] = {{"A", "T"}, {"C", "G"}};
+        for (auto& pr : pairs) {
+            const int top = id_of(pr[0]), bot = id_of(pr[1]);
+            if (top < 0) continue;   // the reference only walks the top base's table (interval_chunks.rs:216)
+            for (auto& kv : sites[top]) {
+                if (!inside(kv.first)) continue;
+                if (bot >= 0) { iv->rule[kv.first] = 3; iv->plus_ids[kv.first] = {top, bot}; iv->minus_ids[kv.first] = {top, bot}; }
+                else { iv->rule[kv.first] = kv.second; if (kv.second == 1) iv->plus_ids[kv.first] = {top}; else if (kv.second == 2) iv->minus_ids[kv.first] = {top}; }
+            }
+        }
+    } else {
+        for (size_t id = 0; id < sites.size(); id++) for (auto& kv : sites[id]) {
+            if (!inside(kv.first)) continue;
+            auto it = iv->rule.find(kv.first);
+            if (it == iv->rule.end()) iv->rule[kv.first] = kv.second; else if (it->second != kv.second) it->second = 3;
+            if (kv.second & 1) iv->plus_ids[kv.first].push_back((int)id);
+            if (kv.second & 2) iv->minus_ids[kv.first].push_back((int)id);
+        }
+    }
+}
+
+// Motif sites of [start,end) and the (possibly extended) interval end (src/fasta.rs:92-226)
+inline uint32_t motif_interval(MotifContext& mc, const RefTarget& c, uint64_t start, uint64_t end, bool combine, std::vector<SiteRules>* sites) {
+    std::string seq;
+    auto scan = [&](uint64_t e) {
+        mc.fasta.slice(c.name, start, e, mc.keep_case, &seq);
+        sites->assign(mc.motifs.size(), SiteRules());
+        for (size_t i = 0; i < mc.motifs.size(); i++) motif_sites(seq, start, mc.motifs[i], &(*sites)[i]);
+    };
+    if (!combine) { scan(end); return (uint32_t)end; }
+    const uint64_t ref_end = c.end();
+    const uint64_t pad = mc.longest * 5;
+    uint64_t cut = end, fetch_end = std::min(end + pad, ref_end);
+    for (;;) {
+        scan(fetch_end);
+        const uint64_t too_close = fetch_end >= mc.longest ? fetch_end - mc.longest : 0;
+        // union of [site, site + len - offset) spans; spans that touch are merged (rust-lapper merge_overlaps)
+        std::vector<std::pair<uint64_t, uint64_t>> spans;
+        for (size_t i = 0; i < sites->size(); i++) {
+            const uint64_t adj = mc.motifs[i].len >= mc.motifs[i].offset ? mc.motifs[i].len - mc.motifs[i].offset : mc.motifs[i].len;
+            for (auto& kv : (*sites)[i]) spans.push_back({kv.first, kv.first + adj});
+        }
+        std::sort(spans.begin(), spans.end());
+        uint64_t search_end = cut;
+        uint64_t cur_b = 0, cur_e = 0;
+        bool open = false;
+        auto test = [&](uint64_t b, uint64_t e) { return b < cut && e > (cut ? cut - 1 : 0); };
+        bool found = false;
+        for (auto& s : spans) {
+            if (open && s.first <= cur_e) { cur_e = std::max(cur_e, s.second); continue; }
+            if (open && test(cur_b, cur_e)) { search_end = cur_e; found = true; break; }
+            cur_b = s.first; cur_e = s.second; open = true;
+        }
+        if (!found && open && test(cur_b, cur_e)) search_end = cur_e;
+        if (search_end < too_close || fetch_end >= ref_end) {
+            for (auto& s : *sites) for (auto it = s.begin(); it != s.end();) { if (it->first > search_end) it = s.erase(it); else ++it; }
+            return (uint32_t)search_end;
+        }
+        cut = fetch_end;
+        fetch_end = std::min(fetch_end + pad, ref_end);
+    }
+}
+
+// ReferenceIntervalsFeeder order (src/interval_chunks.rs:563-643); `groups` = MultiChromCoordinates membership
+inline std::vector<RefInterval> reference_intervals(const std::vector<RefTarget>& targets, uint32_t interval_size, bool combine,
+                                                    MotifContext* mc, std::vector<std::vector<size_t>>* groups = nullptr) {
+    std::vector<RefInterval> out;
+    std::vector<size_t> grp;
+    uint64_t grp_len = 0;
+    for (auto& c : targets) {
+        if (!c.length) continue;
+        uint32_t at = c.start;
+        for (;;) {
+            RefInterval iv;
+            iv.tid = c.tid; iv.start = at;
+            uint32_t e = (uint32_t)std::min<uint64_t>((uint64_t)at + interval_size, c.end());
+            if (mc) {
+                std::vector<SiteRules> sites;
+                e = std::min(motif_interval(*mc, c, at, e, combine, &sites), c.end());
+                iv.end = e;
+                fill_focus(&iv, sites, mc->motifs, combine);
+            } else iv.end = e;
+            grp_len += iv.end - iv.start;
+            grp.push_back(out.size());
+            out.push_back(std::move(iv));
+            if (grp_len >= interval_size) { if (groups) groups->push_back(grp); grp.clear(); grp_len = 0; }
+            if (e >= c.end()) break;
+            at = e;
+        }
+    }
+    if (groups && !grp.empty()) groups->push_back(grp);
+    return out;
+}
+
+// ---------------------------------------------------------------- rows -> bedMethyl --------------
+struct OutRow { mkp_row r; int motif_idx; char strand; };
+
+inline std::string code_text(uint32_t code) { return (code & 0x80000000u) ? std::to_string(code & 0x7fffffffu) : std::string(1, (char)code); }
+
+// Expand device rows of one interval into output rows: motif-id replication (pileup/mod.rs:331-363) and
+// strand combination (pileup/mod.rs:469-561).
+inline void finish_interval_rows(const RefInterval& iv, const mkp_row* rows, size_t n, const std::vector<MotifSpec>* motifs,
+                                 bool combine_strands, std::vector<OutRow>* out) {
+    std::vector<OutRow> tmp;
+    for (size_t i = 0; i < n; i++) {
+        const mkp_row& r = rows[i];
+        const std::vector<int>* ids = nullptr;
+        if (!iv.all_positions) {
+            const auto& m = r.strand == '+' ? iv.plus_ids : iv.minus_ids;
+            auto it = m.find(r.pos);
+            if (it != m.end()) ids = &it->second;
+        }
+        if (ids) for (int id : *ids) tmp.push_back({r, id, (char)r.strand}); else tmp.push_back({r, -1, (char)r.strand});
+    }
+    if (!(combine_strands && !iv.all_positions && motifs)) { out->insert(out->end(), tmp.begin(), tmp.end()); return; }
+    // rows are position sorted: index by position
+    std::map<uint32_t, std::pair<size_t, size_t>> span;
+    for (size_t i = 0; i < tmp.size();) { size_t j = i; while (j < tmp.size() && tmp[j].r.pos == tmp[i].r.pos) j++; span[tmp[i].r.pos] = {i, j}; i = j; }
+    for (auto& kv : iv.plus_ids) {
+        const uint32_t p = kv.first;
+        for (int id : kv.second) {
+            const MotifSpec& m = (*motifs)[id];
+            if (!m.palindromic) continue;
+            const int64_t partner = (int64_t)p + (m.rc_offset - m.offset);
+            if (partner < 0) continue;
+            std::map<uint32_t, mkp_row> acc;
+            auto take = [&](uint32_t at, char strand) {
+                auto it = span.find(at);
+                if (it == span.end()) return;
+                for (size_t i = it->second.first; i < it->second.second; i++) {
+                    const OutRow& o = tmp[i];
+                    if (o.strand != strand || o.motif_idx != id) continue;
+                    auto a = acc.find(o.r.code);
+                    if (a == acc.end()) { mkp_row z; memset(&z, 0, sizeof z); z.pos = p; z.code = o.r.code; z.strand = '.'; z.primary_base = o.r.primary_base; a = acc.emplace(o.r.code, z).first; }
+                    mkp_row& A = a->second;
+                    A.n_mod += o.r.n_mod; A.n_canon += o.r.n_canon; A.n_other += o.r.n_other; A.n_delete += o.r.n_delete;
+                    A.n_filtered += o.r.n_filtered; A.n_diff += o.r.n_diff; A.n_nocall += o.r.n_nocall;
+                }
+            };
+            take(p, '+');
+            take((uint32_t)partner, '-');
+            for (auto& a : acc) out->push_back({a.second, id, '.'});
+        }
+    }
+}
+
+struct BedFormat { bool mixed_delim = false; std::vector<std::string> motif_labels; };
+
+inline char* put_u32(char* p, uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *p++ = t[--n]; return p; }
+
+inline void format_bed_row(const OutRow& o, const std::string& chrom, const BedFormat& fmt, std::string* out) {
+    const mkp_row& r = o.r;
+    const uint32_t cov = r.n_mod + r.n_canon + r.n_other;
+    char buf[256];
+    char* p = buf;
+    const char sp = fmt.mixed_delim ? ' ' : '\t';
+    std::string name = code_text(r.code);
+    if (fmt.motif_labels.size() >= 2 && o.motif_idx >= 0 && (size_t)o.motif_idx < fmt.motif_labels.size()) name += "," + fmt.motif_labels[o.motif_idx];
+    out->append(chrom);
+    *p++ = '\t'; p = put_u32(p, r.pos); *p++ = '\t'; p = put_u32(p, r.pos + 1); *p++ = '\t';
+    out->append(buf, p - buf); out->append(name); p = buf;
+    *p++ = '\t'; p = put_u32(p, cov); *p++ = '\t'; *p++ = o.strand; *p++ = '\t'; p = put_u32(p, r.pos); *p++ = '\t'; p = put_u32(p, r.pos + 1);
+    memcpy(p, "\t255,0,0\t", 9); p += 9;
+    p = put_u32(p, cov); *p++ = sp;
+    // writers.rs:140: format!("{:.2}", fraction_modified * 100f32) with f32 arithmetic
+    const float frac = (float)r.n_mod / (float)cov;
+    volatile float pct = frac * 100.0f;
+    p += snprintf(p, 32, "%.2f", (double)pct);
+    *p++ = sp; p = put_u32(p, r.n_mod); *p++ = sp; p = put_u32(p, r.n_canon); *p++ = sp; p = put_u32(p, r.n_other);
+    *p++ = sp; p = put_u32(p, r.n_delete); *p++ = sp; p = put_u32(p, r.n_filtered); *p++ = sp; p = put_u32(p, r.n_diff);
+    *p++ = sp; p = put_u32(p, r.n_nocall); *p++ = '\n';
+    out->append(buf, p - buf);
+}
+
+inline const char* bed_header_line() {
+    return "chrom\tchromStart\tchromEnd\tname\tscore\tstrand\tthickStart\tthickEnd\tcolor\tvalid_coverage\tpercent_modified\t"
+           "count_modified\tcount_canonical\tcount_other_mod\tcount_delete\tcount_fail\tcount_diff\tcount_nocall\n";
+}
+
+// focus bitmaps of a chunk [cs,ce) from its intervals
+inline void focus_bitmaps(const std::vector<RefInterval>& ivs, size_t i0, size_t i1, uint32_t cs, uint32_t ce,
+                          std::vector<uint32_t>* fpos, std::vector<uint32_t>* fneg) {
+    const size_t nw = (ce - cs + 31) / 32;
+    fpos->assign(nw, 0); fneg->assign(nw, 0);
+    for (size_t i = i0; i < i1; i++) for (auto& kv : ivs[i].rule) {
+        const uint32_t x = kv.first - cs;
+        if (kv.second & 1) (*fpos)[x >> 5] |= 1u << (x & 31);
+        if (kv.second & 2) (*fneg)[x >> 5] |= 1u << (x & 31);
+    }
+}
+
+// thresholds.rs:17-39 on a histogram whose bins are exact values k/1024
+inline bool percentile_from_hist(const uint64_t* h, float q, float* out) {
+    uint64_t n = 0;
+    for (int k = 0; k <= 1024; k++) n += h[k];
+    if (n < 2) return false;
+    auto value_at = [&](uint64_t idx) { uint64_t acc = 0; for (int k = 0; k <= 1024; k++) { acc += h[k]; if (idx < acc) return (float)k / 1024.0f; } return 1.0f; };
+    if (q == 1.0f) { *out = value_at(n - 1); return true; }
+    const float l = (float)(n - 1);
+    const float x = l * q;
+    const float left = std::floor(x);
+    const uint64_t right = (uint64_t)std::ceil(x);
+    const float g = x - std::trunc(x);
+    const float y0 = value_at((uint64_t)left), y1 = value_at(right);
+    volatile float a = y0 * (1.0f - g);
+    volatile float b = y1 * g;
+    *out = a + b;
+    return true;
+}
+
+}  // namespace mkh

@@ -1,0 +1,485 @@
+// `modkit pileup` orchestration on top of the device C ABI (include/mkp.h).
+// Mirrors ModBamPileup::run (src/pileup/subcommand.rs:381-817): same flags, same defaults, same error
+// messages where they are observable, same output ordering (feeder order, positions ascending).
+#pragma once
+#include <chrono>
+#include <unordered_set>
+
+#include "pileup_host.hpp"
+
+namespace mkh {
+
+struct PileupOptions {
+    std::string in_bam, out_bed;
+    int threads = 4;
+    uint32_t interval_size = 100000, sampling_interval_size = 1000000;
+    size_t num_reads = 10042;
+    bool have_frac = false; double frac = 0;
+    bool no_filtering = false, include_unmapped = false, force_allow = false, cpg = false, mask = false;
+    bool traditional = false, combine_mods = false, combine_strands = false, mixed = false, header = false, invert_edge = false;
+    float percentile = 0.1f;
+    std::vector<std::string> filter_thresholds, mod_thresholds, motif_parts;
+    std::string region, sample_region, ignore, ref_fp, edge, stats_json;
+    int device = 0;
+    uint32_t chunk_bp = 16u << 20;     // reference span handed to the GPU per call
+    bool quiet = false;
+};
+
+struct Region { std::string name; uint32_t start = 0, end = 0; };
+
+inline bool parse_code(const std::string& raw, uint32_t* out) {
+    if (raw.size() == 1) { *out = (uint8_t)raw[0]; return true; }
+    if (raw.empty()) return false;
+    uint64_t v = 0;
+    for (char c : raw) { if (c < '0' || c > '9') return false; v = v * 10 + (c - '0'); if (v > 0x7fffffffull) return false; }
+    *out = 0x80000000u | (uint32_t)v;
+    return true;
+}
+
+inline Region parse_region_arg(const std::string& raw, const BamReader& bam) {   // util.rs:475-523
+    auto colon = raw.find(':');
+    if (colon == std::string::npos) {
+        for (size_t i = 0; i < bam.ref_names.size(); i++) if (bam.ref_names[i] == raw) return Region{raw, 0, bam.ref_lens[i]};
+        throw std::runtime_error("contig " + raw + " missing from header");
+    }
+    Region r;
+    r.name = raw.substr(0, colon);
+    const std::string rest = raw.substr(colon + 1);
+    auto dash = rest.find('-');
+    if (rest.find(':') != std::string::npos || dash == std::string::npos || rest.find('-', dash + 1) != std::string::npos)
+        throw std::runtime_error("invalid region " + raw);
+    auto num = [&](std::string s) {
+        s.erase(std::remove(s.begin(), s.end(), ','), s.end());
+        if (s.empty() || s.find_first_not_of("0123456789") != std::string::npos) throw std::runtime_error("invalid region " + raw);
+        return (uint32_t)std::stoull(s);
+    };
+    r.start = num(rest.substr(0, dash));
+    r.end = num(rest.substr(dash + 1));
+    if (r.end <= r.start) throw std::runtime_error("invalid region " + raw);
+    return r;
+}
+
+struct DeviceGuard {
+    mkp_ctx* ctx = nullptr;
+    ~DeviceGuard() { if (ctx) mkp_destroy(ctx); }
+};
+
+// ---- threshold estimation: host schedule (reads_sampler/*), device decode + histogram --------------
+struct SamplerConfig {
+    int threads = 4;
+    uint32_t sampling_interval_size = 1000000;
+    bool take_all = false;
+    size_t num_reads = 10042;
+    const Region* region = nullptr;
+    bool include_unmapped = false;
+    bool edge_on = false;
+};
+
+inline bool sampler_flag_ok(const uint8_t* rec, bool require_mapped) {
+    const uint16_t flag = load_le<uint16_t>(rec + 14);
+    if (flag & (0x100 | 0x400 | 0x800)) return false;
+    if (load_le<int32_t>(rec + 16) == 0) return false;
+    if (require_mapped && (flag & 0x4)) return false;
+    return true;
+}
+
+// Fills hist[4][1025]; returns number of reads selected
+inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const SamplerConfig& cfg, uint64_t* hist, uint64_t* inexact) {
+    int region_tid = -1;
+    if (cfg.region) {
+        for (size_t i = 0; i < bam.ref_names.size(); i++) if (bam.ref_names[i] == cfg.region->name) region_tid = (int)i;
+        if (region_tid < 0) throw std::runtime_error("did not find target_id for region in header");
+    }
+    uint64_t total_mapped = 0, total_unmapped = 0;
+    std::map<uint32_t, uint64_t> mapped;
+    for (uint32_t t = 0; t < bam.ref_names.size(); t++) {
+        if (cfg.region && (int)t != region_tid) continue;
+        mapped[t] = bam.stats.n_mapped[t];
+        total_mapped += bam.stats.n_mapped[t];
+        total_unmapped += bam.stats.n_unmapped[t];
+    }
+    if (!cfg.region) total_unmapped += bam.stats.n_no_coor;
+    const uint64_t total = cfg.include_unmapped ? total_mapped + total_unmapped : total_mapped;
+    if (!total) throw std::runtime_error("zero reads found in bam index");
+    std::map<uint32_t, int64_t> quota;   // -1 = all
+    for (auto& kv : mapped) {
+        if (!kv.second) continue;
+        if (cfg.take_all) { quota[kv.first] = -1; continue; }
+        const float frac = (float)kv.second / (float)total;
+        quota[kv.first] = (int64_t)std::min<uint64_t>((uint64_t)std::ceil((float)cfg.num_reads * frac), kv.second);
+    }
+    std::vector<RefTarget> contigs;
+    std::map<uint32_t, uint32_t> contig_len;
+    for (uint32_t t = 0; t < bam.ref_names.size(); t++) {
+        if (!quota.count(t)) continue;
+        RefTarget c{t, 0, bam.ref_lens[t], bam.ref_names[t]};
+        if (cfg.region) { c.start = cfg.region->start; c.length = cfg.region->end - cfg.region->start; }
+        contigs.push_back(c);
+        contig_len[t] = c.length;
+    }
+    std::vector<std::vector<size_t>> groups;
+    std::vector<RefInterval> ivs;
+    if (!contigs.empty()) ivs = reference_intervals(contigs, cfg.sampling_interval_size, false, nullptr, &groups);
+    const size_t B = std::max<size_t>(1, (size_t)std::floor((float)cfg.threads * 1.5f));
+    const bool only_mapped = !cfg.include_unmapped;
+    std::map<uint32_t, size_t> so_far;
+    std::unordered_set<uint64_t> selected_ids;     // record identity = offset in the stream
+    PackedChunk selected;                           // every selected read, once
+    PackedChunk cand;
+    std::vector<uint8_t> contributes;
+
+    auto decode_contributes = [&](PackedChunk& pc) {
+        contributes.assign(pc.hdrs.size(), 0);
+        if (pc.hdrs.empty()) return;
+        mkp_chunk ch;
+        memset(&ch, 0, sizeof ch);
+        ch.start = 0; ch.end = 32; ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
+        if (mkp_upload_chunk(ctx, &ch)) throw std::runtime_error(mkp_last_error(ctx));
+        if (mkp_sample_histogram(ctx, cfg.include_unmapped ? 1 : 0, nullptr, nullptr, contributes.data(), nullptr)) throw std::runtime_error(mkp_last_error(ctx));
+    };
+
+    struct Grp { uint32_t tid, start, end; int64_t n; };
+    for (size_t sb = 0; sb < groups.size(); sb += B) {
+        std::vector<size_t> coords;
+        for (size_t k = sb; k < std::min(groups.size(), sb + B); k++) for (size_t i : groups[k]) coords.push_back(i);
+        std::sort(coords.begin(), coords.end(), [&](size_t a, size_t b) { return ivs[a].tid != ivs[b].tid ? ivs[a].tid < ivs[b].tid : ivs[a].start < ivs[b].start; });
+        std::map<uint32_t, uint32_t> len_c;
+        for (size_t i : coords) len_c[ivs[i].tid] += ivs[i].end - ivs[i].start;
+        std::map<uint32_t, int64_t> k_c;
+        for (auto& kv : len_c) {
+            auto q = quota.find(kv.first);
+            if (q == quota.end()) continue;
+            if (q->second < 0) { k_c[kv.first] = -1; continue; }
+            const size_t done = so_far.count(kv.first) ? so_far[kv.first] : 0;
+            if ((size_t)q->second <= done) continue;
+            const float f = (float)kv.second / (float)contig_len[kv.first];
+            k_c[kv.first] = (int64_t)std::ceil(f * (float)((size_t)q->second - done));
+        }
+        std::vector<Grp> todo;
+        bool have = false;
+        Grp slack{};
+        for (size_t i : coords) {
+            const RefInterval& iv = ivs[i];
+            auto kc = k_c.find(iv.tid);
+            if (kc == k_c.end()) continue;
+            if (kc->second < 0) { todo.push_back({iv.tid, iv.start, iv.end, -1}); continue; }
+            const float f = (float)(iv.end - iv.start) / (float)len_c[iv.tid];
+            const int64_t x = (int64_t)std::ceil((float)kc->second * f);
+            Grp cur{iv.tid, iv.start, iv.end, x};
+            if (x < 50) {
+                if (!have) { slack = cur; have = true; }
+                else if (slack.tid == cur.tid) {
+                    Grp m{cur.tid, std::min(slack.start, cur.start), std::max(slack.end, cur.end), slack.n + x};
+                    if (m.n < 50) slack = m; else { todo.push_back(m); have = false; }
+                } else { todo.push_back(slack); slack = cur; }
+            } else if (have) {
+                have = false;
+                if (slack.tid == cur.tid) todo.push_back({cur.tid, std::min(slack.start, cur.start), std::max(slack.end, cur.end), slack.n + x});
+                else { todo.push_back(slack); todo.push_back(cur); }
+            } else todo.push_back(cur);
+        }
+        if (have) todo.push_back(slack);
+        // candidates of every interval of this super batch in one device pass; extend while an interval is short
+        for (const Grp& g : todo) {
+            std::vector<RecRef> recs;
+            bam.for_overlapping(g.tid, g.start, g.end, [&](const RecRef& r) { if (sampler_flag_ok(bam.rec(r), only_mapped || cfg.edge_on)) recs.push_back(r); });
+            size_t used = 0, cursor = 0;
+            while (cursor < recs.size() && (g.n < 0 || used < (size_t)g.n)) {
+                const size_t want = g.n < 0 ? recs.size() : std::min(recs.size(), cursor + (size_t)(g.n - (int64_t)used) * 2 + 32);
+                cand.clear();
+                for (size_t k = cursor; k < want; k++) { pack_record(bam.rec(recs[k]), recs[k].size, &cand); cand.recs.push_back(recs[k]); }
+                decode_contributes(cand);
+                for (size_t k = 0; k < cand.hdrs.size() && (g.n < 0 || used < (size_t)g.n); k++) {
+                    if (!contributes[k]) continue;
+                    used++;
+                    if (selected_ids.insert(cand.recs[k].off).second) { pack_record(bam.rec(cand.recs[k]), cand.recs[k].size, &selected); selected.recs.push_back(cand.recs[k]); }
+                }
+                cursor = want;
+            }
+            so_far[g.tid] += used;
+        }
+    }
+    if (!only_mapped) {   // reads without coordinates (reads_sampler/mod.rs:85-129)
+        const size_t limit = cfg.take_all ? (size_t)-1 : (cfg.num_reads > selected_ids.size() ? cfg.num_reads - selected_ids.size() : 0);
+        cand.clear();
+        for (auto& r : bam.unplaced) if (sampler_flag_ok(bam.rec(r), cfg.edge_on)) { pack_record(bam.rec(r), r.size, &cand); cand.recs.push_back(r); }
+        decode_contributes(cand);
+        size_t used = 0;
+        for (size_t k = 0; k < cand.hdrs.size() && used < limit; k++) {
+            if (!contributes[k]) continue;
+            used++;
+            if (selected_ids.insert(cand.recs[k].off).second) { pack_record(bam.rec(cand.recs[k]), cand.recs[k].size, &selected); selected.recs.push_back(cand.recs[k]); }
+        }
+    }
+    memset(hist, 0, 4 * 1025 * sizeof(uint64_t));
+    if (inexact) *inexact = 0;
+    if (!selected.hdrs.empty()) {
+        mkp_chunk ch;
+        memset(&ch, 0, sizeof ch);
+        ch.start = 0; ch.end = 32; ch.hdrs = selected.hdrs.data(); ch.n_reads = (uint32_t)selected.hdrs.size(); ch.heap = selected.heap.data(); ch.heap_bytes = selected.heap.size();
+        if (mkp_upload_chunk(ctx, &ch)) throw std::runtime_error(mkp_last_error(ctx));
+        if (mkp_sample_histogram(ctx, cfg.include_unmapped ? 1 : 0, nullptr, hist, nullptr, inexact)) throw std::runtime_error(mkp_last_error(ctx));
+    }
+    return selected.hdrs.size();
+}
+
+struct RunSummary {
+    uint64_t positions = 0, rows = 0, reads_packed = 0, algorithmic_bytes = 0, chunks = 0;
+    double load_s = 0, threshold_s = 0, interval_s = 0, pack_s = 0, gpu_s = 0, write_s = 0, total_s = 0, kernel_ms = 0;
+    float thresholds[4] = {0, 0, 0, 0};
+    bool threshold_set[4] = {false, false, false, false};
+};
+
+inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* error) {
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    try {
+        const auto t0 = clk::now();
+        if (o.percentile > 1.0f) throw std::runtime_error("filter percentile must be <= 1.0");
+        BamReader bam;
+        bam.open(o.in_bam, o.threads);
+        const auto t_load = clk::now();
+        Region region, sregion;
+        const Region* rp = nullptr; const Region* srp = nullptr;
+        if (!o.region.empty()) { region = parse_region_arg(o.region, bam); rp = &region; }
+        if (!o.sample_region.empty()) { sregion = parse_region_arg(o.sample_region, bam); srp = &sregion; }
+        std::vector<RefTarget> targets;
+        for (uint32_t t = 0; t < bam.ref_names.size(); t++) {
+            if (rp) { if (bam.ref_names[t] == rp->name) targets.push_back({t, rp->start, rp->end - rp->start, rp->name}); }
+            else targets.push_back({t, 0, bam.ref_lens[t], bam.ref_names[t]});
+        }
+        uint64_t any_mapped = 0;
+        for (auto& t : targets) any_mapped += bam.stats.n_mapped[t.tid];
+        if (!any_mapped) throw std::runtime_error("did not find any mapped reads, perform alignment first or use modkit extract and/or modkit summary to inspect unaligned modBAMs");
+        bool combine_strands = o.combine_strands;
+        if (combine_strands && !(o.cpg || !o.motif_parts.empty())) throw std::runtime_error("need to specify either --motif or --cpg to combine strands");
+
+        mkp_params P;
+        memset(&P, 0, sizeof P);
+        P.force_allow_implicit = o.force_allow;
+        if (o.traditional) { P.numeric_mode = 2; P.collapse_code = 'h'; combine_strands = true; }
+        else if (o.combine_mods) P.numeric_mode = 1;
+        else if (!o.ignore.empty()) { uint32_t c; if (!parse_code(o.ignore, &c)) throw std::runtime_error("failed to parse mod code " + o.ignore); P.numeric_mode = 2; P.collapse_code = c; }
+        if (!o.edge.empty()) {
+            P.edge_filter_on = 1; P.edge_filter_inverted = o.invert_edge;
+            auto c = o.edge.find(',');
+            if (c == std::string::npos) P.edge_filter_start = P.edge_filter_end = (uint32_t)std::stoul(o.edge);
+            else { P.edge_filter_start = (uint32_t)std::stoul(o.edge.substr(0, c)); P.edge_filter_end = (uint32_t)std::stoul(o.edge.substr(c + 1)); }
+        }
+        // motifs (subcommand.rs:526-539, 592-612)
+        std::vector<std::string> parts = o.motif_parts;
+        MotifContext mc;
+        bool have_motifs = false;
+        if (!parts.empty()) {
+            if (o.traditional) throw std::runtime_error("cannot use presets and motifs together");
+            if (parts.size() % 2) throw std::runtime_error("illegal number of parts for motif");
+            for (size_t i = 0; i < parts.size(); i += 2) for (size_t j = i + 2; j < parts.size(); j += 2)
+                if (parts[i] == parts[j] && parts[i + 1] == parts[j + 1]) throw std::runtime_error("cannot have the same motif more than once");
+            bool cg0 = false;
+            for (size_t i = 0; i < parts.size(); i += 2) cg0 = cg0 || (parts[i] == "CG" && parts[i + 1] == "0");
+            if (o.cpg && !cg0) { parts.push_back("CG"); parts.push_back("0"); }
+            for (size_t i = 0; i < parts.size(); i += 2) mc.motifs.push_back(parse_motif(parts[i], std::stoi(parts[i + 1])));
+            have_motifs = true;
+        } else if (o.traditional || o.cpg) { mc.motifs.push_back(parse_motif("CG", 0)); have_motifs = true; }
+        BedFormat fmt;
+        fmt.mixed_delim = o.mixed;
+        for (auto& m : mc.motifs) fmt.motif_labels.push_back(m.label());
+        if (have_motifs) {
+            if (o.ref_fp.empty()) throw std::runtime_error("reference fasta is required for using --motif or --cpg options");
+            if (combine_strands) for (auto& m : mc.motifs) if (!m.palindromic) throw std::runtime_error("cannot combine strands with a motif that is not a palindrome");
+            mc.fasta.open(o.ref_fp);
+            mc.keep_case = o.mask;
+            for (auto& m : mc.motifs) mc.longest = std::max<uint64_t>(mc.longest, m.len);
+        }
+        // output first, like the reference, so a bad path fails before any work
+        FILE* out = (o.out_bed == "-" || o.out_bed == "stdout") ? stdout : fopen(o.out_bed.c_str(), "w");
+        if (!out) throw std::runtime_error("failed to make output file");
+        if (o.header) fputs(bed_header_line(), out);
+
+        DeviceGuard dev;
+        int rc = mkp_create(o.device, &dev.ctx);
+        if (rc) throw std::runtime_error("no usable CUDA device (mkp_create returned " + std::to_string(rc) + "); this build has no CPU fallback");
+
+        // thresholds (subcommand.rs:615-638, command_utils.rs:49-134)
+        for (auto& raw : o.mod_thresholds) {
+            auto c = raw.find(':');
+            uint32_t code;
+            if (c == std::string::npos || raw.find(':', c + 1) != std::string::npos || !parse_code(raw.substr(0, c), &code))
+                throw std::runtime_error("encountered illegal per-mod threshold: " + raw + ". Should be mod_code:threshold e.g. h:0.8");
+            if (P.n_mod_thresholds >= MKP_MAX_MOD_THRESHOLDS) throw std::runtime_error("too many per-mod thresholds");
+            P.mod_code[P.n_mod_thresholds] = code;
+            P.mod_threshold[P.n_mod_thresholds++] = std::stof(raw.substr(c + 1));
+        }
+        if (!o.filter_thresholds.empty()) {
+            bool have_default = false;
+            for (auto& raw : o.filter_thresholds) {
+                auto c = raw.find(':');
+                if (c == std::string::npos) {
+                    if (have_default) throw std::runtime_error("default threshold encountered more than once");
+                    P.default_threshold = std::stof(raw); have_default = true;
+                } else {
+                    const char* B = "ACGT";
+                    const char* f = raw.empty() ? nullptr : strchr(B, raw[0]);
+                    if (!f || !raw[0]) throw std::runtime_error("failed to parse base " + raw);
+                    if (P.base_threshold_set[f - B]) throw std::runtime_error(std::string("repeated threshold for base ") + raw[0]);
+                    P.base_threshold_set[f - B] = 1;
+                    P.base_threshold[f - B] = std::stof(raw.substr(c + 1));
+                }
+            }
+        } else if (!o.no_filtering) {
+            if (mkp_set_params(dev.ctx, &P)) throw std::runtime_error(mkp_last_error(dev.ctx));
+            SamplerConfig sc;
+            sc.threads = o.threads; sc.sampling_interval_size = o.sampling_interval_size;
+            if (o.have_frac) { if (o.frac != 1.0) throw std::runtime_error("only --sampling-frac 1.0 is reproducible without the reference's RNG; use -n or -f 1.0"); sc.take_all = true; }
+            sc.num_reads = o.num_reads;
+            sc.region = srp ? srp : rp;
+            sc.include_unmapped = o.include_unmapped;
+            sc.edge_on = P.edge_filter_on;
+            std::vector<uint64_t> hist(4 * 1025);
+            uint64_t inexact = 0;
+            sample_histogram(bam, dev.ctx, sc, hist.data(), &inexact);
+            if (inexact) throw std::runtime_error("sampled probabilities are not multiples of 1/1024 (" + std::to_string(inexact) + " values): exact histogram quantile impossible; pass --filter-threshold");
+            for (int b = 0; b < 4; b++) {
+                float thr;
+                uint64_t n = 0;
+                for (int k = 0; k <= 1024; k++) n += hist[b * 1025 + k];
+                if (!n) continue;
+                if (!percentile_from_hist(hist.data() + b * 1025, o.percentile, &thr)) throw std::runtime_error("not enough datapoints to estimate a threshold");
+                P.base_threshold_set[b] = 1;
+                P.base_threshold[b] = thr;
+                if (!o.quiet) fprintf(stderr, "> Using filter threshold %.9g for %c.\n", thr, "ACGT"[b]);
+            }
+        }
+        if (mkp_set_params(dev.ctx, &P)) throw std::runtime_error(mkp_last_error(dev.ctx));
+        if (summary) for (int b = 0; b < 4; b++) { summary->thresholds[b] = P.base_threshold[b]; summary->threshold_set[b] = P.base_threshold_set[b]; }
+        const auto t_thr = clk::now();
+
+        std::vector<RefInterval> ivs = reference_intervals(targets, o.interval_size, combine_strands, have_motifs ? &mc : nullptr);
+        const auto t_iv = clk::now();
+        RunSummary S;
+        for (auto& iv : ivs) S.positions += iv.end - iv.start;
+
+        PackedChunk pc;
+        std::vector<uint32_t> fpos, fneg;
+        std::vector<OutRow> orows;
+        std::string text;
+        for (size_t i0 = 0; i0 < ivs.size();) {
+            // a chunk = consecutive intervals of one contig up to chunk_bp
+            size_t i1 = i0 + 1;
+            while (i1 < ivs.size() && ivs[i1].tid == ivs[i0].tid && ivs[i1].start == ivs[i1 - 1].end && ivs[i1].end - ivs[i0].start <= o.chunk_bp) i1++;
+            const uint32_t cs = ivs[i0].start, ce = ivs[i1 - 1].end;
+            if (ce <= cs) { i0 = i1; continue; }
+            const auto ta = clk::now();
+            pc.clear();
+            pack_region(bam, ivs[i0].tid, cs, ce, &pc);
+            const auto tb = clk::now();
+            S.pack_s += secs(ta, tb);
+            if (pc.hdrs.empty()) { i0 = i1; continue; }
+            mkp_chunk ch;
+            memset(&ch, 0, sizeof ch);
+            ch.start = cs; ch.end = ce; ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
+            if (have_motifs) { focus_bitmaps(ivs, i0, i1, cs, ce, &fpos, &fneg); ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data(); }
+            const mkp_row* rows = nullptr;
+            size_t n_rows = 0;
+            mkp_stats st;
+            if (mkp_pileup_chunk(dev.ctx, &ch, &rows, &n_rows, &st)) throw std::runtime_error(mkp_last_error(dev.ctx));
+            const auto tc = clk::now();
+            S.gpu_s += secs(tb, tc);
+            S.kernel_ms += st.kernel_ms[7];
+            S.reads_packed += pc.hdrs.size();
+            S.algorithmic_bytes += pc.algorithmic_bytes() + 40 * n_rows;
+            S.chunks++;
+            // rows are position sorted: hand each interval its slice
+            size_t r0 = 0;
+            const std::string& chrom = bam.ref_names[ivs[i0].tid];
+            text.clear();
+            for (size_t i = i0; i < i1; i++) {
+                while (r0 < n_rows && rows[r0].pos < ivs[i].start) r0++;
+                size_t r1 = r0;
+                while (r1 < n_rows && rows[r1].pos < ivs[i].end) r1++;
+                orows.clear();
+                finish_interval_rows(ivs[i], rows + r0, r1 - r0, have_motifs ? &mc.motifs : nullptr, combine_strands, &orows);
+                for (auto& orow : orows) format_bed_row(orow, chrom, fmt, &text);
+                S.rows += orows.size();
+                r0 = r1;
+            }
+            fwrite(text.data(), 1, text.size(), out);
+            S.write_s += secs(tc, clk::now());
+            i0 = i1;
+        }
+        if (out != stdout) fclose(out); else fflush(out);
+        const auto t1 = clk::now();
+        S.load_s = secs(t0, t_load); S.threshold_s = secs(t_load, t_thr); S.interval_s = secs(t_thr, t_iv); S.total_s = secs(t0, t1);
+        for (int b = 0; b < 4; b++) { S.thresholds[b] = P.base_threshold[b]; S.threshold_set[b] = P.base_threshold_set[b]; }
+        if (summary) *summary = S;
+        if (!o.quiet)
+            fprintf(stderr, "> Done, processed %llu rows. positions=%llu reads=%llu chunks=%llu load=%.3fs thresholds=%.3fs intervals=%.3fs pack=%.3fs gpu=%.3fs (kernels %.3f ms) write=%.3fs total=%.3fs\n",
+                    (unsigned long long)S.rows, (unsigned long long)S.positions, (unsigned long long)S.reads_packed, (unsigned long long)S.chunks,
+                    S.load_s, S.threshold_s, S.interval_s, S.pack_s, S.gpu_s, S.kernel_ms, S.write_s, S.total_s);
+        if (!o.stats_json.empty()) {
+            FILE* jf = fopen(o.stats_json.c_str(), "w");
+            if (jf) {
+                fprintf(jf, "{\"positions\": %llu, \"rows\": %llu, \"reads\": %llu, \"chunks\": %llu, \"algorithmic_bytes\": %llu, \"load_s\": %.6f, \"thresholds_s\": %.6f, \"intervals_s\": %.6f, \"pack_s\": %.6f, \"gpu_s\": %.6f, \"kernel_ms\": %.6f, \"write_s\": %.6f, \"total_s\": %.6f}\n",
+                        (unsigned long long)S.positions, (unsigned long long)S.rows, (unsigned long long)S.reads_packed, (unsigned long long)S.chunks, (unsigned long long)S.algorithmic_bytes,
+                        S.load_s, S.threshold_s, S.interval_s, S.pack_s, S.gpu_s, S.kernel_ms, S.write_s, S.total_s);
+                fclose(jf);
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        if (error) *error = e.what();
+        return 1;
+    }
+}
+
+// clap-compatible subset of the `modkit pileup` flag surface (src/pileup/subcommand.rs:37-379)
+inline bool parse_pileup_args(int argc, const char* const* argv, PileupOptions* o, std::string* err) {
+    std::vector<std::string> pos;
+    for (int i = 0; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) throw std::runtime_error("a value is required for '" + a + "' but none was supplied"); return argv[++i]; };
+        try {
+            if (a == "-t" || a == "--threads") o->threads = std::stoi(val());
+            else if (a == "-i" || a == "--interval-size") o->interval_size = (uint32_t)std::stoul(val());
+            else if (a == "--region") o->region = val();
+            else if (a == "--sample-region") o->sample_region = val();
+            else if (a == "--sampling-interval-size") o->sampling_interval_size = (uint32_t)std::stoul(val());
+            else if (a == "-n" || a == "--num-reads") o->num_reads = std::stoul(val());
+            else if (a == "-f" || a == "--sampling-frac") { o->have_frac = true; o->frac = std::stod(val()); }
+            else if (a == "--seed" || a == "--max-depth" || a == "--queue-size" || a == "--chunk-size" || a == "--log-filepath" || a == "--log") val();
+            else if (a == "--no-filtering") o->no_filtering = true;
+            else if (a == "-p" || a == "--filter-percentile") o->percentile = std::stof(val());
+            else if (a == "--filter-threshold" || a == "--pass_threshold") o->filter_thresholds.push_back(val());
+            else if (a == "--mod-thresholds" || a == "--mod-threshold") o->mod_thresholds.push_back(val());
+            else if (a == "--include-unmapped") o->include_unmapped = true;
+            else if (a == "--ignore") o->ignore = val();
+            else if (a == "--force-allow-implicit") o->force_allow = true;
+            else if (a == "--motif") { o->motif_parts.push_back(val()); o->motif_parts.push_back(val()); }
+            else if (a == "--cpg") o->cpg = true;
+            else if (a == "-r" || a == "--ref" || a == "--reference") o->ref_fp = val();
+            else if (a == "-k" || a == "--mask") o->mask = true;
+            else if (a == "--preset") { if (val() != "traditional") throw std::runtime_error("invalid value for '--preset'"); o->traditional = true; }
+            else if (a == "--combine-mods") o->combine_mods = true;
+            else if (a == "--combine-strands") o->combine_strands = true;
+            else if (a == "--edge-filter") o->edge = val();
+            else if (a == "--invert-edge-filter") o->invert_edge = true;
+            else if (a == "--only-tabs" || a == "--suppress-progress") {}
+            else if (a == "--mixed-delim" || a == "--mixed-delimiters") o->mixed = true;
+            else if (a == "--header" || a == "--with-header" || a == "--include_header") o->header = true;
+            else if (a == "--device") o->device = std::stoi(val());
+            else if (a == "--gpu-chunk-bp") o->chunk_bp = (uint32_t)std::stoul(val());
+            else if (a == "--stats-json") o->stats_json = val();
+            else if (a == "--quiet") o->quiet = true;
+            else if (a == "--include-bed" || a == "--include-positions" || a == "--partition-tag" || a == "--bedgraph" || a == "--prefix") {
+                *err = "flag " + a + " is not supported by this build (SURVEY 8f: next tier)"; return false;
+            }
+            else if (a.size() > 1 && a[0] == '-') { *err = "unexpected argument '" + a + "' found"; return false; }
+            else pos.push_back(a);
+        } catch (const std::exception& e) { *err = e.what(); return false; }
+    }
+    if (pos.size() != 2) { *err = "the following required arguments were not provided: <IN_BAM> <OUT_BED>"; return false; }
+    o->in_bam = pos[0]; o->out_bed = pos[1];
+    return true;
+}
+
+}  // namespace mkh

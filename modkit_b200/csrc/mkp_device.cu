@@ -1,0 +1,363 @@
+// C ABI (include/mkp.h) over the sm_100a kernels in mkp_kernels.cuh.
+// One mkp_ctx per GPU: grow-only device buffers, one stream, CUDA events around every stage.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mkp_kernels.cuh"
+
+using namespace mkp;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+}  // namespace
+
+struct mkp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[10];
+    std::string err;
+    mkp_params params;
+    bool have_params = false;
+    int sm_count = 148;
+    // resident chunk
+    DevBuf d_hdrs, d_heap, d_entry_off, d_focus_pos, d_focus_neg;
+    uint32_t n_reads = 0, cs = 0, ce = 0, n_words = 0;
+    bool have_focus = false;
+    uint64_t total_entries = 0;
+    uint32_t max_ncigar = 1, max_blocks = 1;
+    uint64_t heap_bytes = 0;
+    // work buffers
+    DevBuf d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr, d_scr_cum;
+    DevBuf d_slots, d_row_counts, d_row_prefix, d_rows, d_hist, d_take;
+    // results
+    size_t n_rows = 0;
+    std::vector<mkp_row> h_rows;
+    std::vector<uint64_t> h_entry_off;
+    mkp_row* h_rows_pinned = nullptr;
+    size_t h_rows_pinned_cap = 0;
+};
+
+// d_small layout (u64 words): [0..31] states, [32] total_calls, [33] hist_inexact ; u32 view from byte 34*8: n_states, err, n_hot, n_rows
+static constexpr size_t SMALL_BYTES = 34 * 8 + 16 * 4;
+
+static int fail(mkp_ctx* c, const std::string& m, int code = -1) { if (c) c->err = m; return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+extern "C" {
+
+int mkp_create(int device, mkp_ctx** out) {
+    if (!out) return -1;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return -2;   // no CUDA device: there is no CPU fallback
+    if (device < 0 || device >= n) return -3;
+    if (cudaSetDevice(device) != cudaSuccess) return -4;
+    mkp_ctx* ctx = new mkp_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -5; }
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    memset(&ctx->params, 0, sizeof ctx->params);
+    *out = ctx;
+    return 0;
+}
+
+void mkp_destroy(mkp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_meta, &ctx->d_P,
+                      &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr,
+                      &ctx->d_scr_cum, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take};
+    for (auto* b : bufs) b->release();
+    if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
+    for (auto& e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mkp_last_error(const mkp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mkp_set_params(mkp_ctx* ctx, const mkp_params* p) {
+    if (!ctx || !p) return -1;
+    if (p->n_mod_thresholds > MKP_MAX_MOD_THRESHOLDS) return fail(ctx, "too many per-mod thresholds");
+    CK(cudaSetDevice(ctx->device));
+    ctx->params = *p;
+    DevParams d;
+    memset(&d, 0, sizeof d);
+    d.default_thr = p->default_threshold;
+    for (int b = 0; b < 4; b++) { d.base_thr[b] = p->base_threshold[b]; d.base_set[b] = p->base_threshold_set[b] ? 1 : 0; }
+    d.n_mod_thr = p->n_mod_thresholds;
+    for (uint32_t i = 0; i < p->n_mod_thresholds; i++) { d.mod_code[i] = p->mod_code[i]; d.mod_thr[i] = p->mod_threshold[i]; }
+    d.numeric_mode = p->numeric_mode; d.collapse_code = p->collapse_code; d.force_allow_implicit = p->force_allow_implicit;
+    d.edge_on = p->edge_filter_on; d.edge_inv = p->edge_filter_inverted; d.edge_start = p->edge_filter_start; d.edge_end = p->edge_filter_end;
+    CK(cudaMemcpyToSymbolAsync(c_par, &d, sizeof d, 0, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_params = true;
+    return 0;
+}
+
+int mkp_upload_chunk(mkp_ctx* ctx, const mkp_chunk* ch) {
+    if (!ctx || !ch) return -1;
+    if (ch->end <= ch->start) return fail(ctx, "empty chunk range");
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_reads = ch->n_reads; ctx->cs = ch->start; ctx->ce = ch->end;
+    ctx->n_words = (ch->end - ch->start + 31) / 32;
+    ctx->heap_bytes = ch->heap_bytes;
+    ctx->h_entry_off.resize((size_t)ch->n_reads + 1);
+    uint64_t acc = 0;
+    uint32_t mc = 1, ml = 1;
+    for (uint32_t i = 0; i < ch->n_reads; i++) {
+        ctx->h_entry_off[i] = acc;
+        acc += ch->hdrs[i].len_ml;
+        mc = std::max(mc, ch->hdrs[i].n_cigar);
+        ml = std::max(ml, ch->hdrs[i].l_seq);
+    }
+    ctx->h_entry_off[ch->n_reads] = acc;
+    ctx->total_entries = acc;
+    ctx->max_ncigar = mc;
+    ctx->max_blocks = (ml + 31) / 32;
+    CK(ctx->d_hdrs.ensure(std::max<size_t>(1, ch->n_reads) * sizeof(mkp_read_hdr)));
+    CK(ctx->d_heap.ensure(ch->heap_bytes + 64));
+    CK(ctx->d_entry_off.ensure(((size_t)ch->n_reads + 1) * 8));
+    if (ch->n_reads) {
+        CK(cudaMemcpyAsync(ctx->d_hdrs.p, ch->hdrs, (size_t)ch->n_reads * sizeof(mkp_read_hdr), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_heap.p, ch->heap, ch->heap_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->d_entry_off.p, ctx->h_entry_off.data(), ((size_t)ch->n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_focus = ch->focus_pos && ch->focus_neg;
+    if (ctx->have_focus) {
+        CK(ctx->d_focus_pos.ensure((size_t)ctx->n_words * 4));
+        CK(ctx->d_focus_neg.ensure((size_t)ctx->n_words * 4));
+        CK(cudaMemcpyAsync(ctx->d_focus_pos.p, ch->focus_pos, (size_t)ctx->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_focus_neg.p, ch->focus_neg, (size_t)ctx->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int decode_grid(const mkp_ctx* ctx, uint32_t n_reads) {
+    int blocks = ctx->sm_count * 12;                   // 48 warps per SM at 4 warps per block
+    int need = (int)((n_reads + 3) / 4);
+    return std::max(1, std::min(blocks, need));
+}
+
+static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
+    const size_t nwarps = (size_t)grid * 4;
+    CK(ctx->d_meta.ensure(std::max<size_t>(1, ctx->n_reads) * sizeof(ReadMeta)));
+    CK(ctx->d_P.ensure(std::max<uint64_t>(1, ctx->total_entries) * 4));
+    CK(ctx->d_calls.ensure(std::max<uint64_t>(1, ctx->total_entries) * 8));
+    CK(ctx->d_hot.ensure((size_t)ctx->n_words * 4 + 4));
+    CK(ctx->d_hot_prefix.ensure((size_t)ctx->n_words * 4 + 4));
+    CK(ctx->d_small.ensure(SMALL_BYTES));
+    CK(ctx->d_scr_cq.ensure(nwarps * ctx->max_ncigar * 4));
+    CK(ctx->d_scr_cr.ensure(nwarps * ctx->max_ncigar * 4));
+    CK(ctx->d_scr_cum.ensure(nwarps * 4 * ((size_t)ctx->max_blocks + 1) * 4));
+    memset(C, 0, sizeof *C);
+    C->hdrs = ctx->d_hdrs.as<mkp_read_hdr>(); C->heap = ctx->d_heap.as<uint8_t>(); C->entry_off = ctx->d_entry_off.as<uint64_t>();
+    C->n_reads = ctx->n_reads; C->cs = ctx->cs; C->ce = ctx->ce;
+    C->focus_pos = ctx->have_focus ? ctx->d_focus_pos.as<uint32_t>() : nullptr;
+    C->focus_neg = ctx->have_focus ? ctx->d_focus_neg.as<uint32_t>() : nullptr;
+    C->meta = ctx->d_meta.as<ReadMeta>(); C->P = ctx->d_P.as<uint32_t>(); C->calls = ctx->d_calls.as<uint2>();
+    C->hot = ctx->d_hot.as<uint32_t>(); C->hot_prefix = ctx->d_hot_prefix.as<uint32_t>();
+    C->states = ctx->d_small.as<unsigned long long>();
+    C->total_calls = C->states + 32;
+    C->hist_inexact = C->states + 33;
+    uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
+    C->n_states = u; C->err = u + 1;
+    C->scr_cq = ctx->d_scr_cq.as<uint32_t>(); C->scr_cr = ctx->d_scr_cr.as<uint32_t>(); C->scr_cum = ctx->d_scr_cum.as<uint32_t>();
+    C->max_ncigar = ctx->max_ncigar; C->max_blocks = ctx->max_blocks;
+    return 0;
+}
+
+static std::string derr_text(uint32_t e) {
+    std::string s;
+    if (e & MKP_DERR_TOO_MANY_STATES) s += "more than 32 distinct (base, mod code) states; ";
+    if (e & MKP_DERR_TOO_MANY_LISTS) s += "more than 16 MM lists in one read; ";
+    if (e & MKP_DERR_TOO_MANY_CODES) s += "more than 4 codes in one MM list or 7 at one position; ";
+    if (e & MKP_DERR_IMPLICIT_MODE) s += "a '.'/default-mode MM list needs implicit canonical fill, which the device path does not implement yet; ";
+    return s;
+}
+
+int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
+    if (!ctx) return -1;
+    if (!ctx->have_params) return fail(ctx, "mkp_set_params was not called");
+    if (ctx->ce <= ctx->cs) return fail(ctx, "no resident chunk");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ChunkDev C;
+    const int grid = decode_grid(ctx, ctx->n_reads);
+    if (int rc = prepare_decode(ctx, &C, grid)) return rc;
+    const uint32_t n_words = ctx->n_words;
+    const uint32_t n_blk = (n_words + 1023) / 1024;
+    CK(ctx->d_block_sums.ensure((size_t)n_blk * 4 + 4));
+    CK(ctx->d_row_counts.ensure((size_t)n_words * 4 + 4));
+    CK(ctx->d_row_prefix.ensure((size_t)n_words * 4 + 4));
+
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaMemsetAsync(ctx->d_hot.p, 0, (size_t)n_words * 4, st));
+    CK(cudaMemsetAsync(ctx->d_small.p, 0xff, 32 * 8, st));
+    CK(cudaMemsetAsync(ctx->d_small.as<uint8_t>() + 32 * 8, 0, SMALL_BYTES - 32 * 8, st));
+    if (ctx->n_reads) k_decode<MODE_PILEUP><<<grid, 128, 0, st>>>(C);
+    CK(cudaEventRecord(ctx->ev[1], st));
+    uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);   // n_states, err, n_hot, n_rows
+    k_block_popc<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>());
+    k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 2);
+    k_word_prefix<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.hot_prefix);
+    CK(cudaEventRecord(ctx->ev[2], st));
+    uint32_t h_small[4];
+    unsigned long long h_calls = 0;
+    CK(cudaMemcpyAsync(h_small, u, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_calls, C.total_calls, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n_states = h_small[0], derr = h_small[1], n_hot = h_small[2];
+    if (derr) {
+        if (stats) { memset(stats, 0, sizeof *stats); stats->device_error = derr; }
+        return fail(ctx, "device decode error: " + derr_text(derr), -10);
+    }
+    const uint32_t stride = SL_MOD + 2 * std::max<uint32_t>(n_states, 1);
+    CK(ctx->d_slots.ensure(std::max<size_t>(1, n_hot) * stride * 4));
+    CK(cudaMemsetAsync(ctx->d_slots.p, 0, (size_t)n_hot * stride * 4, st));
+    CountDev D;
+    D.hdrs = C.hdrs; D.heap = C.heap; D.meta = C.meta; D.calls = C.calls; D.n_reads = C.n_reads; D.cs = C.cs; D.ce = C.ce;
+    D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
+    D.slots = ctx->d_slots.as<uint32_t>(); D.stride = stride; D.n_states = std::max<uint32_t>(n_states, 1);
+    CK(cudaEventRecord(ctx->ev[3], st));
+    if (ctx->n_reads && n_hot) {
+        int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
+        k_count_calls<<<g2, 256, 0, st>>>(D);
+    }
+    CK(cudaEventRecord(ctx->ev[4], st));
+    if (ctx->n_reads && n_hot) {
+        int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
+        k_count_bases<<<g2, 256, 0, st>>>(D);
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    RowDev R;
+    R.hot = C.hot; R.hot_prefix = C.hot_prefix; R.n_words = n_words; R.cs = C.cs; R.ce = C.ce;
+    R.slots = D.slots; R.stride = stride; R.n_states = D.n_states; R.states = C.states; R.numeric_mode = ctx->params.numeric_mode;
+    R.row_counts = ctx->d_row_counts.as<uint32_t>(); R.row_prefix = ctx->d_row_prefix.as<uint32_t>(); R.rows = nullptr;
+    const int rg = (n_words + 255) / 256;
+    k_rows<false><<<rg, 256, 0, st>>>(R);
+    k_block_sum<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>());
+    k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 3);
+    k_value_prefix<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_row_prefix.as<uint32_t>());
+    uint32_t n_rows = 0;
+    CK(cudaMemcpyAsync(&n_rows, u + 3, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(ctx->d_rows.ensure(std::max<size_t>(1, n_rows) * sizeof(mkp_row)));
+    R.rows = ctx->d_rows.as<mkp_row>();
+    CK(cudaEventRecord(ctx->ev[6], st));
+    if (n_rows) k_rows<true><<<rg, 256, 0, st>>>(R);
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    ctx->n_rows = n_rows;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_rows = n_rows; stats->n_hot = n_hot; stats->n_calls = h_calls; stats->n_states = n_states;
+        // stage times: 0 decode, 1 rank, 2 (sync+alloc), 3 count_calls, 4 count_bases, 5 row count+scan, 6 row emit
+        for (int i = 0; i < 7; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]); stats->kernel_ms[i] = ms; }
+        float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[7]); stats->kernel_ms[7] = tot;
+    }
+    return 0;
+}
+
+int mkp_fetch_rows(mkp_ctx* ctx, const mkp_row** rows, size_t* n_rows) {
+    if (!ctx || !rows || !n_rows) return -1;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_rows > ctx->h_rows_pinned_cap) {
+        if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
+        ctx->h_rows_pinned = nullptr; ctx->h_rows_pinned_cap = 0;
+        size_t want = ctx->n_rows + ctx->n_rows / 8 + 1024;
+        CK(cudaMallocHost((void**)&ctx->h_rows_pinned, want * sizeof(mkp_row)));
+        ctx->h_rows_pinned_cap = want;
+    }
+    if (ctx->n_rows) {
+        CK(cudaMemcpyAsync(ctx->h_rows_pinned, ctx->d_rows.p, ctx->n_rows * sizeof(mkp_row), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *rows = ctx->h_rows_pinned;
+    *n_rows = ctx->n_rows;
+    return 0;
+}
+
+int mkp_pileup_chunk(mkp_ctx* ctx, const mkp_chunk* ch, const mkp_row** rows, size_t* n_rows, mkp_stats* stats) {
+    if (int rc = mkp_upload_chunk(ctx, ch)) return rc;
+    if (int rc = mkp_pileup_resident(ctx, stats)) return rc;
+    return mkp_fetch_rows(ctx, rows, n_rows);
+}
+
+int mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* take, uint64_t* hist, uint8_t* contributes, uint64_t* inexact) {
+    if (!ctx) return -1;
+    if (!ctx->have_params) return fail(ctx, "mkp_set_params was not called");
+    if (ctx->ce <= ctx->cs) return fail(ctx, "no resident chunk");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ChunkDev C;
+    const int grid = decode_grid(ctx, ctx->n_reads);
+    if (int rc = prepare_decode(ctx, &C, grid)) return rc;
+    CK(cudaMemsetAsync(ctx->d_small.p, 0xff, 32 * 8, st));
+    CK(cudaMemsetAsync(ctx->d_small.as<uint8_t>() + 32 * 8, 0, SMALL_BYTES - 32 * 8, st));
+    C.hist_include_unaligned = include_unaligned ? 1 : 0;
+    if (take) {
+        CK(ctx->d_take.ensure(std::max<size_t>(1, ctx->n_reads)));
+        CK(cudaMemcpyAsync(ctx->d_take.p, take, ctx->n_reads, cudaMemcpyHostToDevice, st));
+        C.take = ctx->d_take.as<uint8_t>();
+    }
+    if (hist) {
+        CK(ctx->d_hist.ensure(4 * 1025 * 8));
+        CK(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * 1025 * 8, st));
+        C.hist = ctx->d_hist.as<unsigned long long>();
+    }
+    if (ctx->n_reads) k_decode<MODE_HIST><<<grid, 128, 0, st>>>(C);
+    CK(cudaGetLastError());
+    uint32_t h_small[2];
+    uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
+    CK(cudaMemcpyAsync(h_small, u, 8, cudaMemcpyDeviceToHost, st));
+    if (hist) CK(cudaMemcpyAsync(hist, ctx->d_hist.p, 4 * 1025 * 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long inx = 0;
+    CK(cudaMemcpyAsync(&inx, C.hist_inexact, 8, cudaMemcpyDeviceToHost, st));
+    std::vector<ReadMeta> metas;
+    if (contributes) {
+        metas.resize(ctx->n_reads);
+        if (ctx->n_reads) CK(cudaMemcpyAsync(metas.data(), ctx->d_meta.p, (size_t)ctx->n_reads * sizeof(ReadMeta), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    if (h_small[1]) return fail(ctx, "device decode error: " + derr_text(h_small[1]), -10);
+    if (contributes) for (uint32_t i = 0; i < ctx->n_reads; i++) contributes[i] = metas[i].n_hist > 0;
+    if (inexact) *inexact = inx;
+    return 0;
+}
+
+size_t mkp_algorithmic_bytes(const mkp_chunk* ch, size_t n_rows) {
+    size_t b = 0;
+    for (uint32_t i = 0; i < ch->n_reads; i++) {
+        const mkp_read_hdr& h = ch->hdrs[i];
+        b += 32 + 4ull * h.n_cigar + (h.l_seq + 1) / 2 + h.len_mm + h.len_ml;
+    }
+    return b + 40 * n_rows;
+}
+
+}  // extern "C"

@@ -1,0 +1,975 @@
+// Device kernels of the B200-native `modkit pileup` hot path (sm_100a).
+//
+// Pipeline per chunk (all on one stream, intermediates stay in L2/HBM):
+//   k_decode      warp per read: CIGAR prefix, MM text parse, delta -> forward position (rank/select on
+//                 the 4-bit SEQ), ML -> probability, list merging, collapse, threshold call, projection
+//                 to reference coordinates; emits compact call records + marks the hot-position bitmap.
+//                 (reference: src/mod_bam.rs:900-1577, src/read_cache.rs:69-211,
+//                  src/threshold_mod_caller.rs:28-63, src/util.rs:122-145)
+//   k_rank_*      popcount prefix over the hot bitmap  -> counter slot index per hot position
+//   k_count_calls one thread per call record: modcall / filtered counters (src/pileup/mod.rs:876-937)
+//   k_count_bases warp per read: walks CIGAR + SEQ with bit-parallel window tests against the hot
+//                 bitmap; base / delete counters and observed-code masks (src/pileup/mod.rs:831-874)
+//   k_rows_*      per slot: FeatureVector::decode (src/pileup/mod.rs:283-445) -> mkp_row
+// Integer/indexing work: no tensor cores; the bound is HBM bandwidth.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mkp.h"
+
+namespace mkp {
+
+constexpr int MAX_LISTS = 16;
+constexpr int MAX_LIST_CODES = 4;
+constexpr int MAX_MAP = 7;          // codes at one read position
+constexpr int MAX_STATES = 32;
+constexpr uint32_t FULL = 0xffffffffu;
+
+// slot layout (u32 words)
+constexpr int SL_BASE = 0;    // [a][b] 8 words, signed
+constexpr int SL_DEL = 8;     // [a]
+constexpr int SL_FILT = 10;   // [s]
+constexpr int SL_CANON = 12;  // [s][pb]
+constexpr int SL_OBS = 20;    // pos mask, neg mask
+constexpr int SL_MOD = 22;    // [s][state]
+
+struct DevParams {
+    float default_thr;
+    float base_thr[4];
+    uint32_t base_set[4];
+    uint32_t n_mod_thr;
+    uint32_t mod_code[MKP_MAX_MOD_THRESHOLDS];
+    float mod_thr[MKP_MAX_MOD_THRESHOLDS];
+    uint32_t numeric_mode, collapse_code, force_allow_implicit;
+    uint32_t edge_on, edge_inv, edge_start, edge_end;
+};
+
+struct ReadMeta {       // 32 bytes, written by k_decode
+    int32_t ref_end;
+    uint32_t flags;     // bit0 admitted, bit1 has mod info (not in skip_set)
+    uint32_t pos_mask, neg_mask;
+    uint32_t n_calls;
+    uint32_t n_hist;    // sampling: values contributed
+    uint64_t entry_off;
+};
+
+struct ChunkDev {
+    const mkp_read_hdr* hdrs;
+    const uint8_t* heap;
+    const uint64_t* entry_off;  // exclusive prefix of len_ml
+    uint32_t n_reads;
+    uint32_t cs, ce;            // chunk range
+    const uint32_t* focus_pos;  // may be null
+    const uint32_t* focus_neg;
+    ReadMeta* meta;
+    uint32_t* P;                // forward positions per raw entry
+    uint2* calls;               // (ref_pos, info)
+    uint32_t* hot;              // bitmap over [cs,ce)
+    uint32_t* hot_prefix;
+    unsigned long long* states; // registry: (pb<<32 | code), ~0 empty
+    uint32_t* n_states;
+    uint32_t* err;
+    unsigned long long* total_calls;
+    // per-warp scratch
+    uint32_t* scr_cq; uint32_t* scr_cr; uint32_t* scr_cum;
+    uint32_t max_ncigar, max_blocks;
+    // sampling
+    unsigned long long* hist;   // [4][1025]
+    unsigned long long* hist_inexact;
+    const uint8_t* take;
+    uint32_t hist_include_unaligned;
+};
+
+__constant__ DevParams c_par;
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, v, d); if (lane_id() >= d) v += t; }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_incl_scan64(unsigned long long v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(FULL, v, d); if (lane_id() >= d) v += t; }
+    return v;
+}
+
+// count of nibbles equal to X in a 32-bit word of BAM 4-bit sequence
+__device__ __forceinline__ uint32_t nib_eq_flags(uint32_t w, uint32_t X) {
+    uint32_t x = w ^ (X * 0x11111111u);
+    uint32_t t = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+    return t ^ 0x11111111u;  // bit 4n set where nibble n == X
+}
+// flags (bit 4n) -> 8-bit mask in base order (base j <-> nibble j^1 inside a little-endian word)
+__device__ __forceinline__ uint32_t nib_flags_to_mask(uint32_t y) {
+    y = (y | (y >> 3)) & 0x03030303u;
+    y = (y | (y >> 6)) & 0x000F000Fu;
+    y = (y | (y >> 12)) & 0xFFu;
+    return ((y & 0x55u) << 1) | ((y & 0xAAu) >> 1);
+}
+__device__ __forceinline__ uint32_t seq_nibble(const uint8_t* seq, uint32_t q) {
+    uint32_t b = seq[q >> 1];
+    return (q & 1) ? (b & 0xf) : (b >> 4);
+}
+// BAM nibble -> 0..3 (A C G T) or 4
+__device__ __forceinline__ int nib_to_base(uint32_t n) { return n == 1 ? 0 : n == 2 ? 1 : n == 4 ? 2 : n == 8 ? 3 : 4; }
+__device__ __forceinline__ uint32_t base_to_nib(int b) { return 1u << b; }
+
+__device__ __forceinline__ bool is_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+__device__ __forceinline__ bool is_digit(uint8_t c) { return c >= '0' && c <= '9'; }
+
+// ---- FxHashMap<ModCodeRepr,f32> iteration order -------------------------
+__device__ __forceinline__ unsigned long long fx_hash_code(uint32_t c) {
+    const unsigned long long K = 0x517cc1b727220a95ull;
+    unsigned long long disc = (c & 0x80000000u) ? 1ull : 0ull;
+    unsigned long long h = disc * K;                       // (rotl(0,5) ^ disc) * K
+    unsigned long long v = (c & 0x80000000u) ? (unsigned long long)(c & 0x7fffffffu) : (unsigned long long)c;
+    h = (((h << 5) | (h >> 59)) ^ v) * K;
+    return h;
+}
+
+struct ProbMap {
+    uint32_t code[MAX_MAP];
+    float p[MAX_MAP];
+    int8_t slot[8];   // slot -> item, -1 empty
+    int n, nb;
+    __device__ void init() { n = 0; nb = 4; for (int i = 0; i < 8; i++) slot[i] = -1; }
+    __device__ void place(int item) {
+        int s = (int)(fx_hash_code(code[item]) & (unsigned long long)(nb - 1));
+        while (slot[s] >= 0) s = (s + 1) & (nb - 1);
+        slot[s] = (int8_t)item;
+    }
+    __device__ int find(uint32_t c) const { for (int i = 0; i < n; i++) if (code[i] == c) return i; return -1; }
+    // returns item index, or -1 on overflow
+    __device__ int insert(uint32_t c, float v) {
+        if (n >= MAX_MAP) return -1;
+        if (nb == 4 && n + 1 > 3) {
+            int8_t old[4];
+            for (int i = 0; i < 4; i++) old[i] = slot[i];
+            nb = 8;
+            for (int i = 0; i < 8; i++) slot[i] = -1;
+            for (int i = 0; i < 4; i++) if (old[i] >= 0) place(old[i]);
+        }
+        code[n] = c; p[n] = v;
+        place(n);
+        return n++;
+    }
+    // item at iteration rank k (k < n)
+    __device__ int item_at(int k) const {
+        for (int s = 0; s < 8; s++) if (slot[s] >= 0) { if (k == 0) return slot[s]; k--; }
+        return -1;
+    }
+    __device__ float sum() const {
+        float s = 0.f;
+        for (int k = 0; k < 8; k++) if (slot[k] >= 0) s = __fadd_rn(s, p[slot[k]]);
+        return s;
+    }
+};
+
+// CollapseMethod::ReDistribute (src/mod_bam.rs:558-600)
+__device__ __forceinline__ void redistribute(const ProbMap& in, uint32_t drop, ProbMap& out) {
+    float marginal = 0.f;
+    int n_other = 0;
+    for (int s = 0; s < 8; s++) if (in.slot[s] >= 0) { int it = in.slot[s]; if (in.code[it] == drop) marginal = __fadd_rn(marginal, in.p[it]); else n_other++; }
+    float share = __fdiv_rn(marginal, __fadd_rn((float)n_other, 1.0f));
+    out.init();
+    for (int s = 0; s < 8; s++) if (in.slot[s] >= 0) { int it = in.slot[s]; if (in.code[it] != drop) out.insert(in.code[it], __fadd_rn(in.p[it], share)); }
+}
+
+// MultipleThresholdModCaller::call (src/threshold_mod_caller.rs:28-63): 0 filtered, 1 canonical, 2 = modified (code in *code)
+__device__ __forceinline__ int make_call(const ProbMap& m, int tb, uint32_t* code) {
+    bool have = false;
+    float best = 0.f;
+    int kind = 0;
+    const uint32_t any_code = (uint32_t)("ACGT"[tb]);
+    for (int s = 0; s < 8; s++) {
+        if (m.slot[s] < 0) continue;
+        int it = m.slot[s];
+        uint32_t c = m.code[it];
+        float thr;
+        bool found = false;
+        for (uint32_t k = 0; k < c_par.n_mod_thr && !found; k++) if (c_par.mod_code[k] == c) { thr = c_par.mod_thr[k]; found = true; }
+        for (uint32_t k = 0; k < c_par.n_mod_thr && !found; k++) if (c_par.mod_code[k] == any_code) { thr = c_par.mod_thr[k]; found = true; }
+        if (!found) thr = c_par.base_set[tb] ? c_par.base_thr[tb] : c_par.default_thr;
+        float pm = m.p[it];
+        if (pm >= thr) { if (!have || pm >= best) { have = true; best = pm; kind = 2; *code = c; } }
+    }
+    float cthr = c_par.base_set[tb] ? c_par.base_thr[tb] : c_par.default_thr;
+    float cp = __fsub_rn(1.0f, m.sum());
+    if (cp >= cthr) { if (!have || cp >= best) { have = true; best = cp; kind = 1; } }
+    return have ? kind : 0;
+}
+// BaseModProbs::argmax_base_mod_call value (src/mod_bam.rs:489-505)
+__device__ __forceinline__ float argmax_prob(const ProbMap& m) {
+    float cp = __fsub_rn(1.0f, m.sum());
+    bool have = false;
+    float mp = 0.f;
+    for (int s = 0; s < 8; s++) if (m.slot[s] >= 0) { float v = m.p[m.slot[s]]; if (!have || v >= mp) { have = true; mp = v; } }
+    return (have && mp > cp) ? mp : cp;
+}
+
+__device__ __forceinline__ int state_id(const ChunkDev& C, int pb, uint32_t code) {
+    unsigned long long key = ((unsigned long long)pb << 32) | code;
+    for (int i = 0; i < MAX_STATES; i++) {
+        unsigned long long v = *((volatile unsigned long long*)&C.states[i]);
+        if (v == key) return i;
+        if (v == ~0ull) {
+            unsigned long long old = atomicCAS(&C.states[i], ~0ull, key);
+            if (old == ~0ull) { atomicMax(C.n_states, (uint32_t)i + 1); return i; }
+            if (old == key) return i;
+        }
+    }
+    atomicOr(C.err, MKP_DERR_TOO_MANY_STATES);
+    return 0;
+}
+
+// per-warp parsed MM list table
+struct ListTab {
+    uint32_t d_start[MAX_LISTS];   // offset of the first delta byte (after the header comma), == d_end when no deltas
+    uint32_t d_end[MAX_LISTS];
+    uint32_t code[MAX_LISTS][MAX_LIST_CODES];
+    uint32_t n_delta[MAX_LISTS];
+    uint32_t ent_off[MAX_LISTS];
+    uint32_t ml_off[MAX_LISTS];
+    uint8_t base[MAX_LISTS];       // fundamental base char
+    uint8_t strand[MAX_LISTS];     // 0 '+', 1 '-'
+    uint8_t mode[MAX_LISTS];       // 0 '?', 1 '.', 2 default
+    uint8_t ncodes[MAX_LISTS];
+    uint32_t n;
+    uint32_t tot[4];               // occurrences of nibble-base x in SEQ (query order)
+};
+
+enum { MODE_PILEUP = 0, MODE_HIST = 1 };
+
+// binary search: first index in sorted P[0..n) with value >= f
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* P, uint32_t n, uint32_t f) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (P[mid] < f) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
+    __shared__ ListTab s_tab[4];
+    const uint32_t lane = lane_id();
+    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    ListTab& T = s_tab[wib];
+    uint32_t* cq = C.scr_cq + (size_t)gw * C.max_ncigar;
+    uint32_t* cr = C.scr_cr + (size_t)gw * C.max_ncigar;
+    uint32_t* cum = C.scr_cum + (size_t)gw * 4 * (C.max_blocks + 1);
+
+    for (uint32_t ri = gw; ri < C.n_reads; ri += nw) {
+        const mkp_read_hdr h = C.hdrs[ri];
+        const uint32_t flag = h.flags & 0xffffu;
+        const uint32_t L = h.l_seq;
+        const bool rev = flag & 0x10;
+        ReadMeta meta;
+        meta.ref_end = h.ref_start;
+        meta.flags = 0; meta.pos_mask = 0; meta.neg_mask = 0; meta.n_calls = 0; meta.n_hist = 0;
+        meta.entry_off = C.entry_off[ri];
+        bool admitted;
+        if (MODE == MODE_PILEUP) admitted = !(flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) && L > 0;
+        else admitted = !(flag & (0x100 | 0x400 | 0x800)) && L > 0 && (C.take == nullptr || C.take[ri]) &&
+                        !((flag & 0x4) && (!C.hist_include_unaligned || c_par.edge_on));
+        if (!admitted) { if (lane == 0) C.meta[ri] = meta; continue; }
+        meta.flags = 1;
+        const uint32_t* cig = (const uint32_t*)(C.heap + h.off);
+        const uint8_t* seq = C.heap + h.off + 4ull * h.n_cigar;
+        const uint8_t* ml = seq + ((L + 1) >> 1);
+        const uint8_t* mm = ml + h.len_ml;
+        // ---- phase 0: CIGAR prefix ------------------------------------------------------------
+        {
+            uint32_t qc = 0, rc = (uint32_t)h.ref_start;
+            for (uint32_t b = 0; b < h.n_cigar; b += 32) {
+                uint32_t i = b + lane;
+                uint32_t c = i < h.n_cigar ? cig[i] : 0;
+                uint32_t op = c & 15, len = c >> 4;
+                uint32_t ql = (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ? len : 0;
+                uint32_t rl = (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ? len : 0;
+                uint32_t qi = warp_incl_scan(ql), rr = warp_incl_scan(rl);
+                if (i < h.n_cigar) { cq[i] = qc + qi - ql; cr[i] = rc + rr - rl; }
+                qc += __shfl_sync(FULL, qi, 31);
+                rc += __shfl_sync(FULL, rr, 31);
+            }
+            meta.ref_end = (int32_t)rc;
+        }
+        bool err = (h.flags & MKP_RF_TAGS_INVALID) != 0;
+        // ---- phase 1: list discovery + headers (lane 0) ------------------------------------------
+        if (lane == 0) {
+            uint32_t n = 0;
+            bool e = err;
+            uint32_t i = 0;
+            const uint32_t M = h.len_mm;
+            while (!e && i < M) {
+                uint32_t j = i;
+                while (j < M && mm[j] != ';') j++;
+                if (j > i) {
+                    if (n >= MAX_LISTS) { atomicOr(C.err, MKP_DERR_TOO_MANY_LISTS); e = true; break; }
+                    uint32_t hl = i;
+                    while (hl < j && mm[hl] != ',') hl++;
+                    // header = mm[i..hl)
+                    uint32_t k = i;
+                    uint8_t fb = mm[k];
+                    if (!(fb == 'A' || fb == 'C' || fb == 'G' || fb == 'T' || fb == 'U' || fb == 'N')) { e = true; break; }
+                    k++;
+                    if (k >= hl) { e = true; break; }
+                    uint8_t st = mm[k];
+                    if (st != '+' && st != '-') { e = true; break; }
+                    k++;
+                    uint32_t nc = 0;
+                    bool seen_chebi = false;
+                    int mode = 2;
+                    if (k < hl && is_digit(mm[k])) {
+                        unsigned long long v = 0;
+                        while (k < hl && is_digit(mm[k])) { v = v * 10 + (mm[k] - '0'); if (v > 0x7fffffffull) { e = true; break; } k++; }
+                        if (e) break;
+                        T.code[n][nc++] = 0x80000000u | (uint32_t)v;
+                        seen_chebi = true;
+                    }
+                    for (; k < hl; k++) {
+                        uint8_t c = mm[k];
+                        if (c == '?') mode = 0;
+                        else if (c == '.') mode = 1;
+                        else if (is_digit(c)) { e = true; break; }
+                        else {
+                            if (seen_chebi) { e = true; break; }
+                            if (nc >= MAX_LIST_CODES) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e = true; break; }
+                            T.code[n][nc++] = c;
+                        }
+                    }
+                    if (e) break;
+                    if (nc == 0) { e = true; break; }
+                    T.base[n] = fb; T.strand[n] = st == '-'; T.mode[n] = (uint8_t)mode; T.ncodes[n] = (uint8_t)nc;
+                    // delta text: (hl+1 .. j) when a comma follows the header
+                    if (hl < j) { T.d_start[n] = hl + 1; T.d_end[n] = j; if (hl + 1 >= j) { /* "C+m?," */ } }
+                    else { T.d_start[n] = j; T.d_end[n] = j; }
+                    // header followed by a comma but no number => separated_list1 fails => read error
+                    T.n_delta[n] = (hl < j) ? 0xffffffffu : 0u;   // 0xffffffff = "must parse >= 1"
+                    n++;
+                }
+                i = j + 1;
+            }
+            T.n = e ? 0xffffffffu : n;
+        }
+        __syncwarp();
+        if (T.n == 0xffffffffu) err = true;
+        const uint32_t nl = err ? 0 : T.n;
+        // ---- phase 2: per-base cumulative counts over SEQ (query order), 32 bases per lane --------
+        uint32_t need = 0;   // nibble-bases needed: bit x for nibble-base index x (0..3 = A C G T in SEQ)
+        for (uint32_t l = 0; l < nl; l++) {
+            uint8_t fb = T.base[l];
+            if (fb == 'N') continue;
+            int b = fb == 'A' ? 0 : fb == 'C' ? 1 : fb == 'G' ? 2 : 3;
+            int x = rev ? 3 - b : b;
+            need |= 1u << x;
+        }
+        const uint32_t nblk = (L + 31) >> 5;
+        if (need) {
+            uint32_t run[4] = {0, 0, 0, 0};
+            const uint32_t* seqw = (const uint32_t*)seq;   // 4-byte aligned
+            const uint32_t nbytes = (L + 1) >> 1;
+            for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
+                uint32_t blk = b0 + lane;
+                uint32_t cnt[4] = {0, 0, 0, 0};
+                if (blk < nblk) {
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        uint32_t byte0 = blk * 16 + w * 4;
+                        if (byte0 >= nbytes) break;
+                        uint32_t word = seqw[blk * 4 + w];   // may read past the SEQ end inside the read block; masked below
+                        uint32_t valid_bytes = nbytes - byte0;
+                        if (valid_bytes < 4) word &= (1u << (8 * valid_bytes)) - 1u;
+                        // an odd-length read has a zero low nibble in its last byte (nibble 0 is '=')
+#pragma unroll
+                        for (int x = 0; x < 4; x++) if (need & (1u << x)) cnt[x] += __popc(nib_eq_flags(word, 1u << x));
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    if (!(need & (1u << x))) continue;
+                    uint32_t inc = warp_incl_scan(cnt[x]);
+                    if (blk < nblk) cum[x * (C.max_blocks + 1) + blk] = run[x] + inc - cnt[x];
+                    run[x] += __shfl_sync(FULL, inc, 31);
+                }
+            }
+            if (lane == 0) for (int x = 0; x < 4; x++) { T.tot[x] = run[x]; if (need & (1u << x)) cum[x * (C.max_blocks + 1) + nblk] = run[x]; }
+        }
+        __syncwarp();
+        // ---- phase 3: tokens -> forward positions ------------------------------------------------------
+        uint32_t* P = C.P + meta.entry_off;
+        uint32_t ent = 0, mlp = 0;
+        for (uint32_t l = 0; l < nl && !err; l++) {
+            const uint32_t ds = T.d_start[l], de = T.d_end[l];
+            const bool must = T.n_delta[l] == 0xffffffffu;
+            const uint8_t fb = T.base[l];
+            int x = -1;
+            uint32_t tot = 0;
+            if (fb != 'N') { int b = fb == 'A' ? 0 : fb == 'C' ? 1 : fb == 'G' ? 2 : 3; x = rev ? 3 - b : b; tot = T.tot[x]; }
+            const uint32_t* cx = x >= 0 ? cum + x * (C.max_blocks + 1) : nullptr;
+            unsigned long long carry = 0;     // sum of (d+1) so far
+            uint32_t ntok = 0;
+            bool stop = false;                // list truncated by a malformed token
+            // tokens: one starts at ds and one after every ',' in [ds,de); grammar ws* digit+ ws* (nom separated_list1)
+            for (uint32_t c0 = ds; must && c0 <= de && !stop && !err; c0 += 32) {
+                const uint32_t tp = c0 + lane;
+                const bool starts = (tp <= de) && (tp == ds || mm[tp - 1] == ',');
+                unsigned long long val = 0;
+                bool ok_start = false, clean = false;
+                if (starts) {
+                    uint32_t k = tp;
+                    while (k < de && is_ws(mm[k])) k++;
+                    uint32_t d0 = k;
+                    while (k < de && is_digit(mm[k])) { val = val * 10 + (mm[k] - '0'); if (val > 0xffffffffull) val = 0x1ffffffffull; k++; }
+                    ok_start = k > d0 && val <= 0xffffffffull;
+                    while (k < de && is_ws(mm[k])) k++;
+                    clean = (k == de) || (mm[k] == ',');
+                }
+                uint32_t m_start = __ballot_sync(FULL, starts);
+                uint32_t m_badstart = __ballot_sync(FULL, starts && !ok_start);
+                uint32_t m_dirty = __ballot_sync(FULL, starts && ok_start && !clean);
+                // first terminating token: a bad start excludes itself, a dirty end includes itself
+                uint32_t first_bad = m_badstart ? (uint32_t)__ffs(m_badstart) - 1 : 32;
+                uint32_t first_dirty = m_dirty ? (uint32_t)__ffs(m_dirty) - 1 : 32;
+                uint32_t keep_mask = m_start;
+                if (first_bad < 32 || first_dirty < 32) {
+                    stop = true;
+                    uint32_t cut = first_bad <= first_dirty ? first_bad : first_dirty + 1;   // lanes < cut are kept
+                    keep_mask &= cut >= 32 ? FULL : ((1u << cut) - 1u);
+                }
+                bool mine = (keep_mask >> lane) & 1u;
+                unsigned long long inc = mine ? (val + 1ull) : 0ull;
+                unsigned long long pre = warp_incl_scan64(inc);
+                uint32_t idx = ntok + __popc(keep_mask & ((1u << lane) - 1u));
+                if (mine) {
+                    unsigned long long k = carry + pre - 1ull;   // 0-based occurrence index (forward order)
+                    uint32_t f;
+                    bool bad = false;
+                    if (fb == 'N') {
+                        f = (uint32_t)k;
+                        if (k >= (unsigned long long)L) bad = true;
+                    } else {
+                        if (k >= (unsigned long long)tot) bad = true;
+                        else {
+                            uint32_t kq = rev ? tot - 1u - (uint32_t)k : (uint32_t)k;   // occurrence index in query order
+                            // block with cx[blk] <= kq < cx[blk+1]
+                            uint32_t lo = 0, hi = nblk;   // invariant: cx[lo] <= kq < cx[hi]
+                            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (cx[mid] <= kq) lo = mid; else hi = mid; }
+                            uint32_t within = kq - cx[lo];
+                            const uint32_t* sw = (const uint32_t*)seq + lo * 4;
+                            uint32_t nbytes = (L + 1) >> 1;
+                            uint32_t q = 0xffffffffu;
+#pragma unroll
+                            for (int w = 0; w < 4; w++) {
+                                uint32_t byte0 = lo * 16 + w * 4;
+                                if (byte0 >= nbytes || q != 0xffffffffu) continue;
+                                uint32_t word = sw[w];
+                                uint32_t vb = nbytes - byte0;
+                                if (vb < 4) word &= (1u << (8 * vb)) - 1u;
+                                uint32_t msk = nib_flags_to_mask(nib_eq_flags(word, 1u << x));
+                                uint32_t pc = __popc(msk);
+                                if (within < pc) { q = lo * 32 + w * 8 + (__fns(msk, 0, within + 1)); }
+                                else within -= pc;
+                            }
+                            if (q >= L) bad = true;
+                            f = rev ? L - 1u - q : q;
+                        }
+                    }
+                    if (bad) err = true; else P[ent + idx] = f;
+                }
+                err = __any_sync(FULL, err);
+                carry += __shfl_sync(FULL, pre, 31);
+                ntok += __popc(keep_mask);
+                if (c0 == ds && must && !(keep_mask & 1u) && lane == 0) err = true;   // first token failed to parse
+                err = __any_sync(FULL, err);
+            }
+            if (must && ntok == 0) err = true;
+            // N lists: the reference checks only deltas after the first against the sequence length; the first
+            // then panics on indexing, which we turn into a read error (handled by `bad` above).
+            __syncwarp();
+            if (lane == 0) { T.n_delta[l] = ntok; T.ent_off[l] = ent; T.ml_off[l] = mlp; }
+            if ((unsigned long long)mlp + (unsigned long long)ntok * T.ncodes[l] > (unsigned long long)h.len_ml) err = true;
+            mlp += ntok * T.ncodes[l];
+            ent += ntok;
+            __syncwarp();
+        }
+        // '.'/default-mode lists (src/read_cache.rs:122-137, src/mod_bam.rs:1041-1043, 1265-1292)
+        bool any_entries = ent > 0;
+        if (!err) {
+            for (uint32_t l = 0; l < nl; l++) {
+                const uint8_t md = T.mode[l];
+                if (md == 0) continue;
+                const uint8_t bl = T.base[l] == 'U' ? 'T' : T.base[l];
+                bool contributes;
+                if (bl == 'N') contributes = T.n_delta[l] > 0;
+                else { int b = bl == 'A' ? 0 : bl == 'C' ? 1 : bl == 'G' ? 2 : 3; contributes = T.tot[rev ? 3 - b : b] > 0; }
+                if (!contributes) continue;
+                // the (strand, base) table keeps the default mode only if every contributing list has it
+                bool all_default = md == 2;
+                for (uint32_t l2 = 0; l2 < nl && all_default; l2++) {
+                    if (l2 == l || T.strand[l2] != T.strand[l]) continue;
+                    const uint8_t b2 = T.base[l2] == 'U' ? 'T' : T.base[l2];
+                    if (b2 != bl && !(b2 == 'N' && T.n_delta[l2] > 0) && bl != 'N') continue;
+                    if (T.mode[l2] != 2 && (T.n_delta[l2] > 0 || T.mode[l2] == 1)) all_default = false;
+                }
+                if (all_default && !c_par.force_allow_implicit) { err = true; break; }   // InvalidImplicitMode: read skipped
+                if (bl == 'N') continue;      // N lists get no implicit fill
+                if (lane == 0) atomicOr(C.err, MKP_DERR_IMPLICIT_MODE);   // implicit fill: not on the device yet
+                err = true;
+                break;
+            }
+        }
+        // ---- phase 4: resolve entries -> calls ---------------------------------------------------
+        uint32_t n_calls = 0, n_hist = 0;
+        uint32_t pos_mask = 0, neg_mask = 0;
+        bool table_survived = false;
+        uint2* calls = C.calls + meta.entry_off;
+        if (!err && any_entries) {
+            const bool trim_ok = !c_par.edge_on || !(L <= c_par.edge_start || L <= c_par.edge_end);
+            for (uint32_t l = 0; l < nl && !err; l++) {
+                const uint32_t n = T.n_delta[l];
+                const uint32_t* Pl = P + T.ent_off[l];
+                const uint32_t st = T.strand[l];
+                for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+                    uint32_t j = j0 + lane;
+                    bool active = j < n;
+                    bool emit = false;
+                    uint32_t rpos = 0, info = 0;
+                    bool e2 = false;
+                    bool hist_ok = false;
+                    float hist_v = 0.f;
+                    int hist_base = 0;
+                    if (active) {
+                        uint32_t f = Pl[j];
+                        uint32_t q = rev ? L - 1u - f : f;
+                        int nb = nib_to_base(seq_nibble(seq, q));
+                        int b = nb > 3 ? 4 : (rev ? 3 - nb : nb);   // forward-read base
+                        if (b > 3) e2 = true;
+                        // absorbed by an earlier list of the same strand?
+                        bool owner = true;
+                        for (uint32_t l2 = 0; l2 < l && owner; l2++) {
+                            if (T.strand[l2] != st || T.n_delta[l2] == 0) continue;
+                            const uint32_t* P2 = P + T.ent_off[l2];
+                            uint32_t n2 = T.n_delta[l2];
+                            if (j < n2 && P2[j] == f) { owner = false; break; }
+                            uint32_t k = lower_bound_u32(P2, n2, f);
+                            if (k < n2 && P2[k] == f) owner = false;
+                        }
+                        if (owner && !e2) {
+                            ProbMap m;
+                            m.init();
+                            const uint8_t* mlq = ml + T.ml_off[l] + (size_t)j * T.ncodes[l];
+                            for (uint32_t c = 0; c < T.ncodes[l] && !e2; c++) {
+                                float p = __fdiv_rn(__fadd_rn((float)mlq[c], 0.5f), 256.0f);
+                                int it = m.find(T.code[l][c]);
+                                if (it < 0) { if (m.insert(T.code[l][c], p) < 0) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
+                                else { if (__fadd_rn(m.p[it], p) > 1.01f) e2 = true; else m.p[it] = __fadd_rn(m.p[it], p); }
+                            }
+                            for (uint32_t l2 = l + 1; l2 < nl && !e2; l2++) {
+                                if (T.strand[l2] != st || T.n_delta[l2] == 0) continue;
+                                const uint32_t* P2 = P + T.ent_off[l2];
+                                uint32_t n2 = T.n_delta[l2];
+                                uint32_t k;
+                                if (j < n2 && P2[j] == f) k = j;
+                                else { k = lower_bound_u32(P2, n2, f); if (!(k < n2 && P2[k] == f)) continue; }
+                                // per-list table first (add_base_mod_prob), then combine_checked into the aggregate
+                                ProbMap t2;
+                                t2.init();
+                                const uint8_t* ml2 = ml + T.ml_off[l2] + (size_t)k * T.ncodes[l2];
+                                for (uint32_t c = 0; c < T.ncodes[l2] && !e2; c++) {
+                                    float p = __fdiv_rn(__fadd_rn((float)ml2[c], 0.5f), 256.0f);
+                                    int it = t2.find(T.code[l2][c]);
+                                    if (it < 0) { if (t2.insert(T.code[l2][c], p) < 0) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
+                                    else { if (__fadd_rn(t2.p[it], p) > 1.01f) e2 = true; else t2.p[it] = __fadd_rn(t2.p[it], p); }
+                                }
+                                for (int s = 0; s < 8 && !e2; s++) {
+                                    if (t2.slot[s] < 0) continue;
+                                    int i2 = t2.slot[s];
+                                    int it = m.find(t2.code[i2]);
+                                    if (it < 0) { if (m.insert(t2.code[i2], t2.p[i2]) < 0) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
+                                    else m.p[it] = __fadd_rn(m.p[it], t2.p[i2]);
+                                }
+                                if (!e2 && m.sum() > 1.01f) e2 = true;
+                            }
+                            if (!e2) {
+                                const int tb = st == 0 ? b : 3 - b;
+                                bool keep = trim_ok;
+                                if (keep && c_par.edge_on) {
+                                    if (c_par.edge_inv) keep = f < c_par.edge_start || f >= L - c_par.edge_end;
+                                    else keep = f >= c_par.edge_start && f < L - c_par.edge_end;
+                                }
+                                if (keep) {
+                                    ProbMap mc;
+                                    const ProbMap* use = &m;
+                                    if (c_par.numeric_mode == 2) { redistribute(m, c_par.collapse_code, mc); use = &mc; }
+                                    // aligned?
+                                    uint32_t lo = 0, hi = h.n_cigar;   // largest i with cq[i] <= q
+                                    bool aligned = false;
+                                    if (hi > 0 && cq[0] <= q) {
+                                        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (cq[mid] <= q) lo = mid; else hi = mid; }
+                                        uint32_t c = cig[lo];
+                                        uint32_t op = c & 15, len = c >> 4;
+                                        if ((op == 0 || op == 7 || op == 8) && q - cq[lo] < len) { aligned = true; rpos = cr[lo] + (q - cq[lo]); }
+                                    }
+                                    if (MODE == MODE_PILEUP) {
+                                        uint32_t mask = 0;
+                                        for (int s = 0; s < 8; s++) if (use->slot[s] >= 0) mask |= 1u << state_id(C, tb, use->code[use->slot[s]]);
+                                        // (mod strand, read orientation) -> reference strand (read_cache.rs:181-188)
+                                        if ((st == 0) != rev) pos_mask |= mask; else neg_mask |= mask;
+                                        table_survived = true;
+                                        if (aligned && rpos >= C.cs && rpos < C.ce) {
+                                            uint32_t code = 0;
+                                            int kind = make_call(*use, tb, &code);
+                                            uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, tb, code);
+                                            // does a '+' list cover the same position (both pos_call and neg_call present)?
+                                            uint32_t nosub = 0;
+                                            if (st == 1) {
+                                                for (uint32_t l2 = 0; l2 < nl && !nosub; l2++) {
+                                                    if (T.strand[l2] != 0 || T.n_delta[l2] == 0) continue;
+                                                    const uint32_t* P2 = P + T.ent_off[l2];
+                                                    uint32_t k = lower_bound_u32(P2, T.n_delta[l2], f);
+                                                    if (k < T.n_delta[l2] && P2[k] == f) nosub = 1;
+                                                }
+                                            }
+                                            uint32_t x = rpos - C.cs;
+                                            bool focus = true;
+                                            if (C.focus_pos) focus = ((C.focus_pos[x >> 5] | C.focus_neg[x >> 5]) >> (x & 31)) & 1u;
+                                            if (focus) { emit = true; info = st | ((uint32_t)b << 1) | (state << 3) | (nosub << 11); }
+                                        }
+                                    } else {
+                                        if (aligned || C.hist_include_unaligned) { hist_ok = true; hist_v = argmax_prob(*use); hist_base = tb; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    err = __any_sync(FULL, e2) || err;
+                    if (MODE == MODE_PILEUP) {
+                        uint32_t em = __ballot_sync(FULL, emit);
+                        if (emit) calls[n_calls + __popc(em & ((1u << lane) - 1u))] = make_uint2(rpos, info);
+                        n_calls += __popc(em);
+                    } else {
+                        uint32_t hm = __ballot_sync(FULL, hist_ok);
+                        if (hist_ok) {
+                            // stash (bin | base<<16 | inexact<<20) in the call buffer; committed after validation
+                            float sc = __fmul_rn(hist_v, 1024.0f);
+                            int bin = (int)rintf(sc);
+                            uint32_t inexact = ((float)bin != sc || bin < 0 || bin > 1024) ? 1u : 0u;
+                            if (bin < 0) bin = 0;
+                            if (bin > 1024) bin = 1024;
+                            calls[n_hist + __popc(hm & ((1u << lane) - 1u))] = make_uint2((uint32_t)bin | ((uint32_t)hist_base << 16) | (inexact << 20), __float_as_uint(hist_v));
+                        }
+                        n_hist += __popc(hm);
+                    }
+                }
+            }
+        }
+        pos_mask = __reduce_or_sync(FULL, pos_mask);
+        neg_mask = __reduce_or_sync(FULL, neg_mask);
+        table_survived = __any_sync(FULL, table_survived);
+        __syncwarp();
+        // ---- phase 5: commit -------------------------------------------------------------------------
+        if (MODE == MODE_PILEUP) {
+            if (!err && table_survived) {
+                meta.flags |= 2;
+                meta.pos_mask = pos_mask; meta.neg_mask = neg_mask; meta.n_calls = n_calls;
+                for (uint32_t k = lane; k < n_calls; k += 32) {
+                    uint32_t x = calls[k].x - C.cs;
+                    atomicOr(&C.hot[x >> 5], 1u << (x & 31));
+                }
+                if (lane == 0 && n_calls) atomicAdd(C.total_calls, (unsigned long long)n_calls);
+            }
+        } else {
+            if (!err && any_entries) {
+                meta.n_hist = n_hist;
+                if (C.hist) {
+                    for (uint32_t k = lane; k < n_hist; k += 32) {
+                        uint32_t v = calls[k].x;
+                        atomicAdd(&C.hist[((v >> 16) & 3u) * 1025u + (v & 0xffffu)], 1ull);
+                        if ((v >> 20) & 1u) atomicAdd(C.hist_inexact, 1ull);
+                    }
+                }
+            }
+        }
+        if (lane == 0) C.meta[ri] = meta;
+        __syncwarp();
+    }
+}
+
+// ---- rank over the hot bitmap -----------------------------------------------------------------------
+__global__ void k_block_popc(const uint32_t* __restrict__ bits, uint32_t n_words, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t s[32];
+    uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+    uint32_t v = i < n_words ? __popc(bits[i]) : 0;
+    uint32_t w = __reduce_add_sync(FULL, v);
+    if (lane_id() == 0) s[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x < 32) { uint32_t t = __reduce_add_sync(FULL, s[threadIdx.x]); if (threadIdx.x == 0) block_sums[blockIdx.x] = t; }
+}
+// single block: exclusive scan of block_sums in place, total -> *total
+__global__ void k_scan_blocks(uint32_t* block_sums, uint32_t n, uint32_t* total) {
+    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_w[32];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b < n; b += 1024) {
+        uint32_t i = b + threadIdx.x;
+        uint32_t v = i < n ? block_sums[i] : 0;
+        uint32_t inc = warp_incl_scan(v);
+        if (lane_id() == 31) s_w[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) { uint32_t t = s_w[threadIdx.x]; uint32_t ti = warp_incl_scan(t); s_w[threadIdx.x] = ti - t; }
+        __syncthreads();
+        uint32_t ex = s_carry + s_w[threadIdx.x >> 5] + inc - v;
+        if (i < n) block_sums[i] = ex;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = ex + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+__global__ void k_word_prefix(const uint32_t* __restrict__ bits, uint32_t n_words, const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ prefix) {
+    __shared__ uint32_t s_w[32];
+    uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+    uint32_t v = i < n_words ? __popc(bits[i]) : 0;
+    uint32_t inc = warp_incl_scan(v);
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) { uint32_t t = s_w[threadIdx.x]; uint32_t ti = warp_incl_scan(t); s_w[threadIdx.x] = ti - t; }
+    __syncthreads();
+    if (i < n_words) prefix[i] = block_sums[blockIdx.x] + s_w[threadIdx.x >> 5] + inc - v;
+}
+
+struct CountDev {
+    const mkp_read_hdr* hdrs;
+    const uint8_t* heap;
+    const ReadMeta* meta;
+    const uint2* calls;
+    uint32_t n_reads, cs, ce;
+    const uint32_t* focus_pos; const uint32_t* focus_neg;
+    const uint32_t* hot; const uint32_t* hot_prefix;
+    uint32_t* slots;
+    uint32_t stride;    // words per slot
+    uint32_t n_states;
+};
+
+__device__ __forceinline__ uint32_t slot_of(const CountDev& D, uint32_t x) {
+    uint32_t w = x >> 5;
+    return D.hot_prefix[w] + __popc(D.hot[w] & ((1u << (x & 31)) - 1u));
+}
+
+// warp per read, lanes over its call records
+__global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
+    const uint32_t lane = lane_id();
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t ri = gw; ri < D.n_reads; ri += nw) {
+        const ReadMeta m = D.meta[ri];
+        if (!(m.flags & 2) || m.n_calls == 0) continue;
+        const uint32_t a = (D.hdrs[ri].flags & 0x10) ? 1u : 0u;
+        const uint2* calls = D.calls + m.entry_off;
+        for (uint32_t k = lane; k < m.n_calls; k += 32) {
+            uint2 c = calls[k];
+            uint32_t x = c.x - D.cs;
+            uint32_t info = c.y;
+            uint32_t st = info & 1u, b = (info >> 1) & 3u, state = (info >> 3) & 0xffu, nosub = (info >> 11) & 1u;
+            uint32_t fp = FULL, fn = FULL;
+            if (D.focus_pos) { fp = D.focus_pos[x >> 5]; fn = D.focus_neg[x >> 5]; }
+            bool ok_pos = (fp >> (x & 31)) & 1u, ok_neg = (fn >> (x & 31)) & 1u;
+            uint32_t* S = D.slots + (size_t)slot_of(D, x) * D.stride;
+            // this (read, position) is not a NoCall: cancel the base counted by k_count_bases on tally[a]
+            if (!nosub && (a == 0 ? ok_pos : ok_neg)) atomicAdd(&S[SL_BASE + a * 4 + b], 0xffffffffu);
+            uint32_t t = st == 0 ? a : 1u - a;          // FeatureVector::add_feature
+            if (!(t == 0 ? ok_pos : ok_neg)) continue;
+            uint32_t pb = st == 0 ? b : 3u - b;
+            if (state == 0) atomicAdd(&S[SL_FILT + t], 1u);
+            else if (state == 1) atomicAdd(&S[SL_CANON + t * 4 + pb], 1u);
+            else atomicAdd(&S[SL_MOD + t * D.n_states + (state - 2)], 1u);
+        }
+    }
+}
+
+// warp per read: every aligned base / deleted position that lands on a hot position
+__global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
+    __shared__ uint32_t s_scan[8][33];
+    __shared__ uint32_t s_op[8][32], s_q[8][32], s_r[8][32];
+    const uint32_t lane = lane_id();
+    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t ri = gw; ri < D.n_reads; ri += nw) {
+        const ReadMeta m = D.meta[ri];
+        if (!(m.flags & 1)) continue;
+        const mkp_read_hdr h = D.hdrs[ri];
+        if ((uint32_t)m.ref_end <= D.cs || (uint32_t)h.ref_start >= D.ce) continue;
+        const uint32_t a = (h.flags & 0x10) ? 1u : 0u;
+        const uint32_t* cig = (const uint32_t*)(D.heap + h.off);
+        const uint8_t* seq = D.heap + h.off + 4ull * h.n_cigar;
+        const bool has_mods = m.flags & 2;
+        uint32_t qc = 0, rc = (uint32_t)h.ref_start;
+        for (uint32_t b0 = 0; b0 < h.n_cigar; b0 += 32) {
+            uint32_t i = b0 + lane;
+            uint32_t c = i < h.n_cigar ? cig[i] : 0;
+            uint32_t op = c & 15, len = c >> 4;
+            uint32_t ql = (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ? len : 0;
+            uint32_t rl = (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ? len : 0;
+            uint32_t qi = warp_incl_scan(ql), rr = warp_incl_scan(rl);
+            uint32_t q0 = qc + qi - ql, r0 = rc + rr - rl;
+            qc += __shfl_sync(FULL, qi, 31);
+            rc += __shfl_sync(FULL, rr, 31);
+            // windows = hot-bitmap words touched by this op inside the chunk (M,=,X and D only)
+            bool counts = (op == 0 || op == 7 || op == 8 || op == 2) && len > 0;
+            uint32_t lo = r0 > D.cs ? r0 : D.cs;
+            uint32_t hi = r0 + len < D.ce ? r0 + len : D.ce;
+            uint32_t nwin = 0;
+            if (counts && lo < hi) nwin = ((hi - 1 - D.cs) >> 5) - ((lo - D.cs) >> 5) + 1;
+            uint32_t wi = warp_incl_scan(nwin);
+            s_scan[wib][lane + 1] = wi;
+            if (lane == 0) s_scan[wib][0] = 0;
+            s_op[wib][lane] = op; s_q[wib][lane] = q0; s_r[wib][lane] = r0;
+            __syncwarp();
+            const uint32_t total = s_scan[wib][32];
+            for (uint32_t t = lane; t < total; t += 32) {
+                // op j with scan[j] <= t < scan[j+1]
+                uint32_t lo_j = 0, hi_j = 32;
+                while (hi_j - lo_j > 1) { uint32_t mid = (lo_j + hi_j) >> 1; if (s_scan[wib][mid] <= t) lo_j = mid; else hi_j = mid; }
+                const uint32_t j = lo_j;
+                const uint32_t jop = s_op[wib][j], jq = s_q[wib][j], jr = s_r[wib][j];
+                uint32_t clen = cig[b0 + j] >> 4;
+                uint32_t olo = jr > D.cs ? jr : D.cs;
+                uint32_t ohi = jr + clen < D.ce ? jr + clen : D.ce;
+                uint32_t w = ((olo - D.cs) >> 5) + (t - s_scan[wib][j]);
+                uint32_t wbase = D.cs + (w << 5);
+                uint32_t bits = D.hot[w];
+                if (!bits) continue;
+                // restrict to [olo, ohi)
+                if (olo > wbase) bits &= FULL << (olo - wbase);
+                if (ohi < wbase + 32) bits &= (1u << (ohi - wbase)) - 1u;
+                if (!bits) continue;
+                uint32_t fp = FULL, fn = FULL;
+                if (D.focus_pos) { fp = D.focus_pos[w]; fn = D.focus_neg[w]; }
+                const uint32_t ok = a == 0 ? fp : fn;
+                const uint32_t pre = D.hot_prefix[w];
+                const uint32_t word = D.hot[w];
+                while (bits) {
+                    uint32_t bit = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    uint32_t slot = pre + __popc(word & ((1u << bit) - 1u));
+                    uint32_t* S = D.slots + (size_t)slot * D.stride;
+                    if (has_mods) {
+                        if (m.pos_mask && (S[SL_OBS] & m.pos_mask) != m.pos_mask) atomicOr(&S[SL_OBS], m.pos_mask);
+                        if (m.neg_mask && (S[SL_OBS + 1] & m.neg_mask) != m.neg_mask) atomicOr(&S[SL_OBS + 1], m.neg_mask);
+                    }
+                    if (!((ok >> bit) & 1u)) continue;
+                    if (jop == 2) { atomicAdd(&S[SL_DEL + a], 1u); continue; }
+                    uint32_t q = jq + (wbase + bit - jr);
+                    int nb = nib_to_base(seq_nibble(seq, q));
+                    if (nb > 3) continue;
+                    uint32_t b = a ? 3 - nb : nb;
+                    atomicAdd(&S[SL_BASE + a * 4 + b], 1u);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct RowDev {
+    const uint32_t* hot; const uint32_t* hot_prefix;
+    uint32_t n_words, cs, ce;
+    const uint32_t* slots;
+    uint32_t stride, n_states;
+    const unsigned long long* states;
+    uint32_t numeric_mode;
+    uint32_t* row_counts;     // per hot-bitmap word
+    const uint32_t* row_prefix;
+    mkp_row* rows;
+};
+
+// rows of one slot, in output order. emit == nullptr => count only
+__device__ __forceinline__ uint32_t slot_rows(const RowDev& R, const uint32_t* S, uint32_t pos, mkp_row* out) {
+    uint32_t n = 0;
+    for (uint32_t s = 0; s < 2; s++) {
+        uint32_t mod_by_base[4] = {0, 0, 0, 0};
+        for (uint32_t id = 0; id < R.n_states; id++) mod_by_base[(uint32_t)(R.states[id] >> 32) & 3u] += S[SL_MOD + s * R.n_states + id];
+        const uint32_t obs = S[SL_OBS + s];
+        const uint32_t row0 = n;
+        for (uint32_t pb = 0; pb < 4; pb++) {
+            uint32_t n_can = S[SL_CANON + s * 4 + pb], total_mod = mod_by_base[pb];
+            if (n_can + total_mod == 0) continue;
+            uint32_t n_diff = 0;
+            for (uint32_t b = 0; b < 4; b++) if (b != pb) n_diff += S[SL_BASE + s * 4 + b] + S[SL_CANON + s * 4 + b] + mod_by_base[b];
+            mkp_row r;
+            r.pos = pos; r.strand = s == 0 ? '+' : '-'; r.primary_base = (uint8_t)pb; r.reserved = 0;
+            r.n_canon = n_can; r.n_delete = S[SL_DEL + s]; r.n_filtered = S[SL_FILT + s]; r.n_diff = n_diff; r.n_nocall = S[SL_BASE + s * 4 + pb];
+            if (R.numeric_mode == 1) {
+                r.code = (uint32_t)("ACGT"[pb]); r.n_mod = total_mod; r.n_other = 0;
+                if (out) out[n] = r;
+                n++;
+            } else {
+                for (uint32_t id = 0; id < R.n_states; id++) {
+                    unsigned long long key = R.states[id];
+                    if (((uint32_t)(key >> 32) & 3u) != pb || !((obs >> id) & 1u)) continue;
+                    uint32_t n_mod = S[SL_MOD + s * R.n_states + id];
+                    r.code = (uint32_t)key; r.n_mod = n_mod; r.n_other = total_mod - n_mod;
+                    if (out) out[n] = r;
+                    n++;
+                }
+            }
+        }
+        // stable insertion sort of this strand's rows by code (derived Ord: Code(char) < ChEbi == u32 order)
+        if (out) for (uint32_t i = row0 + 1; i < n; i++) {
+            mkp_row key = out[i];
+            uint32_t j = i;
+            while (j > row0 && out[j - 1].code > key.code) { out[j] = out[j - 1]; j--; }
+            out[j] = key;
+        }
+    }
+    return n;
+}
+
+// thread per hot-bitmap word
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_rows(RowDev R) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= R.n_words) return;
+    uint32_t bits = R.hot[w];
+    if (!bits) { if (!EMIT) R.row_counts[w] = 0; return; }
+    uint32_t slot = R.hot_prefix[w];
+    uint32_t n = 0;
+    mkp_row* out = EMIT ? R.rows + R.row_prefix[w] : nullptr;
+    while (bits) {
+        uint32_t bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        n += slot_rows(R, R.slots + (size_t)slot * R.stride, R.cs + (w << 5) + bit, EMIT ? out + n : nullptr);
+        slot++;
+    }
+    if (!EMIT) R.row_counts[w] = n;
+}
+
+// exclusive scan of arbitrary u32 array via the same 3-kernel scheme (counts -> prefix)
+__global__ void k_block_sum(const uint32_t* __restrict__ v, uint32_t n, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t s[32];
+    uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+    uint32_t x = i < n ? v[i] : 0;
+    uint32_t w = __reduce_add_sync(FULL, x);
+    if (lane_id() == 0) s[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x < 32) { uint32_t t = __reduce_add_sync(FULL, s[threadIdx.x]); if (threadIdx.x == 0) block_sums[blockIdx.x] = t; }
+}
+__global__ void k_value_prefix(const uint32_t* __restrict__ v, uint32_t n, const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ prefix) {
+    __shared__ uint32_t s_w[32];
+    uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+    uint32_t x = i < n ? v[i] : 0;
+    uint32_t inc = warp_incl_scan(x);
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) { uint32_t t = s_w[threadIdx.x]; uint32_t ti = warp_incl_scan(t); s_w[threadIdx.x] = ti - t; }
+    __syncthreads();
+    if (i < n) prefix[i] = block_sums[blockIdx.x] + s_w[threadIdx.x >> 5] + inc - x;
+}
+
+}  // namespace mkp
