@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — genomic positions/sec to bedMethyl rows for the `modkit pileup` hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
+
+Workload (config.workload): BASELINE.json configs[2] at full size — a chr20-sized contig (64,444,167 bp, synthetic,
+CpG o/e 0.25), 50x ONT-like reads, C+h?/C+m? dual-mod lists, `--cpg` (CG motif focus), threshold estimated from
+sampled reads. Weak scaling: every rank owns one such contig (interval-range sharding, no data-path collective);
+the only collective is the start-up sum of the sampled-probability histograms (NCCL all-reduce).
+
+A step = one pass of the hot path over the rank's resident chunk (decode MM/ML -> project through CIGAR ->
+threshold -> count -> rows). `value` is device-resident throughput, `e2e` the same through mkp_pileup_chunk on
+pinned HOST buffers (H2D of the packed reads + D2H of the rows inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/, the Rust crate cannot be built here) on a
+bounded window of the same workload with every host core.
+"""
+import argparse
+import ctypes
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONTIG_LEN = 64_444_167
+COVERAGE = 50
+MODS = "hm"
+SEED = 20260924
+CPU_WINDOW = 16_000_000        # bounded CPU sample: first 16 Mb of the same contig (same reads: deterministic generator)
+
+
+def sh(cmd, **kw):
+    return subprocess.run(cmd, check=True, capture_output=True, text=True, **kw)
+
+
+def ensure_tools():
+    import __graft_entry__ as ge
+    ge.build()
+    return (os.path.join(ROOT, "tools", "_build", "synth_modbam"), os.path.join(ROOT, "oracle", "_build", "modkit_oracle"))
+
+
+def workdir(rank):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 64 << 30 else tempfile.gettempdir()
+    d = os.path.join(base, "modkit_b200_bench_%d_r%d" % (os.getpid(), rank))
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no-samples"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(float(r[2]) for r in self.rows),
+                "samples": len(self.rows), "reasons": reasons}
+
+
+def gen_workload(synth, d, rank, contig_len, coverage, window=None, threads=None):
+    prefix = os.path.join(d, "w%d%s" % (rank, "_win" if window else ""))
+    cmd = [synth, "--out", prefix, "--contig", "syn%d:%d" % (rank + 1, contig_len), "--coverage", str(coverage), "--mods", MODS,
+           "--seed", str(SEED + rank), "--level", "1", "--threads", str(threads or min(64, os.cpu_count() or 8))]
+    if window:
+        cmd += ["--region-only", "0-%d" % window]
+    info = json.loads(sh(cmd).stdout)
+    return prefix, info
+
+
+def cpu_reference_run(oracle, prefix, contig, window, threshold, threads):
+    """One timed pass of the CPU restatement over [0, window) of the workload; returns (positions/s of the pileup phase, dict)."""
+    with tempfile.TemporaryDirectory() as td:
+        tj = os.path.join(td, "t.json")
+        subprocess.run([oracle, "pileup", "-t", str(threads), "--cpg", "--ref", prefix + ".fa", "--filter-threshold", "C:%.9g" % threshold,
+                        "--region", "%s:0-%d" % (contig, window), "--timing-json", tj, prefix + ".bam", os.path.join(td, "o.bed")],
+                       check=True, capture_output=True)
+        t = json.load(open(tj))
+    # hot path = per-interval pileup (decode+project+threshold+count+format); BAM inflate/parse reported separately
+    return t["positions"] / t["pileup_s"], t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--contig-len", type=int, default=CONTIG_LEN)
+    ap.add_argument("--coverage", type=float, default=COVERAGE)
+    ap.add_argument("--keep", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = {"workload": "BASELINE configs[2]: synthetic chr20-sized contig per GPU (%d bp), %gx ONT-like reads, C+h?/C+m? MM/ML, modkit pileup --cpg, estimated threshold (-p 0.1)" % (a.contig_len, a.coverage),
+                "contig_len": a.contig_len, "coverage": a.coverage, "mods": MODS, "interval_size": 100000, "sharding": "one contig (interval range) per GPU",
+                "l2_policy": "inputs (>2 GB packed reads per GPU) exceed the 126 MB L2; no explicit flush"}
+    nproc = os.cpu_count() or 1
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        synth, oracle = ensure_tools()
+        d = workdir(0)
+        try:
+            window = min(CPU_WINDOW, a.contig_len)
+            prefix, info = gen_workload(synth, d, 0, a.contig_len, a.coverage, window=window)
+            vals, last = [], None
+            for i in range(a.warmup + a.steps):
+                v, last = cpu_reference_run(oracle, prefix, "syn1", window, 0.8, nproc)
+                if i >= a.warmup:
+                    vals.append(v)
+            value = sum(vals) / len(vals)
+            line = {"impl": "reference", "metric": "genomic positions/sec to bedMethyl", "value": value, "unit": "positions/s", "n_gpus": a.gpus,
+                    "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * window / value, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "u32 counts (f32 probabilities)", "data": "synthetic", "config": workload,
+                    "cpu_baseline": {"value": value, "unit": "positions/s", "cores": nproc, "kind": "port",
+                                     "sample": "first %d bp of the workload contig (%d reads), pileup phase of the C++ restatement of modkit 0.4.4 (reference not buildable: no Rust toolchain), --filter-threshold C:0.8" % (window, info["reads"]),
+                                     "load_s": last["load_s"], "pileup_s": last["pileup_s"]},
+                    "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+        finally:
+            if not a.keep:
+                shutil.rmtree(d, ignore_errors=True)
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import modkit_b200
+    from modkit_b200 import sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        synth, oracle = ensure_tools()
+    if world > 1:
+        dist.barrier()
+    synth, oracle = os.path.join(ROOT, "tools", "_build", "synth_modbam"), os.path.join(ROOT, "oracle", "_build", "modkit_oracle")
+    modkit_b200.load_library(build_if_missing=False)
+    d = workdir(rank)
+    try:
+        t0 = time.time()
+        threads = max(4, min(64, nproc // max(1, world)))
+        prefix, info = gen_workload(synth, d, rank, a.contig_len, a.coverage, threads=threads)
+        contig = "syn%d" % (rank + 1)
+        t_gen = time.time() - t0
+        t0 = time.time()
+        bam = modkit_b200.Bam(prefix + ".bam", threads=threads)
+        t_load = time.time() - t0
+        t0 = time.time()
+        pk = bam.pack(0, 0, a.contig_len)
+        t_pack = time.time() - t0
+        t0 = time.time()
+        fpos, fneg = modkit_b200.motif_focus(prefix + ".fa", contig, 0, a.contig_len, 100000, "CG:0", False)
+        pk.set_focus(fpos, fneg)
+        t_focus = time.time() - t0
+        ctx = modkit_b200.Context(local_rank)
+        ctx.set_params(modkit_b200.make_params())
+
+        # ---- start-up: threshold from sampled reads; the single collective = histogram all-reduce (NCCL)
+        # sample = reads overlapping the first 2 Mb of the rank's contig (bench shortcut for the -n 10042 schedule; the
+        # exact schedule is exercised by the CLI and the parity tests)
+        spk = bam.pack(0, 0, min(2_000_000, a.contig_len))
+        ctx.upload(spk)
+        hist, _, inexact = ctx.sample_histogram()
+        assert inexact == 0
+        hist = sharding.allreduce_histogram(hist, device=torch.device("cuda", local_rank))
+        thr = float(sharding.percentile_from_histogram(hist[1], 0.1))
+        ctx.set_params(modkit_b200.make_params(base_thresholds={"C": thr}))
+        spk.free()
+
+        # pinned host copies of the packed reads for the e2e arm
+        ch = pk.chunk()
+        n_hdr_bytes = 32 * pk.n_reads
+        pin_hdr = torch.empty(n_hdr_bytes, dtype=torch.uint8, pin_memory=True)
+        pin_heap = torch.empty(pk.heap_bytes, dtype=torch.uint8, pin_memory=True)
+        ctypes.memmove(pin_hdr.data_ptr(), ctypes.cast(ch.hdrs, ctypes.c_void_p).value, n_hdr_bytes)
+        ctypes.memmove(pin_heap.data_ptr(), ch.heap, pk.heap_bytes)
+        pch = modkit_b200.Chunk()
+        pch.start, pch.end, pch.n_reads, pch.heap_bytes = ch.start, ch.end, ch.n_reads, ch.heap_bytes
+        pch.hdrs = ctypes.cast(pin_hdr.data_ptr(), ctypes.POINTER(modkit_b200.ReadHdr))
+        pch.heap = pin_heap.data_ptr()
+        pch.focus_pos, pch.focus_neg = ch.focus_pos, ch.focus_neg
+        lib = modkit_b200.load_library()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- value: device-resident passes
+        ctx.upload(pk)
+        for _ in range(a.warmup):
+            st = ctx.pileup_resident()
+        stage = np.zeros(8)
+        barrier()
+        with ClockSampler(local_rank) as clocks:
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                st = ctx.pileup_resident()
+                stage += np.array(list(st.kernel_ms))
+            barrier()
+            t_res = time.perf_counter() - t0
+        stage /= a.steps
+        n_rows = int(st.n_rows)
+        # ---- e2e: host buffers -> rows on the host, every step
+        rows_p, n_p, st2 = ctypes.c_void_p(), ctypes.c_size_t(), modkit_b200.Stats()
+        for _ in range(2):
+            assert lib.mkp_pileup_chunk(ctx._h, ctypes.byref(pch), ctypes.byref(rows_p), ctypes.byref(n_p), ctypes.byref(st2)) == 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            assert lib.mkp_pileup_chunk(ctx._h, ctypes.byref(pch), ctypes.byref(rows_p), ctypes.byref(n_p), ctypes.byref(st2)) == 0
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        assert n_p.value == n_rows
+
+        # max over ranks
+        times = torch.tensor([t_res, t_e2e, stage[7] * 1e-3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        t_res, t_e2e, t_kern = [float(x) for x in times.cpu()]
+        positions_total = a.contig_len * world
+        value = positions_total * a.steps / t_res
+        e2e = positions_total * a.steps / t_e2e
+
+        if rank == 0:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            alg = pk.algorithmic_bytes + 40 * n_rows
+            names = ["decode", "rank", "alloc_sync", "count_calls", "count_bases", "rows_count", "rows_emit"]
+            dom = int(np.argmax(stage[:7]))
+            ach = alg / (stage[dom] * 1e-3) / 1e9
+            # CPU baseline on the same box: bounded window of the same workload, all host cores
+            window = min(CPU_WINDOW, a.contig_len)
+            cpu_v, cpu_t = cpu_reference_run(oracle, prefix, contig, window, thr, nproc)
+            line = {"metric": "genomic positions/sec to bedMethyl", "value": value, "unit": "positions/s", "n_gpus": world, "steps": a.steps,
+                    "warmup": a.warmup, "ms_per_step": 1e3 * t_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "u32 counts (f32 probabilities)", "data": "synthetic", "config": workload, "impl": "b200",
+                    "e2e": {"value": e2e, "unit": "positions/s", "h2d_bytes_per_step": int(n_hdr_bytes + pk.heap_bytes + 8 * (pk.n_reads + 1) + 2 * fpos.nbytes),
+                            "d2h_bytes_per_step": int(40 * n_rows + 64), "ms_per_step": 1e3 * t_e2e / a.steps},
+                    "gpu_launches": 11 * a.steps,
+                    "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s", "traffic": None,
+                                 "algorithmic_bytes_per_launch": int(alg), "kernel_ms": float(stage[dom]),
+                                 "whole_path": {"achieved": alg / (stage[7] * 1e-3) / 1e9, "frac": alg / (stage[7] * 1e-3) / 1e9 / peak, "ms": float(stage[7])}},
+                    "stage_ms": {n: float(stage[i]) for i, n in enumerate(names)},
+                    "cpu_baseline": {"value": cpu_v, "unit": "positions/s", "cores": nproc, "kind": "port",
+                                     "sample": "first %d bp of the same contig, pileup phase of the C++ restatement of modkit 0.4.4 (oracle/), %d threads; BAM inflate+parse excluded (%.2f s)" % (window, nproc, cpu_t["load_s"])},
+                    "clocks": clocks.summary(),
+                    "rows_per_step": n_rows, "reads_per_gpu": int(pk.n_reads), "threshold_C": thr,
+                    "setup_s": {"generate": t_gen, "bam_load": t_load, "pack": t_pack, "focus": t_focus}}
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    finally:
+        if not a.keep:
+            shutil.rmtree(d, ignore_errors=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

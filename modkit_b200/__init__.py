@@ -1,0 +1,319 @@
+"""modkit_b200 — B200-native `modkit pileup` hot path.
+
+Python mirror of the host interface (ctypes over the in-tree C ABI, include/mkp.h + the mkh_* host API).
+The reference seam is `process_region_batch` (src/pileup/mod.rs:684-716): reads of one genomic chunk go in,
+`PileupFeatureCounts` rows come out. There is no CPU fallback: without the CUDA library or a GPU every entry
+point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libmodkit_b200.so")
+_lib = None
+
+
+class MkpError(RuntimeError):
+    pass
+
+
+class ReadHdr(C.Structure):
+    _fields_ = [("ref_start", C.c_int32), ("l_seq", C.c_uint32), ("n_cigar", C.c_uint32), ("flags", C.c_uint32),
+                ("off", C.c_uint64), ("len_ml", C.c_uint32), ("len_mm", C.c_uint32)]
+
+
+class Params(C.Structure):
+    _fields_ = [("default_threshold", C.c_float), ("base_threshold", C.c_float * 4), ("base_threshold_set", C.c_uint8 * 4),
+                ("n_mod_thresholds", C.c_uint32), ("mod_code", C.c_uint32 * 16), ("mod_threshold", C.c_float * 16),
+                ("numeric_mode", C.c_uint8), ("collapse_code", C.c_uint32), ("force_allow_implicit", C.c_uint8),
+                ("edge_filter_on", C.c_uint8), ("edge_filter_inverted", C.c_uint8),
+                ("edge_filter_start", C.c_uint32), ("edge_filter_end", C.c_uint32)]
+
+
+class Chunk(C.Structure):
+    _fields_ = [("start", C.c_uint32), ("end", C.c_uint32), ("hdrs", C.POINTER(ReadHdr)), ("n_reads", C.c_uint32),
+                ("heap", C.c_void_p), ("heap_bytes", C.c_uint64), ("focus_pos", C.c_void_p), ("focus_neg", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("n_hot", C.c_uint64), ("n_calls", C.c_uint64), ("n_reads_used", C.c_uint32),
+                ("n_reads_skipped", C.c_uint32), ("n_states", C.c_uint32), ("device_error", C.c_uint32), ("kernel_ms", C.c_float * 8)]
+
+
+ROW_DTYPE = np.dtype([("pos", "<u4"), ("code", "<u4"), ("strand", "u1"), ("primary_base", "u1"), ("reserved", "<u2"),
+                      ("n_mod", "<u4"), ("n_canon", "<u4"), ("n_other", "<u4"), ("n_delete", "<u4"),
+                      ("n_filtered", "<u4"), ("n_diff", "<u4"), ("n_nocall", "<u4")])
+assert ROW_DTYPE.itemsize == 40
+
+MKP_SYMBOLS = ["mkp_create", "mkp_destroy", "mkp_last_error", "mkp_set_params", "mkp_upload_chunk", "mkp_pileup_resident",
+               "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_algorithmic_bytes"]
+MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_refs", "mkh_bam_ref_name", "mkh_bam_ref_len",
+               "mkh_bam_n_mapped", "mkh_bam_n_records", "mkh_pack_region", "mkh_packed_free", "mkh_packed_n_reads",
+               "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
+               "mkh_motif_focus"]
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library(build_if_missing=True):
+    """dlopen the in-tree native library (building it with nvcc when absent). Never falls back to Python."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        if not build_if_missing:
+            raise MkpError("native library missing: " + _LIB_PATH)
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(_LIB_PATH)
+    lib.mkp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.mkp_destroy.argtypes = [C.c_void_p]
+    lib.mkp_destroy.restype = None
+    lib.mkp_last_error.argtypes = [C.c_void_p]
+    lib.mkp_last_error.restype = C.c_char_p
+    lib.mkp_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    lib.mkp_upload_chunk.argtypes = [C.c_void_p, C.POINTER(Chunk)]
+    lib.mkp_pileup_resident.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.mkp_fetch_rows.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.mkp_pileup_chunk.argtypes = [C.c_void_p, C.POINTER(Chunk), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(Stats)]
+    lib.mkp_sample_histogram.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.mkp_algorithmic_bytes.argtypes = [C.POINTER(Chunk), C.c_size_t]
+    lib.mkp_algorithmic_bytes.restype = C.c_size_t
+    lib.mkh_pileup_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    lib.mkh_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.mkh_bam_close.argtypes = [C.c_void_p]
+    lib.mkh_bam_close.restype = None
+    lib.mkh_bam_n_refs.argtypes = [C.c_void_p]
+    lib.mkh_bam_n_refs.restype = C.c_uint32
+    lib.mkh_bam_ref_name.argtypes = [C.c_void_p, C.c_uint32]
+    lib.mkh_bam_ref_name.restype = C.c_char_p
+    lib.mkh_bam_ref_len.argtypes = [C.c_void_p, C.c_uint32]
+    lib.mkh_bam_ref_len.restype = C.c_uint32
+    lib.mkh_bam_n_mapped.argtypes = [C.c_void_p, C.c_uint32]
+    lib.mkh_bam_n_mapped.restype = C.c_uint64
+    lib.mkh_bam_n_records.argtypes = [C.c_void_p, C.c_uint32]
+    lib.mkh_bam_n_records.restype = C.c_uint64
+    lib.mkh_pack_region.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.mkh_packed_free.argtypes = [C.c_void_p]
+    lib.mkh_packed_free.restype = None
+    lib.mkh_packed_n_reads.argtypes = [C.c_void_p]
+    lib.mkh_packed_n_reads.restype = C.c_uint32
+    lib.mkh_packed_hdrs.argtypes = [C.c_void_p]
+    lib.mkh_packed_hdrs.restype = C.POINTER(ReadHdr)
+    lib.mkh_packed_heap.argtypes = [C.c_void_p]
+    lib.mkh_packed_heap.restype = C.c_void_p
+    lib.mkh_packed_heap_bytes.argtypes = [C.c_void_p]
+    lib.mkh_packed_heap_bytes.restype = C.c_uint64
+    lib.mkh_packed_algorithmic_bytes.argtypes = [C.c_void_p]
+    lib.mkh_packed_algorithmic_bytes.restype = C.c_uint64
+    lib.mkh_format_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_void_p, C.c_uint64]
+    lib.mkh_format_rows.restype = C.c_uint64
+    lib.mkh_motif_focus.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def pileup_main(args):
+    """In-process `modkit pileup <args>`; returns the exit code (0 ok, 1 runtime error, 2 usage)."""
+    lib = load_library()
+    argv = (C.c_char_p * len(args))(*[str(a).encode() for a in args])
+    return lib.mkh_pileup_main(len(args), argv)
+
+
+class Bam:
+    def __init__(self, path, threads=4):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        if self._lib.mkh_bam_open(str(path).encode(), threads, C.byref(self._h)):
+            raise MkpError("cannot open BAM " + str(path))
+
+    def close(self):
+        if self._h:
+            self._lib.mkh_bam_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def refs(self):
+        n = self._lib.mkh_bam_n_refs(self._h)
+        return [(self._lib.mkh_bam_ref_name(self._h, i).decode(), self._lib.mkh_bam_ref_len(self._h, i)) for i in range(n)]
+
+    def n_mapped(self, tid):
+        return self._lib.mkh_bam_n_mapped(self._h, tid)
+
+    def pack(self, tid, start, end):
+        p = C.c_void_p()
+        if self._lib.mkh_pack_region(self._h, tid, start, end, C.byref(p)):
+            raise MkpError("pack_region failed")
+        return Packed(self._lib, p, start, end)
+
+
+class Packed:
+    """Packed read blocks of one chunk (host memory owned by the native library)."""
+
+    def __init__(self, lib, handle, start, end):
+        self._lib, self._h, self.start, self.end = lib, handle, start, end
+        self.n_reads = lib.mkh_packed_n_reads(handle)
+        self.heap_bytes = lib.mkh_packed_heap_bytes(handle)
+        self.algorithmic_bytes = lib.mkh_packed_algorithmic_bytes(handle)
+        self._focus = None
+
+    def set_focus(self, pos_bits, neg_bits):
+        self._focus = (np.ascontiguousarray(pos_bits, dtype=np.uint32), np.ascontiguousarray(neg_bits, dtype=np.uint32))
+
+    def chunk(self):
+        ch = Chunk()
+        ch.start, ch.end = self.start, self.end
+        ch.hdrs = self._lib.mkh_packed_hdrs(self._h)
+        ch.n_reads = self.n_reads
+        ch.heap = self._lib.mkh_packed_heap(self._h)
+        ch.heap_bytes = self.heap_bytes
+        if self._focus is not None:
+            ch.focus_pos = self._focus[0].ctypes.data
+            ch.focus_neg = self._focus[1].ctypes.data
+        return ch
+
+    def headers(self):
+        n = self.n_reads
+        buf = C.cast(self._lib.mkh_packed_hdrs(self._h), C.POINTER(C.c_uint8 * (32 * n))).contents if n else b""
+        dt = np.dtype([("ref_start", "<i4"), ("l_seq", "<u4"), ("n_cigar", "<u4"), ("flags", "<u4"), ("off", "<u8"), ("len_ml", "<u4"), ("len_mm", "<u4")])
+        return np.frombuffer(buf, dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+
+    def free(self):
+        if self._h:
+            self._lib.mkh_packed_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def make_params(default_threshold=0.0, base_thresholds=None, mod_thresholds=None, numeric_mode=0, collapse_code=0,
+                force_allow_implicit=False, edge_filter=None, edge_inverted=False):
+    p = Params()
+    p.default_threshold = default_threshold
+    for b, v in (base_thresholds or {}).items():
+        i = "ACGT".index(b)
+        p.base_threshold[i] = v
+        p.base_threshold_set[i] = 1
+    for i, (code, v) in enumerate((mod_thresholds or {}).items()):
+        p.mod_code[i] = ord(code) if isinstance(code, str) else (0x80000000 | int(code))
+        p.mod_threshold[i] = v
+        p.n_mod_thresholds = i + 1
+    p.numeric_mode = numeric_mode
+    p.collapse_code = ord(collapse_code) if isinstance(collapse_code, str) else collapse_code
+    p.force_allow_implicit = 1 if force_allow_implicit else 0
+    if edge_filter is not None:
+        p.edge_filter_on = 1
+        p.edge_filter_inverted = 1 if edge_inverted else 0
+        p.edge_filter_start, p.edge_filter_end = edge_filter
+    return p
+
+
+class Context:
+    """One GPU context (mkp_ctx). Raises when no CUDA device is usable: there is no CPU path."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.mkp_create(device, C.byref(self._h))
+        if rc:
+            raise MkpError("mkp_create failed (%d): no usable CUDA device; this package has no CPU fallback" % rc)
+
+    def _check(self, rc):
+        if rc:
+            raise MkpError(self._lib.mkp_last_error(self._h).decode())
+
+    def set_params(self, params):
+        self._check(self._lib.mkp_set_params(self._h, C.byref(params)))
+
+    def upload(self, packed):
+        ch = packed.chunk()
+        self._check(self._lib.mkp_upload_chunk(self._h, C.byref(ch)))
+
+    def pileup_resident(self):
+        st = Stats()
+        self._check(self._lib.mkp_pileup_resident(self._h, C.byref(st)))
+        return st
+
+    def fetch_rows(self):
+        rows = C.c_void_p()
+        n = C.c_size_t()
+        self._check(self._lib.mkp_fetch_rows(self._h, C.byref(rows), C.byref(n)))
+        if not n.value:
+            return np.zeros(0, dtype=ROW_DTYPE)
+        buf = (C.c_uint8 * (40 * n.value)).from_address(rows.value)
+        return np.frombuffer(buf, dtype=ROW_DTYPE)   # view of ctx-owned pinned memory; copy() to keep
+
+    def pileup_chunk(self, packed):
+        ch = packed.chunk()
+        rows = C.c_void_p()
+        n = C.c_size_t()
+        st = Stats()
+        self._check(self._lib.mkp_pileup_chunk(self._h, C.byref(ch), C.byref(rows), C.byref(n), C.byref(st)))
+        if not n.value:
+            return np.zeros(0, dtype=ROW_DTYPE), st
+        buf = (C.c_uint8 * (40 * n.value)).from_address(rows.value)
+        return np.frombuffer(buf, dtype=ROW_DTYPE), st
+
+    def sample_histogram(self, include_unaligned=False, take=None, want_contributes=False):
+        hist = np.zeros((4, 1025), dtype=np.uint64)
+        n = 0
+        contrib = None
+        inexact = C.c_uint64()
+        take_p = None
+        if take is not None:
+            take = np.ascontiguousarray(take, dtype=np.uint8)
+            take_p = take.ctypes.data
+            n = len(take)
+        if want_contributes:
+            contrib = np.zeros(max(1, self._n_reads_hint), dtype=np.uint8)
+        self._check(self._lib.mkp_sample_histogram(self._h, 1 if include_unaligned else 0, take_p, hist.ctypes.data,
+                                                   contrib.ctypes.data if contrib is not None else None, C.byref(inexact)))
+        return hist, contrib, inexact.value
+
+    _n_reads_hint = 0
+
+    def close(self):
+        if self._h:
+            self._lib.mkp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def format_rows(rows, chrom, mixed_delim=False):
+    lib = load_library()
+    rows = np.ascontiguousarray(rows)
+    n = lib.mkh_format_rows(rows.ctypes.data, len(rows), chrom.encode(), 1 if mixed_delim else 0, None, 0)
+    buf = C.create_string_buffer(n)
+    lib.mkh_format_rows(rows.ctypes.data, len(rows), chrom.encode(), 1 if mixed_delim else 0, buf, n)
+    return buf.raw[:n].decode()
+
+
+def motif_focus(fasta, contig, start, end, interval_size=100000, motifs="CG:0", combine_strands=False):
+    """Focus bitmaps (+ rule, - rule) over [start,end) on the reference's interval grid."""
+    lib = load_library()
+    nw = (end - start + 31) // 32
+    pos = np.zeros(nw, dtype=np.uint32)
+    neg = np.zeros(nw, dtype=np.uint32)
+    if lib.mkh_motif_focus(str(fasta).encode(), contig.encode(), start, end, interval_size, motifs.encode(), 1 if combine_strands else 0,
+                           pos.ctypes.data, neg.ctypes.data):
+        raise MkpError("motif_focus failed")
+    return pos, neg

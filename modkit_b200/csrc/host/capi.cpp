@@ -50,4 +50,30 @@ uint64_t mkh_format_rows(const mkp_row* rows, uint64_t n, const char* chrom, int
     return text.size();
 }
 
+// Focus bitmaps (FocusPositions::check_position rules) of [start,end) for a motif list given as "CG:0,GATC:1".
+// Intervals follow the reference grid (interval_size from `start`), so motif hits straddling an interval boundary are
+// dropped exactly like the reference does (src/fasta.rs:207-227).
+int mkh_motif_focus(const char* fasta, const char* contig, uint32_t start, uint32_t end, uint32_t interval_size,
+                    const char* motifs, int combine_strands, uint32_t* pos_bits, uint32_t* neg_bits) {
+    try {
+        MotifContext mc;
+        mc.fasta.open(fasta);
+        std::string ms = motifs;
+        for (size_t i = 0; i < ms.size();) {
+            size_t j = ms.find(',', i); if (j == std::string::npos) j = ms.size();
+            std::string one = ms.substr(i, j - i); size_t c = one.find(':');
+            mc.motifs.push_back(parse_motif(one.substr(0, c), std::stoi(one.substr(c + 1))));
+            mc.longest = std::max<uint64_t>(mc.longest, mc.motifs.back().len);
+            i = j + 1;
+        }
+        std::vector<RefTarget> t{{0, start, end - start, contig}};
+        std::vector<RefInterval> ivs = reference_intervals(t, interval_size, combine_strands != 0, &mc);
+        std::vector<uint32_t> fp, fn;
+        focus_bitmaps(ivs, 0, ivs.size(), start, end, &fp, &fn);
+        memcpy(pos_bits, fp.data(), fp.size() * 4);
+        memcpy(neg_bits, fn.data(), fn.size() * 4);
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "mkh_motif_focus: %s\n", e.what()); return -1; }
+}
+
 }  // extern "C"

@@ -45,13 +45,16 @@ struct DevParams {
     uint32_t edge_on, edge_inv, edge_start, edge_end;
 };
 
-struct ReadMeta {       // 32 bytes, written by k_decode
+struct ReadMeta {       // 40 bytes, written by k_decode
     int32_t ref_end;
     uint32_t flags;     // bit0 admitted, bit1 has mod info (not in skip_set)
     uint32_t pos_mask, neg_mask;
     uint32_t n_calls;
     uint32_t n_hist;    // sampling: values contributed
     uint64_t entry_off;
+    // implicit ('.'/default mode) tables: imp[s] byte b = 0x80 | state of the inferred-canonical entry of the
+    // (mod strand s, forward base b) table (src/mod_bam.rs:1265-1292); 0 = no implicit table
+    uint32_t imp[2];
 };
 
 struct ChunkDev {
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
         const bool rev = flag & 0x10;
         ReadMeta meta;
         meta.ref_end = h.ref_start;
-        meta.flags = 0; meta.pos_mask = 0; meta.neg_mask = 0; meta.n_calls = 0; meta.n_hist = 0;
+        meta.flags = 0; meta.pos_mask = 0; meta.neg_mask = 0; meta.n_calls = 0; meta.n_hist = 0; meta.imp[0] = 0; meta.imp[1] = 0;
         meta.entry_off = C.entry_off[ri];
         bool admitted;
         if (MODE == MODE_PILEUP) admitted = !(flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) && L > 0;
@@ -498,6 +501,7 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
         }
         // '.'/default-mode lists (src/read_cache.rs:122-137, src/mod_bam.rs:1041-1043, 1265-1292)
         bool any_entries = ent > 0;
+        uint32_t imp_lists[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // lists that infer canonical on (strand, base)
         if (!err) {
             for (uint32_t l = 0; l < nl; l++) {
                 const uint8_t md = T.mode[l];
@@ -517,15 +521,14 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
                 }
                 if (all_default && !c_par.force_allow_implicit) { err = true; break; }   // InvalidImplicitMode: read skipped
                 if (bl == 'N') continue;      // N lists get no implicit fill
-                if (lane == 0) atomicOr(C.err, MKP_DERR_IMPLICIT_MODE);   // implicit fill: not on the device yet
-                err = true;
-                break;
+                { int b = bl == 'A' ? 0 : bl == 'C' ? 1 : bl == 'G' ? 2 : 3; imp_lists[T.strand[l]][b] |= 1u << l; any_entries = true; }
             }
         }
         // ---- phase 4: resolve entries -> calls ---------------------------------------------------
         uint32_t n_calls = 0, n_hist = 0;
         uint32_t pos_mask = 0, neg_mask = 0;
         bool table_survived = false;
+        uint32_t imp_explicit[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // HIST: explicit values on implicit tables (per lane)
         uint2* calls = C.calls + meta.entry_off;
         if (!err && any_entries) {
             const bool trim_ok = !c_par.edge_on || !(L <= c_par.edge_start || L <= c_par.edge_end);
@@ -548,6 +551,20 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
                         int nb = nib_to_base(seq_nibble(seq, q));
                         int b = nb > 3 ? 4 : (rev ? 3 - nb : nb);   // forward-read base
                         if (b > 3) e2 = true;
+                        // ExplicitConflictInferred (mod_bam.rs:629-634): an implicit list of this (strand, base) table
+                        // that does not list f explicitly holds an inferred entry there
+                        if (b <= 3) {
+                            uint32_t others = imp_lists[st][b] & ~(1u << l);
+                            while (others && !e2) {
+                                const uint32_t l2 = __ffs(others) - 1;
+                                others &= others - 1;
+                                const uint32_t* P2 = P + T.ent_off[l2];
+                                const uint32_t n2 = T.n_delta[l2];
+                                if (j < n2 && P2[j] == f) continue;
+                                const uint32_t k = lower_bound_u32(P2, n2, f);
+                                if (!(k < n2 && P2[k] == f)) e2 = true;
+                            }
+                        }
                         // absorbed by an earlier list of the same strand?
                         bool owner = true;
                         for (uint32_t l2 = 0; l2 < l && owner; l2++) {
@@ -640,7 +657,10 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
                                             if (focus) { emit = true; info = st | ((uint32_t)b << 1) | (state << 3) | (nosub << 11); }
                                         }
                                     } else {
-                                        if (aligned || C.hist_include_unaligned) { hist_ok = true; hist_v = argmax_prob(*use); hist_base = tb; }
+                                        if (aligned || C.hist_include_unaligned) {
+                                            hist_ok = true; hist_v = argmax_prob(*use); hist_base = tb;
+                                            if (imp_lists[st][b]) imp_explicit[st * 4 + b]++;
+                                        }
                                     }
                                 }
                             }
@@ -667,6 +687,75 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
                 }
             }
         }
+        // ---- phase 4b: implicit tables (every other occurrence of the base is an inferred-canonical entry) ----
+        uint32_t imp_meta[2] = {0, 0};
+        unsigned long long imp_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (!err) {
+            const bool trim_ok = !c_par.edge_on || !(L <= c_par.edge_start || L <= c_par.edge_end);
+            for (uint32_t sb = 0; sb < 8; sb++) {
+                const uint32_t s = sb >> 2, b = sb & 3;
+                const uint32_t lists = imp_lists[s][b];
+                if (!lists || !trim_ok) continue;
+                const uint32_t xn = 1u << (rev ? 3 - b : b);          // SEQ nibble of the forward base b
+                // survives the edge filter?  (any occurrence of the base with a kept forward position)
+                bool any = false;
+                for (uint32_t q = lane; q < L && !any; q += 32) {
+                    if (seq_nibble(seq, q) != xn) continue;
+                    const uint32_t f = rev ? L - 1u - q : q;
+                    bool keep = true;
+                    if (c_par.edge_on) keep = c_par.edge_inv ? (f < c_par.edge_start || f >= L - c_par.edge_end) : (f >= c_par.edge_start && f < L - c_par.edge_end);
+                    any = keep;
+                }
+                if (!__any_sync(FULL, any)) continue;
+                ProbMap m, mc;
+                m.init();
+                for (uint32_t l = 0; l < nl; l++) if ((lists >> l) & 1u) for (uint32_t c = 0; c < T.ncodes[l]; c++) if (m.find(T.code[l][c]) < 0) m.insert(T.code[l][c], 0.f);
+                const ProbMap* use = &m;
+                if (c_par.numeric_mode == 2) { redistribute(m, c_par.collapse_code, mc); use = &mc; }
+                const int tb = s == 0 ? (int)b : 3 - (int)b;
+                table_survived = true;
+                if (MODE == MODE_PILEUP) {
+                    uint32_t mask = 0;
+                    for (int k = 0; k < 8; k++) if (use->slot[k] >= 0) mask |= 1u << state_id(C, tb, use->code[use->slot[k]]);
+                    if ((s == 0) != rev) pos_mask |= mask; else neg_mask |= mask;
+                    uint32_t code = 0;
+                    const int kind = make_call(*use, tb, &code);
+                    const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, tb, code);
+                    imp_meta[s] |= (0x80u | state) << (8 * b);
+                } else {
+                    // values: argmax of an all-zero map = canonical probability 1.0 for every passing inferred position
+                    unsigned long long n_pass = 0;
+                    if (C.hist_include_unaligned) {
+                        for (uint32_t q = lane; q < L; q += 32) {
+                            if (seq_nibble(seq, q) != xn) continue;
+                            const uint32_t f = rev ? L - 1u - q : q;
+                            bool keep = true;
+                            if (c_par.edge_on) keep = c_par.edge_inv ? (f < c_par.edge_start || f >= L - c_par.edge_end) : (f >= c_par.edge_start && f < L - c_par.edge_end);
+                            if (keep) n_pass++;
+                        }
+                    } else {
+                        uint32_t qc2 = 0;
+                        for (uint32_t i = 0; i < h.n_cigar; i++) {
+                            const uint32_t c = cig[i], op = c & 15, len = c >> 4;
+                            if (op == 0 || op == 7 || op == 8) {
+                                for (uint32_t k = lane; k < len; k += 32) {
+                                    const uint32_t q = qc2 + k;
+                                    if (q >= L || seq_nibble(seq, q) != xn) continue;
+                                    const uint32_t f = rev ? L - 1u - q : q;
+                                    bool keep = true;
+                                    if (c_par.edge_on) keep = c_par.edge_inv ? (f < c_par.edge_start || f >= L - c_par.edge_end) : (f >= c_par.edge_start && f < L - c_par.edge_end);
+                                    if (keep) n_pass++;
+                                }
+                            }
+                            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) qc2 += len;
+                        }
+                    }
+                    n_pass = __reduce_add_sync(FULL, (uint32_t)n_pass);
+                    const uint32_t n_exp = __reduce_add_sync(FULL, imp_explicit[sb]);
+                    imp_hist[sb] = n_pass > n_exp ? n_pass - n_exp : 0;
+                }
+            }
+        }
         pos_mask = __reduce_or_sync(FULL, pos_mask);
         neg_mask = __reduce_or_sync(FULL, neg_mask);
         table_survived = __any_sync(FULL, table_survived);
@@ -676,20 +765,51 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
             if (!err && table_survived) {
                 meta.flags |= 2;
                 meta.pos_mask = pos_mask; meta.neg_mask = neg_mask; meta.n_calls = n_calls;
+                meta.imp[0] = imp_meta[0]; meta.imp[1] = imp_meta[1];
                 for (uint32_t k = lane; k < n_calls; k += 32) {
                     uint32_t x = calls[k].x - C.cs;
                     atomicOr(&C.hot[x >> 5], 1u << (x & 31));
                 }
                 if (lane == 0 && n_calls) atomicAdd(C.total_calls, (unsigned long long)n_calls);
+                if (imp_meta[0] | imp_meta[1]) {
+                    // every aligned occurrence of an implicit table's base is a call position
+                    uint32_t qc2 = 0, rc2 = (uint32_t)h.ref_start;
+                    for (uint32_t i = 0; i < h.n_cigar; i++) {
+                        const uint32_t c = cig[i], op = c & 15, len = c >> 4;
+                        if (op == 0 || op == 7 || op == 8) {
+                            for (uint32_t k = lane; k < len; k += 32) {
+                                const uint32_t q = qc2 + k, r = rc2 + k;
+                                if (q >= L || r < C.cs || r >= C.ce) continue;
+                                const int nb = nib_to_base(seq_nibble(seq, q));
+                                if (nb > 3) continue;
+                                const uint32_t b = rev ? 3 - nb : nb;
+                                if (!(((imp_meta[0] | imp_meta[1]) >> (8 * b)) & 0x80u)) continue;
+                                const uint32_t f = rev ? L - 1u - q : q;
+                                if (c_par.edge_on && !(c_par.edge_inv ? (f < c_par.edge_start || f >= L - c_par.edge_end) : (f >= c_par.edge_start && f < L - c_par.edge_end))) continue;
+                                const uint32_t x = r - C.cs;
+                                if (C.focus_pos && !(((C.focus_pos[x >> 5] | C.focus_neg[x >> 5]) >> (x & 31)) & 1u)) continue;
+                                atomicOr(&C.hot[x >> 5], 1u << (x & 31));
+                            }
+                        }
+                        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) qc2 += len;
+                        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rc2 += len;
+                    }
+                }
             }
         } else {
             if (!err && any_entries) {
-                meta.n_hist = n_hist;
+                unsigned long long extra = 0;
+                for (int sb = 0; sb < 8; sb++) extra += imp_hist[sb];
+                meta.n_hist = n_hist + (uint32_t)(extra < 0x7fffffffull ? extra : 0x7fffffffull);
                 if (C.hist) {
                     for (uint32_t k = lane; k < n_hist; k += 32) {
                         uint32_t v = calls[k].x;
                         atomicAdd(&C.hist[((v >> 16) & 3u) * 1025u + (v & 0xffffu)], 1ull);
                         if ((v >> 20) & 1u) atomicAdd(C.hist_inexact, 1ull);
+                    }
+                    if (lane == 0) for (int sb = 0; sb < 8; sb++) if (imp_hist[sb]) {
+                        const int tb = (sb >> 2) == 0 ? (sb & 3) : 3 - (sb & 3);
+                        atomicAdd(&C.hist[tb * 1025u + 1024u], imp_hist[sb]);
                     }
                 }
             }
@@ -761,6 +881,14 @@ __device__ __forceinline__ uint32_t slot_of(const CountDev& D, uint32_t x) {
     return D.hot_prefix[w] + __popc(D.hot[w] & ((1u << (x & 31)) - 1u));
 }
 
+// FeatureVector::add_feature + Tally::add_feature (src/pileup/mod.rs:176-193, 238-281) as counter updates
+__device__ __forceinline__ void add_feature(uint32_t* S, uint32_t n_states, uint32_t t, uint32_t pb, uint32_t state, bool ok_pos, bool ok_neg, uint32_t delta) {
+    if (!(t == 0 ? ok_pos : ok_neg)) return;
+    if (state == 0) atomicAdd(&S[SL_FILT + t], delta);
+    else if (state == 1) atomicAdd(&S[SL_CANON + t * 4 + pb], delta);
+    else atomicAdd(&S[SL_MOD + t * n_states + (state - 2)], delta);
+}
+
 // warp per read, lanes over its call records
 __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
     const uint32_t lane = lane_id();
@@ -780,14 +908,13 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
             if (D.focus_pos) { fp = D.focus_pos[x >> 5]; fn = D.focus_neg[x >> 5]; }
             bool ok_pos = (fp >> (x & 31)) & 1u, ok_neg = (fn >> (x & 31)) & 1u;
             uint32_t* S = D.slots + (size_t)slot_of(D, x) * D.stride;
-            // this (read, position) is not a NoCall: cancel the base counted by k_count_bases on tally[a]
-            if (!nosub && (a == 0 ? ok_pos : ok_neg)) atomicAdd(&S[SL_BASE + a * 4 + b], 0xffffffffu);
-            uint32_t t = st == 0 ? a : 1u - a;          // FeatureVector::add_feature
-            if (!(t == 0 ? ok_pos : ok_neg)) continue;
-            uint32_t pb = st == 0 ? b : 3u - b;
-            if (state == 0) atomicAdd(&S[SL_FILT + t], 1u);
-            else if (state == 1) atomicAdd(&S[SL_CANON + t * 4 + pb], 1u);
-            else atomicAdd(&S[SL_MOD + t * D.n_states + (state - 2)], 1u);
+            // cancel what k_count_bases adds for this (read, position): the inferred entry of this table if the
+            // table is implicit, else the NoCall base on tally[a] (unless the other strand's table is implicit
+            // there, in which case no NoCall is counted, or the '+' record of a +/- pair already cancels it)
+            const uint32_t imp_own = (m.imp[st] >> (8 * b)) & 0xffu, imp_other = (m.imp[1 - st] >> (8 * b)) & 0xffu;
+            if (imp_own & 0x80u) add_feature(S, D.n_states, st == 0 ? a : 1u - a, st == 0 ? b : 3u - b, imp_own & 0x7fu, ok_pos, ok_neg, 0xffffffffu);
+            else if (!(imp_other & 0x80u) && !nosub && (a == 0 ? ok_pos : ok_neg)) atomicAdd(&S[SL_BASE + a * 4 + b], 0xffffffffu);
+            add_feature(S, D.n_states, st == 0 ? a : 1u - a, st == 0 ? b : 3u - b, state, ok_pos, ok_neg, 1u);
         }
     }
 }
@@ -863,13 +990,21 @@ __global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
                         if (m.pos_mask && (S[SL_OBS] & m.pos_mask) != m.pos_mask) atomicOr(&S[SL_OBS], m.pos_mask);
                         if (m.neg_mask && (S[SL_OBS + 1] & m.neg_mask) != m.neg_mask) atomicOr(&S[SL_OBS + 1], m.neg_mask);
                     }
-                    if (!((ok >> bit) & 1u)) continue;
-                    if (jop == 2) { atomicAdd(&S[SL_DEL + a], 1u); continue; }
+                    if (jop == 2) { if ((ok >> bit) & 1u) atomicAdd(&S[SL_DEL + a], 1u); continue; }
                     uint32_t q = jq + (wbase + bit - jr);
                     int nb = nib_to_base(seq_nibble(seq, q));
                     if (nb > 3) continue;
                     uint32_t b = a ? 3 - nb : nb;
-                    atomicAdd(&S[SL_BASE + a * 4 + b], 1u);
+                    uint32_t ip = (m.imp[0] >> (8 * b)) & 0xffu, in = (m.imp[1] >> (8 * b)) & 0xffu;
+                    if ((ip | in) & 0x80u) {
+                        // inferred-canonical entries of implicit tables, subject to the edge filter
+                        const uint32_t f = a ? h.l_seq - 1u - q : q;
+                        if (c_par.edge_on && !(c_par.edge_inv ? (f < c_par.edge_start || f >= h.l_seq - c_par.edge_end) : (f >= c_par.edge_start && f < h.l_seq - c_par.edge_end))) ip = in = 0;
+                    }
+                    const bool okp = (fp >> bit) & 1u, okn = (fn >> bit) & 1u;
+                    if (!((ip | in) & 0x80u)) { if ((ok >> bit) & 1u) atomicAdd(&S[SL_BASE + a * 4 + b], 1u); continue; }
+                    if (ip & 0x80u) add_feature(S, D.n_states, a, b, ip & 0x7fu, okp, okn, 1u);
+                    if (in & 0x80u) add_feature(S, D.n_states, 1u - a, 3u - b, in & 0x7fu, okp, okn, 1u);
                 }
             }
             __syncwarp();

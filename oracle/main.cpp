@@ -15,8 +15,73 @@ using namespace orc;
 
 static void die(const std::string& m) { fprintf(stderr, "> Error! %s\n", m.c_str()); exit(1); }
 
+// Known-answer helpers for tests/ (mirror the reference's in-crate unit tests):
+//   decode SEQ MM ML_CSV [ignore_code]  -> one line per table entry: strand base pos inferred code:prob[,code:prob] canonical_prob
+//   call BASE code:p[,code:p] default [B:thr ...] [mod=c:thr ...] -> filtered | canonical P | modified CODE P
+//   percentile Q v0,v1,...
+static int kat_main(int argc, char** argv) {
+    std::string cmd = argv[1];
+    if (cmd == "decode") {
+        if (argc < 5) return 2;
+        std::string seq = argv[2], mm = argv[3], mlcsv = argv[4];
+        std::vector<uint8_t> ml;
+        for (size_t i = 0; i < mlcsv.size();) { size_t j = mlcsv.find(',', i); if (j == std::string::npos) j = mlcsv.size(); if (j > i) ml.push_back((uint8_t)std::stoi(mlcsv.substr(i, j - i))); i = j + 1; }
+        std::vector<MmList> lists;
+        if (!parse_mm(mm.data(), mm.size(), &lists)) { printf("ERROR parse\n"); return 0; }
+        ModBaseInfo info;
+        if (!build_mod_base_info(lists, ml.data(), ml.size(), seq, &info)) { printf("ERROR build\n"); return 0; }
+        for (int st = 0; st < 2; st++) for (int b = 0; b < 4; b++) {
+            if (!info.present[st][b]) continue;
+            for (auto& kv : info.tab[st][b].pos) {
+                BaseModProbs bmp = kv.second;
+                if (argc > 5) { ModCode c; parse_mod_code(argv[5], &c); bmp = redistribute(bmp, c); }
+                printf("%c %c %u %d ", st ? '-' : '+', BASES[b], kv.first, bmp.inferred ? 1 : 0);
+                bool first = true;
+                bmp.probs.for_each([&](ModCode c, float p) { printf("%s%s:%.9g", first ? "" : ",", code_to_string(c).c_str(), p); first = false; });
+                printf(" %.9g mode=%d\n", bmp.canonical_prob(), info.tab[st][b].mode);
+            }
+        }
+        return 0;
+    }
+    if (cmd == "call") {
+        if (argc < 5) return 2;
+        int b = base_idx(argv[2][0]);
+        BaseModProbs bmp;
+        std::string ps = argv[3];
+        for (size_t i = 0; i < ps.size();) {
+            size_t j = ps.find(',', i); if (j == std::string::npos) j = ps.size();
+            std::string kv = ps.substr(i, j - i); size_t c = kv.find(':');
+            ModCode code; parse_mod_code(kv.substr(0, c), &code);
+            *bmp.probs.entry_or_insert(code, 0.f) = std::stof(kv.substr(c + 1));
+            i = j + 1;
+        }
+        Caller caller;
+        caller.default_thr = std::stof(argv[4]);
+        for (int i = 5; i < argc; i++) {
+            std::string a = argv[i];
+            if (a.rfind("mod=", 0) == 0) { size_t c = a.find(':'); ModCode code; parse_mod_code(a.substr(4, c - 4), &code); caller.mod_thr.push_back({code, std::stof(a.substr(c + 1))}); }
+            else { int bb = base_idx(a[0]); caller.base_set[bb] = true; caller.base_thr[bb] = std::stof(a.substr(2)); }
+        }
+        Call c = make_call(caller, b, bmp);
+        if (c.kind == CALL_FILTERED) printf("filtered\n");
+        else if (c.kind == CALL_CANONICAL) printf("canonical %.9g\n", bmp.canonical_prob());
+        else printf("modified %s %.9g\n", code_to_string(c.code).c_str(), *bmp.probs.get(c.code));
+        return 0;
+    }
+    if (cmd == "percentile") {
+        std::vector<float> xs;
+        std::string vs = argv[3];
+        for (size_t i = 0; i < vs.size();) { size_t j = vs.find(',', i); if (j == std::string::npos) j = vs.size(); xs.push_back(std::stof(vs.substr(i, j - i))); i = j + 1; }
+        std::sort(xs.begin(), xs.end());
+        printf("%.9g\n", percentile_linear_interp(xs, std::stof(argv[2])));
+        return 0;
+    }
+    return 2;
+}
+
 int main(int argc, char** argv) {
     try {
+        if (argc >= 2 && (std::string(argv[1]) == "decode" || std::string(argv[1]) == "call" || std::string(argv[1]) == "percentile")) return kat_main(argc, argv);
         if (argc < 2 || std::string(argv[1]) != "pileup") die("usage: modkit_oracle pileup [flags] <in.bam> <out.bed>");
         std::vector<std::string> pos;
         int threads = 4;

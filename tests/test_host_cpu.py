@@ -1,0 +1,96 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol include/mkp.h declares, the
+host BAM reader / packer agrees with an independent pure-Python parse, and the CUDA path fails loudly (never
+silently falls back) when there is no GPU. No device compute here."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import FIX, GEN, ROOT
+
+import bamio
+
+
+def test_header_symbols_exported(native_lib):
+    import modkit_b200
+    text = open(os.path.join(ROOT, "include", "mkp.h")).read()
+    declared = set(re.findall(r"\b(mkp_[a-z_]+)\s*\(", text))
+    assert declared == set(modkit_b200.MKP_SYMBOLS)
+    for name in sorted(declared) + modkit_b200.MKH_SYMBOLS:
+        assert hasattr(native_lib, name), name
+
+
+def test_struct_layouts_match_header():
+    import modkit_b200
+    assert ctypes.sizeof(modkit_b200.ReadHdr) == 32
+    assert modkit_b200.ROW_DTYPE.itemsize == 40
+
+
+def test_no_gpu_fails_loudly(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import modkit_b200
+    with pytest.raises(modkit_b200.MkpError):
+        modkit_b200.Context(0)
+    rc = modkit_b200.pileup_main(["--no-filtering", "--quiet", os.path.join(FIX, "bc_anchored_10_reads.sorted.bam"), str(tmp_path / "x.bed")])
+    assert rc == 1   # "> Error! no usable CUDA device ... no CPU fallback"
+
+
+@pytest.mark.parametrize("bam_name", ["bc_anchored_10_reads.sorted.bam", "duplex_modbam.sorted.bam"])
+def test_packer_matches_python_parse(bam_name):
+    import modkit_b200
+    path = os.path.join(FIX, bam_name)
+    ref = bamio.Bam(path)
+    b = modkit_b200.Bam(path, threads=2)
+    assert b.refs == ref.refs
+    by_tid = {}
+    for r in ref.records:
+        f = bamio.rec_fields(r)
+        by_tid.setdefault(f["tid"], []).append((r, f))
+    for tid, recs in by_tid.items():
+        if tid < 0:
+            continue
+        assert b.n_mapped(tid) == sum(1 for _, f in recs if not f["flag"] & 4)
+        pk = b.pack(tid, 0, ref.refs[tid][1])
+        hd = pk.headers()
+        assert len(hd) == len(recs)
+        heap = ctypes.string_at(pk.chunk().heap, pk.heap_bytes)
+        for h, (r, f) in zip(hd, recs):
+            assert h["ref_start"] == f["pos"] and h["l_seq"] == f["l_seq"] and h["n_cigar"] == len(f["cigar"])
+            assert (h["flags"] & 0xffff) == f["flag"] and h["off"] % 16 == 0
+            o = int(h["off"])
+            assert heap[o:o + 4 * len(f["cigar"])] == struct.pack("<%dI" % len(f["cigar"]), *f["cigar"])
+            o += 4 * len(f["cigar"])
+            assert heap[o:o + len(f["seq"])] == f["seq"]
+            o += len(f["seq"])
+            mm = bamio.get_aux(r, b"MM") or bamio.get_aux(r, b"Mm")
+            ml = bamio.get_aux(r, b"ML") or bamio.get_aux(r, b"Ml")
+            if mm is None or ml is None:
+                assert h["flags"] & (1 << 16)
+                continue
+            assert heap[o:o + h["len_ml"]] == ml and heap[o + h["len_ml"]:o + h["len_ml"] + h["len_mm"]] == mm
+        # the byte count the roofline uses
+        assert pk.algorithmic_bytes == sum(32 + 4 * int(h["n_cigar"]) + (int(h["l_seq"]) + 1) // 2 + int(h["len_mm"]) + int(h["len_ml"]) for h in hd)
+
+
+def test_region_fetch_semantics():
+    import modkit_b200
+    path = os.path.join(GEN, "hg002_updated.bam")
+    ref = bamio.Bam(path)
+    b = modkit_b200.Bam(path, threads=2)
+    tid = [i for i, (n, _) in enumerate(ref.refs) if n == "chr20"][0]
+
+    def span(f):
+        rl = sum(c >> 4 for c in f["cigar"] if (c & 15) in (0, 2, 3, 7, 8))
+        return f["pos"], f["pos"] + (rl if rl and not f["flag"] & 4 else 1)
+
+    fs = [bamio.rec_fields(r) for r in ref.records]
+    pos = sorted(f["pos"] for f in fs if f["tid"] == tid)
+    lo, hi = pos[len(pos) // 3], pos[len(pos) // 3] + 5000
+    want = [f["pos"] for f in fs if f["tid"] == tid and span(f)[0] < hi and span(f)[1] > lo]
+    got = b.pack(tid, lo, hi).headers()["ref_start"].tolist()
+    assert got == want
