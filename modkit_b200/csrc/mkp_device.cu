@@ -185,7 +185,7 @@ static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
     C->total_calls = C->states + 32;
     C->hist_inexact = C->states + 33;
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
-    C->n_states = u; C->err = u + 1;
+    C->n_states = u; C->err = u + 1; C->work = u + 4;
     C->scr_cq = ctx->d_scr_cq.as<uint32_t>(); C->scr_cr = ctx->d_scr_cr.as<uint32_t>(); C->scr_cum = ctx->d_scr_cum.as<uint32_t>();
     C->max_ncigar = ctx->max_ncigar; C->max_blocks = ctx->max_blocks;
     return 0;

@@ -73,6 +73,7 @@ struct ChunkDev {
     unsigned long long* states; // registry: (pb<<32 | code), ~0 empty
     uint32_t* n_states;
     uint32_t* err;
+    uint32_t* work;             // dynamic read counter
     unsigned long long* total_calls;
     // per-warp scratch
     uint32_t* scr_cq; uint32_t* scr_cr; uint32_t* scr_cum;
@@ -213,8 +214,16 @@ __device__ __forceinline__ float argmax_prob(const ProbMap& m) {
     return (have && mp > cp) ? mp : cp;
 }
 
-__device__ __forceinline__ int state_id(const ChunkDev& C, int pb, uint32_t code) {
-    unsigned long long key = ((unsigned long long)pb << 32) | code;
+// Registry of (primary base, mod code) states. A per-thread 4-entry cache keeps the hot path off the (single,
+// heavily shared) global table: every warp asking L2 for the same sector serialises at one slice.
+struct StateCache {
+    unsigned long long key[4];
+    int id[4];
+    int next;
+    __device__ void init() { for (int i = 0; i < 4; i++) { key[i] = ~0ull; id[i] = 0; } next = 0; }
+};
+
+__device__ __noinline__ int state_id_global(const ChunkDev& C, unsigned long long key) {
     for (int i = 0; i < MAX_STATES; i++) {
         unsigned long long v = *((volatile unsigned long long*)&C.states[i]);
         if (v == key) return i;
@@ -226,6 +235,15 @@ __device__ __forceinline__ int state_id(const ChunkDev& C, int pb, uint32_t code
     }
     atomicOr(C.err, MKP_DERR_TOO_MANY_STATES);
     return 0;
+}
+
+__device__ __forceinline__ int state_id(const ChunkDev& C, StateCache& sc, int pb, uint32_t code) {
+    const unsigned long long key = ((unsigned long long)pb << 32) | code;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (sc.key[i] == key) return sc.id[i];
+    const int id = state_id_global(C, key);
+    sc.key[sc.next] = key; sc.id[sc.next] = id; sc.next = (sc.next + 1) & 3;
+    return id;
 }
 
 // per-warp parsed MM list table
@@ -256,16 +274,25 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* P, uint32_t 
 template <int MODE>
 __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
     __shared__ ListTab s_tab[4];
+    __shared__ __align__(16) uint8_t s_txt[4][160];
+    __shared__ uint8_t s_tok[4][132];
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     ListTab& T = s_tab[wib];
+    StateCache scache;
+    scache.init();
     uint32_t* cq = C.scr_cq + (size_t)gw * C.max_ncigar;
     uint32_t* cr = C.scr_cr + (size_t)gw * C.max_ncigar;
     uint32_t* cum = C.scr_cum + (size_t)gw * 4 * (C.max_blocks + 1);
 
-    for (uint32_t ri = gw; ri < C.n_reads; ri += nw) {
+    for (;;) {
+        // dynamic work distribution: reads differ in length by 2-3 orders of magnitude
+        uint32_t ri = 0;
+        if (lane == 0) ri = atomicAdd(C.work, 1u);
+        ri = __shfl_sync(FULL, ri, 0);
+        if (ri >= C.n_reads) break;
         const mkp_read_hdr h = C.hdrs[ri];
         const uint32_t flag = h.flags & 0xffffu;
         const uint32_t L = h.l_seq;
@@ -301,62 +328,71 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
             meta.ref_end = (int32_t)rc;
         }
         bool err = (h.flags & MKP_RF_TAGS_INVALID) != 0;
-        // ---- phase 1: list discovery + headers (lane 0) ------------------------------------------
-        if (lane == 0) {
-            uint32_t n = 0;
-            bool e = err;
-            uint32_t i = 0;
+        // ---- phase 1: list discovery: warp-parallel scan for ';' and the first ',' of each part; the few
+        //      header bytes of each part are parsed by lane 0 (src/mod_bam.rs:900-1000) ------------------
+        {
             const uint32_t M = h.len_mm;
-            while (!e && i < M) {
-                uint32_t j = i;
-                while (j < M && mm[j] != ';') j++;
-                if (j > i) {
-                    if (n >= MAX_LISTS) { atomicOr(C.err, MKP_DERR_TOO_MANY_LISTS); e = true; break; }
-                    uint32_t hl = i;
-                    while (hl < j && mm[hl] != ',') hl++;
-                    // header = mm[i..hl)
-                    uint32_t k = i;
-                    uint8_t fb = mm[k];
-                    if (!(fb == 'A' || fb == 'C' || fb == 'G' || fb == 'T' || fb == 'U' || fb == 'N')) { e = true; break; }
-                    k++;
-                    if (k >= hl) { e = true; break; }
-                    uint8_t st = mm[k];
-                    if (st != '+' && st != '-') { e = true; break; }
-                    k++;
-                    uint32_t nc = 0;
-                    bool seen_chebi = false;
-                    int mode = 2;
-                    if (k < hl && is_digit(mm[k])) {
-                        unsigned long long v = 0;
-                        while (k < hl && is_digit(mm[k])) { v = v * 10 + (mm[k] - '0'); if (v > 0x7fffffffull) { e = true; break; } k++; }
-                        if (e) break;
-                        T.code[n][nc++] = 0x80000000u | (uint32_t)v;
-                        seen_chebi = true;
-                    }
-                    for (; k < hl; k++) {
-                        uint8_t c = mm[k];
-                        if (c == '?') mode = 0;
-                        else if (c == '.') mode = 1;
-                        else if (is_digit(c)) { e = true; break; }
-                        else {
-                            if (seen_chebi) { e = true; break; }
-                            if (nc >= MAX_LIST_CODES) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e = true; break; }
-                            T.code[n][nc++] = c;
+            uint32_t n = 0, seg = 0, hdr_end = 0xffffffffu;   // uniform across the warp
+            bool e0 = false;                                   // lane 0 only
+            auto close_part = [&](uint32_t j) {                // part = mm[seg..j)
+                if (j > seg) {
+                    if (n >= MAX_LISTS) { if (lane == 0) { atomicOr(C.err, MKP_DERR_TOO_MANY_LISTS); e0 = true; } }
+                    else if (lane == 0 && !e0) {
+                        const uint32_t hl = hdr_end == 0xffffffffu ? j : hdr_end;
+                        uint32_t k = seg;
+                        const uint8_t fb = mm[k];
+                        bool e = !(fb == 'A' || fb == 'C' || fb == 'G' || fb == 'T' || fb == 'U' || fb == 'N');
+                        k++;
+                        uint8_t st = 0;
+                        if (!e) { if (k >= hl) e = true; else { st = mm[k]; if (st != '+' && st != '-') e = true; k++; } }
+                        uint32_t nc = 0;
+                        bool seen_chebi = false;
+                        int mode = 2;
+                        if (!e && k < hl && is_digit(mm[k])) {
+                            unsigned long long v = 0;
+                            while (k < hl && is_digit(mm[k])) { v = v * 10 + (mm[k] - '0'); if (v > 0x7fffffffull) { e = true; break; } k++; }
+                            T.code[n][nc++] = 0x80000000u | (uint32_t)v;
+                            seen_chebi = true;
                         }
+                        for (; !e && k < hl; k++) {
+                            const uint8_t c = mm[k];
+                            if (c == '?') mode = 0;
+                            else if (c == '.') mode = 1;
+                            else if (is_digit(c) || seen_chebi) e = true;
+                            else if (nc >= MAX_LIST_CODES) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e = true; }
+                            else T.code[n][nc++] = c;
+                        }
+                        if (nc == 0) e = true;
+                        T.base[n] = fb; T.strand[n] = st == '-'; T.mode[n] = (uint8_t)mode; T.ncodes[n] = (uint8_t)nc;
+                        // delta text mm[d_start..d_end) starts right after the header comma; n_delta = 0xffffffff marks
+                        // "a comma follows the header, so at least one number must parse" (nom separated_list1)
+                        if (hl < j) { T.d_start[n] = hl + 1; T.d_end[n] = j; T.n_delta[n] = 0xffffffffu; }
+                        else { T.d_start[n] = j; T.d_end[n] = j; T.n_delta[n] = 0u; }
+                        if (e) e0 = true;
                     }
-                    if (e) break;
-                    if (nc == 0) { e = true; break; }
-                    T.base[n] = fb; T.strand[n] = st == '-'; T.mode[n] = (uint8_t)mode; T.ncodes[n] = (uint8_t)nc;
-                    // delta text: (hl+1 .. j) when a comma follows the header
-                    if (hl < j) { T.d_start[n] = hl + 1; T.d_end[n] = j; if (hl + 1 >= j) { /* "C+m?," */ } }
-                    else { T.d_start[n] = j; T.d_end[n] = j; }
-                    // header followed by a comma but no number => separated_list1 fails => read error
-                    T.n_delta[n] = (hl < j) ? 0xffffffffu : 0u;   // 0xffffffff = "must parse >= 1"
-                    n++;
+                    if (n < MAX_LISTS) n++;
                 }
-                i = j + 1;
+                seg = j + 1;
+                hdr_end = 0xffffffffu;
+            };
+            for (uint32_t c0 = 0; c0 < M && !err; c0 += 32) {
+                const uint32_t i = c0 + lane;
+                const uint8_t ch = i < M ? mm[i] : 0;
+                const uint32_t semi = __ballot_sync(FULL, ch == ';'), comma = __ballot_sync(FULL, ch == ',');
+                uint32_t lo = 0;
+                while (lo < 32) {
+                    const uint32_t keep = FULL << lo;
+                    const uint32_t sm = semi & keep, cm = comma & keep;
+                    const uint32_t sp = sm ? (uint32_t)__ffs(sm) - 1 : 32u, cp = cm ? (uint32_t)__ffs(cm) - 1 : 32u;
+                    if (hdr_end == 0xffffffffu && cp < sp) hdr_end = c0 + cp;
+                    if (sp == 32) break;
+                    close_part(c0 + sp);
+                    lo = sp + 1;
+                }
             }
-            T.n = e ? 0xffffffffu : n;
+            if (!err && seg < M) close_part(M);
+            if (__shfl_sync(FULL, e0 ? 1 : 0, 0)) err = true;
+            if (lane == 0) T.n = err ? 0xffffffffu : n;
         }
         __syncwarp();
         if (T.n == 0xffffffffu) err = true;
@@ -416,78 +452,102 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
             unsigned long long carry = 0;     // sum of (d+1) so far
             uint32_t ntok = 0;
             bool stop = false;                // list truncated by a malformed token
-            // tokens: one starts at ds and one after every ',' in [ds,de); grammar ws* digit+ ws* (nom separated_list1)
-            for (uint32_t c0 = ds; must && c0 <= de && !stop && !err; c0 += 32) {
-                const uint32_t tp = c0 + lane;
-                const bool starts = (tp <= de) && (tp == ds || mm[tp - 1] == ',');
-                unsigned long long val = 0;
-                bool ok_start = false, clean = false;
-                if (starts) {
-                    uint32_t k = tp;
-                    while (k < de && is_ws(mm[k])) k++;
-                    uint32_t d0 = k;
-                    while (k < de && is_digit(mm[k])) { val = val * 10 + (mm[k] - '0'); if (val > 0xffffffffull) val = 0x1ffffffffull; k++; }
-                    ok_start = k > d0 && val <= 0xffffffffull;
-                    while (k < de && is_ws(mm[k])) k++;
-                    clean = (k == de) || (mm[k] == ',');
-                }
-                uint32_t m_start = __ballot_sync(FULL, starts);
-                uint32_t m_badstart = __ballot_sync(FULL, starts && !ok_start);
-                uint32_t m_dirty = __ballot_sync(FULL, starts && ok_start && !clean);
-                // first terminating token: a bad start excludes itself, a dirty end includes itself
-                uint32_t first_bad = m_badstart ? (uint32_t)__ffs(m_badstart) - 1 : 32;
-                uint32_t first_dirty = m_dirty ? (uint32_t)__ffs(m_dirty) - 1 : 32;
-                uint32_t keep_mask = m_start;
-                if (first_bad < 32 || first_dirty < 32) {
-                    stop = true;
-                    uint32_t cut = first_bad <= first_dirty ? first_bad : first_dirty + 1;   // lanes < cut are kept
-                    keep_mask &= cut >= 32 ? FULL : ((1u << cut) - 1u);
-                }
-                bool mine = (keep_mask >> lane) & 1u;
-                unsigned long long inc = mine ? (val + 1ull) : 0ull;
-                unsigned long long pre = warp_incl_scan64(inc);
-                uint32_t idx = ntok + __popc(keep_mask & ((1u << lane) - 1u));
-                if (mine) {
-                    unsigned long long k = carry + pre - 1ull;   // 0-based occurrence index (forward order)
-                    uint32_t f;
+            // Tokens start after every ',' of mm[ds-1 .. de) (mm[ds-1] is the header comma); grammar per token:
+            // ws* digit+ ws* (nom separated_list1). 128 text bytes per round are staged in shared memory, the token
+            // starts are compacted, then every lane parses / selects one token.
+            uint8_t* txt = s_txt[wib];
+            uint8_t* tok = s_tok[wib];
+            for (uint32_t c0 = ds - 1; must && c0 < de && !stop && !err; c0 += 128) {
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 5; k++) { const uint32_t o = lane + 32 * k, g = c0 + o; txt[o] = g < de ? mm[g] : 0; }
+                __syncwarp();
+                // commas among the first 128 staged bytes (only those before `de`)
+                const uint32_t w4 = ((const uint32_t*)txt)[lane];
+                const uint32_t xr = w4 ^ 0x2c2c2c2cu;
+                uint32_t zf = ~(((xr & 0x7f7f7f7fu) + 0x7f7f7f7fu) | xr | 0x7f7f7f7fu);   // 0x80 in every byte that is ','
+                const uint32_t nvalid = de - c0;                                           // staged bytes that are text
+                if (4 * lane + 4 > nvalid) { const uint32_t keepb = nvalid > 4 * lane ? nvalid - 4 * lane : 0; zf &= keepb ? (0xffffffffu >> (8 * (4 - keepb))) : 0u; }
+                const uint32_t ncom = __popc(zf);
+                const uint32_t incl = warp_incl_scan(ncom);
+                uint32_t at = incl - ncom;
+                while (zf) { const uint32_t bi = (uint32_t)(__ffs(zf) - 1) >> 3; zf &= zf - 1; tok[at++] = (uint8_t)(4 * lane + bi + 1); }
+                const uint32_t nt = __shfl_sync(FULL, incl, 31);
+                __syncwarp();
+                for (uint32_t g0 = 0; g0 < nt && !stop && !err; g0 += 32) {
+                    const bool starts = g0 + lane < nt;
+                    unsigned long long val = 0;
+                    bool ok_start = false, clean = false;
+                    if (starts) {
+                        uint32_t k = tok[g0 + lane];                      // offset in the staged text; text ends at nvalid
+                        auto chr = [&](uint32_t o) -> uint8_t { return o < 160 ? txt[o] : mm[c0 + o]; };
+                        while (k < nvalid && is_ws(chr(k))) k++;
+                        const uint32_t d0 = k;
+                        while (k < nvalid && is_digit(chr(k))) { val = val * 10 + (chr(k) - '0'); if (val > 0xffffffffull) val = 0x1ffffffffull; k++; }
+                        ok_start = k > d0 && val <= 0xffffffffull;
+                        while (k < nvalid && is_ws(chr(k))) k++;
+                        clean = (k >= nvalid) || (chr(k) == ',');
+                    }
+                    const uint32_t m_start = __ballot_sync(FULL, starts);
+                    const uint32_t m_badstart = __ballot_sync(FULL, starts && !ok_start);
+                    const uint32_t m_dirty = __ballot_sync(FULL, starts && ok_start && !clean);
+                    // first terminating token: a bad start excludes itself, a dirty end includes itself
+                    const uint32_t first_bad = m_badstart ? (uint32_t)__ffs(m_badstart) - 1 : 32;
+                    const uint32_t first_dirty = m_dirty ? (uint32_t)__ffs(m_dirty) - 1 : 32;
+                    uint32_t keep_mask = m_start;
+                    if (first_bad < 32 || first_dirty < 32) {
+                        stop = true;
+                        const uint32_t cut = first_bad <= first_dirty ? first_bad : first_dirty + 1;   // lanes < cut are kept
+                        keep_mask &= cut >= 32 ? FULL : ((1u << cut) - 1u);
+                    }
+                    if (ntok == 0 && g0 == 0 && !(keep_mask & 1u)) err = true;             // the first token must parse
+                    const bool mine = (keep_mask >> lane) & 1u;
+                    const unsigned long long inc = mine ? (val + 1ull) : 0ull;
+                    const unsigned long long pre = warp_incl_scan64(inc);
+                    const uint32_t idx = ntok + __popc(keep_mask & ((1u << lane) - 1u));
                     bool bad = false;
-                    if (fb == 'N') {
-                        f = (uint32_t)k;
-                        if (k >= (unsigned long long)L) bad = true;
-                    } else {
-                        if (k >= (unsigned long long)tot) bad = true;
-                        else {
-                            uint32_t kq = rev ? tot - 1u - (uint32_t)k : (uint32_t)k;   // occurrence index in query order
-                            // block with cx[blk] <= kq < cx[blk+1]
+                    if (mine) {
+                        const unsigned long long k = carry + pre - 1ull;   // 0-based occurrence index (forward order)
+                        uint32_t f = 0;
+                        if (fb == 'N') {
+                            f = (uint32_t)k;
+                            if (k >= (unsigned long long)L) bad = true;
+                        } else if (k >= (unsigned long long)tot) {
+                            bad = true;
+                        } else {
+                            const uint32_t kq = rev ? tot - 1u - (uint32_t)k : (uint32_t)k;   // occurrence index in query order
                             uint32_t lo = 0, hi = nblk;   // invariant: cx[lo] <= kq < cx[hi]
-                            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (cx[mid] <= kq) lo = mid; else hi = mid; }
+                            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cx[mid] <= kq) lo = mid; else hi = mid; }
                             uint32_t within = kq - cx[lo];
                             const uint32_t* sw = (const uint32_t*)seq + lo * 4;
-                            uint32_t nbytes = (L + 1) >> 1;
-                            uint32_t q = 0xffffffffu;
+                            const uint32_t nbytes = (L + 1) >> 1;
+                            uint32_t bm = 0;                                 // occurrences of the base in this 32-base block
 #pragma unroll
                             for (int w = 0; w < 4; w++) {
-                                uint32_t byte0 = lo * 16 + w * 4;
-                                if (byte0 >= nbytes || q != 0xffffffffu) continue;
+                                const uint32_t byte0 = lo * 16 + w * 4;
+                                if (byte0 >= nbytes) continue;
                                 uint32_t word = sw[w];
-                                uint32_t vb = nbytes - byte0;
+                                const uint32_t vb = nbytes - byte0;
                                 if (vb < 4) word &= (1u << (8 * vb)) - 1u;
-                                uint32_t msk = nib_flags_to_mask(nib_eq_flags(word, 1u << x));
-                                uint32_t pc = __popc(msk);
-                                if (within < pc) { q = lo * 32 + w * 8 + (__fns(msk, 0, within + 1)); }
-                                else within -= pc;
+                                bm |= nib_flags_to_mask(nib_eq_flags(word, 1u << x)) << (8 * w);
                             }
+                            // position of the (within+1)-th set bit
+                            uint32_t pos = 0, c;
+                            c = __popc(bm & 0xffffu); if (within >= c) { within -= c; pos += 16; bm >>= 16; }
+                            c = __popc(bm & 0xffu);   if (within >= c) { within -= c; pos += 8;  bm >>= 8; }
+                            c = __popc(bm & 0xfu);    if (within >= c) { within -= c; pos += 4;  bm >>= 4; }
+                            c = __popc(bm & 0x3u);    if (within >= c) { within -= c; pos += 2;  bm >>= 2; }
+                            c = bm & 1u;              if (within >= c) { pos += 1; }
+                            const uint32_t q = lo * 32 + pos;
                             if (q >= L) bad = true;
                             f = rev ? L - 1u - q : q;
                         }
+                        if (!bad) P[ent + idx] = f;
                     }
-                    if (bad) err = true; else P[ent + idx] = f;
+                    if (__any_sync(FULL, bad)) err = true;
+                    carry += __shfl_sync(FULL, pre, 31);
+                    ntok += __popc(keep_mask);
                 }
-                err = __any_sync(FULL, err);
-                carry += __shfl_sync(FULL, pre, 31);
-                ntok += __popc(keep_mask);
-                if (c0 == ds && must && !(keep_mask & 1u) && lane == 0) err = true;   // first token failed to parse
-                err = __any_sync(FULL, err);
             }
             if (must && ntok == 0) err = true;
             // N lists: the reference checks only deltas after the first against the sequence length; the first
@@ -633,14 +693,14 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
                                     }
                                     if (MODE == MODE_PILEUP) {
                                         uint32_t mask = 0;
-                                        for (int s = 0; s < 8; s++) if (use->slot[s] >= 0) mask |= 1u << state_id(C, tb, use->code[use->slot[s]]);
+                                        for (int s = 0; s < 8; s++) if (use->slot[s] >= 0) mask |= 1u << state_id(C, scache, tb, use->code[use->slot[s]]);
                                         // (mod strand, read orientation) -> reference strand (read_cache.rs:181-188)
                                         if ((st == 0) != rev) pos_mask |= mask; else neg_mask |= mask;
                                         table_survived = true;
                                         if (aligned && rpos >= C.cs && rpos < C.ce) {
                                             uint32_t code = 0;
                                             int kind = make_call(*use, tb, &code);
-                                            uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, tb, code);
+                                            uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, code);
                                             // does a '+' list cover the same position (both pos_call and neg_call present)?
                                             uint32_t nosub = 0;
                                             if (st == 1) {
@@ -716,11 +776,11 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
                 table_survived = true;
                 if (MODE == MODE_PILEUP) {
                     uint32_t mask = 0;
-                    for (int k = 0; k < 8; k++) if (use->slot[k] >= 0) mask |= 1u << state_id(C, tb, use->code[use->slot[k]]);
+                    for (int k = 0; k < 8; k++) if (use->slot[k] >= 0) mask |= 1u << state_id(C, scache, tb, use->code[use->slot[k]]);
                     if ((s == 0) != rev) pos_mask |= mask; else neg_mask |= mask;
                     uint32_t code = 0;
                     const int kind = make_call(*use, tb, &code);
-                    const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, tb, code);
+                    const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, code);
                     imp_meta[s] |= (0x80u | state) << (8 * b);
                 } else {
                     // values: argmax of an all-zero map = canonical probability 1.0 for every passing inferred position
