@@ -272,8 +272,8 @@ def main():
                 pass
             peak = float(peaks.get("hbm_gbs", 6650.0))
             alg = pk.algorithmic_bytes + 40 * n_rows
-            names = ["decode", "rank", "alloc_sync", "count_calls", "count_bases", "rows_count", "rows_emit"]
-            dom = int(np.argmax(stage[:7]))
+            names = ["parse", "resolve", "rank", "count_calls", "count_bases", "rows", "host_sync_alloc"]
+            dom = int(np.argmax(stage[:6]))
             ach = alg / (stage[dom] * 1e-3) / 1e9
             # CPU baseline on the same box: bounded window of the same workload, all host cores
             window = min(CPU_WINDOW, a.contig_len)
@@ -283,7 +283,7 @@ def main():
                     "dtype": "u32 counts (f32 probabilities)", "data": "synthetic", "config": workload, "impl": "b200",
                     "e2e": {"value": e2e, "unit": "positions/s", "h2d_bytes_per_step": int(n_hdr_bytes + pk.heap_bytes + 8 * (pk.n_reads + 1) + 2 * fpos.nbytes),
                             "d2h_bytes_per_step": int(40 * n_rows + 64), "ms_per_step": 1e3 * t_e2e / a.steps},
-                    "gpu_launches": 11 * a.steps,
+                    "gpu_launches": 12 * a.steps,
                     "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                  "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s", "traffic": None,
                                  "algorithmic_bytes_per_launch": int(alg), "kernel_ms": float(stage[dom]),

@@ -48,7 +48,7 @@ struct mkp_ctx {
     uint32_t max_ncigar = 1, max_blocks = 1;
     uint64_t heap_bytes = 0;
     // work buffers
-    DevBuf d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr, d_scr_cum;
+    DevBuf d_rl, d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr, d_scr_cum;
     DevBuf d_slots, d_row_counts, d_row_prefix, d_rows, d_hist, d_take;
     // results
     size_t n_rows = 0;
@@ -87,7 +87,7 @@ void mkp_destroy(mkp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_meta, &ctx->d_P,
+    DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_rl, &ctx->d_meta, &ctx->d_P,
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr,
                       &ctx->d_scr_cum, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take};
     for (auto* b : bufs) b->release();
@@ -166,6 +166,7 @@ static int decode_grid(const mkp_ctx* ctx, uint32_t n_reads) {
 static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
     const size_t nwarps = (size_t)grid * 4;
     CK(ctx->d_meta.ensure(std::max<size_t>(1, ctx->n_reads) * sizeof(ReadMeta)));
+    CK(ctx->d_rl.ensure(std::max<size_t>(1, ctx->n_reads) * sizeof(ReadLists)));
     CK(ctx->d_P.ensure(std::max<uint64_t>(1, ctx->total_entries) * 4));
     CK(ctx->d_calls.ensure(std::max<uint64_t>(1, ctx->total_entries) * 8));
     CK(ctx->d_hot.ensure((size_t)ctx->n_words * 4 + 4));
@@ -188,6 +189,7 @@ static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
     C->n_states = u; C->err = u + 1; C->work = u + 4;
     C->scr_cq = ctx->d_scr_cq.as<uint32_t>(); C->scr_cr = ctx->d_scr_cr.as<uint32_t>(); C->scr_cum = ctx->d_scr_cum.as<uint32_t>();
     C->max_ncigar = ctx->max_ncigar; C->max_blocks = ctx->max_blocks;
+    C->rl = ctx->d_rl.as<ReadLists>();
     return 0;
 }
 
@@ -215,17 +217,22 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     CK(ctx->d_row_counts.ensure((size_t)n_words * 4 + 4));
     CK(ctx->d_row_prefix.ensure((size_t)n_words * 4 + 4));
 
+    // events: 0 start | 1 after parse | 2 after resolve | 3 after rank | 4 before counts | 5 after count_calls |
+    //         6 after count_bases | 7 after row count+scan | 8 before emit | 9 end
     CK(cudaEventRecord(ctx->ev[0], st));
     CK(cudaMemsetAsync(ctx->d_hot.p, 0, (size_t)n_words * 4, st));
     CK(cudaMemsetAsync(ctx->d_small.p, 0xff, 32 * 8, st));
     CK(cudaMemsetAsync(ctx->d_small.as<uint8_t>() + 32 * 8, 0, SMALL_BYTES - 32 * 8, st));
-    if (ctx->n_reads) k_decode<MODE_PILEUP><<<grid, 128, 0, st>>>(C);
+    C.mode = MODE_PILEUP;
+    if (ctx->n_reads) k_parse<<<grid, 128, 0, st>>>(C);
     CK(cudaEventRecord(ctx->ev[1], st));
+    if (ctx->n_reads) k_resolve<MODE_PILEUP><<<grid, 128, 0, st>>>(C);
+    CK(cudaEventRecord(ctx->ev[2], st));
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);   // n_states, err, n_hot, n_rows
     k_block_popc<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>());
     k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 2);
     k_word_prefix<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.hot_prefix);
-    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaEventRecord(ctx->ev[3], st));
     uint32_t h_small[4];
     unsigned long long h_calls = 0;
     CK(cudaMemcpyAsync(h_small, u, 16, cudaMemcpyDeviceToHost, st));
@@ -243,17 +250,12 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     D.hdrs = C.hdrs; D.heap = C.heap; D.meta = C.meta; D.calls = C.calls; D.n_reads = C.n_reads; D.cs = C.cs; D.ce = C.ce;
     D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
     D.slots = ctx->d_slots.as<uint32_t>(); D.stride = stride; D.n_states = std::max<uint32_t>(n_states, 1);
-    CK(cudaEventRecord(ctx->ev[3], st));
-    if (ctx->n_reads && n_hot) {
-        int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
-        k_count_calls<<<g2, 256, 0, st>>>(D);
-    }
     CK(cudaEventRecord(ctx->ev[4], st));
-    if (ctx->n_reads && n_hot) {
-        int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
-        k_count_bases<<<g2, 256, 0, st>>>(D);
-    }
+    const int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
+    if (ctx->n_reads && n_hot) k_count_calls<<<g2, 256, 0, st>>>(D);
     CK(cudaEventRecord(ctx->ev[5], st));
+    if (ctx->n_reads && n_hot) k_count_bases<<<g2, 256, 0, st>>>(D);
+    CK(cudaEventRecord(ctx->ev[6], st));
     RowDev R;
     R.hot = C.hot; R.hot_prefix = C.hot_prefix; R.n_words = n_words; R.cs = C.cs; R.ce = C.ce;
     R.slots = D.slots; R.stride = stride; R.n_states = D.n_states; R.states = C.states; R.numeric_mode = ctx->params.numeric_mode;
@@ -263,23 +265,26 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     k_block_sum<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>());
     k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 3);
     k_value_prefix<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_row_prefix.as<uint32_t>());
+    CK(cudaEventRecord(ctx->ev[7], st));
     uint32_t n_rows = 0;
     CK(cudaMemcpyAsync(&n_rows, u + 3, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(ctx->d_rows.ensure(std::max<size_t>(1, n_rows) * sizeof(mkp_row)));
     R.rows = ctx->d_rows.as<mkp_row>();
-    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaEventRecord(ctx->ev[8], st));
     if (n_rows) k_rows<true><<<rg, 256, 0, st>>>(R);
-    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaEventRecord(ctx->ev[9], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     ctx->n_rows = n_rows;
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->n_rows = n_rows; stats->n_hot = n_hot; stats->n_calls = h_calls; stats->n_states = n_states;
-        // stage times: 0 decode, 1 rank, 2 (sync+alloc), 3 count_calls, 4 count_bases, 5 row count+scan, 6 row emit
-        for (int i = 0; i < 7; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]); stats->kernel_ms[i] = ms; }
-        float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[7]); stats->kernel_ms[7] = tot;
+        // kernel_ms: 0 parse, 1 resolve, 2 rank, 3 count_calls, 4 count_bases, 5 rows (count+scan+emit), 6 host syncs/allocs, 7 total
+        auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
+        stats->kernel_ms[0] = el(0, 1); stats->kernel_ms[1] = el(1, 2); stats->kernel_ms[2] = el(2, 3);
+        stats->kernel_ms[3] = el(4, 5); stats->kernel_ms[4] = el(5, 6); stats->kernel_ms[5] = el(6, 7) + el(8, 9);
+        stats->kernel_ms[6] = el(3, 4) + el(7, 8); stats->kernel_ms[7] = el(0, 9);
     }
     return 0;
 }
@@ -331,7 +336,8 @@ int mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* tak
         CK(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * 1025 * 8, st));
         C.hist = ctx->d_hist.as<unsigned long long>();
     }
-    if (ctx->n_reads) k_decode<MODE_HIST><<<grid, 128, 0, st>>>(C);
+    C.mode = MODE_HIST;
+    if (ctx->n_reads) { k_parse<<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST><<<grid, 128, 0, st>>>(C); }
     CK(cudaGetLastError());
     uint32_t h_small[2];
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);

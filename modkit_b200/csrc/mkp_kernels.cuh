@@ -57,6 +57,8 @@ struct ReadMeta {       // 40 bytes, written by k_decode
     uint32_t imp[2];
 };
 
+struct ReadLists;
+
 struct ChunkDev {
     const mkp_read_hdr* hdrs;
     const uint8_t* heap;
@@ -83,6 +85,8 @@ struct ChunkDev {
     unsigned long long* hist_inexact;
     const uint8_t* take;
     uint32_t hist_include_unaligned;
+    uint32_t mode;              // MODE_PILEUP / MODE_HIST (admission rules of k_parse)
+    struct ReadLists* rl;
 };
 
 __constant__ DevParams c_par;
@@ -140,14 +144,14 @@ struct ProbMap {
     int8_t slot[8];   // slot -> item, -1 empty
     int n, nb;
     __device__ void init() { n = 0; nb = 4; for (int i = 0; i < 8; i++) slot[i] = -1; }
-    __device__ void place(int item) {
+    __device__ __noinline__ void place(int item) {
         int s = (int)(fx_hash_code(code[item]) & (unsigned long long)(nb - 1));
         while (slot[s] >= 0) s = (s + 1) & (nb - 1);
         slot[s] = (int8_t)item;
     }
     __device__ int find(uint32_t c) const { for (int i = 0; i < n; i++) if (code[i] == c) return i; return -1; }
     // returns item index, or -1 on overflow
-    __device__ int insert(uint32_t c, float v) {
+    __device__ __noinline__ int insert(uint32_t c, float v) {
         if (n >= MAX_MAP) return -1;
         if (nb == 4 && n + 1 > 3) {
             int8_t old[4];
@@ -173,7 +177,7 @@ struct ProbMap {
 };
 
 // CollapseMethod::ReDistribute (src/mod_bam.rs:558-600)
-__device__ __forceinline__ void redistribute(const ProbMap& in, uint32_t drop, ProbMap& out) {
+__device__ __noinline__ void redistribute(const ProbMap& in, uint32_t drop, ProbMap& out) {
     float marginal = 0.f;
     int n_other = 0;
     for (int s = 0; s < 8; s++) if (in.slot[s] >= 0) { int it = in.slot[s]; if (in.code[it] == drop) marginal = __fadd_rn(marginal, in.p[it]); else n_other++; }
@@ -183,7 +187,7 @@ __device__ __forceinline__ void redistribute(const ProbMap& in, uint32_t drop, P
 }
 
 // MultipleThresholdModCaller::call (src/threshold_mod_caller.rs:28-63): 0 filtered, 1 canonical, 2 = modified (code in *code)
-__device__ __forceinline__ int make_call(const ProbMap& m, int tb, uint32_t* code) {
+__device__ __noinline__ int make_call(const ProbMap& m, int tb, uint32_t* code) {
     bool have = false;
     float best = 0.f;
     int kind = 0;
@@ -206,7 +210,7 @@ __device__ __forceinline__ int make_call(const ProbMap& m, int tb, uint32_t* cod
     return have ? kind : 0;
 }
 // BaseModProbs::argmax_base_mod_call value (src/mod_bam.rs:489-505)
-__device__ __forceinline__ float argmax_prob(const ProbMap& m) {
+__device__ __noinline__ float argmax_prob(const ProbMap& m) {
     float cp = __fsub_rn(1.0f, m.sum());
     bool have = false;
     float mp = 0.f;
@@ -264,6 +268,10 @@ struct ListTab {
 
 enum { MODE_PILEUP = 0, MODE_HIST = 1 };
 
+// per-read hand-over between k_parse and k_resolve (global memory; only the used records are touched)
+struct ListRec { uint32_t n_delta, ent_off, ml_off; uint32_t code[MAX_LIST_CODES]; uint8_t base, strand, mode, ncodes; };   // 32 bytes
+struct ReadLists { uint32_t n, ent, flags, pad; uint16_t imp_lists[8]; ListRec rec[MAX_LISTS]; };
+
 // binary search: first index in sorted P[0..n) with value >= f
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* P, uint32_t n, uint32_t f) {
     uint32_t lo = 0, hi = n;
@@ -271,8 +279,9 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* P, uint32_t 
     return lo;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
+// Kernel A: per read, everything that depends only on the read's own bytes: admission, reference span, MM list
+// discovery, per-base occurrence counts, MM token parse + select -> forward positions P[] and the list table.
+__global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
     __shared__ ListTab s_tab[4];
     __shared__ __align__(16) uint8_t s_txt[4][160];
     __shared__ uint8_t s_tok[4][132];
@@ -281,10 +290,6 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     ListTab& T = s_tab[wib];
-    StateCache scache;
-    scache.init();
-    uint32_t* cq = C.scr_cq + (size_t)gw * C.max_ncigar;
-    uint32_t* cr = C.scr_cr + (size_t)gw * C.max_ncigar;
     uint32_t* cum = C.scr_cum + (size_t)gw * 4 * (C.max_blocks + 1);
 
     for (;;) {
@@ -302,10 +307,10 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
         meta.flags = 0; meta.pos_mask = 0; meta.neg_mask = 0; meta.n_calls = 0; meta.n_hist = 0; meta.imp[0] = 0; meta.imp[1] = 0;
         meta.entry_off = C.entry_off[ri];
         bool admitted;
-        if (MODE == MODE_PILEUP) admitted = !(flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) && L > 0;
+        if (C.mode == MODE_PILEUP) admitted = !(flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) && L > 0;
         else admitted = !(flag & (0x100 | 0x400 | 0x800)) && L > 0 && (C.take == nullptr || C.take[ri]) &&
                         !((flag & 0x4) && (!C.hist_include_unaligned || c_par.edge_on));
-        if (!admitted) { if (lane == 0) C.meta[ri] = meta; continue; }
+        if (!admitted) { if (lane == 0) { C.meta[ri] = meta; C.rl[ri].n = 0; C.rl[ri].flags = 1; } continue; }
         meta.flags = 1;
         const uint32_t* cig = (const uint32_t*)(C.heap + h.off);
         const uint8_t* seq = C.heap + h.off + 4ull * h.n_cigar;
@@ -321,7 +326,6 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
                 uint32_t ql = (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ? len : 0;
                 uint32_t rl = (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ? len : 0;
                 uint32_t qi = warp_incl_scan(ql), rr = warp_incl_scan(rl);
-                if (i < h.n_cigar) { cq[i] = qc + qi - ql; cr[i] = rc + rr - rl; }
                 qc += __shfl_sync(FULL, qi, 31);
                 rc += __shfl_sync(FULL, rr, 31);
             }
@@ -584,6 +588,85 @@ __global__ void __launch_bounds__(128) k_decode(ChunkDev C) {
                 { int b = bl == 'A' ? 0 : bl == 'C' ? 1 : bl == 'G' ? 2 : 3; imp_lists[T.strand[l]][b] |= 1u << l; any_entries = true; }
             }
         }
+        // ---- hand-over to k_resolve: list table (only the used records), implicit-table masks, flags -------
+        __syncwarp();
+        {
+            ReadLists* R = C.rl + ri;
+            if (lane == 0) {
+                R->n = nl; R->ent = ent; R->flags = (err ? 1u : 0u) | (any_entries ? 2u : 0u);
+                for (int k = 0; k < 8; k++) R->imp_lists[k] = (uint16_t)imp_lists[k >> 2][k & 3];
+                C.meta[ri] = meta;
+            }
+            if (lane < nl) {
+                ListRec rec;
+                rec.n_delta = T.n_delta[lane]; rec.ent_off = T.ent_off[lane]; rec.ml_off = T.ml_off[lane];
+                for (int c = 0; c < MAX_LIST_CODES; c++) rec.code[c] = T.code[lane][c];
+                rec.base = T.base[lane]; rec.strand = T.strand[lane]; rec.mode = T.mode[lane]; rec.ncodes = T.ncodes[lane];
+                R->rec[lane] = rec;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Kernel B: per read with mod info: CIGAR prefix, then every list entry -> merged probabilities -> collapse ->
+// threshold call -> reference position; call records, observed-code masks, implicit tables, hot-bitmap marks.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
+    __shared__ ListTab s_tab[4];
+    const uint32_t lane = lane_id();
+    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    ListTab& T = s_tab[wib];
+    StateCache scache;
+    scache.init();
+    uint32_t* cq = C.scr_cq + (size_t)gw * C.max_ncigar;
+    uint32_t* cr = C.scr_cr + (size_t)gw * C.max_ncigar;
+
+    for (;;) {
+        uint32_t ri = 0;
+        if (lane == 0) ri = atomicAdd(C.work + 1, 1u);
+        ri = __shfl_sync(FULL, ri, 0);
+        if (ri >= C.n_reads) break;
+        ReadMeta meta = C.meta[ri];
+        if (!(meta.flags & 1)) continue;
+        const ReadLists* R = C.rl + ri;
+        const uint32_t nl = R->n;
+        bool err = R->flags & 1u;
+        const bool any_entries = R->flags & 2u;
+        if (err || !any_entries) continue;          // skip_set: counts only as bases (meta already says so)
+        const mkp_read_hdr h = C.hdrs[ri];
+        const uint32_t L = h.l_seq;
+        const bool rev = h.flags & 0x10;
+        const uint32_t* cig = (const uint32_t*)(C.heap + h.off);
+        const uint8_t* seq = C.heap + h.off + 4ull * h.n_cigar;
+        const uint8_t* ml = seq + ((L + 1) >> 1);
+        uint32_t imp_lists[2][4];
+        for (int k = 0; k < 8; k++) imp_lists[k >> 2][k & 3] = R->imp_lists[k];
+        __syncwarp();
+        if (lane < nl) {
+            const ListRec rec = R->rec[lane];
+            T.n_delta[lane] = rec.n_delta; T.ent_off[lane] = rec.ent_off; T.ml_off[lane] = rec.ml_off;
+            for (int c = 0; c < MAX_LIST_CODES; c++) T.code[lane][c] = rec.code[c];
+            T.base[lane] = rec.base; T.strand[lane] = rec.strand; T.mode[lane] = rec.mode; T.ncodes[lane] = rec.ncodes;
+        }
+        // CIGAR prefix: query / reference start of every op
+        {
+            uint32_t qc = 0, rc = (uint32_t)h.ref_start;
+            for (uint32_t b = 0; b < h.n_cigar; b += 32) {
+                uint32_t i = b + lane;
+                uint32_t c = i < h.n_cigar ? cig[i] : 0;
+                uint32_t op = c & 15, len = c >> 4;
+                uint32_t ql = (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ? len : 0;
+                uint32_t rl = (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ? len : 0;
+                uint32_t qi = warp_incl_scan(ql), rr = warp_incl_scan(rl);
+                if (i < h.n_cigar) { cq[i] = qc + qi - ql; cr[i] = rc + rr - rl; }
+                qc += __shfl_sync(FULL, qi, 31);
+                rc += __shfl_sync(FULL, rr, 31);
+            }
+        }
+        __syncwarp();
+        uint32_t* P = C.P + meta.entry_off;
         // ---- phase 4: resolve entries -> calls ---------------------------------------------------
         uint32_t n_calls = 0, n_hist = 0;
         uint32_t pos_mask = 0, neg_mask = 0;
