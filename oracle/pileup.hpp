@@ -27,6 +27,16 @@ struct StateTable {
     std::mutex mu;
     std::vector<std::pair<int, ModCode>> states;
     int id_of(int pb, ModCode c) {
+        // thread-local front cache: the shared table is append-only, so a cached id never goes stale
+        static thread_local std::vector<std::pair<std::pair<int, ModCode>, int>> cache;
+        static thread_local const StateTable* owner = nullptr;
+        if (owner != this) { cache.clear(); owner = this; }
+        for (auto& e : cache) if (e.first.first == pb && e.first.second == c) return e.second;
+        int id = id_of_locked(pb, c);
+        cache.push_back({{pb, c}, id});
+        return id;
+    }
+    int id_of_locked(int pb, ModCode c) {
         std::lock_guard<std::mutex> g(mu);
         for (size_t i = 0; i < states.size(); i++) if (states[i].first == pb && states[i].second == c) return (int)i;
         states.push_back({pb, c});
@@ -209,9 +219,10 @@ inline void process_interval(const BamFile& bam, const Interval& iv, const Pileu
     std::vector<const BamRecord*> recs;
     bam.fetch(iv.tid, start, end, [&](const BamRecord& r) { if (admitted_for_pileup(r)) recs.push_back(&r); });
     if (recs.empty()) return;
-    std::vector<ReadCalls> calls(recs.size());
+    static thread_local std::vector<ReadCalls> calls;
+    if (calls.size() < recs.size()) calls.resize(recs.size());
     for (size_t i = 0; i < recs.size(); i++) decode_read_for_pileup(*recs[i], P, st, &calls[i]);
-    if (n_processed) for (auto& c : calls) { if (c.skipped) { if (n_skipped) (*n_skipped)++; } else (*n_processed)++; }
+    if (n_processed) for (size_t i = 0; i < recs.size(); i++) { if (calls[i].skipped) { if (n_skipped) (*n_skipped)++; } else (*n_processed)++; }
     const size_t NS = st.size();
     std::vector<std::pair<int, ModCode>> states(NS);
     for (size_t i = 0; i < NS; i++) states[i] = st.get((int)i);
@@ -221,9 +232,13 @@ inline void process_interval(const BamFile& bam, const Interval& iv, const Pileu
     if (!iv.focus.all)
         for (auto& kv : iv.focus.rule) if (kv.first >= start && kv.first < end) rule[kv.first - start] = kv.second;
 
-    std::vector<StrandTally> tally(2 * W);
-    std::vector<uint32_t> mods(2 * W * std::max<size_t>(NS, 1), 0);
-    std::vector<int32_t> obs(2 * (W + 1) * std::max<size_t>(NS, 1), 0);  // difference arrays [strand][state][pos]
+    // per-thread scratch, reused across intervals (allocation + page-fault cost would otherwise dominate)
+    static thread_local std::vector<StrandTally> tally;
+    static thread_local std::vector<uint32_t> mods;
+    static thread_local std::vector<int32_t> obs;     // difference arrays [strand][state][pos]
+    tally.assign(2 * W, StrandTally());
+    mods.assign(2 * W * std::max<size_t>(NS, 1), 0);
+    obs.assign(2 * (W + 1) * std::max<size_t>(NS, 1), 0);
     auto OBS = [&](int s, int id, size_t x) -> int32_t& { return obs[((size_t)s * NS + id) * (W + 1) + x]; };
     auto MODS = [&](int s, size_t x, int id) -> uint32_t& { return mods[((size_t)s * W + x) * NS + id]; };
 
