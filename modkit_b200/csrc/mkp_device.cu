@@ -49,7 +49,7 @@ struct mkp_ctx {
     uint64_t heap_bytes = 0;
     // work buffers
     DevBuf d_rl, d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr, d_scr_cum;
-    DevBuf d_slots, d_row_counts, d_row_prefix, d_rows, d_hist, d_take;
+    DevBuf d_obs_word, d_slots, d_row_counts, d_row_prefix, d_rows, d_hist, d_take;
     // results
     size_t n_rows = 0;
     std::vector<mkp_row> h_rows;
@@ -89,7 +89,7 @@ void mkp_destroy(mkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_rl, &ctx->d_meta, &ctx->d_P,
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr,
-                      &ctx->d_scr_cum, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take};
+                      &ctx->d_scr_cum, &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -246,10 +246,13 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     const uint32_t stride = SL_MOD + 2 * std::max<uint32_t>(n_states, 1);
     CK(ctx->d_slots.ensure(std::max<size_t>(1, n_hot) * stride * 4));
     CK(cudaMemsetAsync(ctx->d_slots.p, 0, (size_t)n_hot * stride * 4, st));
+    CK(ctx->d_obs_word.ensure((size_t)n_words * 8 + 8));
+    CK(cudaMemsetAsync(ctx->d_obs_word.p, 0, (size_t)n_words * 8, st));
     CountDev D;
     D.hdrs = C.hdrs; D.heap = C.heap; D.meta = C.meta; D.calls = C.calls; D.n_reads = C.n_reads; D.cs = C.cs; D.ce = C.ce;
     D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
     D.slots = ctx->d_slots.as<uint32_t>(); D.stride = stride; D.n_states = std::max<uint32_t>(n_states, 1);
+    D.n_words = n_words; D.obs_word = ctx->d_obs_word.as<uint32_t>(); D.work = u + 5;
     CK(cudaEventRecord(ctx->ev[4], st));
     const int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
     if (ctx->n_reads && n_hot) k_count_calls<<<g2, 256, 0, st>>>(D);
@@ -259,6 +262,7 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     RowDev R;
     R.hot = C.hot; R.hot_prefix = C.hot_prefix; R.n_words = n_words; R.cs = C.cs; R.ce = C.ce;
     R.slots = D.slots; R.stride = stride; R.n_states = D.n_states; R.states = C.states; R.numeric_mode = ctx->params.numeric_mode;
+    R.obs_word = D.obs_word;
     R.row_counts = ctx->d_row_counts.as<uint32_t>(); R.row_prefix = ctx->d_row_prefix.as<uint32_t>(); R.rows = nullptr;
     const int rg = (n_words + 255) / 256;
     k_rows<false><<<rg, 256, 0, st>>>(R);

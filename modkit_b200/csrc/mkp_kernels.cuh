@@ -24,6 +24,7 @@ constexpr int MAX_LISTS = 16;
 constexpr int MAX_LIST_CODES = 4;
 constexpr int MAX_MAP = 7;          // codes at one read position
 constexpr int MAX_STATES = 32;
+constexpr int CQ_CAP = 640;         // CIGAR ops whose prefix sums fit in shared memory per warp
 constexpr uint32_t FULL = 0xffffffffu;
 
 // slot layout (u32 words)
@@ -215,6 +216,80 @@ __device__ __noinline__ float argmax_prob(const ProbMap& m) {
     bool have = false;
     float mp = 0.f;
     for (int s = 0; s < 8; s++) if (m.slot[s] >= 0) { float v = m.p[m.slot[s]]; if (!have || v >= mp) { have = true; mp = v; } }
+    return (have && mp > cp) ? mp : cp;
+}
+
+// ---- probabilities of one read position in insertion order (BaseModProbs) ---------------------------------------
+struct Items {
+    uint32_t code[MAX_MAP];
+    float p[MAX_MAP];
+    int n;
+    __device__ __forceinline__ int find(uint32_t c) const { for (int i = 0; i < n; i++) if (code[i] == c) return i; return -1; }
+    __device__ __forceinline__ bool push(uint32_t c, float v) { if (n >= MAX_MAP) return false; code[n] = c; p[n] = v; n++; return true; }
+};
+// low two bits of the Fx hash: K = 1 (mod 4), rotl(K,5) = 2 (mod 4)
+__device__ __forceinline__ uint32_t bucket4(uint32_t c) { return (c & 0x80000000u) ? ((2u ^ c) & 3u) : (c & 3u); }
+__device__ __noinline__ void iter_order_slow(const Items& it, int* ord) {
+    ProbMap m;
+    m.init();
+    for (int i = 0; i < it.n; i++) m.insert(it.code[i], it.p[i]);
+    int k = 0;
+    for (int s = 0; s < 8; s++) if (m.slot[s] >= 0) ord[k++] = m.slot[s];
+}
+// FxHashMap iteration order of the items (1 and 2 entries in closed form: 4 buckets, linear probing)
+__device__ __forceinline__ void iter_order(const Items& it, int* ord) {
+    if (it.n <= 1) { ord[0] = 0; return; }
+    if (it.n == 2) {
+        const uint32_t b0 = bucket4(it.code[0]), b1 = bucket4(it.code[1]);
+        const bool swap = b0 != b1 ? (b1 < b0) : (b0 == 3);
+        ord[0] = swap ? 1 : 0; ord[1] = swap ? 0 : 1;
+        return;
+    }
+    iter_order_slow(it, ord);
+}
+__device__ __forceinline__ float items_sum(const Items& it, const int* ord) {
+    float s = 0.f;
+    for (int k = 0; k < it.n; k++) s = __fadd_rn(s, it.p[ord[k]]);
+    return s;
+}
+// CollapseMethod::ReDistribute (src/mod_bam.rs:558-600)
+__device__ __forceinline__ void redistribute_items(const Items& in, const int* ord, uint32_t drop, Items& out) {
+    float marginal = 0.f;
+    int n_other = 0;
+    for (int k = 0; k < in.n; k++) { const int i = ord[k]; if (in.code[i] == drop) marginal = __fadd_rn(marginal, in.p[i]); else n_other++; }
+    const float share = __fdiv_rn(marginal, __fadd_rn((float)n_other, 1.0f));
+    out.n = 0;
+    for (int k = 0; k < in.n; k++) { const int i = ord[k]; if (in.code[i] != drop) out.push(in.code[i], __fadd_rn(in.p[i], share)); }
+}
+// MultipleThresholdModCaller::call (src/threshold_mod_caller.rs:28-63): 0 filtered, 1 canonical, 2 modified (*code)
+__device__ __forceinline__ int make_call_items(const Items& it, const int* ord, int tb, uint32_t* code) {
+    bool have = false;
+    float best = 0.f;
+    int kind = 0;
+    const uint32_t any_code = (uint32_t)("ACGT"[tb]);
+    const float base_thr = c_par.base_set[tb] ? c_par.base_thr[tb] : c_par.default_thr;
+    for (int k = 0; k < it.n; k++) {
+        const int i = ord[k];
+        const uint32_t c = it.code[i];
+        float thr = base_thr;
+        if (c_par.n_mod_thr) {
+            bool found = false;
+            for (uint32_t t = 0; t < c_par.n_mod_thr && !found; t++) if (c_par.mod_code[t] == c) { thr = c_par.mod_thr[t]; found = true; }
+            for (uint32_t t = 0; t < c_par.n_mod_thr && !found; t++) if (c_par.mod_code[t] == any_code) { thr = c_par.mod_thr[t]; found = true; }
+        }
+        const float pm = it.p[i];
+        if (pm >= thr && (!have || pm >= best)) { have = true; best = pm; kind = 2; *code = c; }
+    }
+    const float cp = __fsub_rn(1.0f, items_sum(it, ord));
+    if (cp >= base_thr && (!have || cp >= best)) { have = true; kind = 1; }
+    return have ? kind : 0;
+}
+// BaseModProbs::argmax_base_mod_call value (src/mod_bam.rs:489-505)
+__device__ __forceinline__ float argmax_items(const Items& it, const int* ord) {
+    const float cp = __fsub_rn(1.0f, items_sum(it, ord));
+    bool have = false;
+    float mp = 0.f;
+    for (int k = 0; k < it.n; k++) { const float v = it.p[ord[k]]; if (!have || v >= mp) { have = true; mp = v; } }
     return (have && mp > cp) ? mp : cp;
 }
 
@@ -614,14 +689,15 @@ __global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
 template <int MODE>
 __global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
     __shared__ ListTab s_tab[4];
+    __shared__ uint32_t s_cq[4][CQ_CAP], s_cr[4][CQ_CAP];   // CIGAR prefix of the current read (global scratch when longer)
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     ListTab& T = s_tab[wib];
     StateCache scache;
     scache.init();
-    uint32_t* cq = C.scr_cq + (size_t)gw * C.max_ncigar;
-    uint32_t* cr = C.scr_cr + (size_t)gw * C.max_ncigar;
+    uint32_t* const gcq = C.scr_cq + (size_t)gw * C.max_ncigar;
+    uint32_t* const gcr = C.scr_cr + (size_t)gw * C.max_ncigar;
 
     for (;;) {
         uint32_t ri = 0;
@@ -639,6 +715,8 @@ __global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
         const uint32_t L = h.l_seq;
         const bool rev = h.flags & 0x10;
         const uint32_t* cig = (const uint32_t*)(C.heap + h.off);
+        uint32_t* const cq = h.n_cigar <= CQ_CAP ? s_cq[wib] : gcq;
+        uint32_t* const cr = h.n_cigar <= CQ_CAP ? s_cr[wib] : gcr;
         const uint8_t* seq = C.heap + h.off + 4ull * h.n_cigar;
         const uint8_t* ml = seq + ((L + 1) >> 1);
         uint32_t imp_lists[2][4];
@@ -719,40 +797,42 @@ __global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
                             if (k < n2 && P2[k] == f) owner = false;
                         }
                         if (owner && !e2) {
-                            ProbMap m;
-                            m.init();
+                            Items m;
+                            m.n = 0;
+                            int ord[MAX_MAP];
                             const uint8_t* mlq = ml + T.ml_off[l] + (size_t)j * T.ncodes[l];
                             for (uint32_t c = 0; c < T.ncodes[l] && !e2; c++) {
-                                float p = __fdiv_rn(__fadd_rn((float)mlq[c], 0.5f), 256.0f);
-                                int it = m.find(T.code[l][c]);
-                                if (it < 0) { if (m.insert(T.code[l][c], p) < 0) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
+                                const float p = __fdiv_rn(__fadd_rn((float)mlq[c], 0.5f), 256.0f);
+                                const int it = m.find(T.code[l][c]);
+                                if (it < 0) { if (!m.push(T.code[l][c], p)) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
                                 else { if (__fadd_rn(m.p[it], p) > 1.01f) e2 = true; else m.p[it] = __fadd_rn(m.p[it], p); }
                             }
                             for (uint32_t l2 = l + 1; l2 < nl && !e2; l2++) {
                                 if (T.strand[l2] != st || T.n_delta[l2] == 0) continue;
                                 const uint32_t* P2 = P + T.ent_off[l2];
-                                uint32_t n2 = T.n_delta[l2];
+                                const uint32_t n2 = T.n_delta[l2];
                                 uint32_t k;
                                 if (j < n2 && P2[j] == f) k = j;
                                 else { k = lower_bound_u32(P2, n2, f); if (!(k < n2 && P2[k] == f)) continue; }
                                 // per-list table first (add_base_mod_prob), then combine_checked into the aggregate
-                                ProbMap t2;
-                                t2.init();
+                                Items t2;
+                                t2.n = 0;
                                 const uint8_t* ml2 = ml + T.ml_off[l2] + (size_t)k * T.ncodes[l2];
                                 for (uint32_t c = 0; c < T.ncodes[l2] && !e2; c++) {
-                                    float p = __fdiv_rn(__fadd_rn((float)ml2[c], 0.5f), 256.0f);
-                                    int it = t2.find(T.code[l2][c]);
-                                    if (it < 0) { if (t2.insert(T.code[l2][c], p) < 0) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
+                                    const float p = __fdiv_rn(__fadd_rn((float)ml2[c], 0.5f), 256.0f);
+                                    const int it = t2.find(T.code[l2][c]);
+                                    if (it < 0) { if (!t2.push(T.code[l2][c], p)) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
                                     else { if (__fadd_rn(t2.p[it], p) > 1.01f) e2 = true; else t2.p[it] = __fadd_rn(t2.p[it], p); }
                                 }
-                                for (int s = 0; s < 8 && !e2; s++) {
-                                    if (t2.slot[s] < 0) continue;
-                                    int i2 = t2.slot[s];
-                                    int it = m.find(t2.code[i2]);
-                                    if (it < 0) { if (m.insert(t2.code[i2], t2.p[i2]) < 0) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
+                                int o2[MAX_MAP];
+                                iter_order(t2, o2);
+                                for (int s2 = 0; s2 < t2.n && !e2; s2++) {
+                                    const int i2 = o2[s2];
+                                    const int it = m.find(t2.code[i2]);
+                                    if (it < 0) { if (!m.push(t2.code[i2], t2.p[i2])) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
                                     else m.p[it] = __fadd_rn(m.p[it], t2.p[i2]);
                                 }
-                                if (!e2 && m.sum() > 1.01f) e2 = true;
+                                if (!e2) { iter_order(m, ord); if (items_sum(m, ord) > 1.01f) e2 = true; }
                             }
                             if (!e2) {
                                 const int tb = st == 0 ? b : 3 - b;
@@ -762,46 +842,50 @@ __global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
                                     else keep = f >= c_par.edge_start && f < L - c_par.edge_end;
                                 }
                                 if (keep) {
-                                    ProbMap mc;
-                                    const ProbMap* use = &m;
-                                    if (c_par.numeric_mode == 2) { redistribute(m, c_par.collapse_code, mc); use = &mc; }
-                                    // aligned?
-                                    uint32_t lo = 0, hi = h.n_cigar;   // largest i with cq[i] <= q
+                                    iter_order(m, ord);
+                                    Items mc;
+                                    const Items* use = &m;
+                                    if (c_par.numeric_mode == 2) { redistribute_items(m, ord, c_par.collapse_code, mc); iter_order(mc, ord); use = &mc; }
+                                    // aligned?  largest i with cq[i] <= q
+                                    uint32_t lo = 0, hi = h.n_cigar;
                                     bool aligned = false;
                                     if (hi > 0 && cq[0] <= q) {
-                                        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (cq[mid] <= q) lo = mid; else hi = mid; }
-                                        uint32_t c = cig[lo];
-                                        uint32_t op = c & 15, len = c >> 4;
-                                        if ((op == 0 || op == 7 || op == 8) && q - cq[lo] < len) { aligned = true; rpos = cr[lo] + (q - cq[lo]); }
+                                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cq[mid] <= q) lo = mid; else hi = mid; }
+                                        const uint32_t c = cig[lo];
+                                        const uint32_t op = c & 15, len = c >> 4, qs = cq[lo];
+                                        if ((op == 0 || op == 7 || op == 8) && q - qs < len) { aligned = true; rpos = cr[lo] + (q - qs); }
                                     }
                                     if (MODE == MODE_PILEUP) {
                                         uint32_t mask = 0;
-                                        for (int s = 0; s < 8; s++) if (use->slot[s] >= 0) mask |= 1u << state_id(C, scache, tb, use->code[use->slot[s]]);
+                                        for (int k2 = 0; k2 < use->n; k2++) mask |= 1u << state_id(C, scache, tb, use->code[k2]);
                                         // (mod strand, read orientation) -> reference strand (read_cache.rs:181-188)
                                         if ((st == 0) != rev) pos_mask |= mask; else neg_mask |= mask;
                                         table_survived = true;
                                         if (aligned && rpos >= C.cs && rpos < C.ce) {
-                                            uint32_t code = 0;
-                                            int kind = make_call(*use, tb, &code);
-                                            uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, code);
-                                            // does a '+' list cover the same position (both pos_call and neg_call present)?
-                                            uint32_t nosub = 0;
-                                            if (st == 1) {
-                                                for (uint32_t l2 = 0; l2 < nl && !nosub; l2++) {
-                                                    if (T.strand[l2] != 0 || T.n_delta[l2] == 0) continue;
-                                                    const uint32_t* P2 = P + T.ent_off[l2];
-                                                    uint32_t k = lower_bound_u32(P2, T.n_delta[l2], f);
-                                                    if (k < T.n_delta[l2] && P2[k] == f) nosub = 1;
-                                                }
-                                            }
-                                            uint32_t x = rpos - C.cs;
+                                            const uint32_t x = rpos - C.cs;
                                             bool focus = true;
                                             if (C.focus_pos) focus = ((C.focus_pos[x >> 5] | C.focus_neg[x >> 5]) >> (x & 31)) & 1u;
-                                            if (focus) { emit = true; info = st | ((uint32_t)b << 1) | (state << 3) | (nosub << 11); }
+                                            if (focus) {
+                                                uint32_t code = 0;
+                                                const int kind = make_call_items(*use, ord, tb, &code);
+                                                const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, code);
+                                                // does a '+' list cover the same position (both pos_call and neg_call present)?
+                                                uint32_t nosub = 0;
+                                                if (st == 1) {
+                                                    for (uint32_t l2 = 0; l2 < nl && !nosub; l2++) {
+                                                        if (T.strand[l2] != 0 || T.n_delta[l2] == 0) continue;
+                                                        const uint32_t* P2 = P + T.ent_off[l2];
+                                                        const uint32_t k = lower_bound_u32(P2, T.n_delta[l2], f);
+                                                        if (k < T.n_delta[l2] && P2[k] == f) nosub = 1;
+                                                    }
+                                                }
+                                                emit = true;
+                                                info = st | ((uint32_t)b << 1) | (state << 3) | (nosub << 11);
+                                            }
                                         }
                                     } else {
                                         if (aligned || C.hist_include_unaligned) {
-                                            hist_ok = true; hist_v = argmax_prob(*use); hist_base = tb;
+                                            hist_ok = true; hist_v = argmax_items(*use, ord); hist_base = tb;
                                             if (imp_lists[st][b]) imp_explicit[st * 4 + b]++;
                                         }
                                     }
@@ -850,19 +934,21 @@ __global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
                     any = keep;
                 }
                 if (!__any_sync(FULL, any)) continue;
-                ProbMap m, mc;
-                m.init();
-                for (uint32_t l = 0; l < nl; l++) if ((lists >> l) & 1u) for (uint32_t c = 0; c < T.ncodes[l]; c++) if (m.find(T.code[l][c]) < 0) m.insert(T.code[l][c], 0.f);
-                const ProbMap* use = &m;
-                if (c_par.numeric_mode == 2) { redistribute(m, c_par.collapse_code, mc); use = &mc; }
+                Items m, mc;
+                m.n = 0;
+                int ord[MAX_MAP];
+                for (uint32_t l = 0; l < nl; l++) if ((lists >> l) & 1u) for (uint32_t c = 0; c < T.ncodes[l]; c++) if (m.find(T.code[l][c]) < 0) m.push(T.code[l][c], 0.f);
+                iter_order(m, ord);
+                const Items* use = &m;
+                if (c_par.numeric_mode == 2) { redistribute_items(m, ord, c_par.collapse_code, mc); iter_order(mc, ord); use = &mc; }
                 const int tb = s == 0 ? (int)b : 3 - (int)b;
                 table_survived = true;
                 if (MODE == MODE_PILEUP) {
                     uint32_t mask = 0;
-                    for (int k = 0; k < 8; k++) if (use->slot[k] >= 0) mask |= 1u << state_id(C, scache, tb, use->code[use->slot[k]]);
+                    for (int k = 0; k < use->n; k++) mask |= 1u << state_id(C, scache, tb, use->code[k]);
                     if ((s == 0) != rev) pos_mask |= mask; else neg_mask |= mask;
                     uint32_t code = 0;
-                    const int kind = make_call(*use, tb, &code);
+                    const int kind = make_call_items(*use, ord, tb, &code);
                     const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, code);
                     imp_meta[s] |= (0x80u | state) << (8 * b);
                 } else {
@@ -1017,6 +1103,9 @@ struct CountDev {
     uint32_t* slots;
     uint32_t stride;    // words per slot
     uint32_t n_states;
+    uint32_t n_words;
+    uint32_t* obs_word;   // [2][n_words] observed-code masks of fully covered bitmap words
+    uint32_t* work;       // dynamic read counter
 };
 
 __device__ __forceinline__ uint32_t slot_of(const CountDev& D, uint32_t x) {
@@ -1035,9 +1124,11 @@ __device__ __forceinline__ void add_feature(uint32_t* S, uint32_t n_states, uint
 // warp per read, lanes over its call records
 __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
     const uint32_t lane = lane_id();
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t ri = gw; ri < D.n_reads; ri += nw) {
+    for (;;) {
+        uint32_t ri = 0;
+        if (lane == 0) ri = atomicAdd(D.work + 1, 1u);
+        ri = __shfl_sync(FULL, ri, 0);
+        if (ri >= D.n_reads) break;
         const ReadMeta m = D.meta[ri];
         if (!(m.flags & 2) || m.n_calls == 0) continue;
         const uint32_t a = (D.hdrs[ri].flags & 0x10) ? 1u : 0u;
@@ -1062,15 +1153,20 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
     }
 }
 
-// warp per read: every aligned base / deleted position that lands on a hot position
+// warp per read: every aligned base / deleted position that lands on a hot position, plus the observed-code
+// coverage of the read (src/pileup/mod.rs:831-835: unioned for every alignment at the position, deletions included,
+// reference skips excluded).  Coverage is recorded per 32-position bitmap word when the read covers the whole word
+// (one coalesced check-then-OR per word) and per hot position only in the partial words at the ends of a run.
 __global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
     __shared__ uint32_t s_scan[8][33];
     __shared__ uint32_t s_op[8][32], s_q[8][32], s_r[8][32];
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t ri = gw; ri < D.n_reads; ri += nw) {
+    for (;;) {
+        uint32_t ri = 0;
+        if (lane == 0) ri = atomicAdd(D.work, 1u);
+        ri = __shfl_sync(FULL, ri, 0);
+        if (ri >= D.n_reads) break;
         const ReadMeta m = D.meta[ri];
         if (!(m.flags & 1)) continue;
         const mkp_read_hdr h = D.hdrs[ri];
@@ -1079,7 +1175,37 @@ __global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
         const uint32_t* cig = (const uint32_t*)(D.heap + h.off);
         const uint8_t* seq = D.heap + h.off + 4ull * h.n_cigar;
         const bool has_mods = m.flags & 2;
+        const bool has_imp = (m.imp[0] | m.imp[1]) != 0;
+        const uint32_t pm = has_mods ? m.pos_mask : 0u, nm = has_mods ? m.neg_mask : 0u;
+        // observed-code coverage of one run [ra, rb) of reference positions
+        auto cover = [&](uint32_t ra, uint32_t rb) {
+            if (!(pm | nm)) return;
+            if (ra < D.cs) ra = D.cs;
+            if (rb > D.ce) rb = D.ce;
+            if (ra >= rb) return;
+            const uint32_t wl = (ra - D.cs + 31) >> 5, wh = (rb - D.cs) >> 5;   // words [wl, wh) are fully covered
+            for (uint32_t w = wl + lane; w < wh; w += 32) {
+                if (pm && (D.obs_word[w] & pm) != pm) atomicOr(&D.obs_word[w], pm);
+                if (nm && (D.obs_word[D.n_words + w] & nm) != nm) atomicOr(&D.obs_word[D.n_words + w], nm);
+            }
+            // partial words: lane = bit
+            auto partial = [&](uint32_t pa, uint32_t pb) {     // [pa,pb) lies inside one bitmap word
+                if (pa >= pb) return;
+                const uint32_t w = (pa - D.cs) >> 5, wbase = D.cs + (w << 5);
+                const uint32_t word = D.hot[w];
+                uint32_t bits = word & (FULL << (pa - wbase));
+                if (pb < wbase + 32) bits &= (1u << (pb - wbase)) - 1u;
+                if ((bits >> lane) & 1u) {
+                    uint32_t* S = D.slots + (size_t)(D.hot_prefix[w] + __popc(word & ((1u << lane) - 1u))) * D.stride;
+                    if (pm && (S[SL_OBS] & pm) != pm) atomicOr(&S[SL_OBS], pm);
+                    if (nm && (S[SL_OBS + 1] & nm) != nm) atomicOr(&S[SL_OBS + 1], nm);
+                }
+            };
+            if (wl > wh) partial(ra, rb);                       // the run starts and ends inside one word
+            else { partial(ra, D.cs + (wl << 5)); partial(D.cs + (wh << 5), rb); }
+        };
         uint32_t qc = 0, rc = (uint32_t)h.ref_start;
+        uint32_t run_start = rc;                                // start of the current run without reference skips
         for (uint32_t b0 = 0; b0 < h.n_cigar; b0 += 32) {
             uint32_t i = b0 + lane;
             uint32_t c = i < h.n_cigar ? cig[i] : 0;
@@ -1090,6 +1216,15 @@ __global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
             uint32_t q0 = qc + qi - ql, r0 = rc + rr - rl;
             qc += __shfl_sync(FULL, qi, 31);
             rc += __shfl_sync(FULL, rr, 31);
+            // reference skips ('N') end a covered run
+            uint32_t skips = __ballot_sync(FULL, op == 3 && len > 0 && i < h.n_cigar);
+            while (skips) {
+                const int sl = __ffs(skips) - 1;
+                skips &= skips - 1;
+                const uint32_t sr = __shfl_sync(FULL, r0, sl), slen = __shfl_sync(FULL, len, sl);
+                cover(run_start, sr);
+                run_start = sr + slen;
+            }
             // windows = hot-bitmap words touched by this op inside the chunk (M,=,X and D only)
             bool counts = (op == 0 || op == 7 || op == 8 || op == 2) && len > 0;
             uint32_t lo = r0 > D.cs ? r0 : D.cs;
@@ -1099,7 +1234,7 @@ __global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
             uint32_t wi = warp_incl_scan(nwin);
             s_scan[wib][lane + 1] = wi;
             if (lane == 0) s_scan[wib][0] = 0;
-            s_op[wib][lane] = op; s_q[wib][lane] = q0; s_r[wib][lane] = r0;
+            s_op[wib][lane] = op | (len << 4); s_q[wib][lane] = q0; s_r[wib][lane] = r0;
             __syncwarp();
             const uint32_t total = s_scan[wib][32];
             for (uint32_t t = lane; t < total; t += 32) {
@@ -1107,37 +1242,35 @@ __global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
                 uint32_t lo_j = 0, hi_j = 32;
                 while (hi_j - lo_j > 1) { uint32_t mid = (lo_j + hi_j) >> 1; if (s_scan[wib][mid] <= t) lo_j = mid; else hi_j = mid; }
                 const uint32_t j = lo_j;
-                const uint32_t jop = s_op[wib][j], jq = s_q[wib][j], jr = s_r[wib][j];
-                uint32_t clen = cig[b0 + j] >> 4;
+                const uint32_t jc = s_op[wib][j], jq = s_q[wib][j], jr = s_r[wib][j];
+                const uint32_t jop = jc & 15, clen = jc >> 4;
                 uint32_t olo = jr > D.cs ? jr : D.cs;
                 uint32_t ohi = jr + clen < D.ce ? jr + clen : D.ce;
                 uint32_t w = ((olo - D.cs) >> 5) + (t - s_scan[wib][j]);
                 uint32_t wbase = D.cs + (w << 5);
-                uint32_t bits = D.hot[w];
+                const uint32_t word = D.hot[w];
+                uint32_t bits = word;
                 if (!bits) continue;
-                // restrict to [olo, ohi)
+                // restrict to [olo, ohi) and to the positions whose strand rule admits what this read can add there
                 if (olo > wbase) bits &= FULL << (olo - wbase);
                 if (ohi < wbase + 32) bits &= (1u << (ohi - wbase)) - 1u;
-                if (!bits) continue;
                 uint32_t fp = FULL, fn = FULL;
                 if (D.focus_pos) { fp = D.focus_pos[w]; fn = D.focus_neg[w]; }
                 const uint32_t ok = a == 0 ? fp : fn;
+                bits &= (has_imp && jop != 2) ? (fp | fn) : ok;
+                if (!bits) continue;
                 const uint32_t pre = D.hot_prefix[w];
-                const uint32_t word = D.hot[w];
                 while (bits) {
                     uint32_t bit = __ffs(bits) - 1;
                     bits &= bits - 1;
                     uint32_t slot = pre + __popc(word & ((1u << bit) - 1u));
                     uint32_t* S = D.slots + (size_t)slot * D.stride;
-                    if (has_mods) {
-                        if (m.pos_mask && (S[SL_OBS] & m.pos_mask) != m.pos_mask) atomicOr(&S[SL_OBS], m.pos_mask);
-                        if (m.neg_mask && (S[SL_OBS + 1] & m.neg_mask) != m.neg_mask) atomicOr(&S[SL_OBS + 1], m.neg_mask);
-                    }
-                    if (jop == 2) { if ((ok >> bit) & 1u) atomicAdd(&S[SL_DEL + a], 1u); continue; }
+                    if (jop == 2) { atomicAdd(&S[SL_DEL + a], 1u); continue; }
                     uint32_t q = jq + (wbase + bit - jr);
                     int nb = nib_to_base(seq_nibble(seq, q));
                     if (nb > 3) continue;
                     uint32_t b = a ? 3 - nb : nb;
+                    if (!has_imp) { atomicAdd(&S[SL_BASE + a * 4 + b], 1u); continue; }
                     uint32_t ip = (m.imp[0] >> (8 * b)) & 0xffu, in = (m.imp[1] >> (8 * b)) & 0xffu;
                     if ((ip | in) & 0x80u) {
                         // inferred-canonical entries of implicit tables, subject to the edge filter
@@ -1152,6 +1285,7 @@ __global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
             }
             __syncwarp();
         }
+        cover(run_start, rc);
     }
 }
 
@@ -1162,18 +1296,19 @@ struct RowDev {
     uint32_t stride, n_states;
     const unsigned long long* states;
     uint32_t numeric_mode;
+    const uint32_t* obs_word;
     uint32_t* row_counts;     // per hot-bitmap word
     const uint32_t* row_prefix;
     mkp_row* rows;
 };
 
 // rows of one slot, in output order. emit == nullptr => count only
-__device__ __forceinline__ uint32_t slot_rows(const RowDev& R, const uint32_t* S, uint32_t pos, mkp_row* out) {
+__device__ __forceinline__ uint32_t slot_rows(const RowDev& R, const uint32_t* S, uint32_t pos, uint32_t w, mkp_row* out) {
     uint32_t n = 0;
     for (uint32_t s = 0; s < 2; s++) {
         uint32_t mod_by_base[4] = {0, 0, 0, 0};
         for (uint32_t id = 0; id < R.n_states; id++) mod_by_base[(uint32_t)(R.states[id] >> 32) & 3u] += S[SL_MOD + s * R.n_states + id];
-        const uint32_t obs = S[SL_OBS + s];
+        const uint32_t obs = S[SL_OBS + s] | R.obs_word[s * R.n_words + w];
         const uint32_t row0 = n;
         for (uint32_t pb = 0; pb < 4; pb++) {
             uint32_t n_can = S[SL_CANON + s * 4 + pb], total_mod = mod_by_base[pb];
@@ -1222,7 +1357,7 @@ __global__ void __launch_bounds__(256) k_rows(RowDev R) {
     while (bits) {
         uint32_t bit = __ffs(bits) - 1;
         bits &= bits - 1;
-        n += slot_rows(R, R.slots + (size_t)slot * R.stride, R.cs + (w << 5) + bit, EMIT ? out + n : nullptr);
+        n += slot_rows(R, R.slots + (size_t)slot * R.stride, R.cs + (w << 5) + bit, w, EMIT ? out + n : nullptr);
         slot++;
     }
     if (!EMIT) R.row_counts[w] = n;
