@@ -24,6 +24,7 @@ constexpr int MAX_LISTS = 16;
 constexpr int MAX_LIST_CODES = 4;
 constexpr int MAX_MAP = 7;          // codes at one read position
 constexpr int MAX_STATES = 32;
+constexpr int CUM_CAP = 512;        // 32-base blocks whose occurrence counts fit in shared memory (reads <= 16 kb)
 constexpr int CQ_CAP = 640;         // CIGAR ops whose prefix sums fit in shared memory per warp
 constexpr uint32_t FULL = 0xffffffffu;
 
@@ -360,6 +361,8 @@ __global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
     __shared__ ListTab s_tab[4];
     __shared__ __align__(16) uint8_t s_txt[4][160];
     __shared__ uint8_t s_tok[4][132];
+    __shared__ uint32_t s_cum[4][2][CUM_CAP + 1];
+    __shared__ uint32_t s_val[4][64];
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -486,6 +489,16 @@ __global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
             need |= 1u << x;
         }
         const uint32_t nblk = (L + 31) >> 5;
+        // occurrence-count tables: shared memory for up to two bases of reads up to CUM_CAP blocks, else global scratch
+        uint32_t* cump[4];
+        {
+            int slot = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                cump[x] = cum + x * (C.max_blocks + 1);
+                if ((need & (1u << x)) && nblk <= CUM_CAP && slot < 2) cump[x] = s_cum[wib][slot++];
+            }
+        }
         if (need) {
             uint32_t run[4] = {0, 0, 0, 0};
             const uint32_t* seqw = (const uint32_t*)seq;   // 4-byte aligned
@@ -510,11 +523,11 @@ __global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
                 for (int x = 0; x < 4; x++) {
                     if (!(need & (1u << x))) continue;
                     uint32_t inc = warp_incl_scan(cnt[x]);
-                    if (blk < nblk) cum[x * (C.max_blocks + 1) + blk] = run[x] + inc - cnt[x];
+                    if (blk < nblk) cump[x][blk] = run[x] + inc - cnt[x];
                     run[x] += __shfl_sync(FULL, inc, 31);
                 }
             }
-            if (lane == 0) for (int x = 0; x < 4; x++) { T.tot[x] = run[x]; if (need & (1u << x)) cum[x * (C.max_blocks + 1) + nblk] = run[x]; }
+            if (lane == 0) for (int x = 0; x < 4; x++) { T.tot[x] = run[x]; if (need & (1u << x)) cump[x][nblk] = run[x]; }
         }
         __syncwarp();
         // ---- phase 3: tokens -> forward positions ------------------------------------------------------
@@ -527,16 +540,120 @@ __global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
             int x = -1;
             uint32_t tot = 0;
             if (fb != 'N') { int b = fb == 'A' ? 0 : fb == 'C' ? 1 : fb == 'G' ? 2 : 3; x = rev ? 3 - b : b; tot = T.tot[x]; }
-            const uint32_t* cx = x >= 0 ? cum + x * (C.max_blocks + 1) : nullptr;
+            const uint32_t* cx = x >= 0 ? cump[x] : nullptr;
             unsigned long long carry = 0;     // sum of (d+1) so far
             uint32_t ntok = 0;
+            // delta values of up to 32 tokens (one per lane, `mine` lanes in token order) -> forward positions P[]
+            auto place = [&](unsigned long long val, bool mine, uint32_t keep_mask) {
+                const unsigned long long inc = mine ? (val + 1ull) : 0ull;
+                const unsigned long long pre = warp_incl_scan64(inc);
+                const uint32_t idx = ntok + __popc(keep_mask & ((1u << lane) - 1u));
+                bool bad = false;
+                if (mine) {
+                    const unsigned long long k = carry + pre - 1ull;   // 0-based occurrence index (forward order)
+                    uint32_t f = 0;
+                    if (fb == 'N') {
+                        f = (uint32_t)k;
+                        if (k >= (unsigned long long)L) bad = true;
+                    } else if (k >= (unsigned long long)tot) {
+                        bad = true;
+                    } else {
+                        const uint32_t kq = rev ? tot - 1u - (uint32_t)k : (uint32_t)k;   // occurrence index in query order
+                        uint32_t lo = 0, hi = nblk;   // invariant: cx[lo] <= kq < cx[hi]
+                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cx[mid] <= kq) lo = mid; else hi = mid; }
+                        uint32_t within = kq - cx[lo];
+                        const uint32_t* sw = (const uint32_t*)seq + lo * 4;
+                        const uint32_t nbytes = (L + 1) >> 1;
+                        uint32_t bm = 0;                                 // occurrences of the base in this 32-base block
+#pragma unroll
+                        for (int w = 0; w < 4; w++) {
+                            const uint32_t byte0 = lo * 16 + w * 4;
+                            if (byte0 >= nbytes) continue;
+                            uint32_t word = sw[w];
+                            const uint32_t vb = nbytes - byte0;
+                            if (vb < 4) word &= (1u << (8 * vb)) - 1u;
+                            bm |= nib_flags_to_mask(nib_eq_flags(word, 1u << x)) << (8 * w);
+                        }
+                        // position of the (within+1)-th set bit
+                        uint32_t pos = 0, c;
+                        c = __popc(bm & 0xffffu); if (within >= c) { within -= c; pos += 16; bm >>= 16; }
+                        c = __popc(bm & 0xffu);   if (within >= c) { within -= c; pos += 8;  bm >>= 8; }
+                        c = __popc(bm & 0xfu);    if (within >= c) { within -= c; pos += 4;  bm >>= 4; }
+                        c = __popc(bm & 0x3u);    if (within >= c) { within -= c; pos += 2;  bm >>= 2; }
+                        c = bm & 1u;              if (within >= c) { pos += 1; }
+                        const uint32_t q = lo * 32 + pos;
+                        if (q >= L) bad = true;
+                        f = rev ? L - 1u - q : q;
+                    }
+                    if (!bad) P[ent + idx] = f;
+                }
+                if (__any_sync(FULL, bad)) err = true;
+                carry += __shfl_sync(FULL, pre, 31);
+                ntok += __popc(keep_mask);
+            };
+            // ---- fast path: the text is exactly digits(,digits)* with <= 9 digits per number. One byte per lane, the
+            //      number in progress is carried by a warp scan of affine maps v -> 10 v + d (reset at ','); finished
+            //      numbers are compacted into a small queue and placed 32 at a time. Anything else (white space, empty
+            //      or over-long tokens, other bytes) falls back to the exact nom-equivalent path below.
+            bool slow = false;
+            if (must) {
+                uint32_t* qv = s_val[wib];
+                uint32_t qn = 0, v_carry = 0, nd_carry = 0;
+                uint8_t prev_last = ',';                      // byte before the current 32-byte window
+                for (uint32_t c0 = ds; c0 < de && !slow && !err; c0 += 32) {
+                    const uint32_t g = c0 + lane;
+                    const bool in = g < de;
+                    const uint8_t ch = in ? mm[g] : 0;
+                    const bool dig = in && is_digit(ch), com = in && ch == ',';
+                    uint8_t nxt = __shfl_down_sync(FULL, ch, 1);
+                    bool nxt_in = g + 1 < de;
+                    if (lane == 31) nxt = nxt_in ? mm[g + 1] : 0;
+                    uint8_t prv = __shfl_up_sync(FULL, ch, 1);
+                    if (lane == 0) prv = prev_last;
+                    // anomalies: a byte that is neither digit nor comma; an empty token (comma after comma / at the very
+                    // start / at the very end)
+                    bool odd = in && !dig && !com;
+                    if (com && (prv == ',' || !nxt_in)) odd = true;
+                    // affine scan: value and digit count of the number ending at this byte
+                    uint32_t a = dig ? 10u : (com ? 0u : 1u), bv = dig ? (uint32_t)(ch - '0') : 0u;
+                    uint32_t ra = com ? 0u : 1u, rb = dig ? 1u : 0u;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t pa = __shfl_up_sync(FULL, a, d), pb = __shfl_up_sync(FULL, bv, d);
+                        const uint32_t pra = __shfl_up_sync(FULL, ra, d), prb = __shfl_up_sync(FULL, rb, d);
+                        if (lane >= (uint32_t)d) { bv = a * pb + bv; a = a * pa; rb = ra * prb + rb; ra = ra * pra; }
+                    }
+                    const uint32_t val = a * v_carry + bv, nd = ra * nd_carry + rb;
+                    if (dig && nd > 9) odd = true;
+                    const bool ends = dig && (!nxt_in || nxt == ',');          // last digit of a number
+                    if (__any_sync(FULL, odd)) { slow = true; break; }
+                    const uint32_t em = __ballot_sync(FULL, ends);
+                    if (ends) qv[qn + __popc(em & ((1u << lane) - 1u))] = val;
+                    qn += __popc(em);
+                    v_carry = __shfl_sync(FULL, val, 31); nd_carry = __shfl_sync(FULL, nd, 31);
+                    prev_last = __shfl_sync(FULL, ch, 31);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        place(qv[lane], true, FULL);
+                        const uint32_t rest = qn - 32;
+                        const uint32_t mv = lane < rest ? qv[32 + lane] : 0;
+                        __syncwarp();
+                        if (lane < rest) qv[lane] = mv;
+                        qn = rest;
+                        __syncwarp();
+                    }
+                }
+                if (!slow && !err && qn) { const bool mine = lane < qn; place(mine ? qv[lane] : 0, mine, qn >= 32 ? FULL : ((1u << qn) - 1u)); }
+                if (!slow && !err && ntok == 0) slow = true;         // (empty text: let the exact path raise the error)
+            }
+            if (slow) { carry = 0; ntok = 0; }
             bool stop = false;                // list truncated by a malformed token
-            // Tokens start after every ',' of mm[ds-1 .. de) (mm[ds-1] is the header comma); grammar per token:
-            // ws* digit+ ws* (nom separated_list1). 128 text bytes per round are staged in shared memory, the token
-            // starts are compacted, then every lane parses / selects one token.
+            // ---- exact path. Tokens start after every ',' of mm[ds-1 .. de) (mm[ds-1] is the header comma); grammar per
+            // token: ws* digit+ ws* (nom separated_list1). 128 text bytes per round are staged in shared memory, the
+            // token starts are compacted, then every lane parses one token.
             uint8_t* txt = s_txt[wib];
             uint8_t* tok = s_tok[wib];
-            for (uint32_t c0 = ds - 1; must && c0 < de && !stop && !err; c0 += 128) {
+            for (uint32_t c0 = ds - 1; must && slow && c0 < de && !stop && !err; c0 += 128) {
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < 5; k++) { const uint32_t o = lane + 32 * k, g = c0 + o; txt[o] = g < de ? mm[g] : 0; }
@@ -580,52 +697,7 @@ __global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
                         keep_mask &= cut >= 32 ? FULL : ((1u << cut) - 1u);
                     }
                     if (ntok == 0 && g0 == 0 && !(keep_mask & 1u)) err = true;             // the first token must parse
-                    const bool mine = (keep_mask >> lane) & 1u;
-                    const unsigned long long inc = mine ? (val + 1ull) : 0ull;
-                    const unsigned long long pre = warp_incl_scan64(inc);
-                    const uint32_t idx = ntok + __popc(keep_mask & ((1u << lane) - 1u));
-                    bool bad = false;
-                    if (mine) {
-                        const unsigned long long k = carry + pre - 1ull;   // 0-based occurrence index (forward order)
-                        uint32_t f = 0;
-                        if (fb == 'N') {
-                            f = (uint32_t)k;
-                            if (k >= (unsigned long long)L) bad = true;
-                        } else if (k >= (unsigned long long)tot) {
-                            bad = true;
-                        } else {
-                            const uint32_t kq = rev ? tot - 1u - (uint32_t)k : (uint32_t)k;   // occurrence index in query order
-                            uint32_t lo = 0, hi = nblk;   // invariant: cx[lo] <= kq < cx[hi]
-                            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cx[mid] <= kq) lo = mid; else hi = mid; }
-                            uint32_t within = kq - cx[lo];
-                            const uint32_t* sw = (const uint32_t*)seq + lo * 4;
-                            const uint32_t nbytes = (L + 1) >> 1;
-                            uint32_t bm = 0;                                 // occurrences of the base in this 32-base block
-#pragma unroll
-                            for (int w = 0; w < 4; w++) {
-                                const uint32_t byte0 = lo * 16 + w * 4;
-                                if (byte0 >= nbytes) continue;
-                                uint32_t word = sw[w];
-                                const uint32_t vb = nbytes - byte0;
-                                if (vb < 4) word &= (1u << (8 * vb)) - 1u;
-                                bm |= nib_flags_to_mask(nib_eq_flags(word, 1u << x)) << (8 * w);
-                            }
-                            // position of the (within+1)-th set bit
-                            uint32_t pos = 0, c;
-                            c = __popc(bm & 0xffffu); if (within >= c) { within -= c; pos += 16; bm >>= 16; }
-                            c = __popc(bm & 0xffu);   if (within >= c) { within -= c; pos += 8;  bm >>= 8; }
-                            c = __popc(bm & 0xfu);    if (within >= c) { within -= c; pos += 4;  bm >>= 4; }
-                            c = __popc(bm & 0x3u);    if (within >= c) { within -= c; pos += 2;  bm >>= 2; }
-                            c = bm & 1u;              if (within >= c) { pos += 1; }
-                            const uint32_t q = lo * 32 + pos;
-                            if (q >= L) bad = true;
-                            f = rev ? L - 1u - q : q;
-                        }
-                        if (!bad) P[ent + idx] = f;
-                    }
-                    if (__any_sync(FULL, bad)) err = true;
-                    carry += __shfl_sync(FULL, pre, 31);
-                    ntok += __popc(keep_mask);
+                    place(val, (keep_mask >> lane) & 1u, keep_mask);
                 }
             }
             if (must && ntok == 0) err = true;
