@@ -245,8 +245,8 @@ def main():
         n_rows = int(st.n_rows)
         # ---- e2e: host buffers -> rows on the host, every step. The contig is cut on the reference-interval grid into
         # sub-chunks that two contexts (two CUDA streams, two host threads) process alternately, so the H2D copy of one
-        # sub-chunk overlaps the kernels of the other. Every sub-chunk goes through mkp_pileup_chunk (upload + kernels +
-        # row fetch) from pinned host memory.
+        # sub-chunk overlaps the kernels of the other. Every sub-chunk goes through mkp_upload_chunk + mkp_pileup_resident +
+        # mkp_fetch_rows (the three calls mkp_pileup_chunk is made of) from pinned host memory.
         n_sub = 8
         grid = 100000
         bounds = [min(a.contig_len, ((a.contig_len * i // n_sub) // grid) * grid) for i in range(n_sub)] + [a.contig_len]
@@ -274,6 +274,7 @@ def main():
         ctx2 = modkit_b200.Context(local_rank)
         ctx2.set_params(modkit_b200.make_params(base_thresholds={"C": thr}))
         e2e_rows = [0]
+        upload_lock = threading.Lock()
 
         def e2e_pass():
             counts = [0, 0]
@@ -281,7 +282,14 @@ def main():
             def worker(t, cx):
                 rp, npp, stt = ctypes.c_void_p(), ctypes.c_size_t(), modkit_b200.Stats()
                 for k in range(t, len(subs), 2):
-                    rc = lib.mkp_pileup_chunk(cx._h, ctypes.byref(subs[k][0]), ctypes.byref(rp), ctypes.byref(npp), ctypes.byref(stt))
+                    # one upload at a time (full PCIe bandwidth), so that one context computes while the other uploads;
+                    # upload + resident pileup + row fetch is exactly what mkp_pileup_chunk does in one call
+                    with upload_lock:
+                        rc = lib.mkp_upload_chunk(cx._h, ctypes.byref(subs[k][0]))
+                    assert rc == 0, lib.mkp_last_error(cx._h)
+                    rc = lib.mkp_pileup_resident(cx._h, ctypes.byref(stt))
+                    assert rc == 0, lib.mkp_last_error(cx._h)
+                    rc = lib.mkp_fetch_rows(cx._h, ctypes.byref(rp), ctypes.byref(npp))
                     assert rc == 0, lib.mkp_last_error(cx._h)
                     counts[t] += npp.value
             ths = [threading.Thread(target=worker, args=(t, cx)) for t, cx in enumerate((ctx, ctx2))]
