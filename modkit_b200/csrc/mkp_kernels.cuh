@@ -829,6 +829,8 @@ __global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
                 const uint32_t n = T.n_delta[l];
                 const uint32_t* Pl = P + T.ent_off[l];
                 const uint32_t st = T.strand[l];
+                const uint8_t lfb = T.base[l];
+                const int lb = lfb == 'A' ? 0 : lfb == 'C' ? 1 : lfb == 'G' ? 2 : (lfb == 'T' || lfb == 'U') ? 3 : 4;
                 for (uint32_t j0 = 0; j0 < n; j0 += 32) {
                     uint32_t j = j0 + lane;
                     bool active = j < n;
@@ -841,9 +843,14 @@ __global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
                     if (active) {
                         uint32_t f = Pl[j];
                         uint32_t q = rev ? L - 1u - f : f;
-                        int nb = nib_to_base(seq_nibble(seq, q));
-                        int b = nb > 3 ? 4 : (rev ? 3 - nb : nb);   // forward-read base
-                        if (b > 3) e2 = true;
+                        // forward-read base at f: the list's own base (the position was selected as one of its occurrences);
+                        // only 'N' lists have to look at the sequence (mod_bam.rs:1245)
+                        int b = lb;
+                        if (lb > 3) {
+                            const int nb = nib_to_base(seq_nibble(seq, q));
+                            b = nb > 3 ? 4 : (rev ? 3 - nb : nb);
+                            if (b > 3) e2 = true;
+                        }
                         // ExplicitConflictInferred (mod_bam.rs:629-634): an implicit list of this (strand, base) table
                         // that does not list f explicitly holds an inferred entry there
                         if (b <= 3) {
