@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "_build", "libmodkit_b200.so")
+_LIB_PATH = os.environ.get("MODKIT_B200_LIB") or os.path.join(_HERE, "_build", "libmodkit_b200.so")   # env override: tuning variants only
 _lib = None
 
 

@@ -357,7 +357,16 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* P, uint32_t 
 
 // Kernel A: per read, everything that depends only on the read's own bytes: admission, reference span, MM list
 // discovery, per-base occurrence counts, MM token parse + select -> forward positions P[] and the list table.
-__global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
+#ifndef MKP_MINB_PARSE
+#define MKP_MINB_PARSE 1
+#endif
+#ifndef MKP_MINB_RESOLVE
+#define MKP_MINB_RESOLVE 1
+#endif
+#ifndef MKP_MINB_BASES
+#define MKP_MINB_BASES 8
+#endif
+__global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
     __shared__ ListTab s_tab[4];
     __shared__ __align__(16) uint8_t s_txt[4][160];
     __shared__ uint8_t s_tok[4][132];
@@ -759,7 +768,7 @@ __global__ void __launch_bounds__(128) k_parse(ChunkDev C) {
 // Kernel B: per read with mod info: CIGAR prefix, then every list entry -> merged probabilities -> collapse ->
 // threshold call -> reference position; call records, observed-code masks, implicit tables, hot-bitmap marks.
 template <int MODE>
-__global__ void __launch_bounds__(128) k_resolve(ChunkDev C) {
+__global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
     __shared__ ListTab s_tab[4];
     __shared__ uint32_t s_cq[4][CQ_CAP], s_cr[4][CQ_CAP];   // CIGAR prefix of the current read (global scratch when longer)
     const uint32_t lane = lane_id();
@@ -1236,7 +1245,7 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
 // coverage of the read (src/pileup/mod.rs:831-835: unioned for every alignment at the position, deletions included,
 // reference skips excluded).  Coverage is recorded per 32-position bitmap word when the read covers the whole word
 // (one coalesced check-then-OR per word) and per hot position only in the partial words at the ends of a run.
-__global__ void __launch_bounds__(256) k_count_bases(CountDev D) {
+__global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D) {
     __shared__ uint32_t s_scan[8][33];
     __shared__ uint32_t s_op[8][32], s_q[8][32], s_r[8][32];
     const uint32_t lane = lane_id();
