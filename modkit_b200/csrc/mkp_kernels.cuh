@@ -840,18 +840,6 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                 const uint32_t st = T.strand[l];
                 const uint8_t lfb = T.base[l];
                 const int lb = lfb == 'A' ? 0 : lfb == 'C' ? 1 : lfb == 'G' ? 2 : (lfb == 'T' || lfb == 'U') ? 3 : 4;
-                // nearest same-strand lists before / after this one: their same-index entries are loaded speculatively
-                // together with this list's (basecallers emit identical delta lists for the codes of one base), so the
-                // common case costs one round trip to memory instead of a chain of dependent ones
-                uint32_t lprev = 0xffffffffu, lnext = 0xffffffffu;
-                for (uint32_t l2 = 0; l2 < l; l2++) if (T.strand[l2] == st && T.n_delta[l2]) lprev = l2;
-                for (uint32_t l2 = nl; l2-- > l + 1;) if (T.strand[l2] == st && T.n_delta[l2]) lnext = l2;
-                const uint32_t* Pprev = lprev != 0xffffffffu ? P + T.ent_off[lprev] : nullptr;
-                const uint32_t* Pnext = lnext != 0xffffffffu ? P + T.ent_off[lnext] : nullptr;
-                const uint32_t nprev = Pprev ? T.n_delta[lprev] : 0, nnext = Pnext ? T.n_delta[lnext] : 0;
-                const uint32_t ncl = T.ncodes[l], ncn = Pnext ? T.ncodes[lnext] : 0;
-                const uint8_t* mlbase = ml + T.ml_off[l];
-                const uint8_t* mlnbase = Pnext ? ml + T.ml_off[lnext] : ml;
                 for (uint32_t j0 = 0; j0 < n; j0 += 32) {
                     uint32_t j = j0 + lane;
                     bool active = j < n;
@@ -861,14 +849,8 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                     bool hist_ok = false;
                     float hist_v = 0.f;
                     int hist_base = 0;
-                    uint32_t f_prev = 0xffffffffu, f_next = 0xffffffffu, mlw = 0, mlwn = 0;
                     if (active) {
-                        const uint32_t f0 = Pl[j];
-                        if (j < nprev) f_prev = Pprev[j];
-                        if (j < nnext) f_next = Pnext[j];
-                        for (uint32_t c = 0; c < ncl; c++) mlw |= (uint32_t)mlbase[(size_t)j * ncl + c] << (8 * c);
-                        if (j < nnext) for (uint32_t c = 0; c < ncn; c++) mlwn |= (uint32_t)mlnbase[(size_t)j * ncn + c] << (8 * c);
-                        uint32_t f = f0;
+                        uint32_t f = Pl[j];
                         uint32_t q = rev ? L - 1u - f : f;
                         // forward-read base at f: the list's own base (the position was selected as one of its occurrences);
                         // only 'N' lists have to look at the sequence (mod_bam.rs:1245)
@@ -898,7 +880,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                             if (T.strand[l2] != st || T.n_delta[l2] == 0) continue;
                             const uint32_t* P2 = P + T.ent_off[l2];
                             uint32_t n2 = T.n_delta[l2];
-                            if (l2 == lprev ? (f_prev == f) : (j < n2 && P2[j] == f)) { owner = false; break; }
+                            if (j < n2 && P2[j] == f) { owner = false; break; }
                             uint32_t k = lower_bound_u32(P2, n2, f);
                             if (k < n2 && P2[k] == f) owner = false;
                         }
@@ -906,8 +888,9 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                             Items m;
                             m.n = 0;
                             int ord[MAX_MAP];
-                            for (uint32_t c = 0; c < ncl && !e2; c++) {
-                                const float p = __fdiv_rn(__fadd_rn((float)((mlw >> (8 * c)) & 0xffu), 0.5f), 256.0f);
+                            const uint8_t* mlq = ml + T.ml_off[l] + (size_t)j * T.ncodes[l];
+                            for (uint32_t c = 0; c < T.ncodes[l] && !e2; c++) {
+                                const float p = __fdiv_rn(__fadd_rn((float)mlq[c], 0.5f), 256.0f);
                                 const int it = m.find(T.code[l][c]);
                                 if (it < 0) { if (!m.push(T.code[l][c], p)) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
                                 else { if (__fadd_rn(m.p[it], p) > 1.01f) e2 = true; else m.p[it] = __fadd_rn(m.p[it], p); }
@@ -917,17 +900,14 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                 const uint32_t* P2 = P + T.ent_off[l2];
                                 const uint32_t n2 = T.n_delta[l2];
                                 uint32_t k;
-                                bool pre = false;          // the speculatively loaded entry of the next list matches
-                                if (l2 == lnext && f_next == f) { k = j; pre = true; }
-                                else if (l2 != lnext && j < n2 && P2[j] == f) k = j;
+                                if (j < n2 && P2[j] == f) k = j;
                                 else { k = lower_bound_u32(P2, n2, f); if (!(k < n2 && P2[k] == f)) continue; }
                                 // per-list table first (add_base_mod_prob), then combine_checked into the aggregate
                                 Items t2;
                                 t2.n = 0;
                                 const uint8_t* ml2 = ml + T.ml_off[l2] + (size_t)k * T.ncodes[l2];
                                 for (uint32_t c = 0; c < T.ncodes[l2] && !e2; c++) {
-                                    const uint32_t qv = pre ? ((mlwn >> (8 * c)) & 0xffu) : (uint32_t)ml2[c];
-                                    const float p = __fdiv_rn(__fadd_rn((float)qv, 0.5f), 256.0f);
+                                    const float p = __fdiv_rn(__fadd_rn((float)ml2[c], 0.5f), 256.0f);
                                     const int it = t2.find(T.code[l2][c]);
                                     if (it < 0) { if (!t2.push(T.code[l2][c], p)) { atomicOr(C.err, MKP_DERR_TOO_MANY_CODES); e2 = true; } }
                                     else { if (__fadd_rn(t2.p[it], p) > 1.01f) e2 = true; else t2.p[it] = __fadd_rn(t2.p[it], p); }
