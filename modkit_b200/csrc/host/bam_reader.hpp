@@ -327,4 +327,79 @@ inline void pack_region(const BamReader& bam, uint32_t tid, uint32_t start, uint
     bam.for_overlapping(tid, start, end, [&](const RecRef& r) { pack_record(bam.rec(r), r.size, out); out->recs.push_back(r); });
 }
 
+// Multi-threaded variant: records are planned (tag lookup, sizes) and copied in parallel; layout identical to pack_region.
+inline void pack_region_mt(const BamReader& bam, uint32_t tid, uint32_t start, uint32_t end, int threads, PackedChunk* out) {
+    std::vector<RecRef> recs;
+    bam.for_overlapping(tid, start, end, [&](const RecRef& r) { recs.push_back(r); });
+    const size_t n = recs.size();
+    if (threads <= 1 || n < 512) { for (auto& r : recs) { pack_record(bam.rec(r), r.size, out); out->recs.push_back(r); } return; }
+    struct Plan { const uint8_t *cigar, *seq, *ml, *mm; uint32_t n_ml, n_mm; };
+    std::vector<Plan> plan(n);
+    const size_t h0 = out->hdrs.size();
+    out->hdrs.resize(h0 + n);
+    std::vector<uint64_t> need(n);
+    auto run = [&](auto&& body) {
+        std::atomic<size_t> next{0};
+        auto work = [&]() { for (;;) { size_t b = next.fetch_add(1024); if (b >= n) break; for (size_t i = b; i < std::min(n, b + 1024); i++) body(i); } };
+        std::vector<std::thread> th;
+        for (int t = 1; t < threads; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+    };
+    run([&](size_t i) {
+        const uint8_t* r = bam.rec(recs[i]);
+        const uint32_t size = recs[i].size;
+        mkp_read_hdr h;
+        memset(&h, 0, sizeof h);
+        h.ref_start = load_le<int32_t>(r + 4);
+        const uint32_t l_name = r[8];
+        uint32_t n_cigar = load_le<uint16_t>(r + 12);
+        const uint32_t flag = load_le<uint16_t>(r + 14);
+        h.l_seq = (uint32_t)std::max(0, load_le<int32_t>(r + 16));
+        const uint8_t* cigar = r + 32 + l_name;
+        const uint8_t* seq = cigar + 4ull * n_cigar;
+        const uint8_t* aux = seq + (h.l_seq + 1) / 2 + h.l_seq;
+        const uint8_t* rend = r + size;
+        AuxHit cg;
+        if (n_cigar == 2 && aux_find(aux, rend, 'C', 'G', &cg) && cg.type == 'B' && cg.sub == 'I') {
+            const uint32_t c0 = load_le<uint32_t>(cigar);
+            if ((c0 & 15) == 4 && (c0 >> 4) == h.l_seq) { cigar = cg.p; n_cigar = cg.n; }
+        }
+        AuxHit mm, ml, mn;
+        bool ok = (aux_find(aux, rend, 'M', 'M', &mm) || aux_find(aux, rend, 'M', 'm', &mm)) && mm.type == 'Z';
+        ok = ok && (aux_find(aux, rend, 'M', 'L', &ml) || aux_find(aux, rend, 'M', 'l', &ml)) && ml.type == 'B' && ml.sub == 'C';
+        if (ok && aux_find(aux, rend, 'M', 'N', &mn)) {
+            int64_t v = -1;
+            switch (mn.type) {
+                case 'c': v = (int8_t)mn.p[0]; break; case 'C': v = mn.p[0]; break;
+                case 's': v = load_le<int16_t>(mn.p); break; case 'S': v = load_le<uint16_t>(mn.p); break;
+                case 'i': v = load_le<int32_t>(mn.p); break; case 'I': v = load_le<uint32_t>(mn.p); break;
+                default: ok = false;
+            }
+            if (ok && (uint64_t)v != (uint64_t)h.l_seq) ok = false;
+        }
+        h.n_cigar = n_cigar;
+        h.flags = flag | (ok ? 0u : MKP_RF_TAGS_INVALID);
+        h.len_ml = ok ? ml.n : 0;
+        h.len_mm = ok ? mm.n : 0;
+        plan[i] = Plan{cigar, seq, ok ? ml.p : nullptr, ok ? mm.p : nullptr, h.len_ml, h.len_mm};
+        need[i] = 4ull * n_cigar + (h.l_seq + 1) / 2 + h.len_ml + h.len_mm;
+        out->hdrs[h0 + i] = h;
+    });
+    uint64_t o = (out->heap.size() + 15) & ~(uint64_t)15;
+    for (size_t i = 0; i < n; i++) { out->hdrs[h0 + i].off = o; o = (o + need[i] + 15) & ~(uint64_t)15; }
+    // pack_record leaves no padding after the last block: keep the same total size
+    const uint64_t total = n ? out->hdrs[h0 + n - 1].off + need[n - 1] : out->heap.size();
+    out->heap.resize(total);
+    run([&](size_t i) {
+        const mkp_read_hdr& h = out->hdrs[h0 + i];
+        uint8_t* d = out->heap.data() + h.off;
+        memcpy(d, plan[i].cigar, 4ull * h.n_cigar); d += 4ull * h.n_cigar;
+        memcpy(d, plan[i].seq, (h.l_seq + 1) / 2); d += (h.l_seq + 1) / 2;
+        if (plan[i].n_ml) { memcpy(d, plan[i].ml, plan[i].n_ml); d += plan[i].n_ml; }
+        if (plan[i].n_mm) memcpy(d, plan[i].mm, plan[i].n_mm);
+    });
+    out->recs.insert(out->recs.end(), recs.begin(), recs.end());
+}
+
 }  // namespace mkh

@@ -30,7 +30,12 @@ uint64_t mkh_bam_n_mapped(const mkh_bam* b, uint32_t tid) { return b->reader.sta
 uint64_t mkh_bam_n_records(const mkh_bam* b, uint32_t tid) { return b->reader.by_tid[tid].size(); }
 
 int mkh_pack_region(const mkh_bam* b, uint32_t tid, uint32_t start, uint32_t end, mkh_packed** out) {
-    try { mkh_packed* p = new mkh_packed(); pack_region(b->reader, tid, start, end, &p->pc); *out = p; return 0; }
+    try {
+        mkh_packed* p = new mkh_packed();
+        pack_region_mt(b->reader, tid, start, end, (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency())), &p->pc);
+        *out = p;
+        return 0;
+    }
     catch (const std::exception& e) { fprintf(stderr, "mkh_pack_region: %s\n", e.what()); return -1; }
 }
 void mkh_packed_free(mkh_packed* p) { delete p; }

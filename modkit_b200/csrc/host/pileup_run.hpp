@@ -371,7 +371,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             if (ce <= cs) { i0 = i1; continue; }
             const auto ta = clk::now();
             pc.clear();
-            pack_region(bam, ivs[i0].tid, cs, ce, &pc);
+            pack_region_mt(bam, ivs[i0].tid, cs, ce, o.threads, &pc);
             const auto tb = clk::now();
             S.pack_s += secs(ta, tb);
             if (pc.hdrs.empty()) { i0 = i1; continue; }
@@ -389,20 +389,41 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             S.reads_packed += pc.hdrs.size();
             S.algorithmic_bytes += pc.algorithmic_bytes() + 40 * n_rows;
             S.chunks++;
-            // rows are position sorted: hand each interval its slice
-            size_t r0 = 0;
+            // rows are position sorted: every interval gets its slice; intervals are finished and formatted in parallel
             const std::string& chrom = bam.ref_names[ivs[i0].tid];
-            text.clear();
-            for (size_t i = i0; i < i1; i++) {
-                while (r0 < n_rows && rows[r0].pos < ivs[i].start) r0++;
-                size_t r1 = r0;
-                while (r1 < n_rows && rows[r1].pos < ivs[i].end) r1++;
-                orows.clear();
-                finish_interval_rows(ivs[i], rows + r0, r1 - r0, have_motifs ? &mc.motifs : nullptr, combine_strands, &orows);
-                for (auto& orow : orows) format_bed_row(orow, chrom, fmt, &text);
-                S.rows += orows.size();
-                r0 = r1;
+            const size_t n_iv = i1 - i0;
+            std::vector<size_t> rlo(n_iv + 1);
+            {
+                size_t r0 = 0;
+                for (size_t i = i0; i < i1; i++) { while (r0 < n_rows && rows[r0].pos < ivs[i].start) r0++; rlo[i - i0] = r0; }
+                size_t r1 = rlo[n_iv - 1];
+                while (r1 < n_rows && rows[r1].pos < ivs[i1 - 1].end) r1++;
+                rlo[n_iv] = r1;
             }
+            const int nt = std::max(1, std::min<int>(o.threads, (int)n_iv));
+            std::vector<std::string> parts(nt);
+            std::vector<uint64_t> part_rows(nt, 0);
+            {
+                auto work = [&](int t) {
+                    std::vector<OutRow> local;
+                    const size_t a = n_iv * t / nt, b = n_iv * (t + 1) / nt;
+                    for (size_t k = a; k < b; k++) {
+                        const size_t r_end = k + 1 < n_iv ? std::max(rlo[k], rlo[k + 1]) : rlo[n_iv];
+                        size_t r1 = rlo[k];
+                        while (r1 < r_end && rows[r1].pos < ivs[i0 + k].end) r1++;
+                        local.clear();
+                        finish_interval_rows(ivs[i0 + k], rows + rlo[k], r1 - rlo[k], have_motifs ? &mc.motifs : nullptr, combine_strands, &local);
+                        for (auto& orow : local) format_bed_row(orow, chrom, fmt, &parts[t]);
+                        part_rows[t] += local.size();
+                    }
+                };
+                std::vector<std::thread> th;
+                for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+                work(0);
+                for (auto& t : th) t.join();
+            }
+            for (int t = 0; t < nt; t++) { fwrite(parts[t].data(), 1, parts[t].size(), out); S.rows += part_rows[t]; }
+            text.clear();
             fwrite(text.data(), 1, text.size(), out);
             S.write_s += secs(tc, clk::now());
             i0 = i1;
