@@ -53,6 +53,83 @@ public:
     }
 };
 
+// ---------------------------------------------------------------- include-bed -----------------------
+// `--include-bed` position filter (src/position_filter.rs:20-365): stranded, merged (overlapping or touching)
+// half-open intervals per contig.
+class IncludeBed {
+public:
+    struct Span { uint64_t b, e; };
+    std::map<uint32_t, std::vector<Span>> plus, minus;
+
+    static void coalesce(std::vector<Span>* v) {
+        std::sort(v->begin(), v->end(), [](const Span& x, const Span& y) { return x.b != y.b ? x.b < y.b : x.e < y.e; });
+        size_t w = 0;
+        for (size_t i = 0; i < v->size(); i++) {
+            if (w && (*v)[i].b <= (*v)[w - 1].e) (*v)[w - 1].e = std::max((*v)[w - 1].e, (*v)[i].e);
+            else (*v)[w++] = (*v)[i];
+        }
+        v->resize(w);
+    }
+    void read(const std::string& path, const std::map<std::string, uint32_t>& name_to_tid) {
+        std::ifstream f(path);
+        if (!f) throw std::runtime_error("failed to open BED file " + path);
+        std::string line, field;
+        std::map<std::string, bool> skipped;
+        while (std::getline(f, line)) {
+            std::vector<std::string> col;
+            std::istringstream ss(line);
+            while (ss >> field) col.push_back(field);
+            if (col.size() < 3 || skipped.count(col[0])) continue;
+            auto num = [](const std::string& t, uint64_t* out) { if (t.empty() || t.find_first_not_of("0123456789") != std::string::npos) return false; *out = std::stoull(t); return true; };
+            Span sp;
+            if (!num(col[1], &sp.b) || !num(col[2], &sp.e)) continue;
+            bool fw = true, rv = true;                     // BED3: both strands
+            if (col.size() >= 6) {
+                if (col[5] == "+") rv = false; else if (col[5] == "-") fw = false; else if (col[5] != ".") continue;
+            } else if (col.size() != 3) continue;          // must be BED3 or BED6+
+            auto t = name_to_tid.find(col[0]);
+            if (t == name_to_tid.end()) { skipped[col[0]] = true; continue; }
+            if (fw) plus[t->second].push_back(sp);
+            if (rv) minus[t->second].push_back(sp);
+        }
+        if (plus.empty() && minus.empty()) throw std::runtime_error("zero valid positions parsed from BED file");
+        for (auto& kv : plus) coalesce(&kv.second);
+        for (auto& kv : minus) coalesce(&kv.second);
+    }
+    static bool touches(const std::vector<Span>& v, uint64_t a, uint64_t b) {   // some span with span.b < b && span.e > a
+        size_t lo = 0, hi = v.size();
+        while (lo < hi) { size_t mid = (lo + hi) / 2; if (v[mid].b < b) lo = mid + 1; else hi = mid; }
+        return lo > 0 && v[lo - 1].e > a;
+    }
+    bool has(uint32_t tid, uint64_t p, bool minus_strand) const {
+        const auto& m = minus_strand ? minus : plus;
+        auto it = m.find(tid);
+        return it != m.end() && touches(it->second, p, p + 1);
+    }
+    bool overlaps_any(uint32_t tid, uint64_t a, uint64_t b) const {
+        auto it = plus.find(tid);
+        if (it != plus.end() && touches(it->second, a, b)) return true;
+        it = minus.find(tid);
+        return it != minus.end() && touches(it->second, a, b);
+    }
+    bool has_contig(uint32_t tid) const { return plus.count(tid) || minus.count(tid); }
+    // strand bitmaps of [cs,ce): the sampling-side position filter and FocusPositions::Regions rules
+    void bitmaps(uint32_t tid, uint32_t cs, uint32_t ce, std::vector<uint32_t>* fp, std::vector<uint32_t>* fn) const {
+        const size_t nw = ((size_t)ce - cs + 31) / 32;
+        fp->assign(nw, 0); fn->assign(nw, 0);
+        auto paint = [&](const std::map<uint32_t, std::vector<Span>>& m, std::vector<uint32_t>* bits) {
+            auto it = m.find(tid);
+            if (it == m.end()) return;
+            for (auto& sp : it->second) {
+                const uint64_t a = std::max<uint64_t>(sp.b, cs), b = std::min<uint64_t>(sp.e, ce);
+                for (uint64_t p = a; p < b; p++) (*bits)[(p - cs) >> 5] |= 1u << ((p - cs) & 31);
+            }
+        };
+        paint(plus, fp);
+        paint(minus, fn);
+    }
+};
+
 // ---------------------------------------------------------------- motifs -------------------------
 struct MotifSpec {
     std::string raw;
@@ -135,6 +212,7 @@ struct MotifContext {
     std::vector<MotifSpec> motifs;
     bool keep_case = false;   // --mask
     uint64_t longest = 0;
+    const IncludeBed* include = nullptr;   // motif hits outside the include-bed (strand-wise) are dropped (fasta.rs:55-69)
 };
 
 inline void fill_focus(RefInterval* iv, const std::vector<SiteRules>& sites, const std::vector<MotifSpec>& motifs, bool combine) {
@@ -188,6 +266,12 @@ inline uint32_t motif_interval(MotifContext& mc, const RefTarget& c, uint64_t st
         mc.fasta.slice(c.name, start, e, mc.keep_case, &seq);
         sites->assign(mc.motifs.size(), SiteRules());
         for (size_t i = 0; i < mc.motifs.size(); i++) motif_sites(seq, start, mc.motifs[i], &(*sites)[i]);
+        if (mc.include) for (auto& st : *sites) for (auto it = st.begin(); it != st.end();) {
+            uint8_t keep = 0;
+            if ((it->second & 1) && mc.include->has(c.tid, it->first, false)) keep |= 1;
+            if ((it->second & 2) && mc.include->has(c.tid, it->first, true)) keep |= 2;
+            if (!keep) it = st.erase(it); else { it->second = keep; ++it; }
+        }
     };
     if (!combine) { scan(end); return (uint32_t)end; }
     const uint64_t ref_end = c.end();
@@ -224,8 +308,36 @@ inline uint32_t motif_interval(MotifContext& mc, const RefTarget& c, uint64_t st
 }
 
 // ReferenceIntervalsFeeder order (src/interval_chunks.rs:563-643); `groups` = MultiChromCoordinates membership
+// optimize_reference_records (src/position_filter.rs:106-212): the targets become spans that cover runs of include-bed
+// intervals (a run is closed once it is longer than interval_size)
+inline std::vector<RefTarget> targets_from_include_bed(const IncludeBed& ib, const std::vector<RefTarget>& targets, uint32_t interval_size) {
+    std::vector<RefTarget> out;
+    std::map<uint32_t, const RefTarget*> by_tid;
+    for (auto& t : targets) by_tid[t.tid] = &t;
+    std::map<uint32_t, bool> tids;
+    for (auto& kv : ib.plus) tids[kv.first] = true;
+    for (auto& kv : ib.minus) tids[kv.first] = true;
+    for (auto& kv : tids) {
+        auto bt = by_tid.find(kv.first);
+        if (bt == by_tid.end()) continue;
+        std::vector<IncludeBed::Span> all;
+        auto a = ib.plus.find(kv.first); if (a != ib.plus.end()) all.insert(all.end(), a->second.begin(), a->second.end());
+        auto b = ib.minus.find(kv.first); if (b != ib.minus.end()) all.insert(all.end(), b->second.begin(), b->second.end());
+        IncludeBed::coalesce(&all);
+        if (all.empty()) continue;
+        IncludeBed::Span cur = all[0];
+        for (size_t i = 1; i < all.size(); i++) {
+            if (cur.e - cur.b > interval_size) { out.push_back({kv.first, (uint32_t)cur.b, (uint32_t)(cur.e - cur.b), bt->second->name}); cur = all[i]; }
+            else cur.e = all[i].e;
+        }
+        out.push_back({kv.first, (uint32_t)cur.b, (uint32_t)(cur.e - cur.b), bt->second->name});
+    }
+    return out;
+}
+
 inline std::vector<RefInterval> reference_intervals(const std::vector<RefTarget>& targets, uint32_t interval_size, bool combine,
-                                                    MotifContext* mc, std::vector<std::vector<size_t>>* groups = nullptr) {
+                                                    MotifContext* mc, std::vector<std::vector<size_t>>* groups = nullptr,
+                                                    const IncludeBed* include = nullptr) {
     std::vector<RefInterval> out;
     std::vector<size_t> grp;
     uint64_t grp_len = 0;
@@ -241,7 +353,19 @@ inline std::vector<RefInterval> reference_intervals(const std::vector<RefTarget>
                 e = std::min(motif_interval(*mc, c, at, e, combine, &sites), c.end());
                 iv.end = e;
                 fill_focus(&iv, sites, mc->motifs, combine);
-            } else iv.end = e;
+            } else {
+                iv.end = e;
+                if (include) {   // FocusPositions::new_regions / check_position (interval_chunks.rs:299-371)
+                    iv.all_positions = false;
+                    auto paint = [&](const std::map<uint32_t, std::vector<IncludeBed::Span>>& m, uint8_t bit) {
+                        auto it = m.find(c.tid);
+                        if (it == m.end()) return;
+                        for (auto& sp : it->second) { const uint64_t a = std::max<uint64_t>(sp.b, iv.start), b = std::min<uint64_t>(sp.e, iv.end); for (uint64_t p = a; p < b; p++) iv.rule[(uint32_t)p] |= bit; }
+                    };
+                    paint(include->plus, 1);
+                    paint(include->minus, 2);
+                }
+            }
             grp_len += iv.end - iv.start;
             grp.push_back(out.size());
             out.push_back(std::move(iv));

@@ -19,7 +19,7 @@ struct PileupOptions {
     bool traditional = false, combine_mods = false, combine_strands = false, mixed = false, header = false, invert_edge = false;
     float percentile = 0.1f;
     std::vector<std::string> filter_thresholds, mod_thresholds, motif_parts;
-    std::string region, sample_region, ignore, ref_fp, edge, stats_json;
+    std::string region, sample_region, ignore, ref_fp, edge, stats_json, include_bed;
     int device = 0;
     uint32_t chunk_bp = 16u << 20;     // reference span handed to the GPU per call
     bool quiet = false;
@@ -73,6 +73,7 @@ struct SamplerConfig {
     const Region* region = nullptr;
     bool include_unmapped = false;
     bool edge_on = false;
+    const IncludeBed* include = nullptr;
 };
 
 inline bool sampler_flag_ok(const uint8_t* rec, bool require_mapped) {
@@ -94,6 +95,7 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
     std::map<uint32_t, uint64_t> mapped;
     for (uint32_t t = 0; t < bam.ref_names.size(); t++) {
         if (cfg.region && (int)t != region_tid) continue;
+        if (!cfg.region && cfg.include && !cfg.include->has_contig(t)) continue;
         mapped[t] = bam.stats.n_mapped[t];
         total_mapped += bam.stats.n_mapped[t];
         total_unmapped += bam.stats.n_unmapped[t];
@@ -124,18 +126,46 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
     const bool only_mapped = !cfg.include_unmapped;
     std::map<uint32_t, size_t> so_far;
     std::unordered_set<uint64_t> selected_ids;     // record identity = offset in the stream
-    PackedChunk selected;                           // every selected read, once
     PackedChunk cand;
-    std::vector<uint8_t> contributes;
+    std::vector<uint8_t> contributes, take;
+    std::vector<uint32_t> fpos, fneg;
+    std::vector<uint64_t> batch_hist(4 * 1025);
+    memset(hist, 0, 4 * 1025 * sizeof(uint64_t));
+    if (inexact) *inexact = 0;
 
-    auto decode_contributes = [&](PackedChunk& pc) {
-        contributes.assign(pc.hdrs.size(), 0);
-        if (pc.hdrs.empty()) return;
+    // One device pass decides which candidate reads contribute (MODE_HIST without a histogram); a second pass over the
+    // same resident chunk adds the values of the newly selected reads to the histogram.
+    auto upload = [&](PackedChunk& pc, uint32_t tid) {
         mkp_chunk ch;
         memset(&ch, 0, sizeof ch);
-        ch.start = 0; ch.end = 32; ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
+        ch.start = 0; ch.end = 32;
+        if (cfg.include) {
+            // chunk range = span of the candidates, bitmaps = the include-bed of this contig
+            int64_t lo = INT64_MAX, hi = 0;
+            for (auto& r : pc.recs) { lo = std::min<int64_t>(lo, r.pos); hi = std::max<int64_t>(hi, r.end); }
+            if (lo < 0) lo = 0;
+            if (hi <= lo) hi = lo + 1;
+            ch.start = (uint32_t)lo; ch.end = (uint32_t)hi;
+            cfg.include->bitmaps(tid, ch.start, ch.end, &fpos, &fneg);
+            ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data();
+        }
+        ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
         if (mkp_upload_chunk(ctx, &ch)) throw std::runtime_error(mkp_last_error(ctx));
+    };
+    auto decode_contributes = [&](PackedChunk& pc, uint32_t tid) {
+        contributes.assign(pc.hdrs.size(), 0);
+        if (pc.hdrs.empty()) return;
+        upload(pc, tid);
         if (mkp_sample_histogram(ctx, cfg.include_unmapped ? 1 : 0, nullptr, nullptr, contributes.data(), nullptr)) throw std::runtime_error(mkp_last_error(ctx));
+    };
+    auto add_selected = [&]() {       // histogram of the reads flagged in `take` (resident chunk)
+        bool any = false;
+        for (uint8_t t : take) any = any || t;
+        if (!any) return;
+        uint64_t inx = 0;
+        if (mkp_sample_histogram(ctx, cfg.include_unmapped ? 1 : 0, take.data(), batch_hist.data(), nullptr, &inx)) throw std::runtime_error(mkp_last_error(ctx));
+        for (int k = 0; k < 4 * 1025; k++) hist[k] += batch_hist[k];
+        if (inexact) *inexact += inx;
     };
 
     struct Grp { uint32_t tid, start, end; int64_t n; };
@@ -179,8 +209,9 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
             } else todo.push_back(cur);
         }
         if (have) todo.push_back(slack);
-        // candidates of every interval of this super batch in one device pass; extend while an interval is short
+        // candidates of one interval at a time: first n contributing records in file order; extend while short
         for (const Grp& g : todo) {
+            if (cfg.include && !cfg.include->overlaps_any(g.tid, g.start, g.end)) continue;
             std::vector<RecRef> recs;
             bam.for_overlapping(g.tid, g.start, g.end, [&](const RecRef& r) { if (sampler_flag_ok(bam.rec(r), only_mapped || cfg.edge_on)) recs.push_back(r); });
             size_t used = 0, cursor = 0;
@@ -188,12 +219,14 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
                 const size_t want = g.n < 0 ? recs.size() : std::min(recs.size(), cursor + (size_t)(g.n - (int64_t)used) * 2 + 32);
                 cand.clear();
                 for (size_t k = cursor; k < want; k++) { pack_record(bam.rec(recs[k]), recs[k].size, &cand); cand.recs.push_back(recs[k]); }
-                decode_contributes(cand);
+                decode_contributes(cand, g.tid);
+                take.assign(cand.hdrs.size(), 0);
                 for (size_t k = 0; k < cand.hdrs.size() && (g.n < 0 || used < (size_t)g.n); k++) {
                     if (!contributes[k]) continue;
                     used++;
-                    if (selected_ids.insert(cand.recs[k].off).second) { pack_record(bam.rec(cand.recs[k]), cand.recs[k].size, &selected); selected.recs.push_back(cand.recs[k]); }
+                    if (selected_ids.insert(cand.recs[k].off).second) take[k] = 1;
                 }
+                add_selected();
                 cursor = want;
             }
             so_far[g.tid] += used;
@@ -203,24 +236,19 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
         const size_t limit = cfg.take_all ? (size_t)-1 : (cfg.num_reads > selected_ids.size() ? cfg.num_reads - selected_ids.size() : 0);
         cand.clear();
         for (auto& r : bam.unplaced) if (sampler_flag_ok(bam.rec(r), cfg.edge_on)) { pack_record(bam.rec(r), r.size, &cand); cand.recs.push_back(r); }
-        decode_contributes(cand);
-        size_t used = 0;
-        for (size_t k = 0; k < cand.hdrs.size() && used < limit; k++) {
-            if (!contributes[k]) continue;
-            used++;
-            if (selected_ids.insert(cand.recs[k].off).second) { pack_record(bam.rec(cand.recs[k]), cand.recs[k].size, &selected); selected.recs.push_back(cand.recs[k]); }
+        if (!cand.hdrs.empty()) {
+            decode_contributes(cand, 0);
+            take.assign(cand.hdrs.size(), 0);
+            size_t used = 0;
+            for (size_t k = 0; k < cand.hdrs.size() && used < limit; k++) {
+                if (!contributes[k]) continue;
+                used++;
+                if (selected_ids.insert(cand.recs[k].off).second) take[k] = 1;
+            }
+            add_selected();
         }
     }
-    memset(hist, 0, 4 * 1025 * sizeof(uint64_t));
-    if (inexact) *inexact = 0;
-    if (!selected.hdrs.empty()) {
-        mkp_chunk ch;
-        memset(&ch, 0, sizeof ch);
-        ch.start = 0; ch.end = 32; ch.hdrs = selected.hdrs.data(); ch.n_reads = (uint32_t)selected.hdrs.size(); ch.heap = selected.heap.data(); ch.heap_bytes = selected.heap.size();
-        if (mkp_upload_chunk(ctx, &ch)) throw std::runtime_error(mkp_last_error(ctx));
-        if (mkp_sample_histogram(ctx, cfg.include_unmapped ? 1 : 0, nullptr, hist, nullptr, inexact)) throw std::runtime_error(mkp_last_error(ctx));
-    }
-    return selected.hdrs.size();
+    return selected_ids.size();
 }
 
 struct RunSummary {
@@ -248,8 +276,16 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             if (rp) { if (bam.ref_names[t] == rp->name) targets.push_back({t, rp->start, rp->end - rp->start, rp->name}); }
             else targets.push_back({t, 0, bam.ref_lens[t], bam.ref_names[t]});
         }
+        IncludeBed include;
+        const IncludeBed* inc = nullptr;
+        if (!o.include_bed.empty()) {
+            std::map<std::string, uint32_t> name_to_tid;
+            for (auto& t : targets) name_to_tid[t.name] = t.tid;
+            include.read(o.include_bed, name_to_tid);
+            inc = &include;
+        }
         uint64_t any_mapped = 0;
-        for (auto& t : targets) any_mapped += bam.stats.n_mapped[t.tid];
+        for (auto& t : targets) if (rp || !inc || inc->has_contig(t.tid)) any_mapped += bam.stats.n_mapped[t.tid];
         if (!any_mapped) throw std::runtime_error("did not find any mapped reads, perform alignment first or use modkit extract and/or modkit summary to inspect unaligned modBAMs");
         bool combine_strands = o.combine_strands;
         if (combine_strands && !(o.cpg || !o.motif_parts.empty())) throw std::runtime_error("need to specify either --motif or --cpg to combine strands");
@@ -289,6 +325,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             if (combine_strands) for (auto& m : mc.motifs) if (!m.palindromic) throw std::runtime_error("cannot combine strands with a motif that is not a palindrome");
             mc.fasta.open(o.ref_fp);
             mc.keep_case = o.mask;
+            mc.include = inc;
             for (auto& m : mc.motifs) mc.longest = std::max<uint64_t>(mc.longest, m.len);
         }
         // output first, like the reference, so a bad path fails before any work
@@ -335,6 +372,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             sc.region = srp ? srp : rp;
             sc.include_unmapped = o.include_unmapped;
             sc.edge_on = P.edge_filter_on;
+            sc.include = inc;
             std::vector<uint64_t> hist(4 * 1025);
             uint64_t inexact = 0;
             sample_histogram(bam, dev.ctx, sc, hist.data(), &inexact);
@@ -354,7 +392,8 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         if (summary) for (int b = 0; b < 4; b++) { summary->thresholds[b] = P.base_threshold[b]; summary->threshold_set[b] = P.base_threshold_set[b]; }
         const auto t_thr = clk::now();
 
-        std::vector<RefInterval> ivs = reference_intervals(targets, o.interval_size, combine_strands, have_motifs ? &mc : nullptr);
+        if (inc) targets = targets_from_include_bed(*inc, targets, o.interval_size);
+        std::vector<RefInterval> ivs = reference_intervals(targets, o.interval_size, combine_strands, have_motifs ? &mc : nullptr, nullptr, inc);
         const auto t_iv = clk::now();
         RunSummary S;
         for (auto& iv : ivs) S.positions += iv.end - iv.start;
@@ -378,7 +417,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             mkp_chunk ch;
             memset(&ch, 0, sizeof ch);
             ch.start = cs; ch.end = ce; ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
-            if (have_motifs) { focus_bitmaps(ivs, i0, i1, cs, ce, &fpos, &fneg); ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data(); }
+            if (have_motifs || inc) { focus_bitmaps(ivs, i0, i1, cs, ce, &fpos, &fneg); ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data(); }
             const mkp_row* rows = nullptr;
             size_t n_rows = 0;
             mkp_stats st;
@@ -491,7 +530,8 @@ inline bool parse_pileup_args(int argc, const char* const* argv, PileupOptions* 
             else if (a == "--gpu-chunk-bp") o->chunk_bp = (uint32_t)std::stoul(val());
             else if (a == "--stats-json") o->stats_json = val();
             else if (a == "--quiet") o->quiet = true;
-            else if (a == "--include-bed" || a == "--include-positions" || a == "--partition-tag" || a == "--bedgraph" || a == "--prefix") {
+            else if (a == "--include-bed" || a == "--include-positions") o->include_bed = val();
+            else if (a == "--partition-tag" || a == "--bedgraph" || a == "--prefix") {
                 *err = "flag " + a + " is not supported by this build (SURVEY 8f: next tier)"; return false;
             }
             else if (a.size() > 1 && a[0] == '-') { *err = "unexpected argument '" + a + "' found"; return false; }

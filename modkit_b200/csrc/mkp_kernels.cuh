@@ -972,7 +972,18 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                             }
                                         }
                                     } else {
-                                        if (aligned || C.hist_include_unaligned) {
+                                        bool pass = aligned || C.hist_include_unaligned;
+                                        if (C.focus_pos) {
+                                            // --include-bed: keep only aligned positions inside the BED on the matching reference
+                                            // strand (read_ids_to_base_mod_probs.rs:1020-1047); chunk bitmaps hold the BED
+                                            pass = false;
+                                            if (aligned && rpos >= C.cs && rpos < C.ce) {
+                                                const uint32_t x = rpos - C.cs;
+                                                const uint32_t* bm = ((st == 0) == rev) ? C.focus_neg : C.focus_pos;
+                                                pass = (bm[x >> 5] >> (x & 31)) & 1u;
+                                            }
+                                        }
+                                        if (pass) {
                                             hist_ok = true; hist_v = argmax_items(*use, ord); hist_base = tb;
                                             if (imp_lists[st][b]) imp_explicit[st * 4 + b]++;
                                         }
@@ -1042,7 +1053,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                 } else {
                     // values: argmax of an all-zero map = canonical probability 1.0 for every passing inferred position
                     unsigned long long n_pass = 0;
-                    if (C.hist_include_unaligned) {
+                    if (C.hist_include_unaligned && !C.focus_pos) {
                         for (uint32_t q = lane; q < L; q += 32) {
                             if (seq_nibble(seq, q) != xn) continue;
                             const uint32_t f = rev ? L - 1u - q : q;
@@ -1051,7 +1062,8 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                             if (keep) n_pass++;
                         }
                     } else {
-                        uint32_t qc2 = 0;
+                        uint32_t qc2 = 0, rc2 = (uint32_t)h.ref_start;
+                        const uint32_t* bm = C.focus_pos ? (((s == 0) == rev) ? C.focus_neg : C.focus_pos) : nullptr;
                         for (uint32_t i = 0; i < h.n_cigar; i++) {
                             const uint32_t c = cig[i], op = c & 15, len = c >> 4;
                             if (op == 0 || op == 7 || op == 8) {
@@ -1061,10 +1073,15 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                     const uint32_t f = rev ? L - 1u - q : q;
                                     bool keep = true;
                                     if (c_par.edge_on) keep = c_par.edge_inv ? (f < c_par.edge_start || f >= L - c_par.edge_end) : (f >= c_par.edge_start && f < L - c_par.edge_end);
+                                    if (keep && bm) {
+                                        const uint32_t r = rc2 + k;
+                                        keep = r >= C.cs && r < C.ce && ((bm[(r - C.cs) >> 5] >> ((r - C.cs) & 31)) & 1u);
+                                    }
                                     if (keep) n_pass++;
                                 }
                             }
                             if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) qc2 += len;
+                            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rc2 += len;
                         }
                     }
                     n_pass = __reduce_add_sync(FULL, (uint32_t)n_pass);

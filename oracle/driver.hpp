@@ -20,6 +20,63 @@ struct RefRecord { uint32_t tid, start, length; std::string name; uint32_t end()
 
 struct Region { std::string name; uint32_t start, end; };
 
+// StrandedPositionFilter (src/position_filter.rs:20-365): per contig, merged [start,stop) intervals per strand.
+// rust-lapper merge_overlaps joins intervals that overlap or touch.
+struct PositionFilter {
+    typedef std::vector<std::pair<uint64_t, uint64_t>> Ivs;
+    std::map<uint32_t, Ivs> pos, neg;
+    static void merge(Ivs* v) {
+        std::sort(v->begin(), v->end());
+        Ivs out;
+        for (auto& iv : *v) { if (!out.empty() && !(out.back().second < iv.first)) out.back().second = std::max(out.back().second, iv.second); else out.push_back(iv); }
+        v->swap(out);
+    }
+    static bool hit(const Ivs& v, uint64_t a, uint64_t b) {   // any interval with start < b && stop > a
+        auto it = std::lower_bound(v.begin(), v.end(), std::make_pair(b, (uint64_t)0));
+        while (it != v.begin()) { --it; if (it->second > a) return it->first < b; if (it->second <= a) break; }
+        return false;
+    }
+    void load(const std::string& path, const std::map<std::string, uint32_t>& chrom_to_tid) {   // from_bed_file :244-345
+        std::ifstream f(path);
+        if (!f) throw std::runtime_error("failed to open BED " + path);
+        std::string line;
+        std::set<std::string> warned;
+        while (std::getline(f, line)) {
+            if (line.empty()) continue;
+            std::istringstream ss(line);
+            std::vector<std::string> parts;
+            std::string tok;
+            while (ss >> tok) parts.push_back(tok);
+            if (parts.size() < 3 || warned.count(parts[0])) continue;
+            uint64_t a, b;
+            try { size_t k; a = std::stoull(parts[1], &k); if (k != parts[1].size()) continue; b = std::stoull(parts[2], &k); if (k != parts[2].size()) continue; } catch (...) { continue; }
+            bool p, n;
+            if (parts.size() == 3) p = n = true;
+            else if (parts.size() >= 6) { if (parts[5] == "+") { p = true; n = false; } else if (parts[5] == "-") { p = false; n = true; } else if (parts[5] == ".") p = n = true; else continue; }
+            else continue;
+            auto it = chrom_to_tid.find(parts[0]);
+            if (it == chrom_to_tid.end()) { warned.insert(parts[0]); continue; }
+            if (p) pos[it->second].push_back({a, b});
+            if (n) neg[it->second].push_back({a, b});
+        }
+        if (pos.empty() && neg.empty()) throw std::runtime_error("zero valid positions parsed from BED file");
+        for (auto& kv : pos) merge(&kv.second);
+        for (auto& kv : neg) merge(&kv.second);
+    }
+    bool contains(uint32_t tid, uint64_t p, bool negative) const {
+        const auto& m = negative ? neg : pos;
+        auto it = m.find(tid);
+        return it != m.end() && hit(it->second, p, p + 1);
+    }
+    bool overlaps(uint32_t tid, uint64_t a, uint64_t b) const {
+        auto it = pos.find(tid);
+        if (it != pos.end() && hit(it->second, a, b)) return true;
+        it = neg.find(tid);
+        return it != neg.end() && hit(it->second, a, b);
+    }
+    bool has_contig(uint32_t tid) const { return pos.count(tid) || neg.count(tid); }
+};
+
 inline Region parse_region(const std::string& raw, const BamFile& bam) {  // util.rs:475-523
     Region r;
     auto c = raw.find(':');
@@ -53,6 +110,49 @@ inline std::vector<RefRecord> get_targets(const BamFile& bam, const Region* regi
         else out.push_back({tid, 0, bam.ref_lens[tid], bam.ref_names[tid]});
     }
     return out;
+}
+
+// optimize_reference_records / group_genome_intervals (src/position_filter.rs:106-212)
+inline std::vector<RefRecord> optimize_reference_records(const PositionFilter& pf, const std::vector<RefRecord>& recs, uint32_t interval_size) {
+    std::map<uint32_t, RefRecord> lut;
+    for (auto& r : recs) lut[r.tid] = r;
+    std::set<uint32_t> tids;
+    for (auto& kv : pf.pos) tids.insert(kv.first);
+    for (auto& kv : pf.neg) tids.insert(kv.first);
+    std::vector<RefRecord> out;
+    for (uint32_t tid : tids) {
+        auto lr = lut.find(tid);
+        if (lr == lut.end()) continue;
+        PositionFilter::Ivs all;
+        auto a = pf.pos.find(tid); if (a != pf.pos.end()) all.insert(all.end(), a->second.begin(), a->second.end());
+        auto b = pf.neg.find(tid); if (b != pf.neg.end()) all.insert(all.end(), b->second.begin(), b->second.end());
+        PositionFilter::merge(&all);
+        if (all.empty()) continue;
+        std::vector<std::pair<uint64_t, uint64_t>> agg;
+        auto cur = all[0];
+        for (size_t i = 1; i < all.size(); i++) {
+            if (cur.second - cur.first > interval_size) { agg.push_back(cur); cur = all[i]; continue; }
+            cur.second = all[i].second;
+        }
+        agg.push_back(cur);
+        for (auto& g : agg) out.push_back({tid, (uint32_t)g.first, (uint32_t)(g.second - g.first), lr->second.name});
+    }
+    return out;
+}
+
+// FocusPositions::new_regions + check_position (src/interval_chunks.rs:299-371)
+inline void focus_from_regions(const PositionFilter& pf, uint32_t tid, uint32_t start, uint32_t end, Focus* f) {
+    f->all = false;
+    auto add = [&](const std::map<uint32_t, PositionFilter::Ivs>& m, uint8_t bit) {
+        auto it = m.find(tid);
+        if (it == m.end()) return;
+        for (auto& iv : it->second) {
+            uint64_t a = std::max<uint64_t>(iv.first, start), b = std::min<uint64_t>(iv.second, end);
+            for (uint64_t p = a; p < b; p++) f->rule[(uint32_t)p] |= bit;
+        }
+    };
+    add(pf.pos, 1);
+    add(pf.neg, 2);
 }
 
 // --- focus positions ------------------------------------------------------------------------
@@ -111,11 +211,24 @@ struct MotifLookup {
     std::vector<Motif> motifs;
     bool mask = false;
     uint64_t longest = 0;
+    const PositionFilter* pf = nullptr;
+    uint32_t cur_tid = 0;
+    // motif hits are restricted to the include-bed positions of the matching strand (src/fasta.rs:55-69)
+    void apply_filter(std::vector<MotifLocs>* locs) const {
+        if (!pf) return;
+        for (auto& l : *locs) for (auto it = l.begin(); it != l.end();) {
+            uint8_t r = it->second, keep = 0;
+            if ((r & 1) && pf->contains(cur_tid, it->first, false)) keep |= 1;
+            if ((r & 2) && pf->contains(cur_tid, it->first, true)) keep |= 2;
+            if (!keep) it = l.erase(it); else { it->second = keep; ++it; }
+        }
+    }
     std::string prep(std::string s) const { if (!mask) for (char& c : s) c = (char)toupper((unsigned char)c); return s; }
     // returns interval end (fasta.rs:192-226 / 92-188)
     uint32_t positions(const std::string& contig, uint64_t ref_end, uint64_t start, uint64_t end, bool combine, std::vector<MotifLocs>* out) {
         if (!combine) {
             *out = motifs_on_seq(prep(fa.fetch(contig, start, end)), start, motifs);
+            apply_filter(out);
             return (uint32_t)end;
         }
         uint64_t buffer = longest * 5;
@@ -124,6 +237,7 @@ struct MotifLookup {
         uint64_t too_close = ewb >= longest ? ewb - longest : 0;
         while (true) {
             std::vector<MotifLocs> locs = motifs_on_seq(prep(fa.fetch(contig, start, ewb)), start, motifs);
+            apply_filter(&locs);
             // merged motif intervals (rust-lapper merge_overlaps: touching intervals merge)
             std::vector<std::pair<uint64_t, uint64_t>> ivs;
             for (size_t id = 0; id < locs.size(); id++) {
@@ -156,7 +270,7 @@ struct MotifLookup {
 // grouping into MultiChromCoordinates (only the sampler needs it).
 inline std::vector<Interval> make_intervals(const std::vector<RefRecord>& contigs, uint32_t interval_size,
                                             bool combine_strands, MotifLookup* lookup,
-                                            std::vector<std::vector<size_t>>* batches = nullptr) {
+                                            std::vector<std::vector<size_t>>* batches = nullptr, const PositionFilter* pf = nullptr) {
     std::vector<Interval> out;
     std::vector<size_t> batch;
     uint64_t batch_len = 0;
@@ -171,12 +285,14 @@ inline std::vector<Interval> make_intervals(const std::vector<RefRecord>& contig
             iv.start = start;
             if (lookup) {
                 std::vector<MotifLocs> locs;
+                lookup->cur_tid = c.tid;
                 end = lookup->positions(c.name, c.end(), start, end, combine_strands, &locs);
                 end = std::min(end, c.end());
                 iv.end = end;
                 focus_from_locs(locs, lookup->motifs, start, end, combine_strands, &iv.focus);
             } else {
                 iv.end = end;
+                if (pf) focus_from_regions(*pf, c.tid, start, end, &iv.focus);
             }
             batch_len += iv.end > iv.start ? iv.end - iv.start : 0;
             batch.push_back(out.size());
@@ -216,6 +332,7 @@ struct SampleOptions {
     bool collapse = false;
     ModCode collapse_code = 0;
     EdgeFilter edge;
+    const PositionFilter* pf = nullptr;
 };
 
 // values (argmax probabilities) per canonical base from one record; false when the record contributes nothing
@@ -237,7 +354,13 @@ inline bool sample_record(const BamRecord& r, const SampleOptions& o, std::vecto
         for (auto& kv : info.tab[s][b].pos) {
             uint32_t f = kv.first;
             if (o.edge.on && !o.edge.keep(f, (size_t)L)) continue;
-            if (only_mapped) { int q = rev ? L - 1 - (int)f : (int)f; if (q < 0 || q >= L || q2r[q] < 0) continue; }
+            int64_t rpos = -1;
+            if (only_mapped) { int q = rev ? L - 1 - (int)f : (int)f; if (q < 0 || q >= L || q2r[q] < 0) continue; rpos = q2r[q]; }
+            if (o.pf) {   // filter_positions: aligned position on the matching reference strand (read_ids_to_base_mod_probs.rs:1020-1047)
+                if (rpos < 0) continue;
+                const bool neg_strand = (s == 0) == rev;
+                if (!o.pf->contains((uint32_t)r.tid(), (uint64_t)rpos, neg_strand)) continue;
+            }
             BaseModProbs bmp = o.collapse ? redistribute(kv.second, o.collapse_code) : kv.second;
             vals[cb].push_back(argmax_prob(bmp));
             kept++;
@@ -265,6 +388,7 @@ inline void estimate_thresholds(const BamFile& bam, const SampleOptions& o, floa
     uint64_t total_mapped = 0, total_unmapped = 0;
     for (uint32_t t = 0; t < bam.ref_names.size(); t++) {
         if (o.region && (int)t != region_tid) continue;
+        if (!o.region && o.pf && !o.pf->has_contig(t)) continue;
         mapped[t] = bam.n_mapped[t];
         total_mapped += bam.n_mapped[t];
         total_unmapped += bam.n_unmapped[t];
@@ -343,6 +467,7 @@ inline void estimate_thresholds(const BamFile& bam, const SampleOptions& o, floa
         if (have_slack) grouped.push_back(slack);
         // 5. per interval: first n contributing admissible records in file order
         for (const Grp& g : grouped) {
+            if (o.pf && !o.pf->overlaps(g.tid, g.start, g.end)) continue;
             size_t used = 0, returned = 0;
             std::unordered_set<const uint8_t*> seen_here;
             std::vector<const BamRecord*> cands;

@@ -92,7 +92,7 @@ int main(int argc, char** argv) {
         bool traditional = false, combine_mods = false, combine_strands = false, mixed = false, header = false, invert_edge = false;
         float percentile = 0.1f;
         std::vector<std::string> filter_thresholds, mod_thresholds, motif_parts;
-        std::string region_s, sample_region_s, ignore_s, ref_fp, edge_s, timing_fp;
+        std::string region_s, sample_region_s, ignore_s, ref_fp, edge_s, timing_fp, include_bed;
         for (int i = 2; i < argc; i++) {
             std::string a = argv[i];
             auto val = [&]() -> std::string { if (i + 1 >= argc) die("missing value for " + a); return argv[++i]; };
@@ -124,6 +124,7 @@ int main(int argc, char** argv) {
             else if (a == "--mixed-delim" || a == "--mixed-delimiters") mixed = true;
             else if (a == "--header" || a == "--with-header" || a == "--include_header") header = true;
             else if (a == "--timing-json") timing_fp = val();
+            else if (a == "--include-bed" || a == "--include-positions") include_bed = val();
             else if (a.size() > 1 && a[0] == '-' && a != "-") die("unsupported flag " + a);
             else pos.push_back(a);
         }
@@ -138,9 +139,17 @@ int main(int argc, char** argv) {
         if (!region_s.empty()) { region = parse_region(region_s, bam); rp = &region; }
         if (!sample_region_s.empty()) { sample_region = parse_region(sample_region_s, bam); srp = &sample_region; }
         std::vector<RefRecord> targets = get_targets(bam, rp);
+        PositionFilter pfilter;
+        const PositionFilter* pf = nullptr;
+        if (!include_bed.empty()) {
+            std::map<std::string, uint32_t> c2t;
+            for (auto& t : targets) c2t[t.name] = t.tid;
+            pfilter.load(include_bed, c2t);
+            pf = &pfilter;
+        }
         {
             uint64_t mapped = 0;
-            for (auto& t : targets) mapped += bam.n_mapped[t.tid];
+            for (auto& t : targets) if (rp || !pf || pf->has_contig(t.tid)) mapped += bam.n_mapped[t.tid];
             if (!mapped) die("did not find any mapped reads, perform alignment first or use modkit extract and/or modkit summary to inspect unaligned modBAMs");
         }
         if (percentile > 1.0f) die("filter percentile must be <= 1.0");
@@ -191,6 +200,7 @@ int main(int argc, char** argv) {
             lookup.fa.open(ref_fp);
             lookup.motifs = motifs;
             lookup.mask = mask;
+            lookup.pf = pf;
             for (auto& m : motifs) lookup.longest = std::max<uint64_t>(lookup.longest, m.length);
         }
         // thresholds
@@ -221,12 +231,14 @@ int main(int argc, char** argv) {
             so.collapse = threshold_collapse;
             so.collapse_code = P.collapse_code;
             so.edge = P.edge;
+            so.pf = pf;
             estimate_thresholds(bam, so, percentile, &P.caller);
             for (int b = 0; b < 4; b++) if (P.caller.base_set[b]) fprintf(stderr, "> Using filter threshold %.9g for %c.\n", P.caller.base_thr[b], BASES[b]);
         }
         auto t_thr = std::chrono::steady_clock::now();
 
-        std::vector<Interval> ivs = make_intervals(targets, interval_size, combine_strands, have_motifs ? &lookup : nullptr);
+        if (pf) targets = optimize_reference_records(*pf, targets, interval_size);
+        std::vector<Interval> ivs = make_intervals(targets, interval_size, combine_strands, have_motifs ? &lookup : nullptr, nullptr, pf);
         uint64_t total_positions = 0;
         for (auto& iv : ivs) total_positions += iv.end - iv.start;
         auto t_ivs = std::chrono::steady_clock::now();

@@ -69,13 +69,23 @@ SYNTH_CASES = [
     ("two_contigs_region", ["--contig", "c1:90000", "--contig", "c2:130000", "--coverage", 15, "--mods", "m", "--seed", 16], ["--region", "c2:20000-100000", "-i", "30011"]),
     ("multi_contig_motifs", ["--contig", "c1:60000", "--contig", "c2:80000", "--contig", "c3:500", "--coverage", 15, "--mods", "hma", "--seed", 17],
      ["--motif", "CG", "0", "--motif", "GATC", "1", "--motif", "A", "0", "--ref", "@FA", "--no-filtering"]),
+    ("include_bed", ["--contig", "c1:150000", "--contig", "c2:90000", "--coverage", 20, "--mods", "hm", "--seed", 18], ["--include-bed", "@BED", "-i", "20000", "-n", "300"]),
+    ("include_bed_cpg_combine", ["--contig", "c1:150000", "--coverage", 20, "--mods", "hm", "--seed", 19], ["--include-bed", "@BED", "--cpg", "--combine-strands", "--ref", "@FA", "-p", "0.2"]),
 ]
 
 
 @pytest.mark.parametrize("name,gen,flags", SYNTH_CASES, ids=[c[0] for c in SYNTH_CASES])
 def test_gpu_matches_oracle_on_synthetic(name, gen, flags, native_lib, oracle_exe, synth_exe, tmp_path):
     prefix, info = synth(synth_exe, tmp_path, name, *gen)
-    flags = [prefix + ".fa" if f == "@FA" else f for f in flags]
+    bed = str(tmp_path / "include.bed")
+    with open(bed, "w") as fh:   # stranded, unstranded (BED3) and overlapping intervals, one contig the BAM does not have
+        for name, length in (("c1", 150000), ("c2", 90000), ("chrNope", 1000)):
+            for k, s0 in enumerate(range(1000, length - 2000, 4700)):
+                strand = "+-."[k % 3]
+                fh.write("%s\t%d\t%d\n" % (name, s0, s0 + 900) if k % 5 == 4 else "%s\t%d\t%d\tx\t0\t%s\n" % (name, s0, s0 + 700 + 300 * (k % 2), strand))
+                if k % 7 == 0:
+                    fh.write("%s\t%d\t%d\tx\t0\t+\n" % (name, s0 + 500, s0 + 1500))
+    flags = [prefix + ".fa" if f == "@FA" else bed if f == "@BED" else f for f in flags]
     exp = run_oracle(oracle_exe, flags, prefix + ".bam", str(tmp_path / "o.bed"))
     rc, got = run_product(flags, prefix + ".bam", str(tmp_path / "g.bed"))
     assert rc == 0
