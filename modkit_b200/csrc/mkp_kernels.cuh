@@ -834,15 +834,23 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
         uint2* calls = C.calls + meta.entry_off;
         if (!err && any_entries) {
             const bool trim_ok = !c_par.edge_on || !(L <= c_par.edge_start || L <= c_par.edge_end);
+            bool imp_any = false;
+            for (int k = 0; k < 8; k++) imp_any = imp_any || imp_lists[k >> 2][k & 3];
+            uint32_t skip_mask = 0;       // lists whose every entry sits at the same index of an earlier same-strand list
             for (uint32_t l = 0; l < nl && !err; l++) {
+                if ((skip_mask >> l) & 1u) continue;    // all its entries are absorbed (basecallers repeat one delta list per code)
                 const uint32_t n = T.n_delta[l];
                 const uint32_t* Pl = P + T.ent_off[l];
                 const uint32_t st = T.strand[l];
                 const uint8_t lfb = T.base[l];
                 const int lb = lfb == 'A' ? 0 : lfb == 'C' ? 1 : lfb == 'G' ? 2 : (lfb == 'T' || lfb == 'U') ? 3 : 4;
+                uint32_t lnext = 0xffffffffu;           // nearest later list of the same strand with entries
+                for (uint32_t l2 = nl; l2-- > l + 1;) if (T.strand[l2] == st && T.n_delta[l2]) lnext = l2;
+                uint32_t cnt_next = 0;
                 for (uint32_t j0 = 0; j0 < n; j0 += 32) {
                     uint32_t j = j0 + lane;
                     bool active = j < n;
+                    bool matched_next = false;
                     bool emit = false;
                     uint32_t rpos = 0, info = 0;
                     bool e2 = false;
@@ -900,7 +908,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                 const uint32_t* P2 = P + T.ent_off[l2];
                                 const uint32_t n2 = T.n_delta[l2];
                                 uint32_t k;
-                                if (j < n2 && P2[j] == f) k = j;
+                                if (j < n2 && P2[j] == f) { k = j; if (l2 == lnext) matched_next = true; }
                                 else { k = lower_bound_u32(P2, n2, f); if (!(k < n2 && P2[k] == f)) continue; }
                                 // per-list table first (add_base_mod_prob), then combine_checked into the aggregate
                                 Items t2;
@@ -993,6 +1001,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                         }
                     }
                     err = __any_sync(FULL, e2) || err;
+                    cnt_next += __popc(__ballot_sync(FULL, matched_next));
                     if (MODE == MODE_PILEUP) {
                         uint32_t em = __ballot_sync(FULL, emit);
                         if (emit) calls[n_calls + __popc(em & ((1u << lane) - 1u))] = make_uint2(rpos, info);
@@ -1011,6 +1020,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                         n_hist += __popc(hm);
                     }
                 }
+                if (!imp_any && lnext != 0xffffffffu && T.base[lnext] != 'N' && T.n_delta[lnext] == cnt_next) skip_mask |= 1u << lnext;
             }
         }
         // ---- phase 4b: implicit tables (every other occurrence of the base is an inferred-canonical entry) ----
