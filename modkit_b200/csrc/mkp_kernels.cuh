@@ -358,10 +358,10 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* P, uint32_t 
 // Kernel A: per read, everything that depends only on the read's own bytes: admission, reference span, MM list
 // discovery, per-base occurrence counts, MM token parse + select -> forward positions P[] and the list table.
 #ifndef MKP_MINB_PARSE
-#define MKP_MINB_PARSE 1
+#define MKP_MINB_PARSE 8
 #endif
 #ifndef MKP_MINB_RESOLVE
-#define MKP_MINB_RESOLVE 1
+#define MKP_MINB_RESOLVE 7
 #endif
 #ifndef MKP_MINB_BASES
 #define MKP_MINB_BASES 8
