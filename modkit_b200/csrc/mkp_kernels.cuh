@@ -837,6 +837,23 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
             bool imp_any = false;
             for (int k = 0; k < 8; k++) imp_any = imp_any || imp_lists[k >> 2][k & 3];
             uint32_t skip_mask = 0;       // lists whose every entry sits at the same index of an earlier same-strand list
+            // register-only fast path: no implicit tables, no 'N' list, and per strand either one list with <= 2 codes or two
+            // single-code lists
+#ifdef MKP_NO_FAST_RESOLVE
+            bool fast_read = false;
+#else
+            bool fast_read = !imp_any;
+#endif
+            {
+                uint32_t cnt[2] = {0, 0}, maxc[2] = {0, 0};
+                for (uint32_t l2 = 0; l2 < nl; l2++) {
+                    if (T.base[l2] == 'N') fast_read = false;
+                    if (!T.n_delta[l2]) continue;
+                    cnt[T.strand[l2]]++;
+                    maxc[T.strand[l2]] = max(maxc[T.strand[l2]], (uint32_t)T.ncodes[l2]);
+                }
+                for (int s2 = 0; s2 < 2; s2++) if (!(cnt[s2] <= 1 ? maxc[s2] <= 2 : (cnt[s2] == 2 && maxc[s2] == 1))) fast_read = false;
+            }
             for (uint32_t l = 0; l < nl && !err; l++) {
                 if ((skip_mask >> l) & 1u) continue;    // all its entries are absorbed (basecallers repeat one delta list per code)
                 const uint32_t n = T.n_delta[l];
@@ -893,6 +910,87 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                             if (k < n2 && P2[k] == f) owner = false;
                         }
                         if (owner && !e2) {
+                            const int tb = st == 0 ? b : 3 - b;
+                            uint32_t mask = 0, ccode = 0;      // observed states, called code
+                            int kind = 0;                      // 0 filtered, 1 canonical, 2 modified
+                            float hv = 0.f;                    // arg-max value (histogram mode)
+                            if (fast_read) {
+                                // ---- register-only path: at most two codes at the position (one list with <= 2 codes, or
+                                //      two single-code lists of the strand). Same arithmetic as the generic path below.
+                                uint32_t c0 = T.code[l][0], c1 = 0;
+                                float p0, p1 = 0.f;
+                                int n2c = 1;
+                                {
+                                    const uint8_t* mlq = ml + T.ml_off[l] + (size_t)j * T.ncodes[l];
+                                    p0 = __fdiv_rn(__fadd_rn((float)mlq[0], 0.5f), 256.0f);
+                                    if (T.ncodes[l] == 2) {
+                                        const float pb = __fdiv_rn(__fadd_rn((float)mlq[1], 0.5f), 256.0f);
+                                        const uint32_t cb = T.code[l][1];
+                                        if (cb == c0) { if (__fadd_rn(p0, pb) > 1.01f) e2 = true; else p0 = __fadd_rn(p0, pb); }
+                                        else { c1 = cb; p1 = pb; n2c = 2; }
+                                    }
+                                }
+                                if (lnext != 0xffffffffu && !e2) {       // the strand's other list (single code by construction)
+                                    const uint32_t* P2 = P + T.ent_off[lnext];
+                                    const uint32_t nn = T.n_delta[lnext];
+                                    uint32_t k = j;
+                                    bool found = j < nn && P2[j] == f;
+                                    if (found) matched_next = true;
+                                    else { k = lower_bound_u32(P2, nn, f); found = k < nn && P2[k] == f; }
+                                    if (found) {
+                                        const float pn = __fdiv_rn(__fadd_rn((float)ml[T.ml_off[lnext] + k], 0.5f), 256.0f);
+                                        const uint32_t cn = T.code[lnext][0];
+                                        if (cn == c0) p0 = __fadd_rn(p0, pn);
+                                        else { c1 = cn; p1 = pn; n2c = 2; }
+                                        if ((n2c == 2 ? __fadd_rn(p0, p1) : p0) > 1.01f) e2 = true;   // combine_checked
+                                    }
+                                }
+                                if (!e2) {
+                                    if (c_par.numeric_mode == 2) {       // ReDistribute (mod_bam.rs:558-600)
+                                        const uint32_t drop = c_par.collapse_code;
+                                        if (n2c == 1) {
+                                            if (c0 == drop) n2c = 0;
+                                            else p0 = __fadd_rn(p0, __fdiv_rn(0.f, 2.0f));
+                                        } else if (c0 == drop) { c0 = c1; p0 = __fadd_rn(p1, __fdiv_rn(p0, 2.0f)); n2c = 1; }
+                                        else if (c1 == drop) { p0 = __fadd_rn(p0, __fdiv_rn(p1, 2.0f)); n2c = 1; }
+                                        else { const float sh = __fdiv_rn(0.f, 3.0f); p0 = __fadd_rn(p0, sh); p1 = __fadd_rn(p1, sh); }
+                                    }
+                                    // FxHashMap iteration order of the (<= 2) codes
+                                    if (n2c == 2) {
+                                        const uint32_t b0 = bucket4(c0), b1 = bucket4(c1);
+                                        if (b0 != b1 ? (b1 < b0) : (b0 == 3)) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float tp = p0; p0 = p1; p1 = tp; }
+                                    }
+                                    const float sum = n2c == 0 ? 0.f : n2c == 1 ? __fadd_rn(0.f, p0) : __fadd_rn(__fadd_rn(0.f, p0), p1);
+                                    const float cp = __fsub_rn(1.0f, sum);
+                                    if (MODE == MODE_PILEUP) {
+                                        if (n2c >= 1) mask |= 1u << state_id(C, scache, tb, c0);
+                                        if (n2c == 2) mask |= 1u << state_id(C, scache, tb, c1);
+                                        const float base_thr = c_par.base_set[tb] ? c_par.base_thr[tb] : c_par.default_thr;
+                                        bool have = false;
+                                        float best = 0.f;
+                                        for (int k2 = 0; k2 < n2c; k2++) {
+                                            const uint32_t cc = k2 == 0 ? c0 : c1;
+                                            const float pp = k2 == 0 ? p0 : p1;
+                                            float thr = base_thr;
+                                            if (c_par.n_mod_thr) {
+                                                const uint32_t any_code = (uint32_t)("ACGT"[tb]);
+                                                bool fnd = false;
+                                                for (uint32_t t = 0; t < c_par.n_mod_thr && !fnd; t++) if (c_par.mod_code[t] == cc) { thr = c_par.mod_thr[t]; fnd = true; }
+                                                for (uint32_t t = 0; t < c_par.n_mod_thr && !fnd; t++) if (c_par.mod_code[t] == any_code) { thr = c_par.mod_thr[t]; fnd = true; }
+                                            }
+                                            if (pp >= thr && (!have || pp >= best)) { have = true; best = pp; kind = 2; ccode = cc; }
+                                        }
+                                        if (cp >= base_thr && (!have || cp >= best)) { have = true; kind = 1; }
+                                        if (!have) kind = 0;
+                                    } else {
+                                        float mp = 0.f;
+                                        bool hm2 = false;
+                                        if (n2c >= 1) { mp = p0; hm2 = true; }
+                                        if (n2c == 2 && p1 >= mp) mp = p1;
+                                        hv = (hm2 && mp > cp) ? mp : cp;
+                                    }
+                                }
+                            } else {
                             Items m;
                             m.n = 0;
                             int ord[MAX_MAP];
@@ -931,17 +1029,23 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                 if (!e2) { iter_order(m, ord); if (items_sum(m, ord) > 1.01f) e2 = true; }
                             }
                             if (!e2) {
-                                const int tb = st == 0 ? b : 3 - b;
+                                iter_order(m, ord);
+                                Items mc;
+                                const Items* use = &m;
+                                if (c_par.numeric_mode == 2) { redistribute_items(m, ord, c_par.collapse_code, mc); iter_order(mc, ord); use = &mc; }
+                                if (MODE == MODE_PILEUP) {
+                                    for (int k2 = 0; k2 < use->n; k2++) mask |= 1u << state_id(C, scache, tb, use->code[k2]);
+                                    kind = make_call_items(*use, ord, tb, &ccode);
+                                } else hv = argmax_items(*use, ord);
+                            }
+                            }
+                            if (!e2) {
                                 bool keep = trim_ok;
                                 if (keep && c_par.edge_on) {
                                     if (c_par.edge_inv) keep = f < c_par.edge_start || f >= L - c_par.edge_end;
                                     else keep = f >= c_par.edge_start && f < L - c_par.edge_end;
                                 }
                                 if (keep) {
-                                    iter_order(m, ord);
-                                    Items mc;
-                                    const Items* use = &m;
-                                    if (c_par.numeric_mode == 2) { redistribute_items(m, ord, c_par.collapse_code, mc); iter_order(mc, ord); use = &mc; }
                                     // aligned?  largest i with cq[i] <= q
                                     uint32_t lo = 0, hi = h.n_cigar;
                                     bool aligned = false;
@@ -952,8 +1056,6 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                         if ((op == 0 || op == 7 || op == 8) && q - qs < len) { aligned = true; rpos = cr[lo] + (q - qs); }
                                     }
                                     if (MODE == MODE_PILEUP) {
-                                        uint32_t mask = 0;
-                                        for (int k2 = 0; k2 < use->n; k2++) mask |= 1u << state_id(C, scache, tb, use->code[k2]);
                                         // (mod strand, read orientation) -> reference strand (read_cache.rs:181-188)
                                         if ((st == 0) != rev) pos_mask |= mask; else neg_mask |= mask;
                                         table_survived = true;
@@ -962,9 +1064,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                             bool focus = true;
                                             if (C.focus_pos) focus = ((C.focus_pos[x >> 5] | C.focus_neg[x >> 5]) >> (x & 31)) & 1u;
                                             if (focus) {
-                                                uint32_t code = 0;
-                                                const int kind = make_call_items(*use, ord, tb, &code);
-                                                const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, code);
+                                                const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, ccode);
                                                 // does a '+' list cover the same position (both pos_call and neg_call present)?
                                                 uint32_t nosub = 0;
                                                 if (st == 1) {
@@ -992,7 +1092,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                             }
                                         }
                                         if (pass) {
-                                            hist_ok = true; hist_v = argmax_items(*use, ord); hist_base = tb;
+                                            hist_ok = true; hist_v = hv; hist_base = tb;
                                             if (imp_lists[st][b]) imp_explicit[st * 4 + b]++;
                                         }
                                     }
