@@ -296,11 +296,10 @@ __device__ __forceinline__ float argmax_items(const Items& it, const int* ord) {
 
 // Registry of (primary base, mod code) states. A per-thread 4-entry cache keeps the hot path off the (single,
 // heavily shared) global table: every warp asking L2 for the same sector serialises at one slice.
-struct StateCache {
-    unsigned long long key[4];
-    int id[4];
-    int next;
-    __device__ void init() { for (int i = 0; i < 4; i++) { key[i] = ~0ull; id[i] = 0; } next = 0; }
+struct StateCache {      // two most recent (key -> id) pairs, in registers
+    unsigned long long k0, k1;
+    int i0, i1;
+    __device__ void init() { k0 = k1 = ~0ull; i0 = i1 = 0; }
 };
 
 __device__ __noinline__ int state_id_global(const ChunkDev& C, unsigned long long key) {
@@ -319,10 +318,10 @@ __device__ __noinline__ int state_id_global(const ChunkDev& C, unsigned long lon
 
 __device__ __forceinline__ int state_id(const ChunkDev& C, StateCache& sc, int pb, uint32_t code) {
     const unsigned long long key = ((unsigned long long)pb << 32) | code;
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (sc.key[i] == key) return sc.id[i];
+    if (sc.k0 == key) return sc.i0;
+    if (sc.k1 == key) return sc.i1;
     const int id = state_id_global(C, key);
-    sc.key[sc.next] = key; sc.id[sc.next] = id; sc.next = (sc.next + 1) & 3;
+    sc.k1 = sc.k0; sc.i1 = sc.i0; sc.k0 = key; sc.i0 = id;
     return id;
 }
 
