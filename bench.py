@@ -335,7 +335,7 @@ def main():
                 pass
             peak = float(peaks.get("hbm_gbs", 6650.0))
             alg = pk.algorithmic_bytes + 40 * n_rows
-            names = ["parse", "resolve", "rank", "count_calls", "count_bases", "rows", "host_sync_alloc"]
+            names = ["parse", "resolve", "rank", "unused", "count_calls+count_bases", "rows", "host_sync_alloc"]
             dom = int(np.argmax(stage[:6]))
             ach = alg / (stage[dom] * 1e-3) / 1e9
             # CPU baseline on the same box: bounded window of the same workload, all host cores
