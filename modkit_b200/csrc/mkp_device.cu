@@ -299,7 +299,8 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
         // kernel_ms: 0 parse, 1 resolve, 2 rank, 3 count_calls, 4 count_bases, 5 rows (count+scan+emit), 6 host syncs/allocs, 7 total
         auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
         stats->kernel_ms[0] = el(0, 1); stats->kernel_ms[1] = el(1, 2); stats->kernel_ms[2] = el(2, 3);
-        stats->kernel_ms[3] = 0.f; stats->kernel_ms[4] = el(4, 6);   // count_calls overlaps count_bases: [4] is the pair stats->kernel_ms[5] = el(6, 7) + el(8, 9);
+        stats->kernel_ms[3] = 0.f; stats->kernel_ms[4] = el(4, 6);   // count_calls overlaps count_bases: [4] is the pair
+        stats->kernel_ms[5] = el(6, 7) + el(8, 9);
         stats->kernel_ms[6] = el(3, 4) + el(7, 8); stats->kernel_ms[7] = el(0, 9);
     }
     return 0;
