@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
     __shared__ ListTab s_tab[4];
     __shared__ __align__(16) uint8_t s_txt[4][160];
     __shared__ uint8_t s_tok[4][132];
-    __shared__ uint32_t s_cum[4][2][CUM_CAP + 1];
+    __shared__ uint32_t s_cb[4][32], s_bm[4][32], s_tp[4][MAX_LISTS];
     __shared__ uint32_t s_val[4][64];
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
         __syncwarp();
         if (T.n == 0xffffffffu) err = true;
         const uint32_t nl = err ? 0 : T.n;
-        // ---- phase 2: per-base cumulative counts over SEQ (query order), 32 bases per lane --------
-        uint32_t need = 0;   // nibble-bases needed: bit x for nibble-base index x (0..3 = A C G T in SEQ)
+        // ---- which bases need rank/select over the SEQ (query-order nibble index x: 0..3 = A C G T as stored) ----
+        uint32_t need = 0;
         for (uint32_t l = 0; l < nl; l++) {
             uint8_t fb = T.base[l];
             if (fb == 'N') continue;
@@ -497,46 +497,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
             need |= 1u << x;
         }
         const uint32_t nblk = (L + 31) >> 5;
-        // occurrence-count tables: shared memory for up to two bases of reads up to CUM_CAP blocks, else global scratch
-        uint32_t* cump[4];
-        {
-            int slot = 0;
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                cump[x] = cum + x * (C.max_blocks + 1);
-                if ((need & (1u << x)) && nblk <= CUM_CAP && slot < 2) cump[x] = s_cum[wib][slot++];
-            }
-        }
-        if (need) {
-            uint32_t run[4] = {0, 0, 0, 0};
-            const uint32_t* seqw = (const uint32_t*)seq;   // 4-byte aligned
-            const uint32_t nbytes = (L + 1) >> 1;
-            for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
-                uint32_t blk = b0 + lane;
-                uint32_t cnt[4] = {0, 0, 0, 0};
-                if (blk < nblk) {
-#pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        uint32_t byte0 = blk * 16 + w * 4;
-                        if (byte0 >= nbytes) break;
-                        uint32_t word = seqw[blk * 4 + w];   // may read past the SEQ end inside the read block; masked below
-                        uint32_t valid_bytes = nbytes - byte0;
-                        if (valid_bytes < 4) word &= (1u << (8 * valid_bytes)) - 1u;
-                        // an odd-length read has a zero low nibble in its last byte (nibble 0 is '=')
-#pragma unroll
-                        for (int x = 0; x < 4; x++) if (need & (1u << x)) cnt[x] += __popc(nib_eq_flags(word, 1u << x));
-                    }
-                }
-#pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    if (!(need & (1u << x))) continue;
-                    uint32_t inc = warp_incl_scan(cnt[x]);
-                    if (blk < nblk) cump[x][blk] = run[x] + inc - cnt[x];
-                    run[x] += __shfl_sync(FULL, inc, 31);
-                }
-            }
-            if (lane == 0) for (int x = 0; x < 4; x++) { T.tot[x] = run[x]; if (need & (1u << x)) cump[x][nblk] = run[x]; }
-        }
+        if (lane < 4) T.tot[lane] = 0;
         __syncwarp();
         // ---- phase 3: tokens -> forward positions ------------------------------------------------------
         uint32_t* P = C.P + meta.entry_off;
@@ -548,52 +509,21 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
             int x = -1;
             uint32_t tot = 0;
             if (fb != 'N') { int b = fb == 'A' ? 0 : fb == 'C' ? 1 : fb == 'G' ? 2 : 3; x = rev ? 3 - b : b; tot = T.tot[x]; }
-            const uint32_t* cx = x >= 0 ? cump[x] : nullptr;
             unsigned long long carry = 0;     // sum of (d+1) so far
             uint32_t ntok = 0;
             // delta values of up to 32 tokens (one per lane, `mine` lanes in token order) -> forward positions P[]
+            // delta values of up to 32 tokens (one per lane, `mine` lanes in token order) -> 0-based occurrence index of the
+            // list's base in forward-read order (for 'N' lists that already is the forward position); stored in P[] and
+            // turned into positions by the streaming pass below
             auto place = [&](unsigned long long val, bool mine, uint32_t keep_mask) {
                 const unsigned long long inc = mine ? (val + 1ull) : 0ull;
                 const unsigned long long pre = warp_incl_scan64(inc);
                 const uint32_t idx = ntok + __popc(keep_mask & ((1u << lane) - 1u));
                 bool bad = false;
                 if (mine) {
-                    const unsigned long long k = carry + pre - 1ull;   // 0-based occurrence index (forward order)
-                    uint32_t f = 0;
-                    if (fb == 'N') {
-                        f = (uint32_t)k;
-                        if (k >= (unsigned long long)L) bad = true;
-                    } else if (k >= (unsigned long long)tot) {
-                        bad = true;
-                    } else {
-                        const uint32_t kq = rev ? tot - 1u - (uint32_t)k : (uint32_t)k;   // occurrence index in query order
-                        uint32_t lo = 0, hi = nblk;   // invariant: cx[lo] <= kq < cx[hi]
-                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cx[mid] <= kq) lo = mid; else hi = mid; }
-                        uint32_t within = kq - cx[lo];
-                        const uint32_t* sw = (const uint32_t*)seq + lo * 4;
-                        const uint32_t nbytes = (L + 1) >> 1;
-                        uint32_t bm = 0;                                 // occurrences of the base in this 32-base block
-#pragma unroll
-                        for (int w = 0; w < 4; w++) {
-                            const uint32_t byte0 = lo * 16 + w * 4;
-                            if (byte0 >= nbytes) continue;
-                            uint32_t word = sw[w];
-                            const uint32_t vb = nbytes - byte0;
-                            if (vb < 4) word &= (1u << (8 * vb)) - 1u;
-                            bm |= nib_flags_to_mask(nib_eq_flags(word, 1u << x)) << (8 * w);
-                        }
-                        // position of the (within+1)-th set bit
-                        uint32_t pos = 0, c;
-                        c = __popc(bm & 0xffffu); if (within >= c) { within -= c; pos += 16; bm >>= 16; }
-                        c = __popc(bm & 0xffu);   if (within >= c) { within -= c; pos += 8;  bm >>= 8; }
-                        c = __popc(bm & 0xfu);    if (within >= c) { within -= c; pos += 4;  bm >>= 4; }
-                        c = __popc(bm & 0x3u);    if (within >= c) { within -= c; pos += 2;  bm >>= 2; }
-                        c = bm & 1u;              if (within >= c) { pos += 1; }
-                        const uint32_t q = lo * 32 + pos;
-                        if (q >= L) bad = true;
-                        f = rev ? L - 1u - q : q;
-                    }
-                    if (!bad) P[ent + idx] = f;
+                    const unsigned long long k = carry + pre - 1ull;
+                    if (k >= (unsigned long long)L) bad = true;          // past the last base whatever the base is
+                    else P[ent + idx] = (uint32_t)k;
                 }
                 if (__any_sync(FULL, bad)) err = true;
                 carry += __shfl_sync(FULL, pre, 31);
@@ -718,6 +648,94 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
             ent += ntok;
             __syncwarp();
         }
+        // ---- streaming select: for every needed base, one pass over the SEQ in forward-read order (32 bases per lane:
+        //      occurrence mask by SWAR nibble compare, warp scan of the popcounts) during which the tokens of all lists of
+        //      that base are placed: a token with occurrence index k lands in the block whose running count brackets k
+        //      (5-step search over the 32 counts in shared memory), at the (k - count)-th set bit of its mask.
+        if (!err && need) {
+            const uint32_t* seqw = (const uint32_t*)seq;   // 4-byte aligned
+            const uint32_t nbytes = (L + 1) >> 1;
+            for (int x = 0; x < 4 && !err; x++) {
+                if (!(need & (1u << x))) continue;
+                const int bfw = rev ? 3 - x : x;                        // forward base of this nibble
+                uint32_t lists = 0;                                      // lists whose base is bfw
+                for (uint32_t l = 0; l < nl; l++) {
+                    const uint8_t fb = T.base[l];
+                    const int b = fb == 'A' ? 0 : fb == 'C' ? 1 : fb == 'G' ? 2 : (fb == 'T' || fb == 'U') ? 3 : 4;
+                    if (b == bfw) lists |= 1u << l;
+                }
+                if (lane < MAX_LISTS) s_tp[wib][lane] = 0;
+                __syncwarp();
+                uint32_t run = 0;                                        // occurrences in the blocks already streamed
+                for (uint32_t i0 = 0; i0 < nblk; i0 += 32) {
+                    const uint32_t bi = i0 + lane;                       // index in streaming (forward-read) order
+                    const bool valid = bi < nblk;
+                    const uint32_t blk = rev ? nblk - 1u - bi : bi;      // block in query order
+                    uint32_t bm = 0;
+                    if (valid) {
+#pragma unroll
+                        for (int w = 0; w < 4; w++) {
+                            const uint32_t byte0 = blk * 16 + w * 4;
+                            if (byte0 >= nbytes) continue;
+                            uint32_t word = seqw[blk * 4 + w];
+                            const uint32_t vb = nbytes - byte0;
+                            if (vb < 4) word &= (1u << (8 * vb)) - 1u;
+                            bm |= nib_flags_to_mask(nib_eq_flags(word, 1u << x)) << (8 * w);
+                        }
+                    }
+                    const uint32_t cnt = __popc(bm);
+                    const uint32_t incl = warp_incl_scan(cnt);
+                    s_cb[wib][lane] = run + incl - cnt;
+                    s_bm[wib][lane] = bm;
+                    const uint32_t hi = run + __shfl_sync(FULL, incl, 31);      // tokens with index in [run, hi) live here
+                    __syncwarp();
+                    uint32_t ls = lists;
+                    while (ls) {
+                        const uint32_t l = __ffs(ls) - 1;
+                        ls &= ls - 1;
+                        const uint32_t n = T.n_delta[l];
+                        uint32_t* Kp = P + T.ent_off[l];
+                        uint32_t tp = s_tp[wib][l];
+                        while (tp < n) {
+                            const uint32_t t = tp + lane;
+                            const uint32_t kv = t < n ? Kp[t] : 0xffffffffu;
+                            const bool in = t < n && kv < hi;
+                            if (in) {
+                                // largest b with s_cb[b] <= kv
+                                uint32_t lo = 0, hb = 32;
+#pragma unroll
+                                for (int st = 0; st < 5; st++) { const uint32_t mid = (lo + hb) >> 1; if (s_cb[wib][mid] <= kv) lo = mid; else hb = mid; }
+                                uint32_t msk = s_bm[wib][lo];
+                                uint32_t within = kv - s_cb[wib][lo];
+                                if (rev) within = __popc(msk) - 1u - within;          // forward order runs down the query
+                                uint32_t pos = 0, c;
+                                c = __popc(msk & 0xffffu); if (within >= c) { within -= c; pos += 16; msk >>= 16; }
+                                c = __popc(msk & 0xffu);   if (within >= c) { within -= c; pos += 8;  msk >>= 8; }
+                                c = __popc(msk & 0xfu);    if (within >= c) { within -= c; pos += 4;  msk >>= 4; }
+                                c = __popc(msk & 0x3u);    if (within >= c) { within -= c; pos += 2;  msk >>= 2; }
+                                c = msk & 1u;              if (within >= c) { pos += 1; }
+                                const uint32_t bq = rev ? nblk - 1u - (i0 + lo) : i0 + lo;
+                                const uint32_t q = bq * 32 + pos;
+                                Kp[t] = rev ? L - 1u - q : q;
+                            }
+                            const uint32_t c_in = __popc(__ballot_sync(FULL, in));
+                            tp += c_in;
+                            if (c_in < 32) break;
+                        }
+                        __syncwarp();
+                        if (lane == 0) s_tp[wib][l] = tp;
+                    }
+                    run = hi;
+                    __syncwarp();
+                }
+                if (lane == 0) T.tot[x] = run;
+                // a token left unplaced refers to an occurrence past the end of the read (mod_bam.rs:705-727)
+                uint32_t ls = lists;
+                while (ls) { const uint32_t l = __ffs(ls) - 1; ls &= ls - 1; if (s_tp[wib][l] < T.n_delta[l]) err = true; }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
         // '.'/default-mode lists (src/read_cache.rs:122-137, src/mod_bam.rs:1041-1043, 1265-1292)
         bool any_entries = ent > 0;
         uint32_t imp_lists[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // lists that infer canonical on (strand, base)
