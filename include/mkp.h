@@ -105,7 +105,7 @@ typedef struct {          /* per-chunk counters, filled by mkp_pileup_* */
 #define MKP_DERR_TOO_MANY_STATES   1u   /* > 32 distinct (base,code) states                      */
 #define MKP_DERR_TOO_MANY_LISTS    2u   /* > 16 MM lists in one read                             */
 #define MKP_DERR_TOO_MANY_CODES    4u   /* > 4 codes at one read position                        */
-#define MKP_DERR_IMPLICIT_MODE     8u   /* '.'/default-mode list needing implicit fill (not yet on device) */
+#define MKP_DERR_IMPLICIT_MODE     8u   /* reserved (implicit '.'/default-mode fill is done on the device)      */
 
 int  mkp_create(int device, mkp_ctx** out);
 void mkp_destroy(mkp_ctx* ctx);
@@ -135,7 +135,8 @@ int  mkp_pileup_chunk(mkp_ctx* ctx, const mkp_chunk* host_chunk, const mkp_row**
 int  mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* take,
                           uint64_t* hist, uint8_t* contributes, uint64_t* inexact);
 
-/* Device pointers of the resident histogram for an NCCL all-reduce by the caller. */
+/* SURVEY §8(d) algorithmic bytes of a chunk: sum over reads of 32 + 4 n_cigar + ceil(l_seq/2) + len_mm + len_ml,
+ * plus 40 bytes per emitted row (roofline accounting only). */
 size_t mkp_algorithmic_bytes(const mkp_chunk* chunk, size_t n_rows);
 
 #ifdef __cplusplus
