@@ -123,6 +123,8 @@ def main():
     ap.add_argument("--contig-len", type=int, default=CONTIG_LEN)
     ap.add_argument("--coverage", type=float, default=COVERAGE)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--workdir", default=None, help="(development) reuse/keep the generated workload in this directory")
+    ap.add_argument("--skip-cpu", action="store_true", help="(development, A/B runs) leave cpu_baseline out")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -178,10 +180,18 @@ def main():
     synth, oracle = os.path.join(ROOT, "tools", "_build", "synth_modbam"), os.path.join(ROOT, "oracle", "_build", "modkit_oracle")
     modkit_b200.load_library(build_if_missing=False)
     d = workdir(rank)
+    if a.workdir:
+        d = a.workdir; os.makedirs(d, exist_ok=True); a.keep = True
     try:
         t0 = time.time()
         threads = max(4, min(64, nproc // max(1, world)))
-        prefix, info = gen_workload(synth, d, rank, a.contig_len, a.coverage, threads=threads)
+        info_path = os.path.join(d, "w%d.info.json" % rank)
+        if a.workdir and os.path.exists(info_path):
+            prefix, info = os.path.join(d, "w%d" % rank), json.load(open(info_path))
+        else:
+            prefix, info = gen_workload(synth, d, rank, a.contig_len, a.coverage, threads=threads)
+            if a.workdir:
+                json.dump(info, open(info_path, "w"))
         contig = "syn%d" % (rank + 1)
         t_gen = time.time() - t0
         t0 = time.time()
@@ -340,7 +350,7 @@ def main():
             ach = alg / (stage[dom] * 1e-3) / 1e9
             # CPU baseline on the same box: bounded window of the same workload, all host cores
             window = min(CPU_WINDOW, a.contig_len)
-            cpu_v, cpu_t = cpu_reference_run(oracle, prefix, contig, window, thr, nproc)
+            cpu_v, cpu_t = (0.0, {"pileup_s": 0.0, "load_s": 0.0}) if a.skip_cpu else cpu_reference_run(oracle, prefix, contig, window, thr, nproc)
             line = {"metric": "genomic positions/sec to bedMethyl", "value": value, "unit": "positions/s", "n_gpus": world, "steps": a.steps,
                     "warmup": a.warmup, "ms_per_step": 1e3 * t_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                     "dtype": "u32 counts (f32 probabilities)", "data": "synthetic", "config": workload, "impl": "b200",

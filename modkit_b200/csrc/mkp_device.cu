@@ -49,7 +49,7 @@ struct mkp_ctx {
     uint32_t max_ncigar = 1, max_blocks = 1;
     uint64_t heap_bytes = 0;
     // work buffers
-    DevBuf d_rl, d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr, d_scr_cum;
+    DevBuf d_rl, d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr;
     DevBuf d_obs_word, d_slots, d_row_counts, d_row_prefix, d_rows, d_hist, d_take;
     // results
     size_t n_rows = 0;
@@ -93,7 +93,7 @@ void mkp_destroy(mkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_rl, &ctx->d_meta, &ctx->d_P,
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr,
-                      &ctx->d_scr_cum, &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take};
+                      &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -180,7 +180,6 @@ static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
     CK(ctx->d_small.ensure(SMALL_BYTES));
     CK(ctx->d_scr_cq.ensure(nwarps * ctx->max_ncigar * 4));
     CK(ctx->d_scr_cr.ensure(nwarps * ctx->max_ncigar * 4));
-    CK(ctx->d_scr_cum.ensure(nwarps * 4 * ((size_t)ctx->max_blocks + 1) * 4));
     memset(C, 0, sizeof *C);
     C->hdrs = ctx->d_hdrs.as<mkp_read_hdr>(); C->heap = ctx->d_heap.as<uint8_t>(); C->entry_off = ctx->d_entry_off.as<uint64_t>();
     C->n_reads = ctx->n_reads; C->cs = ctx->cs; C->ce = ctx->ce;
@@ -193,7 +192,7 @@ static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
     C->hist_inexact = C->states + 33;
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
     C->n_states = u; C->err = u + 1; C->work = u + 4;
-    C->scr_cq = ctx->d_scr_cq.as<uint32_t>(); C->scr_cr = ctx->d_scr_cr.as<uint32_t>(); C->scr_cum = ctx->d_scr_cum.as<uint32_t>();
+    C->scr_cq = ctx->d_scr_cq.as<uint32_t>(); C->scr_cr = ctx->d_scr_cr.as<uint32_t>();
     C->max_ncigar = ctx->max_ncigar; C->max_blocks = ctx->max_blocks;
     C->rl = ctx->d_rl.as<ReadLists>();
     return 0;

@@ -80,7 +80,7 @@ struct ChunkDev {
     uint32_t* work;             // dynamic read counter
     unsigned long long* total_calls;
     // per-warp scratch
-    uint32_t* scr_cq; uint32_t* scr_cr; uint32_t* scr_cum;
+    uint32_t* scr_cq; uint32_t* scr_cr;
     uint32_t max_ncigar, max_blocks;
     // sampling
     unsigned long long* hist;   // [4][1025]
@@ -370,13 +370,10 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
     __shared__ __align__(16) uint8_t s_txt[4][160];
     __shared__ uint8_t s_tok[4][132];
     __shared__ uint32_t s_cb[4][32], s_bm[4][32], s_tp[4][MAX_LISTS];
-    __shared__ uint32_t s_val[4][64];
+    __shared__ uint32_t s_val[4][96];
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     ListTab& T = s_tab[wib];
-    uint32_t* cum = C.scr_cum + (size_t)gw * 4 * (C.max_blocks + 1);
 
     for (;;) {
         // dynamic work distribution: reads differ in length by 2-3 orders of magnitude
@@ -465,18 +462,36 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
                 seg = j + 1;
                 hdr_end = 0xffffffffu;
             };
-            for (uint32_t c0 = 0; c0 < M && !err; c0 += 32) {
-                const uint32_t i = c0 + lane;
-                const uint8_t ch = i < M ? mm[i] : 0;
-                const uint32_t semi = __ballot_sync(FULL, ch == ';'), comma = __ballot_sync(FULL, ch == ',');
+            // four text bytes per lane (one aligned word), 128 per round; SWAR byte compare gives a 0x80 flag per
+            // matching byte, the first flagged byte at or after a given offset is a warp min-reduction
+            const int iM = (int)M;
+            for (int c0 = -(int)((uintptr_t)mm & 3u); c0 < iM && !err; c0 += 128) {
+                const int g0 = c0 + 4 * (int)lane;
+                uint32_t zs = 0, zc = 0;
+                if (g0 < iM && g0 + 4 > 0) {
+                    const uint32_t w = *(const uint32_t*)(mm + g0);
+                    const uint32_t xs = w ^ 0x3b3b3b3bu, xc = w ^ 0x2c2c2c2cu;
+                    zs = ~(((xs & 0x7f7f7f7fu) + 0x7f7f7f7fu) | xs | 0x7f7f7f7fu);
+                    zc = ~(((xc & 0x7f7f7f7fu) + 0x7f7f7f7fu) | xc | 0x7f7f7f7fu);
+                    uint32_t keepm = 0xffffffffu;
+                    if (g0 < 0) keepm &= 0xffffffffu << (8 * (-g0));
+                    if (g0 + 4 > iM) keepm &= 0xffffffffu >> (8 * (g0 + 4 - iM));
+                    zs &= keepm; zc &= keepm;
+                }
+                if (hdr_end != 0xffffffffu && !__any_sync(FULL, zs != 0)) continue;
+                // offset (0..127 in this round, 128 = none) of the first flagged byte at or after offset t
+                auto first_from = [&](uint32_t z, uint32_t t) -> uint32_t {
+                    const uint32_t lb = 4 * lane;
+                    if (t > lb) z = t - lb >= 4 ? 0u : (z & (0xffffffffu << (8 * (t - lb))));
+                    const uint32_t cand = z ? lb + (((uint32_t)__ffs(z) - 1u) >> 3) : 128u;
+                    return __reduce_min_sync(FULL, cand);
+                };
                 uint32_t lo = 0;
-                while (lo < 32) {
-                    const uint32_t keep = FULL << lo;
-                    const uint32_t sm = semi & keep, cm = comma & keep;
-                    const uint32_t sp = sm ? (uint32_t)__ffs(sm) - 1 : 32u, cp = cm ? (uint32_t)__ffs(cm) - 1 : 32u;
-                    if (hdr_end == 0xffffffffu && cp < sp) hdr_end = c0 + cp;
-                    if (sp == 32) break;
-                    close_part(c0 + sp);
+                while (lo < 128) {
+                    const uint32_t sp = first_from(zs, lo);
+                    if (hdr_end == 0xffffffffu) { const uint32_t cp = first_from(zc, lo); if (cp < sp) hdr_end = (uint32_t)(c0 + (int)cp); }
+                    if (sp == 128) break;
+                    close_part((uint32_t)(c0 + (int)sp));
                     lo = sp + 1;
                 }
             }
@@ -505,10 +520,6 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
         for (uint32_t l = 0; l < nl && !err; l++) {
             const uint32_t ds = T.d_start[l], de = T.d_end[l];
             const bool must = T.n_delta[l] == 0xffffffffu;
-            const uint8_t fb = T.base[l];
-            int x = -1;
-            uint32_t tot = 0;
-            if (fb != 'N') { int b = fb == 'A' ? 0 : fb == 'C' ? 1 : fb == 'G' ? 2 : 3; x = rev ? 3 - b : b; tot = T.tot[x]; }
             unsigned long long carry = 0;     // sum of (d+1) so far
             uint32_t ntok = 0;
             // delta values of up to 32 tokens (one per lane, `mine` lanes in token order) -> forward positions P[]
@@ -529,52 +540,71 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
                 carry += __shfl_sync(FULL, pre, 31);
                 ntok += __popc(keep_mask);
             };
-            // ---- fast path: the text is exactly digits(,digits)* with <= 9 digits per number. One byte per lane, the
-            //      number in progress is carried by a warp scan of affine maps v -> 10 v + d (reset at ','); finished
-            //      numbers are compacted into a small queue and placed 32 at a time. Anything else (white space, empty
-            //      or over-long tokens, other bytes) falls back to the exact nom-equivalent path below.
+            // ---- fast path: the text is exactly digits(,digits)* with <= 9 digits per number. Four text bytes per lane
+            //      (one aligned word), 128 per round. The number in progress is an affine map v -> 10 v + d (reset at
+            //      ','): every lane composes its four bytes, a TRUNCATED warp scan (distance 1 and 2: three lanes = 12
+            //      bytes back) gives the value / digit count entering the lane, which is exact for numbers of <= 9
+            //      digits, and any 10th digit is seen by the same window and sends the list to the exact path.
+            //      Finished numbers (<= 2 per lane) are compacted into a queue and placed 32 at a time. Anything else
+            //      (white space, empty or over-long tokens, other bytes) falls back to the exact path below.
             bool slow = false;
             if (must) {
                 uint32_t* qv = s_val[wib];
                 uint32_t qn = 0, v_carry = 0, nd_carry = 0;
-                uint8_t prev_last = ',';                      // byte before the current 32-byte window
-                for (uint32_t c0 = ds; c0 < de && !slow && !err; c0 += 32) {
-                    const uint32_t g = c0 + lane;
-                    const bool in = g < de;
-                    const uint8_t ch = in ? mm[g] : 0;
-                    const bool dig = in && is_digit(ch), com = in && ch == ',';
-                    uint8_t nxt = __shfl_down_sync(FULL, ch, 1);
-                    bool nxt_in = g + 1 < de;
-                    if (lane == 31) nxt = nxt_in ? mm[g + 1] : 0;
-                    uint8_t prv = __shfl_up_sync(FULL, ch, 1);
-                    if (lane == 0) prv = prev_last;
-                    // anomalies: a byte that is neither digit nor comma; an empty token (comma after comma / at the very
-                    // start / at the very end)
-                    bool odd = in && !dig && !com;
-                    if (com && (prv == ',' || !nxt_in)) odd = true;
-                    // affine scan: value and digit count of the number ending at this byte
-                    uint32_t a = dig ? 10u : (com ? 0u : 1u), bv = dig ? (uint32_t)(ch - '0') : 0u;
-                    uint32_t ra = com ? 0u : 1u, rb = dig ? 1u : 0u;
+                const int ids = (int)ds, ide = (int)de;
+                for (int c0 = ids - (int)((uintptr_t)(mm + ds) & 3u); c0 < ide && !slow && !err; c0 += 128) {
+                    const int g0 = c0 + 4 * (int)lane;
+                    const uint32_t w = g0 < ide ? *(const uint32_t*)(mm + g0) : 0u;
+                    uint32_t nb = __shfl_down_sync(FULL, w, 1) & 0xffu;
+                    if (lane == 31) nb = g0 + 4 < ide ? mm[g0 + 4] : 0u;
+                    const uint32_t wn = (w >> 8) | (nb << 24);        // byte j = the byte after byte j of w
+                    bool odd = false;
+                    uint32_t A = 1, B = 0, R = 1u << 16;              // v_out = A v_in + B; R = carries_in << 16 | digits
+                    uint32_t dm = 0, cm = 0, em = 0;                  // per byte: digit, comma, last digit of a number
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t pa = __shfl_up_sync(FULL, a, d), pb = __shfl_up_sync(FULL, bv, d);
-                        const uint32_t pra = __shfl_up_sync(FULL, ra, d), prb = __shfl_up_sync(FULL, rb, d);
-                        if (lane >= (uint32_t)d) { bv = a * pb + bv; a = a * pa; rb = ra * prb + rb; ra = ra * pra; }
+                    for (int j = 0; j < 4; j++) {
+                        const int g = g0 + j;
+                        const bool in = g >= ids && g < ide, nin = g + 1 < ide;
+                        const uint32_t ch = (w >> (8 * j)) & 0xffu, nx = (wn >> (8 * j)) & 0xffu;
+                        const bool dig = in && (ch - '0') < 10u, com = in && ch == ',';
+                        // anomalies: a byte that is neither digit nor comma; an empty token (comma at the very start,
+                        // before another comma, or at the very end)
+                        if (in && !dig && !com) odd = true;
+                        if (com && (!nin || nx == ',' || g == ids)) odd = true;
+                        if (dig) { B = B * 10u + (ch - '0'); A *= 10u; R += 1u; dm |= 1u << j; if (!nin || nx == ',') em |= 1u << j; }
+                        if (com) { A = 0; B = 0; R = 0; cm |= 1u << j; }
                     }
-                    const uint32_t val = a * v_carry + bv, nd = ra * nd_carry + rb;
-                    if (dig && nd > 9) odd = true;
-                    const bool ends = dig && (!nxt_in || nxt == ',');          // last digit of a number
+                    if (lane == 0) { B = A * v_carry + B; if (R >> 16) R += nd_carry; A = 0; R &= 0xffffu; }   // absorb the carry
+#pragma unroll
+                    for (int d = 1; d <= 2; d <<= 1) {
+                        const uint32_t pA = __shfl_up_sync(FULL, A, d), pB = __shfl_up_sync(FULL, B, d), pR = __shfl_up_sync(FULL, R, d);
+                        if (lane >= (uint32_t)d) { B = A * pB + B; A = A * pA; if (R >> 16) R = pR + (R & 0xffffu); }
+                    }
+                    uint32_t v = __shfl_up_sync(FULL, B, 1), n = __shfl_up_sync(FULL, R, 1) & 0xffffu;   // entering this lane
+                    if (lane == 0) { v = v_carry; n = nd_carry; }
+                    uint32_t e0 = 0, e1 = 0, ec = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if ((dm >> j) & 1u) {
+                            v = v * 10u + (((w >> (8 * j)) & 0xffu) - '0'); n++;
+                            if (n > 9) odd = true;
+                            if ((em >> j) & 1u) { if (ec == 0) e0 = v; else e1 = v; ec++; }
+                        } else if ((cm >> j) & 1u) { v = 0; n = 0; }
+                    }
                     if (__any_sync(FULL, odd)) { slow = true; break; }
-                    const uint32_t em = __ballot_sync(FULL, ends);
-                    if (ends) qv[qn + __popc(em & ((1u << lane) - 1u))] = val;
-                    qn += __popc(em);
-                    v_carry = __shfl_sync(FULL, val, 31); nd_carry = __shfl_sync(FULL, nd, 31);
-                    prev_last = __shfl_sync(FULL, ch, 31);
+                    const uint32_t m1 = __ballot_sync(FULL, ec >= 1), m2 = __ballot_sync(FULL, ec == 2);
+                    const uint32_t lt = (1u << lane) - 1u;
+                    const uint32_t at = qn + __popc(m1 & lt) + __popc(m2 & lt);
+                    if (ec >= 1) qv[at] = e0;
+                    if (ec == 2) qv[at + 1] = e1;
+                    qn += __popc(m1) + __popc(m2);
+                    v_carry = __shfl_sync(FULL, v, 31); nd_carry = __shfl_sync(FULL, n, 31);
                     __syncwarp();
-                    if (qn >= 32) {
-                        place(qv[lane], true, FULL);
-                        const uint32_t rest = qn - 32;
-                        const uint32_t mv = lane < rest ? qv[32 + lane] : 0;
+                    uint32_t qh = 0;
+                    while (qn - qh >= 32 && !err) { place(qv[qh + lane], true, FULL); qh += 32; }
+                    if (qh) {
+                        const uint32_t rest = qn - qh;
+                        const uint32_t mv = lane < rest ? qv[qh + lane] : 0;
                         __syncwarp();
                         if (lane < rest) qv[lane] = mv;
                         qn = rest;
