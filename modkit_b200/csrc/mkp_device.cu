@@ -178,8 +178,8 @@ static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
     CK(ctx->d_hot.ensure((size_t)ctx->n_words * 4 + 4));
     CK(ctx->d_hot_prefix.ensure((size_t)ctx->n_words * 4 + 4));
     CK(ctx->d_small.ensure(SMALL_BYTES));
-    CK(ctx->d_scr_cq.ensure(nwarps * ctx->max_ncigar * 4));
-    CK(ctx->d_scr_cr.ensure(nwarps * ctx->max_ncigar * 4));
+    CK(ctx->d_scr_cq.ensure(nwarps * ((size_t)ctx->max_ncigar + 4) * 4));
+    CK(ctx->d_scr_cr.ensure(nwarps * ((size_t)ctx->max_ncigar + 4) * 4));
     memset(C, 0, sizeof *C);
     C->hdrs = ctx->d_hdrs.as<mkp_read_hdr>(); C->heap = ctx->d_heap.as<uint8_t>(); C->entry_off = ctx->d_entry_off.as<uint64_t>();
     C->n_reads = ctx->n_reads; C->cs = ctx->cs; C->ce = ctx->ce;
@@ -234,7 +234,7 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     if (ctx->n_reads) k_resolve<MODE_PILEUP><<<grid, 128, 0, st>>>(C);
     CK(cudaEventRecord(ctx->ev[2], st));
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);   // n_states, err, n_hot, n_rows
-    k_block_popc<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>());
+    k_block_popc<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.focus_pos, C.focus_neg);
     k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 2);
     k_word_prefix<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.hot_prefix);
     CK(cudaEventRecord(ctx->ev[3], st));

@@ -26,6 +26,7 @@ constexpr int MAX_MAP = 7;          // codes at one read position
 constexpr int MAX_STATES = 32;
 constexpr int CUM_CAP = 512;        // 32-base blocks whose occurrence counts fit in shared memory (reads <= 16 kb)
 constexpr int CQ_CAP = 640;         // CIGAR ops whose prefix sums fit in shared memory per warp
+constexpr int QT_CAP = 512;         // buckets of the query -> op table
 constexpr uint32_t FULL = 0xffffffffu;
 
 // slot layout (u32 words)
@@ -399,20 +400,15 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
         const uint8_t* seq = C.heap + h.off + 4ull * h.n_cigar;
         const uint8_t* ml = seq + ((L + 1) >> 1);
         const uint8_t* mm = ml + h.len_ml;
-        // ---- phase 0: CIGAR prefix ------------------------------------------------------------
+        // ---- phase 0: reference span (k_resolve builds the per-op prefix; here only the end is needed) ----
         {
-            uint32_t qc = 0, rc = (uint32_t)h.ref_start;
-            for (uint32_t b = 0; b < h.n_cigar; b += 32) {
-                uint32_t i = b + lane;
-                uint32_t c = i < h.n_cigar ? cig[i] : 0;
-                uint32_t op = c & 15, len = c >> 4;
-                uint32_t ql = (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ? len : 0;
-                uint32_t rl = (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ? len : 0;
-                uint32_t qi = warp_incl_scan(ql), rr = warp_incl_scan(rl);
-                qc += __shfl_sync(FULL, qi, 31);
-                rc += __shfl_sync(FULL, rr, 31);
+            uint32_t rsum = 0;
+#pragma unroll 4
+            for (uint32_t i = lane; i < h.n_cigar; i += 32) {
+                const uint32_t c = cig[i], op = c & 15;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rsum += c >> 4;
             }
-            meta.ref_end = (int32_t)rc;
+            meta.ref_end = (int32_t)((uint32_t)h.ref_start + __reduce_add_sync(FULL, rsum));
         }
         bool err = (h.flags & MKP_RF_TAGS_INVALID) != 0;
         // ---- phase 1: list discovery: warp-parallel scan for ';' and the first ',' of each part; the few
@@ -817,15 +813,18 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
 template <int MODE>
 __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
     __shared__ ListTab s_tab[4];
-    __shared__ uint32_t s_cq[4][CQ_CAP], s_cr[4][CQ_CAP];   // CIGAR prefix of the current read (global scratch when longer)
+    // CIGAR prefix of the current read (global scratch when longer): s_cq = 2 * query start + (op is M/=/X), one
+    // sentinel entry 2 * query length at the end; s_cr = reference start; s_qt = op holding every (1 << shift)-th query base
+    __shared__ __align__(16) uint32_t s_cq[4][CQ_CAP + 4], s_cr[4][CQ_CAP];
+    __shared__ uint16_t s_qt[4][QT_CAP + 2];
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     ListTab& T = s_tab[wib];
     StateCache scache;
     scache.init();
-    uint32_t* const gcq = C.scr_cq + (size_t)gw * C.max_ncigar;
-    uint32_t* const gcr = C.scr_cr + (size_t)gw * C.max_ncigar;
+    uint32_t* const gcq = C.scr_cq + (size_t)gw * (C.max_ncigar + 4);
+    uint32_t* const gcr = C.scr_cr + (size_t)gw * (C.max_ncigar + 4);
 
     for (;;) {
         uint32_t ri = 0;
@@ -845,6 +844,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
         const uint32_t* cig = (const uint32_t*)(C.heap + h.off);
         uint32_t* const cq = h.n_cigar <= CQ_CAP ? s_cq[wib] : gcq;
         uint32_t* const cr = h.n_cigar <= CQ_CAP ? s_cr[wib] : gcr;
+        uint16_t* const qt = s_qt[wib];
         const uint8_t* seq = C.heap + h.off + 4ull * h.n_cigar;
         const uint8_t* ml = seq + ((L + 1) >> 1);
         uint32_t imp_lists[2][4];
@@ -856,20 +856,53 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
             for (int c = 0; c < MAX_LIST_CODES; c++) T.code[lane][c] = rec.code[c];
             T.base[lane] = rec.base; T.strand[lane] = rec.strand; T.mode[lane] = rec.mode; T.ncodes[lane] = rec.ncodes;
         }
-        // CIGAR prefix: query / reference start of every op
+        // CIGAR prefix: query / reference start of every op; four ops per lane (one 16-byte load), 128 per round
+        const uint32_t nc = h.n_cigar;
+        uint32_t q_total = 0;
         {
             uint32_t qc = 0, rc = (uint32_t)h.ref_start;
-            for (uint32_t b = 0; b < h.n_cigar; b += 32) {
-                uint32_t i = b + lane;
-                uint32_t c = i < h.n_cigar ? cig[i] : 0;
-                uint32_t op = c & 15, len = c >> 4;
-                uint32_t ql = (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ? len : 0;
-                uint32_t rl = (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ? len : 0;
-                uint32_t qi = warp_incl_scan(ql), rr = warp_incl_scan(rl);
-                if (i < h.n_cigar) { cq[i] = qc + qi - ql; cr[i] = rc + rr - rl; }
+            for (uint32_t b = 0; b < nc; b += 128) {
+                const uint32_t i = b + 4 * lane;
+                uint4 c4 = make_uint4(0, 0, 0, 0);
+                if (i < nc) c4 = *(const uint4*)(cig + i);    // 16-byte aligned; words past nc belong to the read's own block
+                const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+                uint32_t ql[4], rl[4], qs = 0, rs = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t c = i + k < nc ? cw[k] : 0u, op = c & 15, len = c >> 4;
+                    ql[k] = (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ? len : 0;
+                    rl[k] = (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ? len : 0;
+                    qs += ql[k]; rs += rl[k];
+                }
+                const uint32_t qi = warp_incl_scan(qs), rr = warp_incl_scan(rs);
+                uint32_t q0 = qc + qi - qs, r0 = rc + rr - rs;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (i + k < nc) {
+                        const uint32_t op = cw[k] & 15;
+                        cq[i + k] = 2u * q0 + ((op == 0 || op == 7 || op == 8) ? 1u : 0u);
+                        cr[i + k] = r0;
+                    }
+                    q0 += ql[k]; r0 += rl[k];
+                }
                 qc += __shfl_sync(FULL, qi, 31);
                 rc += __shfl_sync(FULL, rr, 31);
             }
+            if (lane == 0) cq[nc] = 2u * qc;
+            q_total = qc;
+        }
+        __syncwarp();
+        // query -> op table: qt[t] = the op that holds query base t << shift (the largest i with cq[i] <= that base)
+        uint32_t qt_shift = 7;
+        while (qt_shift < 31 && (q_total >> qt_shift) >= (uint32_t)QT_CAP) qt_shift++;
+        const bool use_qt = nc > 0 && nc <= 65535u;
+        if (use_qt) {
+            const uint32_t B = 1u << qt_shift;
+            for (uint32_t i = lane; i < nc; i += 32) {
+                const uint32_t s0 = cq[i] >> 1, e0 = cq[i + 1] >> 1;
+                for (uint32_t m = (s0 + B - 1) & ~(B - 1); m < e0; m += B) qt[m >> qt_shift] = (uint16_t)i;
+            }
+            if (lane == 0) qt[(q_total + B - 1) >> qt_shift] = (uint16_t)(nc - 1);
         }
         __syncwarp();
         uint32_t* P = C.P + meta.entry_off;
@@ -981,11 +1014,14 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                     const uint32_t* P2 = P + T.ent_off[lnext];
                                     const uint32_t nn = T.n_delta[lnext];
                                     uint32_t k = j;
-                                    bool found = j < nn && P2[j] == f;
+                                    const uint8_t* mln = ml + T.ml_off[lnext];
+                                    const uint32_t p2j = j < nn ? P2[j] : 0xffffffffu;
+                                    uint8_t qn = j < nn ? mln[j] : 0;          // same index in the other list: the usual case
+                                    bool found = j < nn && p2j == f;
                                     if (found) matched_next = true;
-                                    else { k = lower_bound_u32(P2, nn, f); found = k < nn && P2[k] == f; }
+                                    else { k = lower_bound_u32(P2, nn, f); found = k < nn && P2[k] == f; if (found) qn = mln[k]; }
                                     if (found) {
-                                        const float pn = __fdiv_rn(__fadd_rn((float)ml[T.ml_off[lnext] + k], 0.5f), 256.0f);
+                                        const float pn = __fdiv_rn(__fadd_rn((float)qn, 0.5f), 256.0f);
                                         const uint32_t cn = T.code[lnext][0];
                                         if (cn == c0) p0 = __fadd_rn(p0, pn);
                                         else { c1 = cn; p1 = pn; n2c = 2; }
@@ -1093,38 +1129,36 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                     else keep = f >= c_par.edge_start && f < L - c_par.edge_end;
                                 }
                                 if (keep) {
-                                    // aligned?  largest i with cq[i] <= q
-                                    uint32_t lo = 0, hi = h.n_cigar;
+                                    // aligned?  the op holding q = largest i with cq[i] >> 1 <= q, narrowed by the table
                                     bool aligned = false;
-                                    if (hi > 0 && cq[0] <= q) {
-                                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cq[mid] <= q) lo = mid; else hi = mid; }
-                                        const uint32_t c = cig[lo];
-                                        const uint32_t op = c & 15, len = c >> 4, qs = cq[lo];
-                                        if ((op == 0 || op == 7 || op == 8) && q - qs < len) { aligned = true; rpos = cr[lo] + (q - qs); }
+                                    if (nc > 0 && q < q_total) {
+                                        uint32_t lo = 0, hi = nc;
+                                        if (use_qt) { const uint32_t t = q >> qt_shift; lo = qt[t]; hi = (uint32_t)qt[t + 1] + 1u; }
+                                        const uint32_t key = 2u * q + 1u;
+                                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cq[mid] <= key) lo = mid; else hi = mid; }
+                                        const uint32_t e = cq[lo];
+                                        if ((e & 1u) && q < (cq[lo + 1] >> 1)) { aligned = true; rpos = cr[lo] + (q - (e >> 1)); }
                                     }
                                     if (MODE == MODE_PILEUP) {
                                         // (mod strand, read orientation) -> reference strand (read_cache.rs:181-188)
                                         if ((st == 0) != rev) pos_mask |= mask; else neg_mask |= mask;
                                         table_survived = true;
+                                        // positions outside the focus set (motif / include-bed) are dropped when the hot bitmap
+                                        // is ranked (k_block_popc) and skipped by k_count_calls: no bitmap lookup here
                                         if (aligned && rpos >= C.cs && rpos < C.ce) {
-                                            const uint32_t x = rpos - C.cs;
-                                            bool focus = true;
-                                            if (C.focus_pos) focus = ((C.focus_pos[x >> 5] | C.focus_neg[x >> 5]) >> (x & 31)) & 1u;
-                                            if (focus) {
-                                                const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, ccode);
-                                                // does a '+' list cover the same position (both pos_call and neg_call present)?
-                                                uint32_t nosub = 0;
-                                                if (st == 1) {
-                                                    for (uint32_t l2 = 0; l2 < nl && !nosub; l2++) {
-                                                        if (T.strand[l2] != 0 || T.n_delta[l2] == 0) continue;
-                                                        const uint32_t* P2 = P + T.ent_off[l2];
-                                                        const uint32_t k = lower_bound_u32(P2, T.n_delta[l2], f);
-                                                        if (k < T.n_delta[l2] && P2[k] == f) nosub = 1;
-                                                    }
+                                            const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, ccode);
+                                            // does a '+' list cover the same position (both pos_call and neg_call present)?
+                                            uint32_t nosub = 0;
+                                            if (st == 1) {
+                                                for (uint32_t l2 = 0; l2 < nl && !nosub; l2++) {
+                                                    if (T.strand[l2] != 0 || T.n_delta[l2] == 0) continue;
+                                                    const uint32_t* P2 = P + T.ent_off[l2];
+                                                    const uint32_t k = lower_bound_u32(P2, T.n_delta[l2], f);
+                                                    if (k < T.n_delta[l2] && P2[k] == f) nosub = 1;
                                                 }
-                                                emit = true;
-                                                info = st | ((uint32_t)b << 1) | (state << 3) | (nosub << 11);
                                             }
+                                            emit = true;
+                                            info = st | ((uint32_t)b << 1) | (state << 3) | (nosub << 11);
                                         }
                                     } else {
                                         bool pass = aligned || C.hist_include_unaligned;
@@ -1151,7 +1185,12 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                     cnt_next += __popc(__ballot_sync(FULL, matched_next));
                     if (MODE == MODE_PILEUP) {
                         uint32_t em = __ballot_sync(FULL, emit);
-                        if (emit) calls[n_calls + __popc(em & ((1u << lane) - 1u))] = make_uint2(rpos, info);
+                        if (emit) {
+                            calls[n_calls + __popc(em & ((1u << lane) - 1u))] = make_uint2(rpos, info);
+                            // marks of a read that fails later stay behind: a hot position without calls yields no rows
+                            const uint32_t x = rpos - C.cs;
+                            atomicOr(&C.hot[x >> 5], 1u << (x & 31));
+                        }
                         n_calls += __popc(em);
                     } else {
                         uint32_t hm = __ballot_sync(FULL, hist_ok);
@@ -1257,10 +1296,6 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                 meta.flags |= 2;
                 meta.pos_mask = pos_mask; meta.neg_mask = neg_mask; meta.n_calls = n_calls;
                 meta.imp[0] = imp_meta[0]; meta.imp[1] = imp_meta[1];
-                for (uint32_t k = lane; k < n_calls; k += 32) {
-                    uint32_t x = calls[k].x - C.cs;
-                    atomicOr(&C.hot[x >> 5], 1u << (x & 31));
-                }
                 if (lane == 0 && n_calls) atomicAdd(C.total_calls, (unsigned long long)n_calls);
                 if (imp_meta[0] | imp_meta[1]) {
                     // every aligned occurrence of an implicit table's base is a call position
@@ -1311,10 +1346,17 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
 }
 
 // ---- rank over the hot bitmap -----------------------------------------------------------------------
-__global__ void k_block_popc(const uint32_t* __restrict__ bits, uint32_t n_words, uint32_t* __restrict__ block_sums) {
+// (marks outside the focus set, which k_resolve does not look at, are cleared here)
+__global__ void k_block_popc(uint32_t* __restrict__ bits, uint32_t n_words, uint32_t* __restrict__ block_sums,
+                             const uint32_t* __restrict__ focus_pos, const uint32_t* __restrict__ focus_neg) {
     __shared__ uint32_t s[32];
     uint32_t i = blockIdx.x * 1024 + threadIdx.x;
-    uint32_t v = i < n_words ? __popc(bits[i]) : 0;
+    uint32_t v = 0;
+    if (i < n_words) {
+        uint32_t word = bits[i];
+        if (focus_pos && word) { const uint32_t keep = word & (focus_pos[i] | focus_neg[i]); if (keep != word) bits[i] = keep; word = keep; }
+        v = __popc(word);
+    }
     uint32_t w = __reduce_add_sync(FULL, v);
     if (lane_id() == 0) s[threadIdx.x >> 5] = w;
     __syncthreads();
@@ -1403,7 +1445,9 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
             uint32_t fp = FULL, fn = FULL;
             if (D.focus_pos) { fp = D.focus_pos[x >> 5]; fn = D.focus_neg[x >> 5]; }
             bool ok_pos = (fp >> (x & 31)) & 1u, ok_neg = (fn >> (x & 31)) & 1u;
-            uint32_t* S = D.slots + (size_t)slot_of(D, x) * D.stride;
+            const uint32_t hw = D.hot[x >> 5];
+            if (!((hw >> (x & 31)) & 1u)) continue;            // outside the focus set
+            uint32_t* S = D.slots + (size_t)(D.hot_prefix[x >> 5] + __popc(hw & ((1u << (x & 31)) - 1u))) * D.stride;
             // cancel what k_count_bases adds for this (read, position): the inferred entry of this table if the
             // table is implicit, else the NoCall base on tally[a] (unless the other strand's table is implicit
             // there, in which case no NoCall is counted, or the '+' record of a +/- pair already cancels it)
