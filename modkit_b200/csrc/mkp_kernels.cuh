@@ -1464,8 +1464,7 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
 // reference skips excluded).  Coverage is recorded per 32-position bitmap word when the read covers the whole word
 // (one coalesced check-then-OR per word) and per hot position only in the partial words at the ends of a run.
 __global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D) {
-    __shared__ uint32_t s_scan[8][33];
-    __shared__ uint32_t s_op[8][32], s_q[8][32], s_r[8][32];
+    __shared__ uint32_t s_op[8][32], s_q[8][32], s_r[8][33];   // the current batch of 32 ops: op|len<<4, query start, reference start
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     for (;;) {
@@ -1531,62 +1530,64 @@ __global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D)
                 cover(run_start, sr);
                 run_start = sr + slen;
             }
-            // windows = hot-bitmap words touched by this op inside the chunk (M,=,X and D only)
-            bool counts = (op == 0 || op == 7 || op == 8 || op == 2) && len > 0;
-            uint32_t lo = r0 > D.cs ? r0 : D.cs;
-            uint32_t hi = r0 + len < D.ce ? r0 + len : D.ce;
-            uint32_t nwin = 0;
-            if (counts && lo < hi) nwin = ((hi - 1 - D.cs) >> 5) - ((lo - D.cs) >> 5) + 1;
-            uint32_t wi = warp_incl_scan(nwin);
-            s_scan[wib][lane + 1] = wi;
-            if (lane == 0) s_scan[wib][0] = 0;
+            // hot-bitmap words under this batch of ops, one per lane: the word is tested first (most hold no position this
+            // read can add to); the op under a hot position is found by one search per word over the batch's reference
+            // starts, then by stepping forward. Only M,=,X (a base) and D (a deletion) count.
+            const uint32_t R0 = __shfl_sync(FULL, r0, 0), R1 = rc;
             s_op[wib][lane] = op | (len << 4); s_q[wib][lane] = q0; s_r[wib][lane] = r0;
+            if (lane == 0) s_r[wib][32] = R1;
             __syncwarp();
-            const uint32_t total = s_scan[wib][32];
-            for (uint32_t t = lane; t < total; t += 32) {
-                // op j with scan[j] <= t < scan[j+1]
-                uint32_t lo_j = 0, hi_j = 32;
-                while (hi_j - lo_j > 1) { uint32_t mid = (lo_j + hi_j) >> 1; if (s_scan[wib][mid] <= t) lo_j = mid; else hi_j = mid; }
-                const uint32_t j = lo_j;
-                const uint32_t jc = s_op[wib][j], jq = s_q[wib][j], jr = s_r[wib][j];
-                const uint32_t jop = jc & 15, clen = jc >> 4;
-                uint32_t olo = jr > D.cs ? jr : D.cs;
-                uint32_t ohi = jr + clen < D.ce ? jr + clen : D.ce;
-                uint32_t w = ((olo - D.cs) >> 5) + (t - s_scan[wib][j]);
-                uint32_t wbase = D.cs + (w << 5);
-                const uint32_t word = D.hot[w];
-                uint32_t bits = word;
-                if (!bits) continue;
-                // restrict to [olo, ohi) and to the positions whose strand rule admits what this read can add there
-                if (olo > wbase) bits &= FULL << (olo - wbase);
-                if (ohi < wbase + 32) bits &= (1u << (ohi - wbase)) - 1u;
-                uint32_t fp = FULL, fn = FULL;
-                if (D.focus_pos) { fp = D.focus_pos[w]; fn = D.focus_neg[w]; }
-                const uint32_t ok = a == 0 ? fp : fn;
-                bits &= (has_imp && jop != 2) ? (fp | fn) : ok;
-                if (!bits) continue;
-                const uint32_t pre = D.hot_prefix[w];
-                while (bits) {
-                    uint32_t bit = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    uint32_t slot = pre + __popc(word & ((1u << bit) - 1u));
-                    uint32_t* S = D.slots + (size_t)slot * D.stride;
-                    if (jop == 2) { atomicAdd(&S[SL_DEL + a], 1u); continue; }
-                    uint32_t q = jq + (wbase + bit - jr);
-                    int nb = nib_to_base(seq_nibble(seq, q));
-                    if (nb > 3) continue;
-                    uint32_t b = a ? 3 - nb : nb;
-                    if (!has_imp) { atomicAdd(&S[SL_BASE + a * 4 + b], 1u); continue; }
-                    uint32_t ip = (m.imp[0] >> (8 * b)) & 0xffu, in = (m.imp[1] >> (8 * b)) & 0xffu;
-                    if ((ip | in) & 0x80u) {
-                        // inferred-canonical entries of implicit tables, subject to the edge filter
-                        const uint32_t f = a ? h.l_seq - 1u - q : q;
-                        if (c_par.edge_on && !(c_par.edge_inv ? (f < c_par.edge_start || f >= h.l_seq - c_par.edge_end) : (f >= c_par.edge_start && f < h.l_seq - c_par.edge_end))) ip = in = 0;
+            const uint32_t blo = R0 > D.cs ? R0 : D.cs, bhi = R1 < D.ce ? R1 : D.ce;
+            if (blo < bhi) {
+                const uint32_t w_first = (blo - D.cs) >> 5, w_last = (bhi - 1 - D.cs) >> 5;
+                for (uint32_t w = w_first + lane; w <= w_last; w += 32) {
+                    const uint32_t word = D.hot[w];
+                    if (!word) continue;
+                    const uint32_t wbase = D.cs + (w << 5);
+                    uint32_t bits = word;
+                    if (blo > wbase) bits &= FULL << (blo - wbase);
+                    if (bhi < wbase + 32) bits &= (1u << (bhi - wbase)) - 1u;
+                    // positions whose strand rule admits what this read can add there
+                    uint32_t fp = FULL, fn = FULL;
+                    if (D.focus_pos) { fp = D.focus_pos[w]; fn = D.focus_neg[w]; }
+                    const uint32_t ok = a == 0 ? fp : fn;
+                    bits &= has_imp ? (fp | fn) : ok;
+                    if (!bits) continue;
+                    const uint32_t pre = D.hot_prefix[w];
+                    // op under the first candidate position: largest j with s_r[j] <= r (ops without reference length share
+                    // their start with the next op, so the largest index is the op that holds r)
+                    uint32_t j = 0;
+                    {
+                        const uint32_t r = wbase + (uint32_t)__ffs(bits) - 1u;
+#pragma unroll
+                        for (int stp = 16; stp >= 1; stp >>= 1) if (s_r[wib][j + stp] <= r) j += stp;
                     }
-                    const bool okp = (fp >> bit) & 1u, okn = (fn >> bit) & 1u;
-                    if (!((ip | in) & 0x80u)) { if ((ok >> bit) & 1u) atomicAdd(&S[SL_BASE + a * 4 + b], 1u); continue; }
-                    if (ip & 0x80u) add_feature(S, D.n_states, a, b, ip & 0x7fu, okp, okn, 1u);
-                    if (in & 0x80u) add_feature(S, D.n_states, 1u - a, 3u - b, in & 0x7fu, okp, okn, 1u);
+                    while (bits) {
+                        const uint32_t bit = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const uint32_t r = wbase + bit;
+                        while (s_r[wib][j + 1] <= r) j++;
+                        const uint32_t jc = s_op[wib][j], jop = jc & 15;
+                        if (!(jop == 0 || jop == 7 || jop == 8 || jop == 2)) continue;       // reference skip
+                        if (jop == 2 && !((ok >> bit) & 1u)) continue;
+                        uint32_t* S = D.slots + (size_t)(pre + __popc(word & ((1u << bit) - 1u))) * D.stride;
+                        if (jop == 2) { atomicAdd(&S[SL_DEL + a], 1u); continue; }
+                        const uint32_t q = s_q[wib][j] + (r - s_r[wib][j]);
+                        const int nb = nib_to_base(seq_nibble(seq, q));
+                        if (nb > 3) continue;
+                        const uint32_t b = a ? 3 - nb : nb;
+                        if (!has_imp) { atomicAdd(&S[SL_BASE + a * 4 + b], 1u); continue; }
+                        uint32_t ip = (m.imp[0] >> (8 * b)) & 0xffu, in = (m.imp[1] >> (8 * b)) & 0xffu;
+                        if ((ip | in) & 0x80u) {
+                            // inferred-canonical entries of implicit tables, subject to the edge filter
+                            const uint32_t f = a ? h.l_seq - 1u - q : q;
+                            if (c_par.edge_on && !(c_par.edge_inv ? (f < c_par.edge_start || f >= h.l_seq - c_par.edge_end) : (f >= c_par.edge_start && f < h.l_seq - c_par.edge_end))) ip = in = 0;
+                        }
+                        const bool okp = (fp >> bit) & 1u, okn = (fn >> bit) & 1u;
+                        if (!((ip | in) & 0x80u)) { if ((ok >> bit) & 1u) atomicAdd(&S[SL_BASE + a * 4 + b], 1u); continue; }
+                        if (ip & 0x80u) add_feature(S, D.n_states, a, b, ip & 0x7fu, okp, okn, 1u);
+                        if (in & 0x80u) add_feature(S, D.n_states, 1u - a, 3u - b, in & 0x7fu, okp, okn, 1u);
+                    }
                 }
             }
             __syncwarp();
