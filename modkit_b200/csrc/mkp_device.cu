@@ -49,7 +49,7 @@ struct mkp_ctx {
     uint32_t max_ncigar = 1, max_blocks = 1;
     uint64_t heap_bytes = 0;
     // work buffers
-    DevBuf d_rl, d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr;
+    DevBuf d_rl, d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr, d_slow;
     DevBuf d_obs_word, d_slots, d_row_counts, d_row_prefix, d_rows, d_hist, d_take;
     // results
     size_t n_rows = 0;
@@ -92,7 +92,7 @@ void mkp_destroy(mkp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_rl, &ctx->d_meta, &ctx->d_P,
-                      &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr,
+                      &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
@@ -195,6 +195,8 @@ static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
     C->scr_cq = ctx->d_scr_cq.as<uint32_t>(); C->scr_cr = ctx->d_scr_cr.as<uint32_t>();
     C->max_ncigar = ctx->max_ncigar; C->max_blocks = ctx->max_blocks;
     C->rl = ctx->d_rl.as<ReadLists>();
+    CK(ctx->d_slow.ensure((size_t)ctx->n_reads * 4 + 4));
+    C->slow_list = ctx->d_slow.as<uint32_t>();
     return 0;
 }
 
@@ -231,7 +233,7 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     C.mode = MODE_PILEUP;
     if (ctx->n_reads) k_parse<<<grid, 128, 0, st>>>(C);
     CK(cudaEventRecord(ctx->ev[1], st));
-    if (ctx->n_reads) k_resolve<MODE_PILEUP><<<grid, 128, 0, st>>>(C);
+    if (ctx->n_reads) { k_resolve<MODE_PILEUP, true><<<grid, 128, 0, st>>>(C); k_resolve<MODE_PILEUP, false><<<grid, 128, 0, st>>>(C); }
     CK(cudaEventRecord(ctx->ev[2], st));
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);   // n_states, err, n_hot, n_rows
     k_block_popc<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.focus_pos, C.focus_neg);
@@ -353,7 +355,7 @@ int mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* tak
         C.hist = ctx->d_hist.as<unsigned long long>();
     }
     C.mode = MODE_HIST;
-    if (ctx->n_reads) { k_parse<<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST><<<grid, 128, 0, st>>>(C); }
+    if (ctx->n_reads) { k_parse<<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST, true><<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST, false><<<grid, 128, 0, st>>>(C); }
     CK(cudaGetLastError());
     uint32_t h_small[2];
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);

@@ -78,7 +78,8 @@ struct ChunkDev {
     unsigned long long* states; // registry: (pb<<32 | code), ~0 empty
     uint32_t* n_states;
     uint32_t* err;
-    uint32_t* work;             // dynamic read counter
+    uint32_t* work;             // dynamic read counters: +0 parse, +1 resolve, +2/+3 counts, +4 queue length, +5 queue cursor
+    uint32_t* slow_list;        // reads left to the generic k_resolve instantiation
     unsigned long long* total_calls;
     // per-warp scratch
     uint32_t* scr_cq; uint32_t* scr_cr;
@@ -303,17 +304,17 @@ struct StateCache {      // two most recent (key -> id) pairs, in registers
     __device__ void init() { k0 = k1 = ~0ull; i0 = i1 = 0; }
 };
 
-__device__ __noinline__ int state_id_global(const ChunkDev& C, unsigned long long key) {
+__device__ __noinline__ int state_id_global(unsigned long long* states, uint32_t* n_states, uint32_t* err, unsigned long long key) {
     for (int i = 0; i < MAX_STATES; i++) {
-        unsigned long long v = *((volatile unsigned long long*)&C.states[i]);
+        unsigned long long v = *((volatile unsigned long long*)&states[i]);
         if (v == key) return i;
         if (v == ~0ull) {
-            unsigned long long old = atomicCAS(&C.states[i], ~0ull, key);
-            if (old == ~0ull) { atomicMax(C.n_states, (uint32_t)i + 1); return i; }
+            unsigned long long old = atomicCAS(&states[i], ~0ull, key);
+            if (old == ~0ull) { atomicMax(n_states, (uint32_t)i + 1); return i; }
             if (old == key) return i;
         }
     }
-    atomicOr(C.err, MKP_DERR_TOO_MANY_STATES);
+    atomicOr(err, MKP_DERR_TOO_MANY_STATES);
     return 0;
 }
 
@@ -321,7 +322,7 @@ __device__ __forceinline__ int state_id(const ChunkDev& C, StateCache& sc, int p
     const unsigned long long key = ((unsigned long long)pb << 32) | code;
     if (sc.k0 == key) return sc.i0;
     if (sc.k1 == key) return sc.i1;
-    const int id = state_id_global(C, key);
+    const int id = state_id_global(C.states, C.n_states, C.err, key);
     sc.k1 = sc.k0; sc.i1 = sc.i0; sc.k0 = key; sc.i0 = id;
     return id;
 }
@@ -359,6 +360,9 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* P, uint32_t 
 // discovery, per-base occurrence counts, MM token parse + select -> forward positions P[] and the list table.
 #ifndef MKP_MINB_PARSE
 #define MKP_MINB_PARSE 8
+#endif
+#ifndef MKP_MINB_RESOLVE_FAST
+#define MKP_MINB_RESOLVE_FAST 8
 #endif
 #ifndef MKP_MINB_RESOLVE
 #define MKP_MINB_RESOLVE 7
@@ -810,8 +814,11 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
 
 // Kernel B: per read with mod info: CIGAR prefix, then every list entry -> merged probabilities -> collapse ->
 // threshold call -> reference position; call records, observed-code masks, implicit tables, hot-bitmap marks.
-template <int MODE>
-__global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
+// FAST_ONLY = true: handles the reads whose lists fit the register-only path (no implicit tables, no 'N' list, at most
+// two codes per position) and queues the others; FAST_ONLY = false: the generic path over the queued reads. Two
+// instantiations keep the common case's register and instruction footprint small.
+template <int MODE, bool FAST_ONLY>
+__global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
     __shared__ ListTab s_tab[4];
     // CIGAR prefix of the current read (global scratch when longer): s_cq = 2 * query start + (op is M/=/X), one
     // sentinel entry 2 * query length at the end; s_cr = reference start; s_qt = op holding every (1 << shift)-th query base
@@ -828,9 +835,15 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
 
     for (;;) {
         uint32_t ri = 0;
-        if (lane == 0) ri = atomicAdd(C.work + 1, 1u);
-        ri = __shfl_sync(FULL, ri, 0);
-        if (ri >= C.n_reads) break;
+        if (FAST_ONLY) {
+            if (lane == 0) ri = atomicAdd(C.work + 1, 1u);
+            ri = __shfl_sync(FULL, ri, 0);
+            if (ri >= C.n_reads) break;
+        } else {
+            if (lane == 0) { ri = atomicAdd(C.work + 5, 1u); ri = ri < C.work[4] ? C.slow_list[ri] : 0xffffffffu; }
+            ri = __shfl_sync(FULL, ri, 0);
+            if (ri == 0xffffffffu) break;
+        }
         ReadMeta meta = C.meta[ri];
         if (!(meta.flags & 1)) continue;
         const ReadLists* R = C.rl + ri;
@@ -855,6 +868,31 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
             T.n_delta[lane] = rec.n_delta; T.ent_off[lane] = rec.ent_off; T.ml_off[lane] = rec.ml_off;
             for (int c = 0; c < MAX_LIST_CODES; c++) T.code[lane][c] = rec.code[c];
             T.base[lane] = rec.base; T.strand[lane] = rec.strand; T.mode[lane] = rec.mode; T.ncodes[lane] = rec.ncodes;
+        }
+        __syncwarp();
+        bool imp_any = false;
+        for (int k = 0; k < 8; k++) imp_any = imp_any || imp_lists[k >> 2][k & 3];
+        // register-only fast path: no implicit tables, no 'N' list, and per strand either one list with <= 2 codes or two
+        // single-code lists
+#ifdef MKP_NO_FAST_RESOLVE
+        bool fast_read = false;
+#else
+        bool fast_read = !imp_any;
+#endif
+        {
+            uint32_t cnt0 = 0, cnt1 = 0, max0 = 0, max1 = 0;
+            for (uint32_t l2 = 0; l2 < nl; l2++) {
+                if (T.base[l2] == 'N') fast_read = false;
+                if (!T.n_delta[l2]) continue;
+                const uint32_t ncd = T.ncodes[l2];
+                if (T.strand[l2]) { cnt1++; max1 = max(max1, ncd); } else { cnt0++; max0 = max(max0, ncd); }
+            }
+            if (!(cnt0 <= 1 ? max0 <= 2 : (cnt0 == 2 && max0 == 1))) fast_read = false;
+            if (!(cnt1 <= 1 ? max1 <= 2 : (cnt1 == 2 && max1 == 1))) fast_read = false;
+        }
+        if (FAST_ONLY && !fast_read) {                 // leave it to the generic instantiation
+            if (lane == 0) C.slow_list[atomicAdd(C.work + 4, 1u)] = ri;
+            continue;
         }
         // CIGAR prefix: query / reference start of every op; four ops per lane (one 16-byte load), 128 per round
         const uint32_t nc = h.n_cigar;
@@ -914,26 +952,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
         uint2* calls = C.calls + meta.entry_off;
         if (!err && any_entries) {
             const bool trim_ok = !c_par.edge_on || !(L <= c_par.edge_start || L <= c_par.edge_end);
-            bool imp_any = false;
-            for (int k = 0; k < 8; k++) imp_any = imp_any || imp_lists[k >> 2][k & 3];
             uint32_t skip_mask = 0;       // lists whose every entry sits at the same index of an earlier same-strand list
-            // register-only fast path: no implicit tables, no 'N' list, and per strand either one list with <= 2 codes or two
-            // single-code lists
-#ifdef MKP_NO_FAST_RESOLVE
-            bool fast_read = false;
-#else
-            bool fast_read = !imp_any;
-#endif
-            {
-                uint32_t cnt[2] = {0, 0}, maxc[2] = {0, 0};
-                for (uint32_t l2 = 0; l2 < nl; l2++) {
-                    if (T.base[l2] == 'N') fast_read = false;
-                    if (!T.n_delta[l2]) continue;
-                    cnt[T.strand[l2]]++;
-                    maxc[T.strand[l2]] = max(maxc[T.strand[l2]], (uint32_t)T.ncodes[l2]);
-                }
-                for (int s2 = 0; s2 < 2; s2++) if (!(cnt[s2] <= 1 ? maxc[s2] <= 2 : (cnt[s2] == 2 && maxc[s2] == 1))) fast_read = false;
-            }
             for (uint32_t l = 0; l < nl && !err; l++) {
                 if ((skip_mask >> l) & 1u) continue;    // all its entries are absorbed (basecallers repeat one delta list per code)
                 const uint32_t n = T.n_delta[l];
@@ -960,14 +979,14 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                         // forward-read base at f: the list's own base (the position was selected as one of its occurrences);
                         // only 'N' lists have to look at the sequence (mod_bam.rs:1245)
                         int b = lb;
-                        if (lb > 3) {
+                        if (!FAST_ONLY && lb > 3) {
                             const int nb = nib_to_base(seq_nibble(seq, q));
                             b = nb > 3 ? 4 : (rev ? 3 - nb : nb);
                             if (b > 3) e2 = true;
                         }
                         // ExplicitConflictInferred (mod_bam.rs:629-634): an implicit list of this (strand, base) table
                         // that does not list f explicitly holds an inferred entry there
-                        if (b <= 3) {
+                        if (!FAST_ONLY && b <= 3) {
                             uint32_t others = imp_lists[st][b] & ~(1u << l);
                             while (others && !e2) {
                                 const uint32_t l2 = __ffs(others) - 1;
@@ -994,7 +1013,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                             uint32_t mask = 0, ccode = 0;      // observed states, called code
                             int kind = 0;                      // 0 filtered, 1 canonical, 2 modified
                             float hv = 0.f;                    // arg-max value (histogram mode)
-                            if (fast_read) {
+                            if (FAST_ONLY || fast_read) {
                                 // ---- register-only path: at most two codes at the position (one list with <= 2 codes, or
                                 //      two single-code lists of the strand). Same arithmetic as the generic path below.
                                 uint32_t c0 = T.code[l][0], c1 = 0;
@@ -1174,7 +1193,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                                         }
                                         if (pass) {
                                             hist_ok = true; hist_v = hv; hist_base = tb;
-                                            if (imp_lists[st][b]) imp_explicit[st * 4 + b]++;
+                                            if (!FAST_ONLY && imp_lists[st][b]) imp_explicit[st * 4 + b]++;
                                         }
                                     }
                                 }
@@ -1212,7 +1231,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
         // ---- phase 4b: implicit tables (every other occurrence of the base is an inferred-canonical entry) ----
         uint32_t imp_meta[2] = {0, 0};
         unsigned long long imp_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (!err) {
+        if (!FAST_ONLY && !err) {
             const bool trim_ok = !c_par.edge_on || !(L <= c_par.edge_start || L <= c_par.edge_end);
             for (uint32_t sb = 0; sb < 8; sb++) {
                 const uint32_t s = sb >> 2, b = sb & 3;
@@ -1297,7 +1316,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_RESOLVE) k_resolve(ChunkDev C) {
                 meta.pos_mask = pos_mask; meta.neg_mask = neg_mask; meta.n_calls = n_calls;
                 meta.imp[0] = imp_meta[0]; meta.imp[1] = imp_meta[1];
                 if (lane == 0 && n_calls) atomicAdd(C.total_calls, (unsigned long long)n_calls);
-                if (imp_meta[0] | imp_meta[1]) {
+                if (!FAST_ONLY && (imp_meta[0] | imp_meta[1])) {
                     // every aligned occurrence of an implicit table's base is a call position
                     uint32_t qc2 = 0, rc2 = (uint32_t)h.ref_start;
                     for (uint32_t i = 0; i < h.n_cigar; i++) {
