@@ -50,7 +50,7 @@ struct DevParams {
 
 struct ReadMeta {       // 40 bytes, written by k_decode
     int32_t ref_end;
-    uint32_t flags;     // bit0 admitted, bit1 has mod info (not in skip_set)
+    uint32_t flags;     // bit0 admitted, bit1 has mod info (not in skip_set), bit2 call records are one position-sorted run
     uint32_t pos_mask, neg_mask;
     uint32_t n_calls;
     uint32_t n_hist;    // sampling: values contributed
@@ -946,6 +946,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
         uint32_t* P = C.P + meta.entry_off;
         // ---- phase 4: resolve entries -> calls ---------------------------------------------------
         uint32_t n_calls = 0, n_hist = 0;
+        uint32_t n_runs = 0;          // lists that emitted call records (each list's records are sorted by position)
         uint32_t pos_mask = 0, neg_mask = 0;
         bool table_survived = false;
         uint32_t imp_explicit[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // HIST: explicit values on implicit tables (per lane)
@@ -963,6 +964,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                 uint32_t lnext = 0xffffffffu;           // nearest later list of the same strand with entries
                 for (uint32_t l2 = nl; l2-- > l + 1;) if (T.strand[l2] == st && T.n_delta[l2]) lnext = l2;
                 uint32_t cnt_next = 0;
+                const uint32_t calls_before = n_calls;
                 for (uint32_t j0 = 0; j0 < n; j0 += 32) {
                     uint32_t j = j0 + lane;
                     bool active = j < n;
@@ -1225,6 +1227,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                         n_hist += __popc(hm);
                     }
                 }
+                if (n_calls != calls_before) n_runs++;
                 if (!imp_any && lnext != 0xffffffffu && T.base[lnext] != 'N' && T.n_delta[lnext] == cnt_next) skip_mask |= 1u << lnext;
             }
         }
@@ -1313,6 +1316,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
         if (MODE == MODE_PILEUP) {
             if (!err && table_survived) {
                 meta.flags |= 2;
+                if (n_runs <= 1 && !(imp_meta[0] | imp_meta[1])) meta.flags |= 4;     // one sorted run: k_count_bases merges it
                 meta.pos_mask = pos_mask; meta.neg_mask = neg_mask; meta.n_calls = n_calls;
                 meta.imp[0] = imp_meta[0]; meta.imp[1] = imp_meta[1];
                 if (lane == 0 && n_calls) atomicAdd(C.total_calls, (unsigned long long)n_calls);
@@ -1472,7 +1476,7 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
             // there, in which case no NoCall is counted, or the '+' record of a +/- pair already cancels it)
             const uint32_t imp_own = (m.imp[st] >> (8 * b)) & 0xffu, imp_other = (m.imp[1 - st] >> (8 * b)) & 0xffu;
             if (imp_own & 0x80u) add_feature(S, D.n_states, st == 0 ? a : 1u - a, st == 0 ? b : 3u - b, imp_own & 0x7fu, ok_pos, ok_neg, 0xffffffffu);
-            else if (!(imp_other & 0x80u) && !nosub && (a == 0 ? ok_pos : ok_neg)) atomicAdd(&S[SL_BASE + a * 4 + b], 0xffffffffu);
+            else if (!(m.flags & 4) && !(imp_other & 0x80u) && !nosub && (a == 0 ? ok_pos : ok_neg)) atomicAdd(&S[SL_BASE + a * 4 + b], 0xffffffffu);
             add_feature(S, D.n_states, st == 0 ? a : 1u - a, st == 0 ? b : 3u - b, state, ok_pos, ok_neg, 1u);
         }
     }
@@ -1484,6 +1488,7 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
 // (one coalesced check-then-OR per word) and per hot position only in the partial words at the ends of a run.
 __global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D) {
     __shared__ uint32_t s_op[8][32], s_q[8][32], s_r[8][33];   // the current batch of 32 ops: op|len<<4, query start, reference start
+    __shared__ uint32_t s_mask[8][32];                          // positions of the current 32 words where this read has a call
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     for (;;) {
@@ -1501,6 +1506,9 @@ __global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D)
         const bool has_mods = m.flags & 2;
         const bool has_imp = (m.imp[0] | m.imp[1]) != 0;
         const uint32_t pm = has_mods ? m.pos_mask : 0u, nm = has_mods ? m.neg_mask : 0u;
+        const bool merge = has_mods && (m.flags & 4) && m.n_calls > 0;
+        const uint2* rcalls = D.calls + m.entry_off;
+        uint32_t cp = 0;                                        // call records consumed so far (ascending position)
         // observed-code coverage of one run [ra, rb) of reference positions
         auto cover = [&](uint32_t ra, uint32_t rb) {
             if (!(pm | nm)) return;
@@ -1559,13 +1567,41 @@ __global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D)
             const uint32_t blo = R0 > D.cs ? R0 : D.cs, bhi = R1 < D.ce ? R1 : D.ce;
             if (blo < bhi) {
                 const uint32_t w_first = (blo - D.cs) >> 5, w_last = (bhi - 1 - D.cs) >> 5;
-                for (uint32_t w = w_first + lane; w <= w_last; w += 32) {
+                for (uint32_t wt = w_first; wt <= w_last; wt += 32) {
+                    const uint32_t w = wt + lane;
+                    // reads whose call records form one run sorted by position (flag 4): a position with a call needs no
+                    // NoCall (k_count_calls does not cancel one for these reads), so the calls under these 32 words are
+                    // streamed in (one cursor per read, ascending positions) and masked out before the per-position work
+                    uint32_t called = 0;
+                    if (merge) {
+                        const uint32_t t_end = D.cs + ((wt + 32) << 5);
+                        const uint32_t lim = bhi < t_end ? bhi : t_end;
+                        s_mask[wib][lane] = 0;
+                        __syncwarp();
+                        for (;;) {
+                            const uint32_t k = cp + lane;
+                            uint32_t x = 0xffffffffu;
+                            if (k < m.n_calls) x = rcalls[a ? m.n_calls - 1u - k : k].x;
+                            const bool take = x < lim;
+                            if (take) {
+                                const uint32_t rel = x - D.cs;
+                                if ((rel >> 5) >= wt) atomicOr(&s_mask[wib][(rel >> 5) - wt], 1u << (rel & 31));
+                            }
+                            const uint32_t nt = __popc(__ballot_sync(FULL, take));
+                            cp += nt;
+                            if (nt < 32) break;
+                        }
+                        __syncwarp();
+                        called = s_mask[wib][lane];
+                    }
+                    if (w > w_last) continue;
                     const uint32_t word = D.hot[w];
                     if (!word) continue;
                     const uint32_t wbase = D.cs + (w << 5);
-                    uint32_t bits = word;
+                    uint32_t bits = word & ~called;
                     if (blo > wbase) bits &= FULL << (blo - wbase);
                     if (bhi < wbase + 32) bits &= (1u << (bhi - wbase)) - 1u;
+                    if (!bits) continue;
                     // positions whose strand rule admits what this read can add there
                     uint32_t fp = FULL, fn = FULL;
                     if (D.focus_pos) { fp = D.focus_pos[w]; fn = D.focus_neg[w]; }
