@@ -135,6 +135,46 @@ int  mkp_pileup_chunk(mkp_ctx* ctx, const mkp_chunk* host_chunk, const mkp_row**
 int  mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* take,
                           uint64_t* hist, uint8_t* contributes, uint64_t* inexact);
 
+
+/* ---- BGZF / BAM ingest on the device (the on-disk format step directly before the path) ----------
+ * Replaces, for the records the path consumes, htslib's bgzf_read_block + inflate + bam_read1 behind
+ * rust-htslib's bam::IndexedReader::{from_path, fetch} (src/pileup/mod.rs:732-743) and the tag lookup of
+ * parse_raw_mod_tags (src/mod_bam.rs:1388-1470).  The host only walks the BGZF member headers (no inflate) and
+ * turns BAI virtual offsets into seed offsets; inflate, record discovery and record slicing run on the GPU and the
+ * packed chunk never exists in host memory.  CRC32 of the members is not verified. */
+typedef struct {
+    uint64_t in_off;      /* offset of the member's raw deflate payload in the file            */
+    uint64_t out_off;     /* offset of its output in the inflated stream                        */
+    uint32_t in_len;      /* payload bytes (BSIZE + 1 - 12 - XLEN - 8)                          */
+    uint32_t out_len;     /* ISIZE                                                              */
+} mkp_bgzf_member;
+
+typedef struct {          /* one alignment record of the inflated stream                        */
+    uint64_t off;         /* offset of its refID field                                          */
+    uint32_t size;        /* block_size                                                         */
+    int32_t  tid, pos;
+    int32_t  end;         /* htslib bam_endpos: pos + reference length (1 without CIGAR)        */
+    uint32_t flag;
+    uint32_t l_seq;
+} mkp_bam_rec;            /* 32 bytes */
+
+/* Copy the BGZF file to the device, inflate all members, walk the record chain.
+ * seeds: sorted offsets (inflated stream) of known record starts, seeds[0] = first record; every segment between
+ * two seeds is walked by its own thread, so more seeds = more parallelism (one seed is valid, only slow).
+ * ms (optional, float[4]): host-to-device copy, inflate, record walk, total. */
+int  mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                  uint64_t inflated_len, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms);
+/* Record table in file order (n_records entries, host memory). */
+int  mkp_bam_records(mkp_ctx* ctx, mkp_bam_rec* out);
+/* Make the records rec_ids[0..n) (indices into the record table, file order) the resident chunk for [start,end):
+ * the device-side equivalent of slicing them on the host + mkp_upload_chunk. */
+int  mkp_bam_chunk(mkp_ctx* ctx, uint32_t start, uint32_t end, const uint32_t* rec_ids, uint32_t n,
+                   const uint32_t* focus_pos, const uint32_t* focus_neg);
+/* Test / debug access: bytes of the inflated stream; headers and heap of the resident chunk
+ * (hdrs: n_reads entries or NULL; heap: *heap_bytes capacity in, bytes out; or NULL to query sizes). */
+int  mkp_bam_inflated(mkp_ctx* ctx, uint64_t off, uint8_t* dst, size_t len);
+int  mkp_fetch_chunk(mkp_ctx* ctx, mkp_read_hdr* hdrs, uint32_t* n_reads, uint8_t* heap, uint64_t* heap_bytes);
+
 /* SURVEY §8(d) algorithmic bytes of a chunk: sum over reads of 32 + 4 n_cigar + ceil(l_seq/2) + len_mm + len_ml,
  * plus 40 bytes per emitted row (roofline accounting only). */
 size_t mkp_algorithmic_bytes(const mkp_chunk* chunk, size_t n_rows);

@@ -48,11 +48,12 @@ ROW_DTYPE = np.dtype([("pos", "<u4"), ("code", "<u4"), ("strand", "u1"), ("prima
 assert ROW_DTYPE.itemsize == 40
 
 MKP_SYMBOLS = ["mkp_create", "mkp_destroy", "mkp_last_error", "mkp_set_params", "mkp_upload_chunk", "mkp_pileup_resident",
-               "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_algorithmic_bytes"]
+               "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_algorithmic_bytes",
+               "mkp_bam_load", "mkp_bam_records", "mkp_bam_chunk", "mkp_bam_inflated", "mkp_fetch_chunk"]
 MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_refs", "mkh_bam_ref_name", "mkh_bam_ref_len",
                "mkh_bam_n_mapped", "mkh_bam_n_records", "mkh_pack_region", "mkh_packed_free", "mkh_packed_n_reads",
                "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
-               "mkh_motif_focus"]
+               "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records"]
 
 
 def library_path():
@@ -83,6 +84,19 @@ def load_library(build_if_missing=True):
     lib.mkp_sample_histogram.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     lib.mkp_algorithmic_bytes.argtypes = [C.POINTER(Chunk), C.c_size_t]
     lib.mkp_algorithmic_bytes.restype = C.c_size_t
+    lib.mkp_bam_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_size_t,
+                                 C.POINTER(C.c_size_t), C.c_void_p]
+    lib.mkp_bam_records.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mkp_bam_chunk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.mkp_bam_inflated.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
+    lib.mkp_fetch_chunk.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.mkh_bam_open_device.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mkh_device_chunk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.mkh_device_chunk.restype = C.c_int64
+    lib.mkh_bam_ingest_ms.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mkh_bam_ingest_ms.restype = None
+    lib.mkh_bam_total_records.argtypes = [C.c_void_p]
+    lib.mkh_bam_total_records.restype = C.c_uint64
     lib.mkh_pileup_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     lib.mkh_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.mkh_bam_close.argtypes = [C.c_void_p]
@@ -124,12 +138,46 @@ def pileup_main(args):
     return lib.mkh_pileup_main(len(args), argv)
 
 
+HDR_DTYPE = np.dtype([("ref_start", "<i4"), ("l_seq", "<u4"), ("n_cigar", "<u4"), ("flags", "<u4"), ("off", "<u8"), ("len_ml", "<u4"), ("len_mm", "<u4")])
+MEMBER_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4")])
+REC_DTYPE = np.dtype([("off", "<u8"), ("size", "<u4"), ("tid", "<i4"), ("pos", "<i4"), ("end", "<i4"), ("flag", "<u4"), ("l_seq", "<u4")])
+assert HDR_DTYPE.itemsize == 32 and MEMBER_DTYPE.itemsize == 24 and REC_DTYPE.itemsize == 32
+
+
 class Bam:
-    def __init__(self, path, threads=4):
+    """A BAM file. With ctx=None the file is inflated and indexed on the host (zlib); with a Context the BGZF members are
+    inflated, the record chain walked and the reads sliced on that GPU (mkp_bam_load / mkp_bam_chunk)."""
+
+    def __init__(self, path, threads=4, ctx=None):
         self._lib = load_library()
         self._h = C.c_void_p()
-        if self._lib.mkh_bam_open(str(path).encode(), threads, C.byref(self._h)):
-            raise MkpError("cannot open BAM " + str(path))
+        self._ctx = ctx
+        if ctx is None:
+            if self._lib.mkh_bam_open(str(path).encode(), threads, C.byref(self._h)):
+                raise MkpError("cannot open BAM " + str(path))
+        elif self._lib.mkh_bam_open_device(str(path).encode(), ctx._h, C.byref(self._h)):
+            raise MkpError("cannot open BAM on the device " + str(path))
+
+    def device_chunk(self, tid, start, end, focus=None):
+        """Device ingest only: the reads overlapping [start,end) become the resident chunk of the context."""
+        fp = fn = None
+        if focus is not None:
+            fp = np.ascontiguousarray(focus[0], dtype=np.uint32); fn = np.ascontiguousarray(focus[1], dtype=np.uint32)
+        n = self._lib.mkh_device_chunk(self._h, tid, start, end, fp.ctypes.data if fp is not None else None, fn.ctypes.data if fn is not None else None)
+        if n < 0:
+            raise MkpError("device chunk failed")
+        self._ctx._n_reads_hint = int(n)
+        return int(n)
+
+    @property
+    def ingest_ms(self):
+        ms = (C.c_float * 4)()
+        self._lib.mkh_bam_ingest_ms(self._h, ms)
+        return dict(zip(["h2d", "inflate", "walk", "total"], [float(x) for x in ms]))
+
+    @property
+    def total_records(self):
+        return int(self._lib.mkh_bam_total_records(self._h))
 
     def close(self):
         if self._h:
@@ -185,8 +233,13 @@ class Packed:
     def headers(self):
         n = self.n_reads
         buf = C.cast(self._lib.mkh_packed_hdrs(self._h), C.POINTER(C.c_uint8 * (32 * n))).contents if n else b""
-        dt = np.dtype([("ref_start", "<i4"), ("l_seq", "<u4"), ("n_cigar", "<u4"), ("flags", "<u4"), ("off", "<u8"), ("len_ml", "<u4"), ("len_mm", "<u4")])
-        return np.frombuffer(buf, dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+        return np.frombuffer(buf, dtype=HDR_DTYPE).copy() if n else np.zeros(0, dtype=HDR_DTYPE)
+
+    def heap(self):
+        n = self.heap_bytes
+        if not n:
+            return np.zeros(0, dtype=np.uint8)
+        return np.frombuffer((C.c_uint8 * n).from_address(self._lib.mkh_packed_heap(self._h)), dtype=np.uint8).copy()
 
     def free(self):
         if self._h:
@@ -285,6 +338,50 @@ class Context:
         return hist, contrib, inexact.value
 
     _n_reads_hint = 0
+
+    # ---- device ingest (mkp_bam_*) ----
+    def bam_load(self, file_bytes, members, inflated_len, seeds):
+        """file_bytes: the BGZF file (bytes / uint8 array); members: MEMBER_DTYPE array; seeds: sorted uint64 record starts."""
+        fb = np.frombuffer(file_bytes, dtype=np.uint8) if not isinstance(file_bytes, np.ndarray) else file_bytes
+        members = np.ascontiguousarray(members, dtype=MEMBER_DTYPE)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        n = C.c_size_t()
+        ms = (C.c_float * 4)()
+        self._check(self._lib.mkp_bam_load(self._h, fb.ctypes.data, fb.size, members.ctypes.data, len(members), inflated_len,
+                                           seeds.ctypes.data, len(seeds), C.byref(n), ms))
+        self._n_records = n.value
+        return n.value, [float(x) for x in ms]
+
+    def bam_records(self):
+        out = np.zeros(self._n_records, dtype=REC_DTYPE)
+        if self._n_records:
+            self._check(self._lib.mkp_bam_records(self._h, out.ctypes.data))
+        return out
+
+    def bam_inflated(self, off, length):
+        out = np.zeros(length, dtype=np.uint8)
+        self._check(self._lib.mkp_bam_inflated(self._h, off, out.ctypes.data, length))
+        return out
+
+    def bam_chunk(self, start, end, rec_ids, focus=None):
+        ids = np.ascontiguousarray(rec_ids, dtype=np.uint32)
+        fp = fn = None
+        if focus is not None:
+            fp = np.ascontiguousarray(focus[0], dtype=np.uint32); fn = np.ascontiguousarray(focus[1], dtype=np.uint32)
+        self._check(self._lib.mkp_bam_chunk(self._h, start, end, ids.ctypes.data, len(ids), fp.ctypes.data if fp is not None else None,
+                                            fn.ctypes.data if fn is not None else None))
+        self._n_reads_hint = len(ids)
+
+    def fetch_chunk(self):
+        """(headers, heap) of the resident chunk, copied back from the device (tests)."""
+        n = C.c_uint32()
+        hb = C.c_uint64(0)
+        self._check(self._lib.mkp_fetch_chunk(self._h, None, C.byref(n), None, C.byref(hb)))
+        hdrs = np.zeros(n.value, dtype=HDR_DTYPE)
+        heap = np.zeros(hb.value, dtype=np.uint8)
+        cap = C.c_uint64(hb.value)
+        self._check(self._lib.mkp_fetch_chunk(self._h, hdrs.ctypes.data if n.value else None, C.byref(n), heap.ctypes.data if hb.value else None, C.byref(cap)))
+        return hdrs, heap
 
     def close(self):
         if self._h:

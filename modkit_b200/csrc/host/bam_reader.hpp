@@ -49,6 +49,9 @@ struct RecRef {
     uint32_t size;       // block_size
     int32_t pos;
     int32_t end;         // htslib bam_endpos
+    uint32_t idx;        // index in file order (record table of the device ingest)
+    uint32_t l_seq;
+    uint16_t flag;
 };
 
 struct BamIndexStats { std::vector<uint64_t> n_mapped, n_unmapped; uint64_t n_no_coor = 0; bool from_bai = false; };
@@ -63,10 +66,13 @@ public:
     std::vector<RecRef> unplaced;
     BamIndexStats stats;
 
-    void open(const std::string& path, int threads) {
-        MappedFile mf;
-        mf.open(path);
-        struct Member { size_t in_off, in_len, out_off; uint32_t out_len; };
+    bool on_device = false;                   // records live in the inflated stream on the GPU (open_device); raw is empty
+    mkp_ctx* dev = nullptr;
+    float ingest_ms[4] = {0, 0, 0, 0};        // device ingest: H2D, inflate, record walk, total
+
+    struct Member { size_t in_off, in_len, out_off; uint32_t out_len; size_t file_off; };
+
+    static std::vector<Member> scan_members(const MappedFile& mf, const std::string& path, size_t* total_out) {
         std::vector<Member> members;
         size_t off = 0, total = 0;
         while (off + 28 <= mf.size) {
@@ -83,10 +89,19 @@ public:
             const size_t mlen = (size_t)bsize + 1;
             if (off + mlen > mf.size) throw std::runtime_error(path + ": truncated BGZF member");
             const uint32_t isize = load_le<uint32_t>(p + mlen - 4);
-            members.push_back({off + 12 + xlen, mlen - 20 - xlen, total, isize});
+            members.push_back({off + 12 + xlen, mlen - 20 - xlen, total, isize, off});
             total += isize;
             off += mlen;
         }
+        *total_out = total;
+        return members;
+    }
+
+    void open(const std::string& path, int threads) {
+        MappedFile mf;
+        mf.open(path);
+        size_t total = 0;
+        std::vector<Member> members = scan_members(mf, path, &total);
         raw.resize(total + 16);
         std::atomic<size_t> next{0};
         std::atomic<bool> bad{false};
@@ -115,7 +130,98 @@ public:
         for (auto& t : th) t.join();
         if (bad) throw std::runtime_error(path + ": inflate failed");
         index_records(total);
-        load_bai(path);
+        load_bai(path, nullptr);
+    }
+
+    // Device ingest (include/mkp.h, mkp_bam_load): the host walks the BGZF member headers, inflates only the members
+    // that hold the BAM header, and turns the BAI's virtual offsets into seed offsets for the record walk.
+    void open_device(const std::string& path, mkp_ctx* ctx) {
+        MappedFile mf;
+        mf.open(path);
+        size_t total = 0;
+        std::vector<Member> members = scan_members(mf, path, &total);
+        // ---- BAM header: inflate leading members until it is complete
+        std::vector<uint8_t> head;
+        size_t m_done = 0;
+        auto more = [&]() {
+            if (m_done >= members.size()) throw std::runtime_error(path + ": truncated BAM header");
+            const Member& m = members[m_done++];
+            const size_t o = head.size();
+            head.resize(o + m.out_len);
+            if (!m.out_len) return;
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("zlib init failed");
+            zs.next_in = (Bytef*)(mf.data + m.in_off); zs.avail_in = (uInt)m.in_len;
+            zs.next_out = head.data() + o; zs.avail_out = m.out_len;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END) throw std::runtime_error(path + ": inflate failed");
+        };
+        auto need = [&](size_t n) { while (head.size() < n) more(); };
+        need(12);
+        if (memcmp(head.data(), "BAM\1", 4) != 0) throw std::runtime_error("not a BAM stream");
+        size_t o = 8 + load_le<uint32_t>(head.data() + 4);
+        need(o + 4);
+        const uint32_t n_ref = load_le<uint32_t>(head.data() + o);
+        o += 4;
+        for (uint32_t i = 0; i < n_ref; i++) {
+            need(o + 4);
+            const uint32_t ln = load_le<uint32_t>(head.data() + o);
+            need(o + 8 + ln);
+            ref_names.emplace_back((const char*)head.data() + o + 4, ln ? ln - 1 : 0);
+            ref_lens.push_back(load_le<uint32_t>(head.data() + o + 4 + ln));
+            o += 8 + ln;
+        }
+        const uint64_t first_rec = o;
+        by_tid.assign(n_ref, {});
+        run_max_end.assign(n_ref, {});
+        stats.n_mapped.assign(n_ref, 0);
+        stats.n_unmapped.assign(n_ref, 0);
+        // ---- seeds: virtual offsets of the index -> offsets in the inflated stream
+        std::vector<uint64_t> voffs;
+        const bool have_bai = load_bai(path, &voffs);
+        std::vector<uint64_t> seeds;
+        seeds.push_back(first_rec);
+        for (uint64_t v : voffs) {
+            const uint64_t coff = v >> 16, uoff = v & 0xffff;
+            auto it = std::lower_bound(members.begin(), members.end(), coff, [](const Member& m, uint64_t c) { return m.file_off < c; });
+            if (it == members.end() || it->file_off != coff) continue;
+            const uint64_t x = it->out_off + uoff;
+            if (x > first_rec && x + 36 <= total) seeds.push_back(x);
+        }
+        std::sort(seeds.begin(), seeds.end());
+        seeds.erase(std::unique(seeds.begin(), seeds.end()), seeds.end());
+        std::vector<mkp_bgzf_member> jobs;
+        jobs.reserve(members.size());
+        for (auto& m : members) if (m.out_len) jobs.push_back({(uint64_t)m.in_off, (uint64_t)m.out_off, (uint32_t)m.in_len, m.out_len});
+        size_t n_rec = 0;
+        if (first_rec >= total) { seeds.clear(); }
+        if (!seeds.empty()) {
+            if (mkp_bam_load(ctx, mf.data, mf.size, jobs.data(), jobs.size(), total, seeds.data(), seeds.size(), &n_rec, ingest_ms))
+                throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(ctx));
+        }
+        std::vector<mkp_bam_rec> recs(n_rec);
+        if (n_rec && mkp_bam_records(ctx, recs.data())) throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(ctx));
+        BamIndexStats scan;
+        scan.n_mapped.assign(n_ref, 0); scan.n_unmapped.assign(n_ref, 0);
+        for (size_t i = 0; i < n_rec; i++) {
+            const mkp_bam_rec& d = recs[i];
+            RecRef r;
+            r.off = d.off; r.size = d.size; r.pos = d.pos; r.end = d.end; r.idx = (uint32_t)i; r.l_seq = d.l_seq; r.flag = (uint16_t)d.flag;
+            if (d.tid >= 0 && (uint32_t)d.tid < n_ref) {
+                by_tid[d.tid].push_back(r);
+                if (d.flag & 4) scan.n_unmapped[d.tid]++; else scan.n_mapped[d.tid]++;
+            } else { unplaced.push_back(r); scan.n_no_coor++; }
+        }
+        if (!have_bai) stats = scan;
+        for (uint32_t t = 0; t < n_ref; t++) {
+            int32_t m = INT32_MIN;
+            run_max_end[t].reserve(by_tid[t].size());
+            for (auto& r : by_tid[t]) { m = std::max(m, r.end); run_max_end[t].push_back(m); }
+        }
+        on_device = true;
+        dev = ctx;
     }
 
     // reads overlapping [beg,end) on tid in file order: half-open record span [pos, endpos)
@@ -125,7 +231,7 @@ public:
         size_t i = std::upper_bound(rm.begin(), rm.end(), (int32_t)std::min<int64_t>(beg, INT32_MAX)) - rm.begin();
         for (; i < v.size() && v[i].pos < end; i++) if (v[i].end > beg) f(v[i]);
     }
-    const uint8_t* rec(const RecRef& r) const { return raw.data() + r.off; }
+    const uint8_t* rec(const RecRef& r) const { if (on_device) throw std::runtime_error("record bytes are on the device"); return raw.data() + r.off; }
 
 private:
     void index_records(size_t total) {
@@ -144,6 +250,7 @@ private:
         run_max_end.assign(n_ref, {});
         stats.n_mapped.assign(n_ref, 0);
         stats.n_unmapped.assign(n_ref, 0);
+        uint32_t n_seen = 0;
         while (o + 4 <= total) {
             const uint32_t bs = load_le<uint32_t>(p + o);
             if (o + 4 + bs > total || bs < 32) throw std::runtime_error("corrupt BAM record");
@@ -153,6 +260,7 @@ private:
             const int32_t tid = load_le<int32_t>(r);
             ref.pos = load_le<int32_t>(r + 4);
             const uint16_t flag = load_le<uint16_t>(r + 14);
+            ref.idx = n_seen++; ref.flag = flag; ref.l_seq = load_le<uint32_t>(r + 16);
             const uint16_t n_cig = load_le<uint16_t>(r + 12);
             int64_t span = 0;
             if (!(flag & 4) && n_cig) {
@@ -181,7 +289,7 @@ private:
     }
 
     // BAI pseudo-bin 37450 (SAMv1 5.2): per-reference mapped/unmapped counts == hts_idx_get_stat
-    void load_bai(const std::string& bam_path) {
+    bool load_bai(const std::string& bam_path, std::vector<uint64_t>* voffs) {
         std::string cand[2] = {bam_path + ".bai", bam_path.size() > 4 ? bam_path.substr(0, bam_path.size() - 4) + ".bai" : std::string()};
         for (auto& path : cand) {
             if (path.empty()) continue;
@@ -212,20 +320,25 @@ private:
                     if (bin == 37450 && n_chunk == 2) {
                         s.n_mapped[r] = load_le<uint64_t>(b.data() + o + 16);
                         s.n_unmapped[r] = load_le<uint64_t>(b.data() + o + 24);
+                    } else if (voffs) {
+                        for (uint32_t c = 0; c < n_chunk; c++) voffs->push_back(load_le<uint64_t>(b.data() + o + 16ull * c));
                     }
                     o += 16ull * n_chunk;
                 }
                 if (!ok || o + 4 > b.size()) { ok = false; break; }
                 const uint32_t n_intv = load_le<uint32_t>(b.data() + o);
+                if (o + 4 + 8ull * n_intv > b.size()) { ok = false; break; }
+                if (voffs) for (uint32_t c = 0; c < n_intv; c++) voffs->push_back(load_le<uint64_t>(b.data() + o + 4 + 8ull * c));
                 o += 4 + 8ull * n_intv;
             }
-            if (!ok) continue;
+            if (!ok) { if (voffs) voffs->clear(); continue; }
             if (o + 8 <= b.size()) s.n_no_coor = load_le<uint64_t>(b.data() + o);
             s.from_bai = true;
             stats = s;
-            return;
+            return true;
         }
         // no usable index: keep the counts taken while scanning the records (identical for a consistent index)
+        return false;
     }
 };
 
@@ -400,6 +513,15 @@ inline void pack_region_mt(const BamReader& bam, uint32_t tid, uint32_t start, u
         if (plan[i].n_mm) memcpy(d, plan[i].mm, plan[i].n_mm);
     });
     out->recs.insert(out->recs.end(), recs.begin(), recs.end());
+}
+
+// Device ingest: the reads overlapping [start,end) become the resident chunk (slicing happens on the GPU).
+inline uint32_t device_chunk(const BamReader& bam, const std::vector<RecRef>& recs, uint32_t start, uint32_t end,
+                             const uint32_t* focus_pos, const uint32_t* focus_neg) {
+    std::vector<uint32_t> ids(recs.size());
+    for (size_t i = 0; i < recs.size(); i++) ids[i] = recs[i].idx;
+    if (mkp_bam_chunk(bam.dev, start, end, ids.data(), (uint32_t)ids.size(), focus_pos, focus_neg)) throw std::runtime_error(mkp_last_error(bam.dev));
+    return (uint32_t)ids.size();
 }
 
 }  // namespace mkh

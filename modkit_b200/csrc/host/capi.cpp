@@ -22,6 +22,21 @@ int mkh_bam_open(const char* path, int threads, mkh_bam** out) {
     try { mkh_bam* b = new mkh_bam(); b->reader.open(path, threads); *out = b; return 0; }
     catch (const std::exception& e) { fprintf(stderr, "mkh_bam_open: %s\n", e.what()); return -1; }
 }
+// device ingest: inflate + record discovery on the GPU of `ctx` (include/mkp.h, mkp_bam_load)
+int mkh_bam_open_device(const char* path, mkp_ctx* ctx, mkh_bam** out) {
+    try { mkh_bam* b = new mkh_bam(); b->reader.open_device(path, ctx); *out = b; return 0; }
+    catch (const std::exception& e) { fprintf(stderr, "mkh_bam_open_device: %s\n", e.what()); return -1; }
+}
+// the reads overlapping [start,end) of tid become the resident chunk of the ingest context; returns the read count or -1
+int64_t mkh_device_chunk(const mkh_bam* b, uint32_t tid, uint32_t start, uint32_t end, const uint32_t* focus_pos, const uint32_t* focus_neg) {
+    try {
+        std::vector<RecRef> recs;
+        b->reader.for_overlapping(tid, start, end, [&](const RecRef& r) { recs.push_back(r); });
+        return (int64_t)device_chunk(b->reader, recs, start, end, focus_pos, focus_neg);
+    } catch (const std::exception& e) { fprintf(stderr, "mkh_device_chunk: %s\n", e.what()); return -1; }
+}
+void mkh_bam_ingest_ms(const mkh_bam* b, float* ms) { for (int i = 0; i < 4; i++) ms[i] = b->reader.ingest_ms[i]; }
+uint64_t mkh_bam_total_records(const mkh_bam* b) { uint64_t n = b->reader.unplaced.size(); for (auto& v : b->reader.by_tid) n += v.size(); return n; }
 void mkh_bam_close(mkh_bam* b) { delete b; }
 uint32_t mkh_bam_n_refs(const mkh_bam* b) { return (uint32_t)b->reader.ref_names.size(); }
 const char* mkh_bam_ref_name(const mkh_bam* b, uint32_t tid) { return b->reader.ref_names[tid].c_str(); }

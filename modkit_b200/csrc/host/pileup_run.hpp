@@ -22,6 +22,7 @@ struct PileupOptions {
     std::string region, sample_region, ignore, ref_fp, edge, stats_json, include_bed;
     int device = 0;
     uint32_t chunk_bp = 16u << 20;     // reference span handed to the GPU per call
+    bool host_ingest = false;          // inflate + slice the BAM on the host (zlib) instead of on the GPU
     bool quiet = false;
 };
 
@@ -76,10 +77,10 @@ struct SamplerConfig {
     const IncludeBed* include = nullptr;
 };
 
-inline bool sampler_flag_ok(const uint8_t* rec, bool require_mapped) {
-    const uint16_t flag = load_le<uint16_t>(rec + 14);
+inline bool sampler_flag_ok(const RecRef& r, bool require_mapped) {
+    const uint16_t flag = r.flag;
     if (flag & (0x100 | 0x400 | 0x800)) return false;
-    if (load_le<int32_t>(rec + 16) == 0) return false;
+    if (r.l_seq == 0) return false;
     if (require_mapped && (flag & 0x4)) return false;
     return true;
 }
@@ -149,12 +150,15 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
             cfg.include->bitmaps(tid, ch.start, ch.end, &fpos, &fneg);
             ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data();
         }
+        if (bam.on_device) { device_chunk(bam, pc.recs, ch.start, ch.end, ch.focus_pos, ch.focus_neg); return; }
         ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
         if (mkp_upload_chunk(ctx, &ch)) throw std::runtime_error(mkp_last_error(ctx));
     };
+    // candidate records: sliced on the host (pack_record) or, with the device ingest, only listed (sliced on the GPU)
+    auto add_candidate = [&](const RecRef& r) { if (!bam.on_device) pack_record(bam.rec(r), r.size, &cand); cand.recs.push_back(r); };
     auto decode_contributes = [&](PackedChunk& pc, uint32_t tid) {
-        contributes.assign(pc.hdrs.size(), 0);
-        if (pc.hdrs.empty()) return;
+        contributes.assign(pc.recs.size(), 0);
+        if (pc.recs.empty()) return;
         upload(pc, tid);
         if (mkp_sample_histogram(ctx, cfg.include_unmapped ? 1 : 0, nullptr, nullptr, contributes.data(), nullptr)) throw std::runtime_error(mkp_last_error(ctx));
     };
@@ -213,15 +217,15 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
         for (const Grp& g : todo) {
             if (cfg.include && !cfg.include->overlaps_any(g.tid, g.start, g.end)) continue;
             std::vector<RecRef> recs;
-            bam.for_overlapping(g.tid, g.start, g.end, [&](const RecRef& r) { if (sampler_flag_ok(bam.rec(r), only_mapped || cfg.edge_on)) recs.push_back(r); });
+            bam.for_overlapping(g.tid, g.start, g.end, [&](const RecRef& r) { if (sampler_flag_ok(r, only_mapped || cfg.edge_on)) recs.push_back(r); });
             size_t used = 0, cursor = 0;
             while (cursor < recs.size() && (g.n < 0 || used < (size_t)g.n)) {
                 const size_t want = g.n < 0 ? recs.size() : std::min(recs.size(), cursor + (size_t)(g.n - (int64_t)used) * 2 + 32);
                 cand.clear();
-                for (size_t k = cursor; k < want; k++) { pack_record(bam.rec(recs[k]), recs[k].size, &cand); cand.recs.push_back(recs[k]); }
+                for (size_t k = cursor; k < want; k++) add_candidate(recs[k]);
                 decode_contributes(cand, g.tid);
-                take.assign(cand.hdrs.size(), 0);
-                for (size_t k = 0; k < cand.hdrs.size() && (g.n < 0 || used < (size_t)g.n); k++) {
+                take.assign(cand.recs.size(), 0);
+                for (size_t k = 0; k < cand.recs.size() && (g.n < 0 || used < (size_t)g.n); k++) {
                     if (!contributes[k]) continue;
                     used++;
                     if (selected_ids.insert(cand.recs[k].off).second) take[k] = 1;
@@ -235,12 +239,12 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
     if (!only_mapped) {   // reads without coordinates (reads_sampler/mod.rs:85-129)
         const size_t limit = cfg.take_all ? (size_t)-1 : (cfg.num_reads > selected_ids.size() ? cfg.num_reads - selected_ids.size() : 0);
         cand.clear();
-        for (auto& r : bam.unplaced) if (sampler_flag_ok(bam.rec(r), cfg.edge_on)) { pack_record(bam.rec(r), r.size, &cand); cand.recs.push_back(r); }
-        if (!cand.hdrs.empty()) {
+        for (auto& r : bam.unplaced) if (sampler_flag_ok(r, cfg.edge_on)) add_candidate(r);
+        if (!cand.recs.empty()) {
             decode_contributes(cand, 0);
-            take.assign(cand.hdrs.size(), 0);
+            take.assign(cand.recs.size(), 0);
             size_t used = 0;
-            for (size_t k = 0; k < cand.hdrs.size() && used < limit; k++) {
+            for (size_t k = 0; k < cand.recs.size() && used < limit; k++) {
                 if (!contributes[k]) continue;
                 used++;
                 if (selected_ids.insert(cand.recs[k].off).second) take[k] = 1;
@@ -264,8 +268,14 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
     try {
         const auto t0 = clk::now();
         if (o.percentile > 1.0f) throw std::runtime_error("filter percentile must be <= 1.0");
+        // the device comes first: with the device ingest (default) the BAM is inflated and sliced on the GPU
+        DeviceGuard dev;
+        {
+            const int rc = mkp_create(o.device, &dev.ctx);
+            if (rc) throw std::runtime_error("no usable CUDA device (mkp_create returned " + std::to_string(rc) + "); this build has no CPU fallback");
+        }
         BamReader bam;
-        bam.open(o.in_bam, o.threads);
+        if (o.host_ingest) bam.open(o.in_bam, o.threads); else bam.open_device(o.in_bam, dev.ctx);
         const auto t_load = clk::now();
         Region region, sregion;
         const Region* rp = nullptr; const Region* srp = nullptr;
@@ -332,10 +342,6 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         FILE* out = (o.out_bed == "-" || o.out_bed == "stdout") ? stdout : fopen(o.out_bed.c_str(), "w");
         if (!out) throw std::runtime_error("failed to make output file");
         if (o.header) fputs(bed_header_line(), out);
-
-        DeviceGuard dev;
-        int rc = mkp_create(o.device, &dev.ctx);
-        if (rc) throw std::runtime_error("no usable CUDA device (mkp_create returned " + std::to_string(rc) + "); this build has no CPU fallback");
 
         // thresholds (subcommand.rs:615-638, command_utils.rs:49-134)
         for (auto& raw : o.mod_thresholds) {
@@ -410,22 +416,30 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             if (ce <= cs) { i0 = i1; continue; }
             const auto ta = clk::now();
             pc.clear();
-            pack_region_mt(bam, ivs[i0].tid, cs, ce, o.threads, &pc);
-            const auto tb = clk::now();
-            S.pack_s += secs(ta, tb);
-            if (pc.hdrs.empty()) { i0 = i1; continue; }
+            if (bam.on_device) bam.for_overlapping(ivs[i0].tid, cs, ce, [&](const RecRef& r) { pc.recs.push_back(r); });
+            else pack_region_mt(bam, ivs[i0].tid, cs, ce, o.threads, &pc);
+            if (pc.recs.empty()) { i0 = i1; continue; }
             mkp_chunk ch;
             memset(&ch, 0, sizeof ch);
             ch.start = cs; ch.end = ce; ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
             if (have_motifs || inc) { focus_bitmaps(ivs, i0, i1, cs, ce, &fpos, &fneg); ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data(); }
+            const auto tb = clk::now();
+            S.pack_s += secs(ta, tb);
             const mkp_row* rows = nullptr;
             size_t n_rows = 0;
             mkp_stats st;
-            if (mkp_pileup_chunk(dev.ctx, &ch, &rows, &n_rows, &st)) throw std::runtime_error(mkp_last_error(dev.ctx));
+            if (bam.on_device) {
+                // slice on the GPU (no packed chunk in host memory), then the same kernels
+                device_chunk(bam, pc.recs, cs, ce, ch.focus_pos, ch.focus_neg);
+                if (mkp_pileup_resident(dev.ctx, &st) || mkp_fetch_rows(dev.ctx, &rows, &n_rows)) throw std::runtime_error(mkp_last_error(dev.ctx));
+                pc.hdrs.resize(pc.recs.size());
+                uint32_t nr = 0;
+                if (mkp_fetch_chunk(dev.ctx, pc.hdrs.data(), &nr, nullptr, nullptr)) throw std::runtime_error(mkp_last_error(dev.ctx));
+            } else if (mkp_pileup_chunk(dev.ctx, &ch, &rows, &n_rows, &st)) throw std::runtime_error(mkp_last_error(dev.ctx));
             const auto tc = clk::now();
             S.gpu_s += secs(tb, tc);
             S.kernel_ms += st.kernel_ms[7];
-            S.reads_packed += pc.hdrs.size();
+            S.reads_packed += pc.recs.size();
             S.algorithmic_bytes += pc.algorithmic_bytes() + 40 * n_rows;
             S.chunks++;
             // rows are position sorted: every interval gets its slice; intervals are finished and formatted in parallel
@@ -479,9 +493,10 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         if (!o.stats_json.empty()) {
             FILE* jf = fopen(o.stats_json.c_str(), "w");
             if (jf) {
-                fprintf(jf, "{\"positions\": %llu, \"rows\": %llu, \"reads\": %llu, \"chunks\": %llu, \"algorithmic_bytes\": %llu, \"load_s\": %.6f, \"thresholds_s\": %.6f, \"intervals_s\": %.6f, \"pack_s\": %.6f, \"gpu_s\": %.6f, \"kernel_ms\": %.6f, \"write_s\": %.6f, \"total_s\": %.6f}\n",
+                fprintf(jf, "{\"positions\": %llu, \"rows\": %llu, \"reads\": %llu, \"chunks\": %llu, \"algorithmic_bytes\": %llu, \"load_s\": %.6f, \"thresholds_s\": %.6f, \"intervals_s\": %.6f, \"pack_s\": %.6f, \"gpu_s\": %.6f, \"kernel_ms\": %.6f, \"write_s\": %.6f, \"total_s\": %.6f, \"ingest\": \"%s\", \"ingest_h2d_ms\": %.3f, \"ingest_inflate_ms\": %.3f, \"ingest_walk_ms\": %.3f}\n",
                         (unsigned long long)S.positions, (unsigned long long)S.rows, (unsigned long long)S.reads_packed, (unsigned long long)S.chunks, (unsigned long long)S.algorithmic_bytes,
-                        S.load_s, S.threshold_s, S.interval_s, S.pack_s, S.gpu_s, S.kernel_ms, S.write_s, S.total_s);
+                        S.load_s, S.threshold_s, S.interval_s, S.pack_s, S.gpu_s, S.kernel_ms, S.write_s, S.total_s,
+                        bam.on_device ? "device" : "host", bam.ingest_ms[0], bam.ingest_ms[1], bam.ingest_ms[2]);
                 fclose(jf);
             }
         }
@@ -528,6 +543,7 @@ inline bool parse_pileup_args(int argc, const char* const* argv, PileupOptions* 
             else if (a == "--header" || a == "--with-header" || a == "--include_header") o->header = true;
             else if (a == "--device") o->device = std::stoi(val());
             else if (a == "--gpu-chunk-bp") o->chunk_bp = (uint32_t)std::stoul(val());
+            else if (a == "--host-ingest") o->host_ingest = true;
             else if (a == "--stats-json") o->stats_json = val();
             else if (a == "--quiet") o->quiet = true;
             else if (a == "--include-bed" || a == "--include-positions") o->include_bed = val();

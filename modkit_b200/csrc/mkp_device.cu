@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "mkp_kernels.cuh"
+#include "mkp_ingest.cuh"
 
 using namespace mkp;
 
@@ -51,6 +52,10 @@ struct mkp_ctx {
     // work buffers
     DevBuf d_rl, d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr, d_slow;
     DevBuf d_obs_word, d_slots, d_row_counts, d_row_prefix, d_rows, d_hist, d_take;
+    // device ingest (BGZF file, inflated BAM stream, record table, slicing scratch)
+    DevBuf d_file, d_members, d_bam, d_seeds, d_seg_counts, d_seg_base, d_recs, d_ids, d_plan, d_need, d_totals;
+    uint64_t bam_len = 0;
+    size_t n_records = 0;
     // results
     size_t n_rows = 0;
     std::vector<mkp_row> h_rows;
@@ -93,7 +98,9 @@ void mkp_destroy(mkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_rl, &ctx->d_meta, &ctx->d_P,
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
-                      &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take};
+                      &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
+                      &ctx->d_file, &ctx->d_members, &ctx->d_bam, &ctx->d_seeds, &ctx->d_seg_counts, &ctx->d_seg_base, &ctx->d_recs, &ctx->d_ids, &ctx->d_plan,
+                      &ctx->d_need, &ctx->d_totals};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -372,6 +379,151 @@ int mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* tak
     if (h_small[1]) return fail(ctx, "device decode error: " + derr_text(h_small[1]), -10);
     if (contributes) for (uint32_t i = 0; i < ctx->n_reads; i++) contributes[i] = metas[i].n_hist > 0;
     if (inexact) *inexact = inx;
+    return 0;
+}
+
+
+// ---- BGZF / BAM ingest on the device (mkp_ingest.cuh) -----------------------------------------------------
+int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                 uint64_t inflated_len, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms) {
+    if (!ctx || !file || !members || !seeds || !n_seeds) return -1;
+    if (n_members >= (1u << 24)) return fail(ctx, "too many BGZF members for one load");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_file.ensure(file_len + 64));
+    CK(ctx->d_members.ensure(std::max<size_t>(1, n_members) * sizeof(mkp_bgzf_member)));
+    CK(ctx->d_bam.ensure(inflated_len + 64));
+    CK(ctx->d_seeds.ensure(n_seeds * 8));
+    CK(ctx->d_seg_counts.ensure(n_seeds * 4 + 4));
+    CK(ctx->d_seg_base.ensure(n_seeds * 4 + 4));
+    CK(ctx->d_small.ensure(SMALL_BYTES));
+    const uint32_t n_blk = (uint32_t)((n_seeds + 1023) / 1024);
+    CK(ctx->d_block_sums.ensure((size_t)n_blk * 4 + 4));
+    uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);    // u+10 status, u+11 work, u+12 record count
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaMemcpyAsync(ctx->d_file.p, file, file_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_members.p, members, n_members * sizeof(mkp_bgzf_member), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_seeds.p, seeds, n_seeds * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(u + 10, 0, 12, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    const size_t smem = (size_t)INF_THREADS * INF_STRIDE * 2;
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    if (n_members) {
+        const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+        const int grid = (int)std::min<size_t>((n_members + INF_THREADS - 1) / INF_THREADS, (size_t)ctx->sm_count * per_sm);
+        k_inflate<<<grid, INF_THREADS, smem, st>>>(ctx->d_file.as<uint8_t>(), ctx->d_members.as<mkp_bgzf_member>(), (uint32_t)n_members,
+                                                  ctx->d_bam.as<uint8_t>(), u + 10, u + 11);
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+    const int wg = (int)((n_seeds + 127) / 128);
+    k_walk<0><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), inflated_len, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
+                                  ctx->d_seg_counts.as<uint32_t>(), nullptr, nullptr, u + 10);
+    k_block_sum<<<n_blk, 1024, 0, st>>>(ctx->d_seg_counts.as<uint32_t>(), (uint32_t)n_seeds, ctx->d_block_sums.as<uint32_t>());
+    k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 12);
+    k_value_prefix<<<n_blk, 1024, 0, st>>>(ctx->d_seg_counts.as<uint32_t>(), (uint32_t)n_seeds, ctx->d_block_sums.as<uint32_t>(), ctx->d_seg_base.as<uint32_t>());
+    uint32_t h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h, u + 10, 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (h[0]) {
+        const uint32_t e = h[0];
+        if ((e >> 24) & 0x7f) return fail(ctx, "inflate failed (code " + std::to_string((e >> 24) & 0x7f) + ") in BGZF member " + std::to_string(e & 0xffffffu));
+        return fail(ctx, (e & 3u) == 2u ? "record chain does not meet a seed offset (stale or foreign index?)" : "corrupt BAM record in the inflated stream");
+    }
+    const size_t nrec = h[2];
+    CK(ctx->d_recs.ensure(std::max<size_t>(1, nrec) * sizeof(mkp_bam_rec)));
+    k_walk<1><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), inflated_len, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
+                                  ctx->d_seg_counts.as<uint32_t>(), ctx->d_seg_base.as<uint32_t>(), ctx->d_recs.as<mkp_bam_rec>(), u + 10);
+    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaMemcpyAsync(h, u + 10, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (h[0]) return fail(ctx, "corrupt BAM record in the inflated stream");
+    ctx->bam_len = inflated_len;
+    ctx->n_records = nrec;
+    if (n_records) *n_records = nrec;
+    if (ms) {
+        cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&ms[2], ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&ms[3], ctx->ev[0], ctx->ev[3]);
+    }
+    return 0;
+}
+
+int mkp_bam_records(mkp_ctx* ctx, mkp_bam_rec* out) {
+    if (!ctx || !out) return -1;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_records) CK(cudaMemcpy(out, ctx->d_recs.p, ctx->n_records * sizeof(mkp_bam_rec), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mkp_bam_inflated(mkp_ctx* ctx, uint64_t off, uint8_t* dst, size_t len) {
+    if (!ctx || !dst) return -1;
+    if (off + len > ctx->bam_len) return fail(ctx, "range outside the inflated stream");
+    CK(cudaSetDevice(ctx->device));
+    if (len) CK(cudaMemcpy(dst, ctx->d_bam.as<uint8_t>() + off, len, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mkp_bam_chunk(mkp_ctx* ctx, uint32_t start, uint32_t end, const uint32_t* rec_ids, uint32_t n, const uint32_t* focus_pos, const uint32_t* focus_neg) {
+    if (!ctx || (n && !rec_ids)) return -1;
+    if (end <= start) return fail(ctx, "empty chunk range");
+    if (!ctx->bam_len) return fail(ctx, "mkp_bam_load was not called");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->n_reads = n; ctx->cs = start; ctx->ce = end;
+    ctx->n_words = (end - start + 31) / 32;
+    CK(ctx->d_hdrs.ensure(std::max<size_t>(1, n) * sizeof(mkp_read_hdr)));
+    CK(ctx->d_entry_off.ensure(((size_t)n + 1) * 8));
+    CK(ctx->d_ids.ensure(std::max<size_t>(1, n) * 4));
+    CK(ctx->d_plan.ensure(std::max<size_t>(1, n) * sizeof(SlicePlan)));
+    CK(ctx->d_need.ensure(std::max<size_t>(1, n) * 4));
+    CK(ctx->d_totals.ensure(4 * 8));
+    uint64_t tot[4] = {0, 0, 1, 1};
+    if (n) {
+        for (uint32_t i = 0; i < n; i++) if (rec_ids[i] >= ctx->n_records) return fail(ctx, "record id out of range");
+        CK(cudaMemcpyAsync(ctx->d_ids.p, rec_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        k_slice_plan<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_recs.as<mkp_bam_rec>(), ctx->d_ids.as<uint32_t>(), n,
+                                                     ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_plan.as<SlicePlan>(), ctx->d_need.as<uint32_t>());
+        k_slice_scan<<<1, 1024, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_need.as<uint32_t>(), n, ctx->d_entry_off.as<uint64_t>(), ctx->d_totals.as<uint64_t>());
+        CK(cudaMemcpyAsync(tot, ctx->d_totals.p, 32, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        CK(ctx->d_heap.ensure(tot[0] + 64));
+        const int grid = std::max(1, std::min(ctx->sm_count * 8, (int)((n + 7) / 8)));
+        k_slice_copy<<<grid, 256, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_plan.as<SlicePlan>(), n, ctx->d_heap.as<uint8_t>());
+    } else {
+        CK(cudaMemsetAsync(ctx->d_entry_off.p, 0, 8, st));
+        CK(ctx->d_heap.ensure(64));
+    }
+    ctx->heap_bytes = tot[0];
+    ctx->total_entries = tot[1];
+    ctx->max_ncigar = (uint32_t)std::max<uint64_t>(1, tot[2]);
+    ctx->max_blocks = (uint32_t)((std::max<uint64_t>(1, tot[3]) + 31) / 32);
+    ctx->have_focus = focus_pos && focus_neg;
+    if (ctx->have_focus) {
+        CK(ctx->d_focus_pos.ensure((size_t)ctx->n_words * 4));
+        CK(ctx->d_focus_neg.ensure((size_t)ctx->n_words * 4));
+        CK(cudaMemcpyAsync(ctx->d_focus_pos.p, focus_pos, (size_t)ctx->n_words * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_focus_neg.p, focus_neg, (size_t)ctx->n_words * 4, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mkp_fetch_chunk(mkp_ctx* ctx, mkp_read_hdr* hdrs, uint32_t* n_reads, uint8_t* heap, uint64_t* heap_bytes) {
+    if (!ctx) return -1;
+    CK(cudaSetDevice(ctx->device));
+    if (n_reads) *n_reads = ctx->n_reads;
+    if (hdrs && ctx->n_reads) CK(cudaMemcpy(hdrs, ctx->d_hdrs.p, (size_t)ctx->n_reads * sizeof(mkp_read_hdr), cudaMemcpyDeviceToHost));
+    if (heap && heap_bytes) {
+        if (*heap_bytes < ctx->heap_bytes) return fail(ctx, "heap buffer too small");
+        if (ctx->heap_bytes) CK(cudaMemcpy(heap, ctx->d_heap.p, ctx->heap_bytes, cudaMemcpyDeviceToHost));
+    }
+    if (heap_bytes) *heap_bytes = ctx->heap_bytes;
     return 0;
 }
 
