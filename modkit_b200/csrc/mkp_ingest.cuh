@@ -432,8 +432,10 @@ __global__ void __launch_bounds__(256) k_slice_copy(const uint8_t* __restrict__ 
         uint8_t* d = heap + h.off;
         const uint32_t nc = 4u * h.n_cigar, ns = (h.l_seq + 1) / 2;
         const uint32_t total = nc + ns + h.len_ml + h.len_mm;
-        // the four pieces back to back; 4 destination bytes per lane and step, sources read bytewise (unaligned)
-        for (uint32_t k = 4 * lane; k < total; k += 128) {
+        // the four pieces back to back, then zeros up to the 16-byte block boundary (like the host packer); 4 destination
+        // bytes per lane and step, sources read bytewise (unaligned)
+        const uint32_t padded = (total + 15u) & ~15u;
+        for (uint32_t k = 4 * lane; k < padded; k += 128) {
             uint32_t word = 0;
 #pragma unroll
             for (int t = 0; t < 4; t++) {
@@ -445,8 +447,7 @@ __global__ void __launch_bounds__(256) k_slice_copy(const uint8_t* __restrict__ 
                 else if (x < total) b = bam[pl.mm + (x - nc - ns - h.len_ml)];
                 word |= (uint32_t)b << (8 * t);
             }
-            if (k + 4 <= total) *(uint32_t*)(d + k) = word;
-            else for (uint32_t t = 0; k + t < total; t++) d[k + t] = (uint8_t)(word >> (8 * t));
+            *(uint32_t*)(d + k) = word;
         }
     }
 }
