@@ -24,7 +24,8 @@ namespace mkp {
 // (count per length + symbols sorted by code) and fronted by a direct-lookup table on the next INF_LBITS / INF_DBITS
 // stream bits; codes longer than that take the bit-by-bit canonical walk.
 constexpr int INF_LBITS = 9, INF_DBITS = 6;
-constexpr int INF_LSYM = 0, INF_DSYM = 288, INF_LCNT = 320, INF_DCNT = 336, INF_OFFS = 352, INF_LTAB = 368,
+constexpr int INF_LSYM = 0, INF_DSYM = 288, INF_LCNT = 320, INF_DCNT = 336, INF_OFFS = 352, INF_LFIRST = 368, INF_LINDEX = 384,
+              INF_DFIRST = 400, INF_DINDEX = 416, INF_LTAB = 432,
               INF_DTAB = INF_LTAB + (1 << INF_LBITS), INF_WORDS = INF_DTAB + (1 << INF_DBITS);
 constexpr int INF_STRIDE = (((INF_WORDS + 1) / 2) | 1) * 2;   // odd number of 32-bit words per decoder: spreads the banks
 __constant__ uint8_t c_clord[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -69,9 +70,11 @@ __device__ __forceinline__ int inf_decode_slow(BitReader& br, const uint16_t* cn
     return -1;
 }
 
-// lens[0..n) -> cnt[16], sym[] (sorted by length, then symbol), tab[1 << tbits] (sym << 4 | len for codes <= tbits).
+// lens[0..n) -> cnt[16], sym[] (sorted by length, then symbol), tab[1 << tbits] (sym << 4 | len for codes <= tbits),
+// first[len] = first canonical code of that length, index[len] = its position in sym[].
 // Returns false for an over-subscribed set of lengths.
-__device__ bool inf_build(const uint8_t* lens, int n, uint16_t* cnt, uint16_t* sym, uint16_t* offs, uint16_t* tab, int tbits) {
+__device__ bool inf_build(const uint8_t* lens, int n, uint16_t* cnt, uint16_t* sym, uint16_t* offs, uint16_t* tab, int tbits,
+                          uint16_t* first, uint16_t* index) {
     for (int i = 0; i < 16; i++) cnt[i] = 0;
     for (int s = 0; s < n; s++) cnt[lens[s]]++;
     cnt[0] = 0;
@@ -79,6 +82,10 @@ __device__ bool inf_build(const uint8_t* lens, int n, uint16_t* cnt, uint16_t* s
     for (int len = 1; len <= 15; len++) { left <<= 1; left -= cnt[len]; if (left < 0) return false; }
     offs[1] = 0;
     for (int len = 1; len < 15; len++) offs[len + 1] = offs[len] + cnt[len];
+    if (first) {
+        uint32_t code = 0;
+        for (int len = 1; len <= 15; len++) { first[len] = (uint16_t)code; index[len] = offs[len]; code = (code + cnt[len]) << 1; }
+    }
     for (int s = 0; s < n; s++) if (lens[s]) sym[offs[lens[s]]++] = (uint16_t)s;
     const int tsz = 1 << tbits;
     for (int i = 0; i < tsz; i++) tab[i] = 0;
@@ -96,14 +103,31 @@ __device__ bool inf_build(const uint8_t* lens, int n, uint16_t* cnt, uint16_t* s
     return true;
 }
 
-__device__ __forceinline__ int inf_decode(BitReader& br, const uint16_t* tab, int tbits, const uint16_t* cnt, const uint16_t* sym) {
+// codes longer than the lookup table: the next 15 stream bits, most significant first, against the first code of
+// every remaining length
+__device__ __forceinline__ int inf_decode_long(BitReader& br, int tbits, const uint16_t* cnt, const uint16_t* sym, const uint16_t* first, const uint16_t* index) {
+    const uint32_t v = __brev((uint32_t)br.bb) >> 17;          // 15 bits, first stream bit on top
+#pragma unroll 1
+    for (int len = tbits + 1; len <= 15; len++) {
+        const uint32_t c = (v >> (15 - len)) - first[len];
+        if (c < cnt[len]) { br.drop(len); return sym[index[len] + c]; }
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int inf_decode(BitReader& br, const uint16_t* tab, int tbits, const uint16_t* cnt, const uint16_t* sym, const uint16_t* first, const uint16_t* index) {
     br.refill();
     const uint16_t e = tab[br.peek(tbits)];
     if (e) { br.drop(e & 15); return e >> 4; }
-    return inf_decode_slow(br, cnt, sym);
+    return inf_decode_long(br, tbits, cnt, sym, first, index);
 }
 
-// One BGZF member (raw deflate payload) per thread.
+// One BGZF member (raw deflate payload) per thread, 32 members in flight per warp. The lanes of a warp run a small
+// state machine and meet again after every step (one symbol, one block header, one job fetch): without that the
+// lanes drift apart for good after the first divergent branch and the warp degenerates into 32 serial threads.
+enum { ST_FETCH = 0, ST_HEADER = 1, ST_SYMBOL = 2, ST_FINISH = 3, ST_DONE = 4, ST_COPY = 5 };
+constexpr int INF_COPY_STEP = 64;
+
 __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restrict__ in, const mkp_bgzf_member* __restrict__ jobs, uint32_t n_jobs,
                                                         uint8_t* out, uint32_t* status, uint32_t* work) {
     extern __shared__ uint16_t inf_smem[];
@@ -111,19 +135,76 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
     uint16_t* const lsym = my + INF_LSYM; uint16_t* const dsym = my + INF_DSYM; uint16_t* const lcnt = my + INF_LCNT;
     uint16_t* const dcnt = my + INF_DCNT; uint16_t* const offs = my + INF_OFFS; uint16_t* const ltab = my + INF_LTAB;
     uint16_t* const dtab = my + INF_DTAB;
+    uint16_t* const lfirst = my + INF_LFIRST; uint16_t* const lindex = my + INF_LINDEX;
+    uint16_t* const dfirst = my + INF_DFIRST; uint16_t* const dindex = my + INF_DINDEX;
     uint8_t lens[320];
+    int state = ST_FETCH;
+    uint32_t cp_len = 0, cp_dist = 0;          // pending match copy (ST_COPY)
+    uint32_t j = 0, o = 0, cap = 0;
+    uint8_t* dst = nullptr;
+    int err = INF_OK;
+    bool last = false;
+    BitReader br;
+    br.init(in, in);
     for (;;) {
-        const uint32_t j = atomicAdd(work, 1u);
-        if (j >= n_jobs) break;
-        const mkp_bgzf_member job = jobs[j];
-        uint8_t* const dst = out + job.out_off;
-        const uint32_t cap = job.out_len;
-        uint32_t o = 0;
-        int err = INF_OK;
-        BitReader br;
-        br.init(in + job.in_off, in + job.in_off + job.in_len);
-        bool last = false;
-        while (!last && !err) {
+        if (state == ST_SYMBOL) {
+            const int sym = inf_decode(br, ltab, INF_LBITS, lcnt, lsym, lfirst, lindex);
+            if (sym < 256) {
+                if (sym < 0) { err = INF_ERR_CODE; state = ST_FINISH; }
+                else if (o >= cap) { err = INF_ERR_SIZE; state = ST_FINISH; }
+                else dst[o++] = (uint8_t)sym;
+            } else if (sym == 256) state = last ? ST_FINISH : ST_HEADER;
+            else if (sym > 285) { err = INF_ERR_CODE; state = ST_FINISH; }
+            else {
+                // length: 257..264 -> 3..10; 265..284 -> 3 + ((4 + (k & 3)) << e) + extra, k = sym - 261, e = k >> 2; 285 -> 258
+                uint32_t len;
+                if (sym < 265) len = (uint32_t)sym - 254u;
+                else if (sym == 285) len = 258;
+                else { const uint32_t k = (uint32_t)sym - 261u, e = k >> 2; len = 3u + ((4u + (k & 3u)) << e) + br.bits((int)e); }
+                const int ds = inf_decode(br, dtab, INF_DBITS, dcnt, dsym, dfirst, dindex);
+                uint32_t dist = 0;
+                if (ds < 0 || ds > 29) err = INF_ERR_CODE;
+                else if (ds < 4) dist = (uint32_t)ds + 1u;
+                else { const uint32_t e = ((uint32_t)ds >> 1) - 1u; dist = 1u + ((2u + ((uint32_t)ds & 1u)) << e) + br.bits((int)e); }
+                if (!err && dist > o) err = INF_ERR_DIST;
+                if (!err && o + len > cap) err = INF_ERR_SIZE;
+                if (err) state = ST_FINISH;
+                else { cp_len = len; cp_dist = dist; state = ST_COPY; }
+            }
+        }
+        if (state == ST_COPY) {
+            // at most INF_COPY_STEP bytes per step, so a lane inside a long match does not hold up the lanes decoding symbols
+            uint8_t* d = dst + o;
+            const uint32_t n = cp_len < (uint32_t)INF_COPY_STEP ? cp_len : (uint32_t)INF_COPY_STEP;
+            if (cp_dist >= 8) {
+                // whole words: destination brought to a 4-byte boundary, source words taken with a funnel shift (with a
+                // distance of 8 or more every aligned source word is complete before it is loaded)
+                const uint8_t* s0 = d - cp_dist;
+                uint32_t k = 0;
+                while (k < n && ((uintptr_t)(d + k) & 3u)) { d[k] = s0[k]; k++; }
+                if (k + 4 <= n) {
+                    const uint8_t* sp = s0 + k;
+                    const uint32_t sh = ((uintptr_t)sp & 3u) * 8u;
+                    const uint32_t* sw = (const uint32_t*)((uintptr_t)sp & ~(uintptr_t)3);
+                    uint32_t lo = *sw++;
+                    for (; k + 4 <= n; k += 4) {
+                        const uint32_t hi = sh ? *sw : 0u;
+                        *(uint32_t*)(d + k) = sh ? __funnelshift_r(lo, hi, sh) : lo;
+                        lo = sh ? hi : *sw;
+                        sw++;
+                    }
+                }
+                for (; k < n; k++) d[k] = s0[k];
+            } else if (cp_dist == 1) {
+                const uint32_t b = d[-1], w4 = b * 0x01010101u;
+                uint32_t k = 0;
+                while (k < n && ((uintptr_t)(d + k) & 3u)) d[k++] = (uint8_t)b;
+                for (; k + 4 <= n; k += 4) *(uint32_t*)(d + k) = w4;
+                for (; k < n; k++) d[k] = (uint8_t)b;
+            } else { const uint8_t* s0 = d - cp_dist; for (uint32_t k = 0; k < n; k++) d[k] = s0[k]; }
+            o += n; cp_len -= n;
+            if (!cp_len) state = ST_SYMBOL;
+        } else if (state == ST_HEADER) {
             last = br.bits(1);
             const uint32_t type = br.bits(2);
             if (type == 0) {
@@ -132,95 +213,75 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
                 br.refill();
                 const uint32_t len = br.bits(16);
                 const uint32_t nlen = br.bits(16);
-                if ((len ^ 0xffffu) != nlen) { err = INF_ERR_STORED; break; }
-                if (o + len > cap) { err = INF_ERR_SIZE; break; }
-                // bytes still in the bit buffer first, then straight from the input
-                uint32_t k = 0;
-                while (k < len && br.nb >= 8) { dst[o + k] = (uint8_t)br.bb; br.drop(8); k++; }
-                if (k < len) {
-                    br.bb = 0; br.nb = 0;
-                    if (br.p + (len - k) > br.end) { err = INF_ERR_INPUT; break; }
-                    for (; k < len; k++) dst[o + k] = *br.p++;
-                }
-                o += len;
-                continue;
-            }
-            if (type == 3) { err = INF_ERR_BLOCK_TYPE; break; }
-            if (type == 1) {
-                for (int s = 0; s < 144; s++) lens[s] = 8;
-                for (int s = 144; s < 256; s++) lens[s] = 9;
-                for (int s = 256; s < 280; s++) lens[s] = 7;
-                for (int s = 280; s < 288; s++) lens[s] = 8;
-                inf_build(lens, 288, lcnt, lsym, offs, ltab, INF_LBITS);
-                for (int s = 0; s < 30; s++) lens[s] = 5;
-                inf_build(lens, 30, dcnt, dsym, offs, dtab, INF_DBITS);
-            } else {
-                const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
-                if (nlen > 286 || ndist > 30) { err = INF_ERR_LENGTHS; break; }
-                for (int s = 0; s < 19; s++) lens[s] = 0;
-                for (int k = 0; k < ncode; k++) {
-                    lens[c_clord[k]] = (uint8_t)br.bits(3);
-                }
-                // the code-length code: small enough for the canonical walk alone (its table lives in the distance slots)
-                if (!inf_build(lens, 19, dcnt, dsym, offs, dtab, 0)) { err = INF_ERR_LENGTHS; break; }
-                int idx = 0;
-                while (idx < nlen + ndist) {
-                    const int sym = inf_decode_slow(br, dcnt, dsym);
-                    if (sym < 0) { err = INF_ERR_CODE; break; }
-                    if (sym < 16) { lens[idx++] = (uint8_t)sym; continue; }
-                    int rep, val = 0;
-                    if (sym == 16) { if (idx == 0) { err = INF_ERR_LENGTHS; break; } val = lens[idx - 1]; rep = 3 + (int)br.bits(2); }
-                    else if (sym == 17) rep = 3 + (int)br.bits(3);
-                    else rep = 11 + (int)br.bits(7);
-                    if (idx + rep > nlen + ndist) { err = INF_ERR_LENGTHS; break; }
-                    while (rep--) lens[idx++] = (uint8_t)val;
-                }
-                if (err) break;
-                if (lens[256] == 0) { err = INF_ERR_LENGTHS; break; }
-                // distance lengths follow the literal/length lengths; build distance first (it reads lens[nlen..])
-                if (!inf_build(lens + nlen, ndist, dcnt, dsym, offs, dtab, INF_DBITS)) { err = INF_ERR_LENGTHS; break; }
-                if (!inf_build(lens, nlen, lcnt, lsym, offs, ltab, INF_LBITS)) { err = INF_ERR_LENGTHS; break; }
-            }
-            // ---- symbols of this block
-#pragma unroll 1
-            for (;;) {
-                const int sym = inf_decode(br, ltab, INF_LBITS, lcnt, lsym);
-                if (sym < 256) {
-                    if (sym < 0) { err = INF_ERR_CODE; break; }
-                    if (o >= cap) { err = INF_ERR_SIZE; break; }
-                    dst[o++] = (uint8_t)sym;
-                    continue;
-                }
-                if (sym == 256) break;
-                if (sym > 285) { err = INF_ERR_CODE; break; }
-                // length: 257..264 -> 3..10; 265..284 -> 3 + ((4 + (k & 3)) << e) + extra, k = sym - 261, e = k >> 2; 285 -> 258
-                uint32_t len;
-                if (sym < 265) len = (uint32_t)sym - 254u;
-                else if (sym == 285) len = 258;
-                else { const uint32_t k = (uint32_t)sym - 261u, e = k >> 2; len = 3u + ((4u + (k & 3u)) << e) + br.bits((int)e); }
-                const int ds = inf_decode(br, dtab, INF_DBITS, dcnt, dsym);
-                if (ds < 0 || ds > 29) { err = INF_ERR_CODE; break; }
-                uint32_t dist;
-                if (ds < 4) dist = (uint32_t)ds + 1u;
-                else { const uint32_t e = ((uint32_t)ds >> 1) - 1u; dist = 1u + ((2u + ((uint32_t)ds & 1u)) << e) + br.bits((int)e); }
-                if (dist > o) { err = INF_ERR_DIST; break; }
-                if (o + len > cap) { err = INF_ERR_SIZE; break; }
-                uint8_t* d = dst + o;
-                o += len;
-                if (dist == 1) { const uint8_t b = d[-1]; for (uint32_t k = 0; k < len; k++) d[k] = b; }
-                else if (dist >= len) {
-                    // source and destination do not overlap: batches of loads before the stores
-                    const uint8_t* s = d - dist;
+                if ((len ^ 0xffffu) != nlen) err = INF_ERR_STORED;
+                else if (o + len > cap) err = INF_ERR_SIZE;
+                else {
+                    // bytes still in the bit buffer first, then straight from the input
                     uint32_t k = 0;
-                    for (; k + 4 <= len; k += 4) { const uint8_t a0 = s[k], a1 = s[k + 1], a2 = s[k + 2], a3 = s[k + 3]; d[k] = a0; d[k + 1] = a1; d[k + 2] = a2; d[k + 3] = a3; }
-                    for (; k < len; k++) d[k] = s[k];
-                } else { const uint8_t* s = d - dist; for (uint32_t k = 0; k < len; k++) d[k] = s[k]; }
+                    while (k < len && br.nb >= 8) { dst[o + k] = (uint8_t)br.bb; br.drop(8); k++; }
+                    if (k < len) {
+                        br.bb = 0; br.nb = 0;
+                        if (br.p + (len - k) > br.end) err = INF_ERR_INPUT;
+                        else for (; k < len; k++) dst[o + k] = *br.p++;
+                    }
+                    o += len;
+                }
+                state = (err || last) ? ST_FINISH : ST_HEADER;
+            } else if (type == 3) { err = INF_ERR_BLOCK_TYPE; state = ST_FINISH; }
+            else {
+                if (type == 1) {
+                    for (int s2 = 0; s2 < 144; s2++) lens[s2] = 8;
+                    for (int s2 = 144; s2 < 256; s2++) lens[s2] = 9;
+                    for (int s2 = 256; s2 < 280; s2++) lens[s2] = 7;
+                    for (int s2 = 280; s2 < 288; s2++) lens[s2] = 8;
+                    inf_build(lens, 288, lcnt, lsym, offs, ltab, INF_LBITS, lfirst, lindex);
+                    for (int s2 = 0; s2 < 30; s2++) lens[s2] = 5;
+                    inf_build(lens, 30, dcnt, dsym, offs, dtab, INF_DBITS, dfirst, dindex);
+                } else {
+                    const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
+                    if (nlen > 286 || ndist > 30) err = INF_ERR_LENGTHS;
+                    if (!err) {
+                        for (int s2 = 0; s2 < 19; s2++) lens[s2] = 0;
+                        for (int k = 0; k < ncode; k++) lens[c_clord[k]] = (uint8_t)br.bits(3);
+                        // the code-length code: small enough for the canonical walk alone (its table lives in the distance slots)
+                        if (!inf_build(lens, 19, dcnt, dsym, offs, dtab, 0, nullptr, nullptr)) err = INF_ERR_LENGTHS;
+                    }
+                    int idx = 0;
+                    while (!err && idx < nlen + ndist) {
+                        const int sym = inf_decode_slow(br, dcnt, dsym);
+                        if (sym < 0) { err = INF_ERR_CODE; break; }
+                        if (sym < 16) { lens[idx++] = (uint8_t)sym; continue; }
+                        int rep, val = 0;
+                        if (sym == 16) { if (idx == 0) { err = INF_ERR_LENGTHS; break; } val = lens[idx - 1]; rep = 3 + (int)br.bits(2); }
+                        else if (sym == 17) rep = 3 + (int)br.bits(3);
+                        else rep = 11 + (int)br.bits(7);
+                        if (idx + rep > nlen + ndist) { err = INF_ERR_LENGTHS; break; }
+                        while (rep--) lens[idx++] = (uint8_t)val;
+                    }
+                    if (!err && lens[256] == 0) err = INF_ERR_LENGTHS;
+                    // distance lengths follow the literal/length lengths; build distance first (it reads lens[nlen..])
+                    if (!err && !inf_build(lens + nlen, ndist, dcnt, dsym, offs, dtab, INF_DBITS, dfirst, dindex)) err = INF_ERR_LENGTHS;
+                    if (!err && !inf_build(lens, nlen, lcnt, lsym, offs, ltab, INF_LBITS, lfirst, lindex)) err = INF_ERR_LENGTHS;
+                }
+                state = err ? ST_FINISH : ST_SYMBOL;
             }
+        } else if (state == ST_FETCH) {
+            j = atomicAdd(work, 1u);
+            if (j >= n_jobs) state = ST_DONE;
+            else {
+                const mkp_bgzf_member job = jobs[j];
+                dst = out + job.out_off; cap = job.out_len; o = 0; err = INF_OK; last = false;
+                br.init(in + job.in_off, in + job.in_off + job.in_len);
+                state = ST_HEADER;
+            }
+        } else if (state == ST_FINISH) {
+            if (!err && o != cap) err = INF_ERR_SIZE;
+            // every input bit consumed lies inside the member (bits still in the buffer are not consumed)
+            if (!err && br.p - (br.nb >> 3) > br.end) err = INF_ERR_OVERRUN;
+            if (err) atomicCAS(status, 0u, ((uint32_t)err << 24) | (j & 0xffffffu) | 0x80000000u);
+            state = ST_FETCH;
         }
-        if (!err && o != cap) err = INF_ERR_SIZE;
-        // every input bit consumed lies inside the member (bits still in the buffer are not consumed)
-        if (!err && br.p - (br.nb >> 3) > br.end) err = INF_ERR_OVERRUN;
-        if (err) { atomicCAS(status, 0u, ((uint32_t)err << 24) | (j & 0xffffffu) | 0x80000000u); }
+        if (__all_sync(0xffffffffu, state == ST_DONE)) break;
     }
 }
 
