@@ -10,7 +10,12 @@
 #include <cmath>
 #include <cstdio>
 #include <fstream>
+#include <atomic>
+#include <exception>
 #include <map>
+#include <unistd.h>
+#include <mutex>
+#include <thread>
 #include <sstream>
 
 #include "bam_reader.hpp"
@@ -46,8 +51,13 @@ public:
         const uint64_t first = en.off + (b / en.bases) * en.width + b % en.bases;
         const uint64_t last = en.off + ((e - 1) / en.bases) * en.width + (e - 1) % en.bases;
         std::string buf(last - first + 1, '\0');
-        fseeko(fh_, (off_t)first, SEEK_SET);
-        const size_t got = fread(&buf[0], 1, buf.size(), fh_);
+        // pread: slices are taken from several threads at once
+        size_t got = 0;
+        while (got < buf.size()) {
+            const ssize_t r = pread(fileno(fh_), &buf[got], buf.size() - got, (off_t)(first + got));
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
         out->reserve(e - b);
         for (size_t i = 0; i < got; i++) { char c = buf[i]; if (c == '\n' || c == '\r') continue; out->push_back(keep_case ? c : (char)toupper((unsigned char)c)); }
     }
@@ -337,10 +347,26 @@ inline std::vector<RefTarget> targets_from_include_bed(const IncludeBed& ib, con
 
 inline std::vector<RefInterval> reference_intervals(const std::vector<RefTarget>& targets, uint32_t interval_size, bool combine,
                                                     MotifContext* mc, std::vector<std::vector<size_t>>* groups = nullptr,
-                                                    const IncludeBed* include = nullptr) {
+                                                    const IncludeBed* include = nullptr, int threads = 1) {
     std::vector<RefInterval> out;
-    std::vector<size_t> grp;
-    uint64_t grp_len = 0;
+    // focus positions of one interval whose end is already fixed
+    auto fill = [&](RefInterval& iv, const RefTarget& c) {
+        if (mc) {
+            std::vector<SiteRules> sites;
+            motif_interval(*mc, c, iv.start, iv.end, false, &sites);
+            fill_focus(&iv, sites, mc->motifs, false);
+        } else if (include) {   // FocusPositions::new_regions / check_position (interval_chunks.rs:299-371)
+            iv.all_positions = false;
+            auto paint = [&](const std::map<uint32_t, std::vector<IncludeBed::Span>>& m, uint8_t bit) {
+                auto it = m.find(c.tid);
+                if (it == m.end()) return;
+                for (auto& sp : it->second) { const uint64_t a = std::max<uint64_t>(sp.b, iv.start), b = std::min<uint64_t>(sp.e, iv.end); for (uint64_t p = a; p < b; p++) iv.rule[(uint32_t)p] |= bit; }
+            };
+            paint(include->plus, 1);
+            paint(include->minus, 2);
+        }
+    };
+    std::vector<const RefTarget*> owner;
     for (auto& c : targets) {
         if (!c.length) continue;
         uint32_t at = c.start;
@@ -348,33 +374,45 @@ inline std::vector<RefInterval> reference_intervals(const std::vector<RefTarget>
             RefInterval iv;
             iv.tid = c.tid; iv.start = at;
             uint32_t e = (uint32_t)std::min<uint64_t>((uint64_t)at + interval_size, c.end());
-            if (mc) {
+            if (mc && combine) {
+                // the interval end moves with the motif hits around it: a sequential chain
                 std::vector<SiteRules> sites;
-                e = std::min(motif_interval(*mc, c, at, e, combine, &sites), c.end());
+                e = std::min(motif_interval(*mc, c, at, e, true, &sites), c.end());
                 iv.end = e;
-                fill_focus(&iv, sites, mc->motifs, combine);
-            } else {
-                iv.end = e;
-                if (include) {   // FocusPositions::new_regions / check_position (interval_chunks.rs:299-371)
-                    iv.all_positions = false;
-                    auto paint = [&](const std::map<uint32_t, std::vector<IncludeBed::Span>>& m, uint8_t bit) {
-                        auto it = m.find(c.tid);
-                        if (it == m.end()) return;
-                        for (auto& sp : it->second) { const uint64_t a = std::max<uint64_t>(sp.b, iv.start), b = std::min<uint64_t>(sp.e, iv.end); for (uint64_t p = a; p < b; p++) iv.rule[(uint32_t)p] |= bit; }
-                    };
-                    paint(include->plus, 1);
-                    paint(include->minus, 2);
-                }
-            }
-            grp_len += iv.end - iv.start;
-            grp.push_back(out.size());
+                fill_focus(&iv, sites, mc->motifs, true);
+            } else iv.end = e;          // fixed grid: focus positions are filled below, in parallel
+            owner.push_back(&c);
             out.push_back(std::move(iv));
-            if (grp_len >= interval_size) { if (groups) groups->push_back(grp); grp.clear(); grp_len = 0; }
             if (e >= c.end()) break;
             at = e;
         }
     }
-    if (groups && !grp.empty()) groups->push_back(grp);
+    if (!(mc && combine) && (mc || include)) {
+        const size_t n = out.size();
+        const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n));
+        std::atomic<size_t> next{0};
+        std::exception_ptr err;
+        std::mutex err_mu;
+        auto work = [&]() {
+            try { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; fill(out[i], *owner[i]); } }
+            catch (...) { std::lock_guard<std::mutex> g(err_mu); if (!err) err = std::current_exception(); }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        if (err) std::rethrow_exception(err);
+    }
+    if (groups) {
+        std::vector<size_t> grp;
+        uint64_t grp_len = 0;
+        for (size_t i = 0; i < out.size(); i++) {
+            grp_len += out[i].end - out[i].start;
+            grp.push_back(i);
+            if (grp_len >= interval_size) { groups->push_back(grp); grp.clear(); grp_len = 0; }
+        }
+        if (!grp.empty()) groups->push_back(grp);
+    }
     return out;
 }
 
