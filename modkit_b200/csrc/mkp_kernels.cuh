@@ -517,11 +517,36 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
         // ---- phase 3: tokens -> forward positions ------------------------------------------------------
         uint32_t* P = C.P + meta.entry_off;
         uint32_t ent = 0, mlp = 0;
+        uint32_t alias_mask = 0;              // lists that share the entries of the list before them
         for (uint32_t l = 0; l < nl && !err; l++) {
             const uint32_t ds = T.d_start[l], de = T.d_end[l];
             const bool must = T.n_delta[l] == 0xffffffffu;
             unsigned long long carry = 0;     // sum of (d+1) so far
             uint32_t ntok = 0;
+            // A list whose delta text repeats the previous list's byte for byte, on the same base (basecallers write one
+            // delta list per code: C+h?,...;C+m?,...), has the same tokens, occurrence indices and positions: it shares the
+            // previous list's entries instead of being tokenised and selected again.
+            if (l > 0 && must && de > ds && T.base[l] == T.base[l - 1] && de - ds == T.d_end[l - 1] - T.d_start[l - 1] && T.n_delta[l - 1] > 0) {
+                const uint32_t pds = T.d_start[l - 1], len = de - ds;
+                bool same = true;
+                for (uint32_t c0 = 0; c0 < len && same; c0 += 128) {
+                    bool eq = true;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) { const uint32_t i = c0 + 32 * t + lane; if (i < len && mm[ds + i] != mm[pds + i]) eq = false; }
+                    same = __all_sync(FULL, eq);
+                }
+                if (same) {
+                    ntok = T.n_delta[l - 1];
+                    const uint32_t shared = T.ent_off[l - 1];
+                    __syncwarp();
+                    if (lane == 0) { T.n_delta[l] = ntok; T.ent_off[l] = shared; T.ml_off[l] = mlp; }
+                    if ((unsigned long long)mlp + (unsigned long long)ntok * T.ncodes[l] > (unsigned long long)h.len_ml) err = true;
+                    mlp += ntok * T.ncodes[l];
+                    alias_mask |= 1u << l;
+                    __syncwarp();
+                    continue;
+                }
+            }
             // delta values of up to 32 tokens (one per lane, `mine` lanes in token order) -> forward positions P[]
             // delta values of up to 32 tokens (one per lane, `mine` lanes in token order) -> 0-based occurrence index of the
             // list's base in forward-read order (for 'N' lists that already is the forward position); stored in P[] and
@@ -694,6 +719,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
                     const int b = fb == 'A' ? 0 : fb == 'C' ? 1 : fb == 'G' ? 2 : (fb == 'T' || fb == 'U') ? 3 : 4;
                     if (b == bfw) lists |= 1u << l;
                 }
+                lists &= ~alias_mask;                                    // shared entries are placed once, by their first list
                 if (lane < MAX_LISTS) s_tp[wib][lane] = 0;
                 __syncwarp();
                 uint32_t run = 0;                                        // occurrences in the blocks already streamed
