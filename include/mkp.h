@@ -161,7 +161,8 @@ typedef struct {          /* one alignment record of the inflated stream        
 /* Copy the BGZF file to the device, inflate all members, walk the record chain.
  * seeds: sorted offsets (inflated stream) of known record starts, seeds[0] = first record; every segment between
  * two seeds is walked by its own thread, so more seeds = more parallelism (one seed is valid, only slow).
- * ms (optional, float[4]): host-to-device copy, inflate, record walk, total. */
+ * ms (optional, float[4]): copy stream busy, start -> last member inflated (the slabs of the file are copied while earlier
+ * slabs are inflated), record walk, total. */
 int  mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
                   uint64_t inflated_len, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms);
 /* Record table in file order (n_records entries, host memory). */

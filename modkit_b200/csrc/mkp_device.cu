@@ -53,7 +53,7 @@ struct mkp_ctx {
     DevBuf d_rl, d_meta, d_P, d_calls, d_hot, d_hot_prefix, d_block_sums, d_small, d_scr_cq, d_scr_cr, d_slow;
     DevBuf d_obs_word, d_slots, d_row_counts, d_row_prefix, d_rows, d_hist, d_take;
     // device ingest (BGZF file, inflated BAM stream, record table, slicing scratch)
-    DevBuf d_file, d_members, d_bam, d_seeds, d_seg_counts, d_seg_base, d_recs, d_ids, d_plan, d_need, d_totals;
+    DevBuf d_file, d_members, d_bam, d_seeds, d_seg_counts, d_seg_base, d_recs, d_ids, d_plan, d_need, d_totals, d_slab_work;
     uint64_t bam_len = 0;
     size_t n_records = 0;
     // results
@@ -100,7 +100,7 @@ void mkp_destroy(mkp_ctx* ctx) {
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
                       &ctx->d_file, &ctx->d_members, &ctx->d_bam, &ctx->d_seeds, &ctx->d_seg_counts, &ctx->d_seg_base, &ctx->d_recs, &ctx->d_ids, &ctx->d_plan,
-                      &ctx->d_need, &ctx->d_totals};
+                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -401,20 +401,49 @@ int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_b
     CK(ctx->d_block_sums.ensure((size_t)n_blk * 4 + 4));
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);    // u+10 status, u+11 work, u+12 record count
     CK(cudaEventRecord(ctx->ev[0], st));
-    CK(cudaMemcpyAsync(ctx->d_file.p, file, file_len, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_members.p, members, n_members * sizeof(mkp_bgzf_member), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_seeds.p, seeds, n_seeds * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(u + 10, 0, 12, st));
-    CK(cudaEventRecord(ctx->ev[1], st));
     const size_t smem = (size_t)INF_THREADS * INF_STRIDE * 2;
     static bool attr_set = false;
     if (!attr_set) { CK(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-    if (n_members) {
-        const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
-        const int grid = (int)std::min<size_t>((n_members + INF_THREADS - 1) / INF_THREADS, (size_t)ctx->sm_count * per_sm);
-        k_inflate<<<grid, INF_THREADS, smem, st>>>(ctx->d_file.as<uint8_t>(), ctx->d_members.as<mkp_bgzf_member>(), (uint32_t)n_members,
-                                                  ctx->d_bam.as<uint8_t>(), u + 10, u + 11);
+    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    const size_t resident = (size_t)ctx->sm_count * per_sm * INF_THREADS;      // decoders in flight
+    // The file goes over in slabs (copy stream); the members of a slab are inflated (compute stream) while the next slab
+    // is on the wire. A slab holds at least two rounds of resident decoders, so small files are a single slab.
+    std::vector<size_t> cut;                     // member index where each slab starts
+    {
+        const size_t min_members = 2 * resident, min_bytes = (size_t)192 << 20;
+        size_t i0 = 0;
+        while (i0 < n_members) {
+            cut.push_back(i0);
+            size_t i1 = i0;
+            const uint64_t b0 = members[i0].in_off;
+            while (i1 < n_members && (i1 - i0 < min_members || members[i1].in_off - b0 < min_bytes)) i1++;
+            if (n_members - i1 < min_members / 2) i1 = n_members;           // no tiny tail slab
+            i0 = i1;
+        }
+        cut.push_back(n_members);
     }
+    const size_t n_slabs = cut.size() - 1;
+    CK(ctx->d_slab_work.ensure(std::max<size_t>(1, n_slabs) * 4));
+    CK(cudaMemsetAsync(ctx->d_slab_work.p, 0, std::max<size_t>(1, n_slabs) * 4, st));
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream2));
+    // members are in file order and do not overlap: bytes before the first payload (BGZF headers) travel with their slab
+    for (size_t sl = 0; sl < n_slabs; sl++) {
+        const size_t a = sl == 0 ? 0 : (size_t)members[cut[sl]].in_off;
+        const size_t b = sl + 1 == n_slabs ? file_len : (size_t)members[cut[sl + 1]].in_off;
+        CK(cudaMemcpyAsync(ctx->d_file.as<uint8_t>() + a, file + a, b - a, cudaMemcpyHostToDevice, ctx->stream2));
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        const size_t nm = cut[sl + 1] - cut[sl];
+        const int grid = (int)std::min<size_t>((nm + INF_THREADS - 1) / INF_THREADS, (size_t)ctx->sm_count * per_sm);
+        k_inflate<<<grid, INF_THREADS, smem, st>>>(ctx->d_file.as<uint8_t>(), ctx->d_members.as<mkp_bgzf_member>() + cut[sl], (uint32_t)nm,
+                                                  ctx->d_bam.as<uint8_t>(), u + 10, ctx->d_slab_work.as<uint32_t>() + sl, (uint32_t)cut[sl]);
+    }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream2));
     CK(cudaEventRecord(ctx->ev[2], st));
     const int wg = (int)((n_seeds + 127) / 128);
     k_walk<0><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), inflated_len, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
@@ -444,8 +473,9 @@ int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_b
     ctx->n_records = nrec;
     if (n_records) *n_records = nrec;
     if (ms) {
-        cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]);
+        // [0] copy stream busy, [1] start -> last member inflated (copies and inflate overlap), [2] record walk, [3] total
+        cudaEventElapsedTime(&ms[0], ctx->ev[4], ctx->ev[1]);
+        cudaEventElapsedTime(&ms[1], ctx->ev[0], ctx->ev[2]);
         cudaEventElapsedTime(&ms[2], ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&ms[3], ctx->ev[0], ctx->ev[3]);
     }

@@ -129,7 +129,7 @@ enum { ST_FETCH = 0, ST_HEADER = 1, ST_SYMBOL = 2, ST_FINISH = 3, ST_DONE = 4, S
 constexpr int INF_COPY_STEP = 64;
 
 __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restrict__ in, const mkp_bgzf_member* __restrict__ jobs, uint32_t n_jobs,
-                                                        uint8_t* out, uint32_t* status, uint32_t* work) {
+                                                        uint8_t* out, uint32_t* status, uint32_t* work, uint32_t job_base) {
     extern __shared__ uint16_t inf_smem[];
     uint16_t* const my = inf_smem + (size_t)threadIdx.x * INF_STRIDE;
     uint16_t* const lsym = my + INF_LSYM; uint16_t* const dsym = my + INF_DSYM; uint16_t* const lcnt = my + INF_LCNT;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
             if (!err && o != cap) err = INF_ERR_SIZE;
             // every input bit consumed lies inside the member (bits still in the buffer are not consumed)
             if (!err && br.p - (br.nb >> 3) > br.end) err = INF_ERR_OVERRUN;
-            if (err) atomicCAS(status, 0u, ((uint32_t)err << 24) | (j & 0xffffffu) | 0x80000000u);
+            if (err) atomicCAS(status, 0u, ((uint32_t)err << 24) | ((job_base + j) & 0xffffffu) | 0x80000000u);
             state = ST_FETCH;
         }
         if (__all_sync(0xffffffffu, state == ST_DONE)) break;
