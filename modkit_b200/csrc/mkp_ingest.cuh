@@ -176,9 +176,32 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
             // at most INF_COPY_STEP bytes per step, so a lane inside a long match does not hold up the lanes decoding symbols
             uint8_t* d = dst + o;
             const uint32_t n = cp_len < (uint32_t)INF_COPY_STEP ? cp_len : (uint32_t)INF_COPY_STEP;
-            if (cp_dist >= 8) {
-                // whole words: destination brought to a 4-byte boundary, source words taken with a funnel shift (with a
-                // distance of 8 or more every aligned source word is complete before it is loaded)
+            if (cp_dist >= (uint32_t)INF_COPY_STEP + 8u) {
+                // the step's source lies entirely below its destination: every source word is loaded before the first
+                // store (one memory latency per step instead of one per word), destination words are assembled with a
+                // funnel shift. Head and tail bytes (destination alignment) go bytewise.
+                const uint8_t* s0 = d - cp_dist;
+                const uint32_t head = min(n, (uint32_t)(-(intptr_t)d & 3));
+                const uint32_t nw = (n - head) >> 2, tail = (n - head) & 3u;
+                const uint8_t* sp = s0 + head;
+                const uint32_t sh = ((uintptr_t)sp & 3u) * 8u;
+                const uint32_t* sw = (const uint32_t*)((uintptr_t)sp & ~(uintptr_t)3);
+                uint32_t w[INF_COPY_STEP / 4 + 1];
+#pragma unroll
+                for (int q = 0; q <= INF_COPY_STEP / 4; q++) w[q] = (uint32_t)q <= nw ? sw[q] : 0u;      // (the last one only feeds the shift)
+                uint8_t hb[3] = {0, 0, 0}, tb[3] = {0, 0, 0};
+#pragma unroll
+                for (int q = 0; q < 3; q++) { if ((uint32_t)q < head) hb[q] = s0[q]; if ((uint32_t)q < tail) tb[q] = sp[4 * nw + q]; }
+#pragma unroll
+                for (int q = 0; q < 3; q++) if ((uint32_t)q < head) d[q] = hb[q];
+                uint32_t* dw = (uint32_t*)(d + head);
+#pragma unroll
+                for (int q = 0; q < INF_COPY_STEP / 4; q++) if ((uint32_t)q < nw) dw[q] = __funnelshift_r(w[q], w[q + 1], sh);
+#pragma unroll
+                for (int q = 0; q < 3; q++) if ((uint32_t)q < tail) d[head + 4 * nw + q] = tb[q];
+            } else if (cp_dist >= 8) {
+                // whole words, one at a time: destination brought to a 4-byte boundary, source words taken with a funnel shift
+                // (with a distance of 8 or more every aligned source word is complete before it is loaded)
                 const uint8_t* s0 = d - cp_dist;
                 uint32_t k = 0;
                 while (k < n && ((uintptr_t)(d + k) & 3u)) { d[k] = s0[k]; k++; }
