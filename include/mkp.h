@@ -158,6 +158,10 @@ typedef struct {          /* one alignment record of the inflated stream        
     uint32_t l_seq;
 } mkp_bam_rec;            /* 32 bytes */
 
+/* Free / total bytes of the context's device (the ingest keeps the file and the inflated stream resident: callers
+ * check that they fit and otherwise slice on the host and use mkp_upload_chunk). */
+int  mkp_device_memory(mkp_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
+
 /* Copy the BGZF file to the device, inflate all members, walk the record chain.
  * seeds: sorted offsets (inflated stream) of known record starts, seeds[0] = first record; every segment between
  * two seeds is walked by its own thread, so more seeds = more parallelism (one seed is valid, only slow).

@@ -54,6 +54,9 @@ struct RecRef {
     uint16_t flag;
 };
 
+// thrown by BamReader::open_device when file + inflated stream exceed the device memory: callers switch to open()
+struct DeviceIngestTooBig : std::runtime_error { using std::runtime_error::runtime_error; };
+
 struct BamIndexStats { std::vector<uint64_t> n_mapped, n_unmapped; uint64_t n_no_coor = 0; bool from_bai = false; };
 
 class BamReader {
@@ -197,6 +200,13 @@ public:
         for (auto& m : members) if (m.out_len) jobs.push_back({(uint64_t)m.in_off, (uint64_t)m.out_off, (uint32_t)m.in_len, m.out_len});
         size_t n_rec = 0;
         if (first_rec >= total) { seeds.clear(); }
+        // the file, the inflated stream and (later) the sliced chunks stay resident: they must fit
+        {
+            size_t free_b = 0, total_b = 0;
+            if (mkp_device_memory(ctx, &free_b, &total_b) == 0 && (double)mf.size + 1.6 * (double)total + (double)(1ull << 30) > (double)free_b)
+                throw DeviceIngestTooBig("BAM does not fit on the device for the GPU ingest (" + std::to_string(total >> 20) + " MiB inflated, " +
+                                         std::to_string(free_b >> 20) + " MiB free)");
+        }
         if (!seeds.empty()) {
             if (mkp_bam_load(ctx, mf.data, mf.size, jobs.data(), jobs.size(), total, seeds.data(), seeds.size(), &n_rec, ingest_ms))
                 throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(ctx));

@@ -280,7 +280,16 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             if (rc) throw std::runtime_error("no usable CUDA device (mkp_create returned " + std::to_string(rc) + "); this build has no CPU fallback");
         }
         BamReader bam;
-        if (o.host_ingest) bam.open(o.in_bam, o.threads); else bam.open_device(o.in_bam, dev.ctx);
+        if (o.host_ingest) bam.open(o.in_bam, o.threads);
+        else {
+            try { bam.open_device(o.in_bam, dev.ctx); }
+            catch (const DeviceIngestTooBig& e) {
+                // a front-end choice, not a compute fallback: the reads are sliced on the host and uploaded chunk by chunk
+                if (!o.quiet) fprintf(stderr, "> %s; reading the BAM on the host instead\n", e.what());
+                bam = BamReader();
+                bam.open(o.in_bam, o.threads);
+            }
+        }
         const auto t_load = clk::now();
         Region region, sregion;
         const Region* rp = nullptr; const Region* srp = nullptr;

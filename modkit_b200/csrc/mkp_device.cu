@@ -384,6 +384,16 @@ int mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* tak
 
 
 // ---- BGZF / BAM ingest on the device (mkp_ingest.cuh) -----------------------------------------------------
+int mkp_device_memory(mkp_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
+    if (!ctx) return -1;
+    CK(cudaSetDevice(ctx->device));
+    size_t f = 0, t = 0;
+    CK(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return 0;
+}
+
 int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
                  uint64_t inflated_len, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms) {
     if (!ctx || !file || !members || !seeds || !n_seeds) return -1;

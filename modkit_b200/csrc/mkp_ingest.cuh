@@ -24,8 +24,10 @@ namespace mkp {
 // (count per length + symbols sorted by code) and fronted by a direct-lookup table on the next INF_LBITS / INF_DBITS
 // stream bits; codes longer than that take the bit-by-bit canonical walk.
 constexpr int INF_LBITS = 9, INF_DBITS = 6;
-constexpr int INF_LSYM = 0, INF_DSYM = 288, INF_LCNT = 320, INF_DCNT = 336, INF_OFFS = 352, INF_LFIRST = 368, INF_LINDEX = 384,
-              INF_DFIRST = 400, INF_DINDEX = 416, INF_LTAB = 432,
+// (the sorted symbol lists, needed only by table builds and by codes longer than the lookup, live in local memory: 1.4 KB
+// of shared memory per decoder = 5 warps of decoders per SM instead of 3)
+constexpr int INF_LCNT = 0, INF_DCNT = 16, INF_OFFS = 32, INF_LFIRST = 48, INF_LINDEX = 64,
+              INF_DFIRST = 80, INF_DINDEX = 96, INF_LTAB = 112,
               INF_DTAB = INF_LTAB + (1 << INF_LBITS), INF_WORDS = INF_DTAB + (1 << INF_DBITS);
 constexpr int INF_STRIDE = (((INF_WORDS + 1) / 2) | 1) * 2;   // odd number of 32-bit words per decoder: spreads the banks
 __constant__ uint8_t c_clord[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -127,12 +129,16 @@ __device__ __forceinline__ int inf_decode(BitReader& br, const uint16_t* tab, in
 // lanes drift apart for good after the first divergent branch and the warp degenerates into 32 serial threads.
 enum { ST_FETCH = 0, ST_HEADER = 1, ST_SYMBOL = 2, ST_FINISH = 3, ST_DONE = 4, ST_COPY = 5 };
 constexpr int INF_COPY_STEP = 64;
+#ifndef INF_SYMS_PER_STEP
+#define INF_SYMS_PER_STEP 4
+#endif
 
 __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restrict__ in, const mkp_bgzf_member* __restrict__ jobs, uint32_t n_jobs,
                                                         uint8_t* out, uint32_t* status, uint32_t* work, uint32_t job_base) {
     extern __shared__ uint16_t inf_smem[];
     uint16_t* const my = inf_smem + (size_t)threadIdx.x * INF_STRIDE;
-    uint16_t* const lsym = my + INF_LSYM; uint16_t* const dsym = my + INF_DSYM; uint16_t* const lcnt = my + INF_LCNT;
+    uint16_t lsym[288], dsym[32];
+    uint16_t* const lcnt = my + INF_LCNT;
     uint16_t* const dcnt = my + INF_DCNT; uint16_t* const offs = my + INF_OFFS; uint16_t* const ltab = my + INF_LTAB;
     uint16_t* const dtab = my + INF_DTAB;
     uint16_t* const lfirst = my + INF_LFIRST; uint16_t* const lindex = my + INF_LINDEX;
@@ -148,14 +154,18 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
     br.init(in, in);
     for (;;) {
         if (state == ST_SYMBOL) {
-            const int sym = inf_decode(br, ltab, INF_LBITS, lcnt, lsym, lfirst, lindex);
-            if (sym < 256) {
-                if (sym < 0) { err = INF_ERR_CODE; state = ST_FINISH; }
-                else if (o >= cap) { err = INF_ERR_SIZE; state = ST_FINISH; }
-                else dst[o++] = (uint8_t)sym;
-            } else if (sym == 256) state = last ? ST_FINISH : ST_HEADER;
-            else if (sym > 285) { err = INF_ERR_CODE; state = ST_FINISH; }
-            else {
+            // up to INF_SYMS_PER_STEP literals per step; the first symbol that is not a literal ends the step
+#pragma unroll 1
+            for (int it = 0; it < INF_SYMS_PER_STEP; it++) {
+                const int sym = inf_decode(br, ltab, INF_LBITS, lcnt, lsym, lfirst, lindex);
+                if (sym < 256) {
+                    if (sym < 0) { err = INF_ERR_CODE; state = ST_FINISH; break; }
+                    if (o >= cap) { err = INF_ERR_SIZE; state = ST_FINISH; break; }
+                    dst[o++] = (uint8_t)sym;
+                    continue;
+                }
+                if (sym == 256) { state = last ? ST_FINISH : ST_HEADER; break; }
+                if (sym > 285) { err = INF_ERR_CODE; state = ST_FINISH; break; }
                 // length: 257..264 -> 3..10; 265..284 -> 3 + ((4 + (k & 3)) << e) + extra, k = sym - 261, e = k >> 2; 285 -> 258
                 uint32_t len;
                 if (sym < 265) len = (uint32_t)sym - 254u;
@@ -170,6 +180,7 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
                 if (!err && o + len > cap) err = INF_ERR_SIZE;
                 if (err) state = ST_FINISH;
                 else { cp_len = len; cp_dist = dist; state = ST_COPY; }
+                break;
             }
         }
         if (state == ST_COPY) {
@@ -266,13 +277,16 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
                     if (!err) {
                         for (int s2 = 0; s2 < 19; s2++) lens[s2] = 0;
                         for (int k = 0; k < ncode; k++) lens[c_clord[k]] = (uint8_t)br.bits(3);
-                        // the code-length code: small enough for the canonical walk alone (its table lives in the distance slots)
-                        if (!inf_build(lens, 19, dcnt, dsym, offs, dtab, 0, nullptr, nullptr)) err = INF_ERR_LENGTHS;
+                        // the code-length code (<= 7 bits): complete lookup in the not yet used literal table
+                        if (!inf_build(lens, 19, dcnt, dsym, offs, ltab, 7, nullptr, nullptr)) err = INF_ERR_LENGTHS;
                     }
                     int idx = 0;
                     while (!err && idx < nlen + ndist) {
-                        const int sym = inf_decode_slow(br, dcnt, dsym);
-                        if (sym < 0) { err = INF_ERR_CODE; break; }
+                        br.refill();
+                        const uint16_t ce = ltab[br.peek(7)];
+                        if (!ce) { err = INF_ERR_CODE; break; }
+                        br.drop(ce & 15);
+                        const int sym = ce >> 4;
                         if (sym < 16) { lens[idx++] = (uint8_t)sym; continue; }
                         int rep, val = 0;
                         if (sym == 16) { if (idx == 0) { err = INF_ERR_LENGTHS; break; } val = lens[idx - 1]; rep = 3 + (int)br.bits(2); }
