@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <charconv>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -386,6 +387,46 @@ inline bool aux_find(const uint8_t* aux, const uint8_t* end, char a, char b, Aux
     return false;
 }
 
+// Rust `{}` of an f32: shortest round-trip decimal, never in exponent form
+inline std::string f32_display(float v) {
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+}
+
+// --partition-tag: get_stringable_aux (src/util.rs:670-688) + parse_tags_from_record (src/pileup/mod.rs:629-646):
+// tag values joined by '_', "missing" for absent ones; false when none of the tags is present (PartitionKey::NoKey)
+inline bool partition_key_of(const uint8_t* r, uint32_t size, const std::vector<std::string>& tags, std::string* key) {
+    const uint32_t l_name = r[8], n_cigar = load_le<uint16_t>(r + 12);
+    const uint32_t l_seq = (uint32_t)std::max(0, load_le<int32_t>(r + 16));
+    const uint8_t* aux = r + 32 + l_name + 4ull * n_cigar + (l_seq + 1) / 2 + l_seq;
+    const uint8_t* end = r + size;
+    bool any = false;
+    std::string k;
+    for (size_t i = 0; i < tags.size(); i++) {
+        AuxHit h;
+        std::string v;
+        bool have = aux < end && aux_find(aux, end, tags[i][0], tags[i][1], &h);
+        if (have) switch (h.type) {
+            case 'Z': case 'H': v.assign((const char*)h.p, h.n); break;
+            case 'A': v.assign(1, (char)h.p[0]); break;
+            case 'c': v = std::to_string((int)(int8_t)h.p[0]); break;
+            case 'C': v = std::to_string((unsigned)h.p[0]); break;
+            case 's': v = std::to_string(load_le<int16_t>(h.p)); break;
+            case 'S': v = std::to_string(load_le<uint16_t>(h.p)); break;
+            case 'i': v = std::to_string(load_le<int32_t>(h.p)); break;
+            case 'I': v = std::to_string(load_le<uint32_t>(h.p)); break;
+            case 'f': v = f32_display(load_le<float>(h.p)); break;
+            default: have = false;
+        }
+        any = any || have;
+        if (i) k += "_";
+        k += have ? v : std::string("missing");
+    }
+    if (any) *key = k;
+    return any;
+}
+
 struct PackedChunk {
     std::vector<mkp_read_hdr> hdrs;
     std::vector<uint8_t> heap;
@@ -451,9 +492,14 @@ inline void pack_region(const BamReader& bam, uint32_t tid, uint32_t start, uint
 }
 
 // Multi-threaded variant: records are planned (tag lookup, sizes) and copied in parallel; layout identical to pack_region.
+inline void pack_records_mt(const BamReader& bam, const std::vector<RecRef>& recs, int threads, PackedChunk* out);
 inline void pack_region_mt(const BamReader& bam, uint32_t tid, uint32_t start, uint32_t end, int threads, PackedChunk* out) {
     std::vector<RecRef> recs;
     bam.for_overlapping(tid, start, end, [&](const RecRef& r) { recs.push_back(r); });
+    pack_records_mt(bam, recs, threads, out);
+}
+// the same for an explicit record list (one partition of a chunk, --partition-tag)
+inline void pack_records_mt(const BamReader& bam, const std::vector<RecRef>& recs, int threads, PackedChunk* out) {
     const size_t n = recs.size();
     if (threads <= 1 || n < 512) { for (auto& r : recs) { pack_record(bam.rec(r), r.size, out); out->recs.push_back(r); } return; }
     struct Plan { const uint8_t *cigar, *seq, *ml, *mm; uint32_t n_ml, n_mm; };

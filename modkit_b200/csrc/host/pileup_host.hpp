@@ -496,6 +496,31 @@ inline void format_bed_row(const OutRow& o, const std::string& chrom, const BedF
     out->append(buf, p - buf);
 }
 
+// --bedgraph (src/writers.rs:318-381): `chrom start end fraction coverage`, one file per (partition, strand, code[, motif])
+inline const char* strand_label(char s) { return s == '+' ? "positive" : s == '-' ? "negative" : s == '.' ? "combined" : "_unknown"; }
+inline std::string bedgraph_label(const OutRow& o, const BedFormat& fmt) {
+    std::string label = code_text(o.r.code);
+    if (o.motif_idx >= 0 && (size_t)o.motif_idx < fmt.motif_labels.size()) {
+        std::string l = fmt.motif_labels[o.motif_idx];
+        l.erase(std::remove(l.begin(), l.end(), ','), l.end());
+        label += "_" + l;
+    }
+    return label;
+}
+inline void format_bedgraph_row(const OutRow& o, const std::string& chrom, std::string* out) {
+    const mkp_row& r = o.r;
+    const uint32_t cov = r.n_mod + r.n_canon + r.n_other;
+    char buf[64];
+    char* p = buf;
+    out->append(chrom);
+    *p++ = '\t'; p = put_u32(p, r.pos); *p++ = '\t'; p = put_u32(p, r.pos + 1); *p++ = '\t';
+    out->append(buf, p - buf);
+    out->append(f32_display((float)r.n_mod / (float)cov));      // `{}` of the f32 fraction
+    p = buf;
+    *p++ = '\t'; p = put_u32(p, cov); *p++ = '\n';
+    out->append(buf, p - buf);
+}
+
 inline const char* bed_header_line() {
     return "chrom\tchromStart\tchromEnd\tname\tscore\tstrand\tthickStart\tthickEnd\tcolor\tvalid_coverage\tpercent_modified\t"
            "count_modified\tcount_canonical\tcount_other_mod\tcount_delete\tcount_fail\tcount_diff\tcount_nocall\n";

@@ -3,6 +3,7 @@
 // messages where they are observable, same output ordering (feeder order, positions ascending).
 #pragma once
 #include <chrono>
+#include <filesystem>
 #include <unordered_set>
 
 #include "pileup_host.hpp"
@@ -23,6 +24,9 @@ struct PileupOptions {
     int device = 0;
     uint32_t chunk_bp = 16u << 20;     // reference span handed to the GPU per call
     bool host_ingest = false;          // inflate + slice the BAM on the host (zlib) instead of on the GPU
+    std::vector<std::string> partition_tags;   // --partition-tag (repeatable): one output file per tag-value combination
+    bool bedgraph = false;             // --bedgraph: out path is a directory of <code>_<strand>.bedgraph files
+    std::string prefix;                // --prefix for the files of --bedgraph / --partition-tag
     bool quiet = false;
 };
 
@@ -280,7 +284,17 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             if (rc) throw std::runtime_error("no usable CUDA device (mkp_create returned " + std::to_string(rc) + "); this build has no CPU fallback");
         }
         BamReader bam;
-        if (o.host_ingest) bam.open(o.in_bam, o.threads);
+        // util.rs:690-712
+        for (size_t i = 0; i < o.partition_tags.size(); i++) {
+            if (o.partition_tags[i].size() != 2) throw std::runtime_error("illegal tag " + o.partition_tags[i] + " should be length 2");
+            for (size_t j = 0; j < i; j++) if (o.partition_tags[j] == o.partition_tags[i]) throw std::runtime_error("cannot repeat partition-tags, got " + o.partition_tags[i] + " twice");
+        }
+        const bool partitioned = !o.partition_tags.empty();
+        const bool to_dir = partitioned || o.bedgraph;     // the output path is a directory (writers.rs:264-381, 1005-1082)
+        if (to_dir && o.header) throw std::runtime_error("the argument '--header' cannot be used with '--bedgraph' / '--partition-tag'");
+        if (o.bedgraph && o.mixed) throw std::runtime_error("the argument '--mixed-delim' cannot be used with '--bedgraph'");
+        // partition keys are read from the records' aux fields on the host: that mode uses the host front end
+        if (o.host_ingest || partitioned) bam.open(o.in_bam, o.threads);
         else {
             try { bam.open_device(o.in_bam, dev.ctx); }
             catch (const DeviceIngestTooBig& e) {
@@ -353,9 +367,31 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             for (auto& m : mc.motifs) mc.longest = std::max<uint64_t>(mc.longest, m.len);
         }
         // output first, like the reference, so a bad path fails before any work
-        FILE* out = (o.out_bed == "-" || o.out_bed == "stdout") ? stdout : fopen(o.out_bed.c_str(), "w");
-        if (!out) throw std::runtime_error("failed to make output file");
-        if (o.header) fputs(bed_header_line(), out);
+        FILE* out = nullptr;
+        struct Router {          // files of the output directory, created on first use
+            std::string dir;
+            std::map<std::string, FILE*> files;
+            FILE* get(const std::string& name) {
+                auto it = files.find(name);
+                if (it != files.end()) return it->second;
+                FILE* f = fopen((dir + "/" + name).c_str(), "w");
+                if (!f) throw std::runtime_error("failed to make output file " + dir + "/" + name);
+                files[name] = f;
+                return f;
+            }
+            ~Router() { for (auto& kv : files) fclose(kv.second); }
+        } router;
+        if (!to_dir) {
+            out = (o.out_bed == "-" || o.out_bed == "stdout") ? stdout : fopen(o.out_bed.c_str(), "w");
+            if (!out) throw std::runtime_error("failed to make output file");
+            if (o.header) fputs(bed_header_line(), out);
+        } else {
+            std::error_code ec;
+            std::filesystem::create_directories(o.out_bed, ec);
+            if (ec) throw std::runtime_error("failed to create output directory " + o.out_bed);
+            router.dir = o.out_bed;
+        }
+        const std::string pfx = o.prefix.empty() ? std::string() : o.prefix + "_";
 
         iv_job.t = std::thread([&]() {
             try {
@@ -437,11 +473,26 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             while (i1 < ivs.size() && ivs[i1].tid == ivs[i0].tid && ivs[i1].start == ivs[i1 - 1].end && ivs[i1].end - ivs[i0].start <= o.chunk_bp) i1++;
             const uint32_t cs = ivs[i0].start, ce = ivs[i1 - 1].end;
             if (ce <= cs) { i0 = i1; continue; }
+            // the reads of the chunk; with --partition-tag one group per key (each an independent pileup:
+            // src/pileup/mod.rs:795-830), in key order
+            std::vector<RecRef> all_recs;
+            bam.for_overlapping(ivs[i0].tid, cs, ce, [&](const RecRef& r) { all_recs.push_back(r); });
+            if (all_recs.empty()) { i0 = i1; continue; }
+            std::map<std::string, std::vector<RecRef>> groups;
+            if (!partitioned) groups[""].swap(all_recs);
+            else for (auto& r : all_recs) {
+                // only alignments the pileup admits create a key (flag filter of the pileup engine, pileup/mod.rs:783-791)
+                if ((r.flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) || r.l_seq == 0) continue;
+                std::string k;
+                groups[partition_key_of(bam.rec(r), r.size, o.partition_tags, &k) ? k : std::string("\1")].push_back(r);
+            }
+            for (auto& grp : groups) {
+            const std::string key_name = !partitioned ? std::string() : (grp.first == "\1" ? std::string("ungrouped") : grp.first);
             const auto ta = clk::now();
             pc.clear();
-            if (bam.on_device) bam.for_overlapping(ivs[i0].tid, cs, ce, [&](const RecRef& r) { pc.recs.push_back(r); });
-            else pack_region_mt(bam, ivs[i0].tid, cs, ce, o.threads, &pc);
-            if (pc.recs.empty()) { i0 = i1; continue; }
+            if (bam.on_device) pc.recs = grp.second;
+            else pack_records_mt(bam, grp.second, o.threads, &pc);
+            if (pc.recs.empty()) continue;
             mkp_chunk ch;
             memset(&ch, 0, sizeof ch);
             ch.start = cs; ch.end = ce; ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
@@ -478,6 +529,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             }
             const int nt = std::max(1, std::min<int>(o.threads, (int)n_iv));
             std::vector<std::string> parts(nt);
+            std::vector<std::map<std::string, std::string>> routed(nt);      // to_dir: file name -> text, per worker
             std::vector<uint64_t> part_rows(nt, 0);
             {
                 auto work = [&](int t) {
@@ -489,7 +541,13 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                         while (r1 < r_end && rows[r1].pos < ivs[i0 + k].end) r1++;
                         local.clear();
                         finish_interval_rows(ivs[i0 + k], rows + rlo[k], r1 - rlo[k], have_motifs ? &mc.motifs : nullptr, combine_strands, &local);
-                        for (auto& orow : local) format_bed_row(orow, chrom, fmt, &parts[t]);
+                        if (!to_dir) for (auto& orow : local) format_bed_row(orow, chrom, fmt, &parts[t]);
+                        else if (!o.bedgraph) { std::string& dst = routed[t][pfx + key_name + ".bed"]; for (auto& orow : local) format_bed_row(orow, chrom, fmt, &dst); }
+                        else for (auto& orow : local) {
+                            std::string label;
+                            std::string& dst = routed[t][pfx + key_name + (key_name.empty() ? "" : "_") + bedgraph_label(orow, fmt) + "_" + strand_label(orow.strand) + ".bedgraph"];
+                            format_bedgraph_row(orow, chrom, &dst);
+                        }
                         part_rows[t] += local.size();
                     }
                 };
@@ -498,13 +556,16 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 work(0);
                 for (auto& t : th) t.join();
             }
-            for (int t = 0; t < nt; t++) { fwrite(parts[t].data(), 1, parts[t].size(), out); S.rows += part_rows[t]; }
-            text.clear();
-            fwrite(text.data(), 1, text.size(), out);
+            for (int t = 0; t < nt; t++) {
+                if (out) fwrite(parts[t].data(), 1, parts[t].size(), out);
+                for (auto& kv : routed[t]) if (!kv.second.empty()) fwrite(kv.second.data(), 1, kv.second.size(), router.get(kv.first));
+                S.rows += part_rows[t];
+            }
             S.write_s += secs(tc, clk::now());
+            }   // partition groups
             i0 = i1;
         }
-        if (out != stdout) fclose(out); else fflush(out);
+        if (out) { if (out != stdout) fclose(out); else fflush(out); }
         const auto t1 = clk::now();
         S.load_s = secs(t0, t_load); S.threshold_s = secs(t_load, t_thr); S.interval_s = iv_secs;   /* runs beside ingest + thresholds; wait time = secs(t_thr, t_iv) */ S.total_s = secs(t0, t1);
         for (int b = 0; b < 4; b++) { S.thresholds[b] = P.base_threshold[b]; S.threshold_set[b] = P.base_threshold_set[b]; }
@@ -570,9 +631,9 @@ inline bool parse_pileup_args(int argc, const char* const* argv, PileupOptions* 
             else if (a == "--stats-json") o->stats_json = val();
             else if (a == "--quiet") o->quiet = true;
             else if (a == "--include-bed" || a == "--include-positions") o->include_bed = val();
-            else if (a == "--partition-tag" || a == "--bedgraph" || a == "--prefix") {
-                *err = "flag " + a + " is not supported by this build (SURVEY 8f: next tier)"; return false;
-            }
+            else if (a == "--partition-tag") o->partition_tags.push_back(val());
+            else if (a == "--bedgraph") o->bedgraph = true;
+            else if (a == "--prefix") o->prefix = val();
             else if (a.size() > 1 && a[0] == '-') { *err = "unexpected argument '" + a + "' found"; return false; }
             else pos.push_back(a);
         } catch (const std::exception& e) { *err = e.what(); return false; }

@@ -8,6 +8,7 @@
 //                          src/reads_sampler/record_sampler.rs, src/read_ids_to_base_mod_probs.rs:223-362,965-1069
 //   bedMethyl writer       src/writers.rs:43-183
 #pragma once
+#include <charconv>
 #include <cmath>
 #include <functional>
 #include <unordered_set>
@@ -536,6 +537,63 @@ inline void format_row(const Row& R, const std::string& chrom, const std::vector
                      R.n_filtered, sp, R.n_diff, sp, R.n_nocall);
     out->append(buf, (size_t)n);
 }
+
+// ---- --partition-tag (src/pileup/mod.rs:629-646, src/util.rs:670-688) and --bedgraph (src/writers.rs:264-381) ----
+// Rust `{}` of an f32: the shortest decimal that round-trips, never in exponent form
+inline std::string f32_display(float v) {
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+}
+
+// get_stringable_aux: text of one aux value, false for absent tags and array types
+inline bool stringable_aux(const BamRecord& r, const std::string& tag, std::string* out) {
+    AuxField f;
+    const char t[2] = {tag[0], tag[1]};
+    if (!find_aux(r, t, &f)) return false;
+    switch (f.type) {
+        case 'Z': case 'H': *out = std::string((const char*)f.p, f.n); return true;
+        case 'A': *out = std::string(1, (char)f.p[0]); return true;
+        case 'c': *out = std::to_string((int)(int8_t)f.p[0]); return true;
+        case 'C': *out = std::to_string((unsigned)f.p[0]); return true;
+        case 's': { int16_t v; memcpy(&v, f.p, 2); *out = std::to_string(v); return true; }
+        case 'S': { uint16_t v; memcpy(&v, f.p, 2); *out = std::to_string(v); return true; }
+        case 'i': { int32_t v; memcpy(&v, f.p, 4); *out = std::to_string(v); return true; }
+        case 'I': { uint32_t v; memcpy(&v, f.p, 4); *out = std::to_string(v); return true; }
+        case 'f': { float v; memcpy(&v, f.p, 4); *out = f32_display(v); return true; }
+        default: return false;
+    }
+}
+
+// parse_tags_from_record: values joined by '_', "missing" for absent ones; false when no tag is present (NoKey)
+inline bool partition_key_of(const BamRecord& r, const std::vector<std::string>& tags, std::string* key) {
+    bool any = false;
+    std::string k;
+    for (size_t i = 0; i < tags.size(); i++) {
+        std::string v;
+        const bool have = stringable_aux(r, tags[i], &v);
+        any = any || have;
+        if (i) k += "_";
+        k += have ? v : std::string("missing");
+    }
+    if (any) *key = k;
+    return any;
+}
+
+// bedGraph line + the label part of its file name (BedGraphWriter::write)
+inline void format_bedgraph_row(const Row& R, const std::string& chrom, const std::vector<std::string>& motif_labels,
+                                std::string* label, std::string* line) {
+    *label = code_to_string(R.code);
+    if (R.motif_idx >= 0 && (size_t)R.motif_idx < motif_labels.size()) {
+        std::string l = motif_labels[R.motif_idx];
+        l.erase(std::remove(l.begin(), l.end(), ','), l.end());
+        *label += "_" + l;
+    }
+    const float frac = (float)R.n_mod / (float)R.cov;
+    *line = chrom + "\t" + std::to_string(R.pos) + "\t" + std::to_string(R.pos + 1) + "\t" + f32_display(frac) + "\t" + std::to_string(R.cov) + "\n";
+}
+
+inline const char* strand_label(char s) { return s == '+' ? "positive" : s == '-' ? "negative" : s == '.' ? "combined" : "_unknown"; }
 
 inline const char* bedmethyl_header() {
     return "chrom\tchromStart\tchromEnd\tname\tscore\tstrand\tthickStart\tthickEnd\tcolor\tvalid_coverage\t"

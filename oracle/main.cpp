@@ -92,7 +92,9 @@ int main(int argc, char** argv) {
         bool traditional = false, combine_mods = false, combine_strands = false, mixed = false, header = false, invert_edge = false;
         float percentile = 0.1f;
         std::vector<std::string> filter_thresholds, mod_thresholds, motif_parts;
-        std::string region_s, sample_region_s, ignore_s, ref_fp, edge_s, timing_fp, include_bed;
+        std::string region_s, sample_region_s, ignore_s, ref_fp, edge_s, timing_fp, include_bed, prefix;
+        std::vector<std::string> partition_tags;
+        bool bedgraph = false;
         for (int i = 2; i < argc; i++) {
             std::string a = argv[i];
             auto val = [&]() -> std::string { if (i + 1 >= argc) die("missing value for " + a); return argv[++i]; };
@@ -125,6 +127,9 @@ int main(int argc, char** argv) {
             else if (a == "--header" || a == "--with-header" || a == "--include_header") header = true;
             else if (a == "--timing-json") timing_fp = val();
             else if (a == "--include-bed" || a == "--include-positions") include_bed = val();
+            else if (a == "--partition-tag") partition_tags.push_back(val());
+            else if (a == "--bedgraph") bedgraph = true;
+            else if (a == "--prefix") prefix = val();
             else if (a.size() > 1 && a[0] == '-' && a != "-") die("unsupported flag " + a);
             else pos.push_back(a);
         }
@@ -243,30 +248,95 @@ int main(int argc, char** argv) {
         for (auto& iv : ivs) total_positions += iv.end - iv.start;
         auto t_ivs = std::chrono::steady_clock::now();
 
-        FILE* out = (pos[1] == "-" || pos[1] == "stdout") ? stdout : fopen(pos[1].c_str(), "w");
-        if (!out) die("failed to make output file");
-        if (header) fputs(bedmethyl_header(), out);
+        // util.rs:690-712
+        for (size_t i = 0; i < partition_tags.size(); i++) {
+            if (partition_tags[i].size() != 2) die("illegal tag " + partition_tags[i] + " should be length 2");
+            for (size_t j = 0; j < i; j++) if (partition_tags[j] == partition_tags[i]) die("cannot repeat partition-tags, got " + partition_tags[i] + " twice");
+        }
+        const bool partitioned = !partition_tags.empty();
+        const bool to_dir = partitioned || bedgraph;       // output path is a directory of files (writers.rs:264-381, 1005-1082)
+        if (to_dir && header) die("--header cannot be used with --bedgraph / --partition-tag");
+        if (bedgraph && mixed) die("--mixed-delim cannot be used with --bedgraph");
+        FILE* out = nullptr;
+        std::map<std::string, FILE*> files;
+        if (!to_dir) {
+            out = (pos[1] == "-" || pos[1] == "stdout") ? stdout : fopen(pos[1].c_str(), "w");
+            if (!out) die("failed to make output file");
+            if (header) fputs(bedmethyl_header(), out);
+        } else {
+            std::string cmd = "mkdir -p '" + pos[1] + "'";
+            if (system(cmd.c_str()) != 0) die("failed to create output directory");
+        }
+        auto sink = [&](const std::string& fname) -> FILE* {
+            auto it = files.find(fname);
+            if (it != files.end()) return it->second;
+            FILE* f = fopen((pos[1] + "/" + fname).c_str(), "w");
+            if (!f) die("failed to make output file " + fname);
+            files[fname] = f;
+            return f;
+        };
 
         StateTable st;
+        typedef std::vector<std::pair<std::string, std::string>> Routed;      // (file name, text) in a fixed order
         std::vector<std::string> results(ivs.size());
+        std::vector<Routed> routed(ivs.size());
         std::vector<char> done(ivs.size(), 0);
         std::atomic<size_t> next{0};
         std::mutex mu;
         std::condition_variable cv;
         size_t n_rows = 0;
+        const std::string pfx = prefix.empty() ? std::string() : prefix + "_";
         auto worker = [&]() {
             while (true) {
                 size_t i = next.fetch_add(1);
                 if (i >= ivs.size()) break;
-                std::vector<Row> rows;
-                process_interval(bam, ivs[i], P, st, have_motifs ? &motifs : nullptr, &rows);
-                std::string text;
                 const std::string& chrom = bam.ref_names[ivs[i].tid];
-                for (auto& R : rows) format_row(R, chrom, motif_labels, mixed, &text);
+                std::string text;
+                Routed rt;
+                size_t nr = 0;
+                if (!to_dir) {
+                    std::vector<Row> rows;
+                    process_interval(bam, ivs[i], P, st, have_motifs ? &motifs : nullptr, &rows);
+                    for (auto& R : rows) format_row(R, chrom, motif_labels, mixed, &text);
+                    nr = rows.size();
+                } else {
+                    // partition keys present among the admitted reads of this interval ("" = no partitioning, "\1" = NoKey)
+                    std::set<std::string> keys;
+                    if (!partitioned) keys.insert("");
+                    else bam.fetch(ivs[i].tid, ivs[i].start, ivs[i].end, [&](const BamRecord& r) {
+                        if (!admitted_for_pileup(r)) return;
+                        std::string k;
+                        keys.insert(partition_key_of(r, partition_tags, &k) ? k : std::string("\1"));
+                    });
+                    std::map<std::string, std::string> by_file;
+                    for (auto& key : keys) {
+                        std::function<bool(const BamRecord&)> keep = [&](const BamRecord& r) {
+                            std::string k;
+                            const bool have = partition_key_of(r, partition_tags, &k);
+                            return key == "\1" ? !have : (have && k == key);
+                        };
+                        std::vector<Row> rows;
+                        process_interval(bam, ivs[i], P, st, have_motifs ? &motifs : nullptr, &rows, nullptr, nullptr, partitioned ? &keep : nullptr);
+                        nr += rows.size();
+                        const std::string key_name = !partitioned ? std::string() : (key == "\1" ? std::string("ungrouped") : key);
+                        if (!bedgraph) {
+                            std::string& t = by_file[pfx + key_name + ".bed"];
+                            for (auto& R : rows) format_row(R, chrom, motif_labels, mixed, &t);
+                        } else {
+                            for (auto& R : rows) {
+                                std::string label, line;
+                                format_bedgraph_row(R, chrom, motif_labels, &label, &line);
+                                by_file[pfx + key_name + (key_name.empty() ? "" : "_") + label + "_" + strand_label(R.strand) + ".bedgraph"] += line;
+                            }
+                        }
+                    }
+                    for (auto& kv : by_file) if (!kv.second.empty()) rt.push_back(kv);
+                }
                 std::lock_guard<std::mutex> g(mu);
                 results[i].swap(text);
+                routed[i].swap(rt);
                 done[i] = 1;
-                n_rows += rows.size();
+                n_rows += nr;
                 cv.notify_all();
             }
         };
@@ -276,12 +346,16 @@ int main(int argc, char** argv) {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return done[i] != 0; });
             std::string text;
+            Routed rt;
             text.swap(results[i]);
+            rt.swap(routed[i]);
             lk.unlock();
-            fwrite(text.data(), 1, text.size(), out);
+            if (out) fwrite(text.data(), 1, text.size(), out);
+            for (auto& kv : rt) fwrite(kv.second.data(), 1, kv.second.size(), sink(kv.first));
         }
         for (auto& t : pool) t.join();
-        if (out != stdout) fclose(out); else fflush(out);
+        if (out) { if (out != stdout) fclose(out); else fflush(out); }
+        for (auto& kv : files) fclose(kv.second);
         auto t1 = std::chrono::steady_clock::now();
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
         fprintf(stderr, "> Done, processed %zu rows. positions=%llu load=%.3fs thresholds=%.3fs intervals=%.3fs pileup=%.3fs total=%.3fs\n",

@@ -13,6 +13,7 @@
 // The reference iterates htslib pileup columns; this restatement walks each read's CIGAR once and
 // scatters into dense per-interval arrays. The per-(read,position) feature rules are identical.
 #pragma once
+#include <functional>
 #include <mutex>
 #include <set>
 
@@ -212,12 +213,15 @@ inline bool admitted_for_pileup(const BamRecord& r) {
 // process_region: rows for one interval, sorted by position then (strand, code)
 inline void process_interval(const BamFile& bam, const Interval& iv, const PileupParams& P, StateTable& st,
                              const std::vector<Motif>* motifs, std::vector<Row>* rows_out,
-                             size_t* n_processed = nullptr, size_t* n_skipped = nullptr) {
+                             size_t* n_processed = nullptr, size_t* n_skipped = nullptr,
+                             const std::function<bool(const BamRecord&)>* keep = nullptr) {
     const uint32_t start = iv.start, end = iv.end;
     if (end <= start) return;
     const size_t W = end - start;
     std::vector<const BamRecord*> recs;
-    bam.fetch(iv.tid, start, end, [&](const BamRecord& r) { if (admitted_for_pileup(r)) recs.push_back(&r); });
+    // `keep`: the reads of one partition (--partition-tag): every partition key is an independent pileup
+    // (tallies and observed-code sets are keyed by PartitionKey, src/pileup/mod.rs:767-830, 942-965)
+    bam.fetch(iv.tid, start, end, [&](const BamRecord& r) { if (admitted_for_pileup(r) && (!keep || (*keep)(r))) recs.push_back(&r); });
     if (recs.empty()) return;
     static thread_local std::vector<ReadCalls> calls;
     if (calls.size() < recs.size()) calls.resize(recs.size());

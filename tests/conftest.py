@@ -59,4 +59,9 @@ def run_product(args, bam, out):
     """In-process call into the native library (the CUDA path); returns (exit code, text)."""
     import modkit_b200
     rc = modkit_b200.pileup_main(list(args) + ["--quiet", bam, out])
-    return rc, (open(out).read() if os.path.exists(out) else "")
+    return rc, (open(out).read() if os.path.isfile(out) else "")
+
+
+def read_dir(path):
+    """{file name: text} of an output directory (--bedgraph / --partition-tag)."""
+    return {f: open(os.path.join(path, f)).read() for f in sorted(os.listdir(path))}

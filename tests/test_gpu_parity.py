@@ -205,3 +205,44 @@ def test_gpu_malformed_mm_tags(native_lib, oracle_exe, tmp_path):
         exp = run_oracle(oracle_exe, flags, bam, str(tmp_path / "o.bed"))
         rc, got = run_product(flags, bam, str(tmp_path / "g.bed"))
         assert rc == 0 and got == exp and exp.count("\n") > 10
+
+
+def test_gpu_partition_tags_and_bedgraph(native_lib, oracle_exe, tmp_path):
+    """--partition-tag / --bedgraph / --prefix (tests/test_pileup.rs:500-633): product directories == oracle directories,
+    and the reference's own assertion (every partition equals the unpartitioned control)."""
+    from conftest import read_dir
+    plain, hap = os.path.join(FIX, "bc_anchored_10_reads.sorted.bam"), os.path.join(FIX, "bc_anchored_10_reads.haplotyped.sorted.bam")
+    rc, control = run_product(["--no-filtering"], plain, str(tmp_path / "control.bed"))
+    assert rc == 0
+    for k, flags in enumerate((["--partition-tag", "RG", "--partition-tag", "HP", "--no-filtering"],
+                               ["--partition-tag", "RG", "--partition-tag", "HP", "--no-filtering", "--bedgraph"],
+                               ["--no-filtering", "--bedgraph", "--prefix", "run7"],
+                               ["--partition-tag", "HP", "--partition-tag", "XX", "-p", "0.25", "--prefix", "p"])):
+        bam = plain if k == 2 else hap
+        gd, od = str(tmp_path / ("g%d" % k)), str(tmp_path / ("o%d" % k))
+        assert run_product(flags, bam, gd)[0] == 0
+        subprocess.check_call([oracle_exe, "pileup"] + flags + [bam, od], stderr=subprocess.DEVNULL)
+        got, exp = read_dir(gd), read_dir(od)
+        assert sorted(got) == sorted(exp) and got == exp and len(got) > 0
+        if k == 0:
+            assert len(got) == 6 and all(t == control for t in got.values())
+        if k == 1:
+            assert len(got) == 24
+        if k == 2:
+            assert sorted(got) == ["run7_h_negative.bedgraph", "run7_h_positive.bedgraph", "run7_m_negative.bedgraph", "run7_m_positive.bedgraph"]
+        if k == 3:
+            assert sorted(got) == ["p_1_missing.bed", "p_2_missing.bed"]
+
+
+def test_gpu_bedgraph_with_motifs(native_lib, oracle_exe, synth_exe, tmp_path):
+    """bedgraph labels carry the motif, strands combine to `combined` files; product == oracle on a synthetic modBAM."""
+    from conftest import read_dir
+    prefix, _ = synth(synth_exe, tmp_path, "bg", "--contig", "syn1:300000", "--coverage", "12", "--mods", "hm", "--seed", "11")
+    for k, flags in enumerate((["--cpg", "--ref", prefix + ".fa", "--bedgraph"],
+                               ["--cpg", "--combine-strands", "--ref", prefix + ".fa", "--bedgraph", "--prefix", "x"])):
+        gd, od = str(tmp_path / ("g%d" % k)), str(tmp_path / ("o%d" % k))
+        assert run_product(flags, prefix + ".bam", gd)[0] == 0
+        subprocess.check_call([oracle_exe, "pileup"] + flags + [prefix + ".bam", od], stderr=subprocess.DEVNULL)
+        got, exp = read_dir(gd), read_dir(od)
+        assert got == exp and len(got) == (4 if k == 0 else 2)
+        assert all("CG0" in name for name in got)

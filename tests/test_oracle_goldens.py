@@ -6,7 +6,7 @@ import subprocess
 
 import pytest
 
-from conftest import FIX, GEN, expand_args, golden_cases, run_oracle
+from conftest import read_dir, FIX, GEN, expand_args, golden_cases, run_oracle
 
 
 @pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
@@ -33,6 +33,34 @@ def test_oracle_no_mod_calls(oracle_exe, tmp_path):
     # tests/test_pileup.rs:143-158
     got = run_oracle(oracle_exe, ["--no-filtering"], os.path.join(FIX, "empty-tags.sorted.bam"), str(tmp_path / "o.bed"))
     assert got == ""
+
+
+def test_oracle_partition_tags_partitioned(oracle_exe, tmp_path):
+    """tests/test_pileup.rs:500-544: six RG x HP partitions of the haplotyped file, each identical to the control."""
+    control = run_oracle(oracle_exe, ["--no-filtering"], os.path.join(FIX, "bc_anchored_10_reads.sorted.bam"), str(tmp_path / "control.bed"))
+    d = tmp_path / "part"
+    subprocess.check_call([oracle_exe, "pileup", "--partition-tag", "RG", "--partition-tag", "HP", "--no-filtering",
+                           os.path.join(FIX, "bc_anchored_10_reads.haplotyped.sorted.bam"), str(d)], stderr=subprocess.DEVNULL)
+    files = read_dir(str(d))
+    assert sorted(files) == ["A_1.bed", "A_2.bed", "B_1.bed", "B_2.bed", "C_1.bed", "C_2.bed"]
+    assert all(t == control for t in files.values()) and len(control) > 1000
+
+
+def test_oracle_partition_tags_bedgraph(oracle_exe, tmp_path):
+    """tests/test_pileup.rs:546-633: 24 bedgraph files (6 partitions x {h,m} x {positive,negative}) equal to the control's."""
+    cd, pd = tmp_path / "control", tmp_path / "part"
+    subprocess.check_call([oracle_exe, "pileup", "--no-filtering", "--bedgraph", os.path.join(FIX, "bc_anchored_10_reads.sorted.bam"), str(cd)], stderr=subprocess.DEVNULL)
+    subprocess.check_call([oracle_exe, "pileup", "--partition-tag", "RG", "--partition-tag", "HP", "--no-filtering", "--bedgraph",
+                           os.path.join(FIX, "bc_anchored_10_reads.haplotyped.sorted.bam"), str(pd)], stderr=subprocess.DEVNULL)
+    control, part = read_dir(str(cd)), read_dir(str(pd))
+    assert sorted(control) == ["h_negative.bedgraph", "h_positive.bedgraph", "m_negative.bedgraph", "m_positive.bedgraph"]
+    assert len(part) == 24
+    for name, text in part.items():
+        _, _, code, strand = name.replace(".bedgraph", "").split("_")
+        assert text == control["%s_%s.bedgraph" % (code, strand)]
+    # the fraction column is Rust's `{}` of an f32 (shortest round-trip decimal)
+    fr = [l.split("\t")[3] for l in control["h_positive.bedgraph"].splitlines()]
+    assert "0.5" in fr and "0.6666667" in fr and "0.16666667" in fr
 
 
 def kat(exe, *args):
