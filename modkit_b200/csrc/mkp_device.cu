@@ -420,10 +420,10 @@ int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_b
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
     const size_t resident = (size_t)ctx->sm_count * per_sm * INF_THREADS;      // decoders in flight
     // The file goes over in slabs (copy stream); the members of a slab are inflated (compute stream) while the next slab
-    // is on the wire. A slab holds at least two rounds of resident decoders, so small files are a single slab.
+    // is on the wire. A slab holds at least one round of resident decoders and 128 MB, so small files are a single slab.
     std::vector<size_t> cut;                     // member index where each slab starts
     {
-        const size_t min_members = 2 * resident, min_bytes = (size_t)192 << 20;
+        const size_t min_members = resident, min_bytes = (size_t)128 << 20;
         size_t i0 = 0;
         while (i0 < n_members) {
             cut.push_back(i0);

@@ -197,17 +197,24 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
                 const uint8_t* sp = s0 + head;
                 const uint32_t sh = ((uintptr_t)sp & 3u) * 8u;
                 const uint32_t* sw = (const uint32_t*)((uintptr_t)sp & ~(uintptr_t)3);
-                uint32_t w[INF_COPY_STEP / 4 + 1];
-#pragma unroll
-                for (int q = 0; q <= INF_COPY_STEP / 4; q++) w[q] = (uint32_t)q <= nw ? sw[q] : 0u;      // (the last one only feeds the shift)
                 uint8_t hb[3] = {0, 0, 0}, tb[3] = {0, 0, 0};
 #pragma unroll
                 for (int q = 0; q < 3; q++) { if ((uint32_t)q < head) hb[q] = s0[q]; if ((uint32_t)q < tail) tb[q] = sp[4 * nw + q]; }
+                uint32_t* dw = (uint32_t*)(d + head);
+                // two halves of 8 words: short matches (the common case) touch only the first
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t q0 = 8u * half;
+                    if (q0 < nw) {
+                        uint32_t w[9];
+#pragma unroll
+                        for (int q = 0; q <= 8; q++) w[q] = q0 + q <= nw ? sw[q0 + q] : 0u;      // (the last one only feeds the shift)
+#pragma unroll
+                        for (int q = 0; q < 8; q++) if (q0 + q < nw) dw[q0 + q] = __funnelshift_r(w[q], w[q + 1], sh);
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < 3; q++) if ((uint32_t)q < head) d[q] = hb[q];
-                uint32_t* dw = (uint32_t*)(d + head);
-#pragma unroll
-                for (int q = 0; q < INF_COPY_STEP / 4; q++) if ((uint32_t)q < nw) dw[q] = __funnelshift_r(w[q], w[q + 1], sh);
 #pragma unroll
                 for (int q = 0; q < 3; q++) if ((uint32_t)q < tail) d[head + 4 * nw + q] = tb[q];
             } else if (cp_dist >= 8) {
