@@ -369,6 +369,16 @@ def main():
             names = ["parse", "resolve", "rank", "unused", "count_calls+count_bases", "rows", "host_sync_alloc"]
             dom = int(np.argmax(stage[:6]))
             ach = alg / (stage[dom] * 1e-3) / 1e9
+            # DRAM traffic of the dominant kernel per launch: one `ncu --set full` capture at this workload, committed under
+            # profiles/ (tools/profile_traffic.sh); null for any other workload
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_full.json")))
+                kname = {"parse": "k_parse", "resolve": "k_resolve<0, 1>", "count_calls+count_bases": "k_count_bases", "rows": "k_rows<1>"}.get(names[dom])
+                if a.contig_len == CONTIG_LEN and a.coverage == COVERAGE and kname in tj["kernels"]:
+                    traffic = int(tj["kernels"][kname]["dram_bytes_read"] + tj["kernels"][kname]["dram_bytes_write"])
+            except Exception:
+                pass
             # CPU baseline on the same box: bounded window of the same workload, all host cores
             window = min(CPU_WINDOW, a.contig_len)
             cpu_v, cpu_t = (0.0, {"pileup_s": 0.0, "load_s": 0.0}) if a.skip_cpu else cpu_reference_run(oracle, prefix, contig, window, thr, nproc)
@@ -381,7 +391,8 @@ def main():
                             "single_context_ms": 1e3 * t_e2e_single},
                     "gpu_launches": 13 * a.steps + 13 * len(subs) * a.steps,
                     "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s", "traffic": None,
+                                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s", "traffic": traffic,
+                                 "traffic_source": "profiles/r01_traffic_full.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)" if traffic else None,
                                  "algorithmic_bytes_per_launch": int(alg), "kernel_ms": float(stage[dom]),
                                  "whole_path": {"achieved": alg / (stage[7] * 1e-3) / 1e9, "frac": alg / (stage[7] * 1e-3) / 1e9 / peak, "ms": float(stage[7])}},
                     "stage_ms": {n: float(stage[i]) for i, n in enumerate(names)},
