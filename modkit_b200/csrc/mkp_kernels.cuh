@@ -1484,6 +1484,9 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
         if (ri >= D.n_reads) break;
         const ReadMeta m = D.meta[ri];
         if (!(m.flags & 2) || m.n_calls == 0) continue;
+#ifndef MKP_NO_FUSED_CALLS
+        if (m.flags & 4) continue;                 // one sorted run of records: counted by k_count_bases while it streams them
+#endif
         const uint32_t a = (D.hdrs[ri].flags & 0x10) ? 1u : 0u;
         const uint2* calls = D.calls + m.entry_off;
         for (uint32_t k = lane; k < m.n_calls; k += 32) {
@@ -1606,12 +1609,23 @@ __global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D)
                         __syncwarp();
                         for (;;) {
                             const uint32_t k = cp + lane;
-                            uint32_t x = 0xffffffffu;
-                            if (k < m.n_calls) x = rcalls[a ? m.n_calls - 1u - k : k].x;
+                            uint32_t x = 0xffffffffu, info = 0;
+                            if (k < m.n_calls) { const uint2 c = rcalls[a ? m.n_calls - 1u - k : k]; x = c.x; info = c.y; }
                             const bool take = x < lim;
                             if (take) {
                                 const uint32_t rel = x - D.cs;
                                 if ((rel >> 5) >= wt) atomicOr(&s_mask[wib][(rel >> 5) - wt], 1u << (rel & 31));
+#ifndef MKP_NO_FUSED_CALLS
+                                // the record's own counter (k_count_calls leaves these reads alone): modcall / canonical / filtered
+                                const uint32_t hw = D.hot[rel >> 5];
+                                if ((hw >> (rel & 31)) & 1u) {                       // else: outside the focus set
+                                    uint32_t fp = FULL, fn = FULL;
+                                    if (D.focus_pos) { fp = D.focus_pos[rel >> 5]; fn = D.focus_neg[rel >> 5]; }
+                                    const uint32_t st = info & 1u, cb = (info >> 1) & 3u, state = (info >> 3) & 0xffu;
+                                    uint32_t* S = D.slots + (size_t)(D.hot_prefix[rel >> 5] + __popc(hw & ((1u << (rel & 31)) - 1u))) * D.stride;
+                                    add_feature(S, D.n_states, st == 0 ? a : 1u - a, st == 0 ? cb : 3u - cb, state, (fp >> (rel & 31)) & 1u, (fn >> (rel & 31)) & 1u, 1u);
+                                }
+#endif
                             }
                             const uint32_t nt = __popc(__ballot_sync(FULL, take));
                             cp += nt;
