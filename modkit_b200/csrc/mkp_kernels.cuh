@@ -25,7 +25,10 @@ constexpr int MAX_LIST_CODES = 4;
 constexpr int MAX_MAP = 7;          // codes at one read position
 constexpr int MAX_STATES = 32;
 constexpr int CUM_CAP = 512;        // 32-base blocks whose occurrence counts fit in shared memory (reads <= 16 kb)
-constexpr int CQ_CAP = 640;         // CIGAR ops whose prefix sums fit in shared memory per warp
+#ifndef MKP_CQ_CAP
+#define MKP_CQ_CAP 640
+#endif
+constexpr int CQ_CAP = MKP_CQ_CAP;  // CIGAR ops whose prefix sums fit in shared memory per warp
 constexpr int QT_CAP = 512;         // buckets of the query -> op table
 constexpr uint32_t FULL = 0xffffffffu;
 
@@ -359,7 +362,7 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* P, uint32_t 
 // Kernel A: per read, everything that depends only on the read's own bytes: admission, reference span, MM list
 // discovery, per-base occurrence counts, MM token parse + select -> forward positions P[] and the list table.
 #ifndef MKP_MINB_PARSE
-#define MKP_MINB_PARSE 8
+#define MKP_MINB_PARSE 10
 #endif
 #ifndef MKP_MINB_RESOLVE_FAST
 #define MKP_MINB_RESOLVE_FAST 8
