@@ -212,7 +212,6 @@ static std::string derr_text(uint32_t e) {
     if (e & MKP_DERR_TOO_MANY_STATES) s += "more than 32 distinct (base, mod code) states; ";
     if (e & MKP_DERR_TOO_MANY_LISTS) s += "more than 16 MM lists in one read; ";
     if (e & MKP_DERR_TOO_MANY_CODES) s += "more than 4 codes in one MM list or 7 at one position; ";
-    if (e & MKP_DERR_IMPLICIT_MODE) s += "a '.'/default-mode MM list needs implicit canonical fill, which the device path does not implement yet; ";
     return s;
 }
 

@@ -56,22 +56,6 @@ struct BitReader {
     __device__ __forceinline__ uint32_t bits(int n) { refill(); const uint32_t v = peek(n); drop(n); return v; }
 };
 
-// canonical walk, one stream bit at a time (codes are sent most significant bit first)
-__device__ __forceinline__ int inf_decode_slow(BitReader& br, const uint16_t* cnt, const uint16_t* sym) {
-    int code = 0, first = 0, index = 0;
-    br.refill();
-#pragma unroll 1
-    for (int len = 1; len <= 15; len++) {
-        code |= (int)(br.bb & 1u);
-        br.drop(1);
-        const int count = cnt[len];
-        if (code - count < first) return sym[index + (code - first)];
-        index += count; first += count;
-        first <<= 1; code <<= 1;
-    }
-    return -1;
-}
-
 // lens[0..n) -> cnt[16], sym[] (sorted by length, then symbol), tab[1 << tbits] (sym << 4 | len for codes <= tbits),
 // first[len] = first canonical code of that length, index[len] = its position in sym[].
 // Returns false for an over-subscribed set of lengths.
