@@ -53,7 +53,8 @@ MKP_SYMBOLS = ["mkp_create", "mkp_destroy", "mkp_last_error", "mkp_set_params", 
 MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_refs", "mkh_bam_ref_name", "mkh_bam_ref_len",
                "mkh_bam_n_mapped", "mkh_bam_n_records", "mkh_pack_region", "mkh_packed_free", "mkh_packed_n_reads",
                "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
-               "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records"]
+               "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records",
+               "mkh_f32_display", "mkh_bam_partition_key"]
 
 
 def library_path():
@@ -95,6 +96,8 @@ def load_library(build_if_missing=True):
     lib.mkh_device_chunk.restype = C.c_int64
     lib.mkh_bam_ingest_ms.argtypes = [C.c_void_p, C.c_void_p]
     lib.mkh_bam_ingest_ms.restype = None
+    lib.mkh_f32_display.argtypes = [C.c_float, C.c_char_p, C.c_int]
+    lib.mkh_bam_partition_key.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int]
     lib.mkh_bam_total_records.argtypes = [C.c_void_p]
     lib.mkh_bam_total_records.restype = C.c_uint64
     lib.mkh_pileup_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
@@ -175,6 +178,14 @@ class Bam:
         self._lib.mkh_bam_ingest_ms(self._h, ms)
         return dict(zip(["h2d", "inflate", "walk", "total"], [float(x) for x in ms]))
 
+    def partition_key(self, tid, i, tags):
+        """--partition-tag key of the i-th record of contig tid (host-opened BAM): the key string, or None for NoKey."""
+        buf = C.create_string_buffer(4096)
+        rc = self._lib.mkh_bam_partition_key(self._h, tid, i, ":".join(tags).encode(), buf, 4096)
+        if rc < 0:
+            raise MkpError("partition key failed")
+        return buf.value.decode() if rc == 1 else None
+
     @property
     def total_records(self):
         return int(self._lib.mkh_bam_total_records(self._h))
@@ -251,6 +262,15 @@ class Packed:
             self.free()
         except Exception:
             pass
+
+
+def f32_display(v):
+    """Rust `{}` of an f32 as the host writes it (bedgraph fraction column, float aux values in partition keys)."""
+    lib = load_library()
+    buf = C.create_string_buffer(64)
+    if lib.mkh_f32_display(float(np.float32(v)), buf, 64) < 0:
+        raise MkpError("f32_display failed")
+    return buf.value.decode()
 
 
 def make_params(default_threshold=0.0, base_thresholds=None, mod_thresholds=None, numeric_mode=0, collapse_code=0,

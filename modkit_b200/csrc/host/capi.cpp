@@ -37,6 +37,21 @@ int64_t mkh_device_chunk(const mkh_bam* b, uint32_t tid, uint32_t start, uint32_
 }
 void mkh_bam_ingest_ms(const mkh_bam* b, float* ms) { for (int i = 0; i < 4; i++) ms[i] = b->reader.ingest_ms[i]; }
 uint64_t mkh_bam_total_records(const mkh_bam* b) { uint64_t n = b->reader.unplaced.size(); for (auto& v : b->reader.by_tid) n += v.size(); return n; }
+// host-side helpers of --partition-tag / --bedgraph, exposed for the CPU tests
+int mkh_f32_display(float v, char* out, int cap) { const std::string s = f32_display(v); if ((int)s.size() + 1 > cap) return -1; memcpy(out, s.c_str(), s.size() + 1); return (int)s.size(); }
+// partition key of the i-th record of tid (file order) for the ':'-separated tag list; returns 1 key, 0 NoKey, -1 error
+int mkh_bam_partition_key(const mkh_bam* b, uint32_t tid, uint64_t i, const char* tags, char* out, int cap) {
+    try {
+        std::vector<std::string> tv;
+        for (const char* p = tags; *p;) { const char* q = strchr(p, ':'); if (!q) q = p + strlen(p); tv.emplace_back(p, q - p); p = *q ? q + 1 : q; }
+        const RecRef& r = b->reader.by_tid.at(tid).at(i);
+        std::string k;
+        const bool have = partition_key_of(b->reader.rec(r), r.size, tv, &k);
+        if ((int)k.size() + 1 > cap) return -1;
+        memcpy(out, k.c_str(), k.size() + 1);
+        return have ? 1 : 0;
+    } catch (const std::exception&) { return -1; }
+}
 void mkh_bam_close(mkh_bam* b) { delete b; }
 uint32_t mkh_bam_n_refs(const mkh_bam* b) { return (uint32_t)b->reader.ref_names.size(); }
 const char* mkh_bam_ref_name(const mkh_bam* b, uint32_t tid) { return b->reader.ref_names[tid].c_str(); }

@@ -94,3 +94,37 @@ def test_region_fetch_semantics():
     want = [f["pos"] for f in fs if f["tid"] == tid and span(f)[0] < hi and span(f)[1] > lo]
     got = b.pack(tid, lo, hi).headers()["ref_start"].tolist()
     assert got == want
+
+
+def test_f32_display_is_shortest_roundtrip_fixed(native_lib):
+    """bedgraph's fraction column is Rust's `{}` of an f32: the shortest decimal that parses back to the same f32, never in
+    exponent form. Checked against numpy's unique positional formatting over fractions n/d and random bit patterns."""
+    import modkit_b200
+    vals = [np.float32(n) / np.float32(d) for d in range(1, 60) for n in range(0, d + 1)]
+    rng = np.random.default_rng(1)
+    vals += list(rng.integers(0x30000000, 0x3f800000, 3000, dtype=np.uint32).view(np.float32))     # (1e-10, 1)
+    vals += [np.float32(1e-7), np.float32(123456.789), np.float32(0.1), np.float32(1.0), np.float32(0.0)]
+    for v in vals:
+        got = modkit_b200.f32_display(v)
+        exp = np.format_float_positional(np.float32(v), unique=True, trim="-")
+        assert got == exp, (float(v), got, exp)
+        assert "e" not in got and np.float32(got) == np.float32(v)
+
+
+def test_partition_keys_of_haplotyped_fixture(native_lib):
+    """parse_tags_from_record (src/pileup/mod.rs:629-646): tag values joined by '_', `missing` for absent tags, None when
+    no tag is present; RG (Z) and HP (integer) on the reference's haplotyped fixture, cross-checked with the Python reader."""
+    import modkit_b200
+    path = os.path.join(FIX, "bc_anchored_10_reads.haplotyped.sorted.bam")
+    bam = modkit_b200.Bam(path, threads=2)
+    recs = bamio.Bam(path).records
+    seen = set()
+    for i, r in enumerate(recs):
+        rg, hp = bamio.get_aux(r, b"RG"), bamio.get_aux(r, b"HP")
+        hpv = int.from_bytes(hp, "little")           # small unsigned integer aux value
+        exp = "%s_%d" % (rg.decode(), hpv)
+        assert bam.partition_key(0, i, ["RG", "HP"]) == exp
+        assert bam.partition_key(0, i, ["HP", "XX"]) == "%d_missing" % hpv
+        assert bam.partition_key(0, i, ["XX", "YY"]) is None
+        seen.add(exp)
+    assert sorted(seen) == ["A_1", "A_2", "B_1", "B_2", "C_1", "C_2"]
