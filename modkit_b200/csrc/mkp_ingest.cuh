@@ -40,14 +40,23 @@ struct BitReader {
     const uint8_t* end;
     unsigned long long bb;   // bit buffer, LSB first
     int nb;                  // valid bits
-    __device__ __forceinline__ void init(const uint8_t* s, const uint8_t* e) { p = s; end = e; bb = 0; nb = 0; }
+    uint32_t nxt;            // the aligned word at p, loaded one refill ahead (its latency hides behind a symbol's work)
+    bool have_nxt;
+    __device__ __forceinline__ void init(const uint8_t* s, const uint8_t* e) { p = s; end = e; bb = 0; nb = 0; nxt = 0; have_nxt = false; }
     // at least 32 valid bits afterwards (zero bits past the end of the input; the caller checks overrun at the end)
     __device__ __forceinline__ void refill() {
         if (nb > 32) return;
 #pragma unroll 1
-        while (((uintptr_t)p & 3u) && nb <= 56) { const unsigned long long b = p < end ? *p : 0; p++; bb |= b << nb; nb += 8; }
+        while (((uintptr_t)p & 3u) && nb <= 56) { const unsigned long long b = p < end ? *p : 0; p++; bb |= b << nb; nb += 8; have_nxt = false; }
         if (nb > 32) return;
-        if (p + 4 <= end) { bb |= (unsigned long long)(*(const uint32_t*)p) << nb; p += 4; nb += 32; return; }
+        if (p + 4 <= end) {
+            const uint32_t w = have_nxt ? nxt : *(const uint32_t*)p;
+            bb |= (unsigned long long)w << nb; p += 4; nb += 32;
+            have_nxt = p + 4 <= end;
+            if (have_nxt) nxt = *(const uint32_t*)p;
+            return;
+        }
+        have_nxt = false;
 #pragma unroll 1
         while (nb <= 56) { const unsigned long long b = p < end ? *p : 0; p++; bb |= b << nb; nb += 8; }
     }
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restri
                     uint32_t k = 0;
                     while (k < len && br.nb >= 8) { dst[o + k] = (uint8_t)br.bb; br.drop(8); k++; }
                     if (k < len) {
-                        br.bb = 0; br.nb = 0;
+                        br.bb = 0; br.nb = 0; br.have_nxt = false;
                         if (br.p + (len - k) > br.end) err = INF_ERR_INPUT;
                         else for (; k < len; k++) dst[o + k] = *br.p++;
                     }
