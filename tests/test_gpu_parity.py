@@ -246,3 +246,24 @@ def test_gpu_bedgraph_with_motifs(native_lib, oracle_exe, synth_exe, tmp_path):
         got, exp = read_dir(gd), read_dir(od)
         assert got == exp and len(got) == (4 if k == 0 else 2)
         assert all("CG0" in name for name in got)
+
+
+def test_gpu_partition_tags_synthetic(native_lib, oracle_exe, synth_exe, tmp_path):
+    """Partitioned pileup on a synthetic modBAM whose reads carry RG:Z (or none), HP as C / i (or none) and XF:f on some:
+    keys with `missing`, the `ungrouped` partition, float-valued keys; several chunks; product directories == oracle's."""
+    from conftest import read_dir
+    prefix, _ = synth(synth_exe, tmp_path, "pt", "--contig", "syn1:260000", "--contig", "syn2:90000", "--coverage", "18", "--mods", "hm",
+                      "--seed", "21", "--partition-tags", "--odd-records")
+    for k, flags in enumerate((["--partition-tag", "RG", "--partition-tag", "HP", "--cpg", "--ref", prefix + ".fa", "--gpu-chunk-bp", "100000"],
+                               ["--partition-tag", "XF", "--prefix", "f", "--no-filtering", "-i", "30011"],
+                               ["--partition-tag", "HP", "--bedgraph", "--cpg", "--combine-strands", "--ref", prefix + ".fa"])):
+        oflags = [f for i, f in enumerate(flags) if f != "--gpu-chunk-bp" and (i == 0 or flags[i - 1] != "--gpu-chunk-bp")]
+        gd, od = str(tmp_path / ("g%d" % k)), str(tmp_path / ("o%d" % k))
+        assert run_product(flags, prefix + ".bam", gd)[0] == 0
+        subprocess.check_call([oracle_exe, "pileup"] + oflags + [prefix + ".bam", od], stderr=subprocess.DEVNULL)
+        got, exp = read_dir(gd), read_dir(od)
+        assert sorted(got) == sorted(exp) and got == exp
+        if k == 0:
+            assert "ungrouped.bed" in got and "A_missing.bed" in got and "missing_3.bed" in got and "B_2.bed" in got
+        if k == 1:
+            assert sorted(got) == ["f_0.1.bed", "f_0.33333334.bed", "f_2.5.bed", "f_ungrouped.bed"]

@@ -4,7 +4,7 @@
 // ever available) the real `modkit` binary.
 //
 //   synth_modbam --out PREFIX [--contig NAME:LEN]... [--coverage 30] [--seed 20260924] [--mods m|hm|hma]
-//                [--mean-len 12000] [--level 1] [--threads 8] [--combined-hm] [--implicit] [--odd-records]
+//                [--mean-len 12000] [--level 1] [--threads 8] [--combined-hm] [--implicit] [--odd-records] [--partition-tags]
 //                [--region-only START-END]   (only reads overlapping the window; reference still full length)
 // Writes PREFIX.fa, PREFIX.fa.fai, PREFIX.bam, PREFIX.bam.bai and prints a JSON summary (exact algorithmic bytes,
 // read-bases, reads) on stdout.
@@ -46,6 +46,7 @@ struct Opts {
     double mean_len = 12000, sigma = 0.6;
     int level = 1, threads = 8;
     bool combined_hm = false, implicit = false, odd = false;
+    bool ptags = false;    // --partition-tags: RG:Z (A/B/C or absent), HP (C or i, or absent), XF:f on some reads
     int64_t win_start = -1, win_end = -1;
 };
 
@@ -215,6 +216,13 @@ static void make_read(const Opts& o, const Contig& c, int32_t tid, uint32_t star
         v.push_back('M'); v.push_back('M'); v.push_back('Z'); v.insert(v.end(), mm.begin(), mm.end()); v.push_back(0);
         v.push_back('M'); v.push_back('L'); v.push_back('B'); v.push_back('C'); put<uint32_t>(v, (uint32_t)ml.size()); v.insert(v.end(), ml.begin(), ml.end());
     }
+    if (o.ptags) {
+        const double u1 = rng.uni(), u2 = rng.uni(), u3 = rng.uni();
+        if (u1 < 0.9) { v.push_back('R'); v.push_back('G'); v.push_back('Z'); v.push_back((uint8_t)("ABC"[(int)(u1 * 10) % 3])); v.push_back(0); }
+        if (u2 < 0.7) { v.push_back('H'); v.push_back('P'); v.push_back('C'); v.push_back((uint8_t)(u2 < 0.35 ? 1 : 2)); }
+        else if (u2 < 0.8) { v.push_back('H'); v.push_back('P'); v.push_back('i'); put<int32_t>(v, 3); }
+        if (u3 < 0.3) { v.push_back('X'); v.push_back('F'); v.push_back('f'); const float f = u3 < 0.1 ? 0.1f : (u3 < 0.2 ? 2.5f : 1.0f / 3.0f); uint32_t b; memcpy(&b, &f, 4); put<uint32_t>(v, b); }
+    }
     const uint32_t bs = (uint32_t)(v.size() - rec0 - 4);
     memcpy(v.data() + rec0, &bs, 4);
     out->recs.push_back({tid, (int32_t)start, (int32_t)ref_end, flag, bs + 4});
@@ -238,6 +246,7 @@ int main(int argc, char** argv) {
         else if (a == "--combined-hm") o.combined_hm = true;
         else if (a == "--implicit") o.implicit = true;
         else if (a == "--odd-records") o.odd = true;
+        else if (a == "--partition-tags") o.ptags = true;
         else if (a == "--region-only") { std::string s = val(); auto d = s.find('-'); o.win_start = std::stoll(s.substr(0, d)); o.win_end = std::stoll(s.substr(d + 1)); }
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
