@@ -56,6 +56,7 @@ struct mkp_ctx {
     DevBuf d_file, d_members, d_bam, d_seeds, d_seg_counts, d_seg_base, d_recs, d_ids, d_plan, d_need, d_totals, d_slab_work;
     uint64_t bam_len = 0;
     size_t n_records = 0;
+    bool inflate_attr_set = false;
     // results
     size_t n_rows = 0;
     std::vector<mkp_row> h_rows;
@@ -414,8 +415,10 @@ int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_b
     CK(cudaMemcpyAsync(ctx->d_seeds.p, seeds, n_seeds * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(u + 10, 0, 12, st));
     const size_t smem = (size_t)INF_THREADS * INF_STRIDE * 2;
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    if (!ctx->inflate_attr_set) {      // per device: the opt-in to > 48 KB of dynamic shared memory
+        CK(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->inflate_attr_set = true;
+    }
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
     const size_t resident = (size_t)ctx->sm_count * per_sm * INF_THREADS;      // decoders in flight
     // The file goes over in slabs (copy stream); the members of a slab are inflated (compute stream) while the next slab
