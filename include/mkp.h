@@ -169,6 +169,12 @@ int  mkp_device_memory(mkp_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
  * slabs are inflated), record walk, total. */
 int  mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
                   uint64_t inflated_len, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms);
+/* The same for a byte range of the file (one or several contigs of a coordinate-sorted BAM, so that files larger than the
+ * device memory are processed range by range): `file` points at the first member of the range, member offsets and
+ * seeds are relative to the range, and the record walk stops at walk_end (<= inflated_len: the offset of the first
+ * record that belongs to the next range; the last members of a range may hold its first bytes). */
+int  mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                        uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms);
 /* Record table in file order (n_records entries, host memory). */
 int  mkp_bam_records(mkp_ctx* ctx, mkp_bam_rec* out);
 /* Make the records rec_ids[0..n) (indices into the record table, file order) the resident chunk for [start,end):

@@ -49,12 +49,12 @@ assert ROW_DTYPE.itemsize == 40
 
 MKP_SYMBOLS = ["mkp_create", "mkp_destroy", "mkp_last_error", "mkp_set_params", "mkp_upload_chunk", "mkp_pileup_resident",
                "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_algorithmic_bytes",
-               "mkp_device_memory", "mkp_bam_load", "mkp_bam_records", "mkp_bam_chunk", "mkp_bam_inflated", "mkp_fetch_chunk"]
+               "mkp_device_memory", "mkp_bam_load", "mkp_bam_load_range", "mkp_bam_records", "mkp_bam_chunk", "mkp_bam_inflated", "mkp_fetch_chunk"]
 MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_refs", "mkh_bam_ref_name", "mkh_bam_ref_len",
                "mkh_bam_n_mapped", "mkh_bam_n_records", "mkh_pack_region", "mkh_packed_free", "mkh_packed_n_reads",
                "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
                "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records",
-               "mkh_f32_display", "mkh_bam_partition_key"]
+               "mkh_f32_display", "mkh_bam_partition_key", "mkh_bam_n_ranges"]
 
 
 def library_path():
@@ -98,6 +98,8 @@ def load_library(build_if_missing=True):
     lib.mkh_bam_ingest_ms.restype = None
     lib.mkh_f32_display.argtypes = [C.c_float, C.c_char_p, C.c_int]
     lib.mkh_bam_partition_key.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int]
+    lib.mkh_bam_n_ranges.argtypes = [C.c_void_p]
+    lib.mkh_bam_n_ranges.restype = C.c_uint32
     lib.mkh_bam_total_records.argtypes = [C.c_void_p]
     lib.mkh_bam_total_records.restype = C.c_uint64
     lib.mkh_pileup_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
@@ -185,6 +187,11 @@ class Bam:
         if rc < 0:
             raise MkpError("partition key failed")
         return buf.value.decode() if rc == 1 else None
+
+    @property
+    def n_ranges(self):
+        """Device ingest: 1 when the whole file is resident, else the number of byte ranges it is loaded in."""
+        return int(self._lib.mkh_bam_n_ranges(self._h))
 
     @property
     def total_records(self):

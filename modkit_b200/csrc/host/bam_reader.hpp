@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <charconv>
 #include <cstdint>
 #include <cstring>
@@ -139,11 +140,16 @@ public:
 
     // Device ingest (include/mkp.h, mkp_bam_load): the host walks the BGZF member headers, inflates only the members
     // that hold the BAM header, and turns the BAI's virtual offsets into seed offsets for the record walk.
+    // A file whose bytes + inflated stream fit in the device memory is loaded once. A bigger coordinate-sorted, indexed file
+    // is loaded range by range (consecutive contigs, mkp_bam_load_range): ensure_tid() switches the resident range.
     void open_device(const std::string& path, mkp_ctx* ctx) {
-        MappedFile mf;
-        mf.open(path);
-        size_t total = 0;
-        std::vector<Member> members = scan_members(mf, path, &total);
+        file_ = std::make_shared<MappedFile>();
+        file_->open(path);
+        const MappedFile& mf = *file_;
+        total_ = 0;
+        members_ = scan_members(mf, path, &total_);
+        const size_t total = total_;
+        const std::vector<Member>& members = members_;
         // ---- BAM header: inflate leading members until it is complete
         std::vector<uint8_t> head;
         size_t m_done = 0;
@@ -177,63 +183,92 @@ public:
             ref_lens.push_back(load_le<uint32_t>(head.data() + o + 4 + ln));
             o += 8 + ln;
         }
-        const uint64_t first_rec = o;
+        first_rec_ = o;
         by_tid.assign(n_ref, {});
         run_max_end.assign(n_ref, {});
         stats.n_mapped.assign(n_ref, 0);
         stats.n_unmapped.assign(n_ref, 0);
         // ---- seeds: virtual offsets of the index -> offsets in the inflated stream
-        std::vector<uint64_t> voffs;
-        const bool have_bai = load_bai(path, &voffs);
-        std::vector<uint64_t> seeds;
-        seeds.push_back(first_rec);
-        for (uint64_t v : voffs) {
+        auto to_offset = [&](uint64_t v, uint64_t* x) {
             const uint64_t coff = v >> 16, uoff = v & 0xffff;
             auto it = std::lower_bound(members.begin(), members.end(), coff, [](const Member& m, uint64_t c) { return m.file_off < c; });
-            if (it == members.end() || it->file_off != coff) continue;
-            const uint64_t x = it->out_off + uoff;
-            if (x > first_rec && x + 36 <= total) seeds.push_back(x);
-        }
-        std::sort(seeds.begin(), seeds.end());
-        seeds.erase(std::unique(seeds.begin(), seeds.end()), seeds.end());
-        std::vector<mkp_bgzf_member> jobs;
-        jobs.reserve(members.size());
-        for (auto& m : members) if (m.out_len) jobs.push_back({(uint64_t)m.in_off, (uint64_t)m.out_off, (uint32_t)m.in_len, m.out_len});
-        size_t n_rec = 0;
-        if (first_rec >= total) { seeds.clear(); }
-        // the file, the inflated stream and (later) the sliced chunks stay resident: they must fit
-        {
-            size_t free_b = 0, total_b = 0;
-            if (mkp_device_memory(ctx, &free_b, &total_b) == 0 && (double)mf.size + 1.6 * (double)total + (double)(1ull << 30) > (double)free_b)
+            if (it == members.end() || it->file_off != coff) return false;
+            *x = it->out_off + uoff;
+            return true;
+        };
+        std::vector<uint64_t> voffs, ref_first;
+        have_bai_ = load_bai(path, &voffs, &ref_first);
+        seeds_.clear();
+        seeds_.push_back(first_rec_);
+        for (uint64_t v : voffs) { uint64_t x; if (to_offset(v, &x) && x > first_rec_ && x + 36 <= total) seeds_.push_back(x); }
+        std::sort(seeds_.begin(), seeds_.end());
+        seeds_.erase(std::unique(seeds_.begin(), seeds_.end()), seeds_.end());
+        if (first_rec_ >= total) seeds_.clear();
+        dev = ctx;
+        on_device = true;
+        // ---- does everything fit at once?
+        size_t free_b = 0, total_b = 0;
+        const bool have_mem = mkp_device_memory(ctx, &free_b, &total_b) == 0;
+        double budget = have_mem ? 0.55 * (double)free_b : 1e18;
+        if (const char* e = getenv("MODKIT_B200_INGEST_BUDGET_MB")) budget = atof(e) * 1048576.0;
+        auto cost = [](double file_bytes, double inflated) { return file_bytes + 1.6 * inflated; };
+        if (cost((double)mf.size, (double)total) <= budget || !have_bai_ || ref_first.size() != n_ref) {
+            if (have_mem && cost((double)mf.size, (double)total) + (double)(1ull << 30) > (double)free_b)
                 throw DeviceIngestTooBig("BAM does not fit on the device for the GPU ingest (" + std::to_string(total >> 20) + " MiB inflated, " +
+                                         std::to_string(free_b >> 20) + " MiB free" + (have_bai_ ? ")" : "; no index for a ranged load)"));
+            ranged_ = false;
+            if (!seeds_.empty()) load_members(0, members.empty() ? 0 : members.size() - 1, first_rec_, total);
+            return;
+        }
+        // ---- ranged: consecutive contigs per load
+        ranged_ = true;
+        loaded_ = -1;
+        std::vector<std::pair<uint64_t, uint32_t>> firsts;        // (offset of the contig's first record, tid)
+        for (uint32_t t = 0; t < n_ref; t++) { uint64_t x; if (ref_first[t] != UINT64_MAX && to_offset(ref_first[t], &x) && x >= first_rec_ && x < total) firsts.push_back({x, t}); }
+        for (size_t i = 1; i < firsts.size(); i++) if (firsts[i].first <= firsts[i - 1].first) throw DeviceIngestTooBig("BAM is not coordinate sorted by contig: no ranged GPU ingest");
+        if (firsts.empty()) firsts.push_back({first_rec_, n_ref});   // only reads without coordinates
+        firsts[0].first = first_rec_;
+        batch_of_tid_.assign(n_ref, -1);
+        batches_.clear();
+        auto member_of = [&](uint64_t off) { return (size_t)(std::upper_bound(members.begin(), members.end(), off, [](uint64_t x, const Member& m) { return x < m.out_off; }) - members.begin()) - 1; };
+        for (size_t i = 0; i < firsts.size();) {
+            Batch bt;
+            bt.start_off = firsts[i].first;
+            bt.m0 = member_of(bt.start_off);
+            size_t j = i;
+            for (;;) {
+                const uint64_t stop = j + 1 < firsts.size() ? firsts[j + 1].first : total;
+                const size_t m1 = member_of(stop - 1);
+                const double fb = (double)(members[m1].in_off + members[m1].in_len - members[bt.m0].file_off);
+                const double ib = (double)(members[m1].out_off + members[m1].out_len - members[bt.m0].out_off);
+                if (j > i && cost(fb, ib) > budget) break;
+                bt.stop_off = stop; bt.m1 = m1;
+                if (firsts[j].second < n_ref) batch_of_tid_[firsts[j].second] = (int)batches_.size();
+                j++;
+                if (j >= firsts.size()) break;
+            }
+            batches_.push_back(bt);
+            i = j;
+        }
+        for (auto& bt : batches_) {
+            const double fb = (double)(members[bt.m1].in_off + members[bt.m1].in_len - members[bt.m0].file_off);
+            const double ib = (double)(members[bt.m1].out_off + members[bt.m1].out_len - members[bt.m0].out_off);
+            if (have_mem && cost(fb, ib) + (double)(1ull << 30) > (double)free_b)
+                throw DeviceIngestTooBig("one contig of the BAM does not fit on the device for the GPU ingest (" + std::to_string((uint64_t)ib >> 20) + " MiB inflated, " +
                                          std::to_string(free_b >> 20) + " MiB free)");
         }
-        if (!seeds.empty()) {
-            if (mkp_bam_load(ctx, mf.data, mf.size, jobs.data(), jobs.size(), total, seeds.data(), seeds.size(), &n_rec, ingest_ms))
-                throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(ctx));
-        }
-        std::vector<mkp_bam_rec> recs(n_rec);
-        if (n_rec && mkp_bam_records(ctx, recs.data())) throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(ctx));
-        BamIndexStats scan;
-        scan.n_mapped.assign(n_ref, 0); scan.n_unmapped.assign(n_ref, 0);
-        for (size_t i = 0; i < n_rec; i++) {
-            const mkp_bam_rec& d = recs[i];
-            RecRef r;
-            r.off = d.off; r.size = d.size; r.pos = d.pos; r.end = d.end; r.idx = (uint32_t)i; r.l_seq = d.l_seq; r.flag = (uint16_t)d.flag;
-            if (d.tid >= 0 && (uint32_t)d.tid < n_ref) {
-                by_tid[d.tid].push_back(r);
-                if (d.flag & 4) scan.n_unmapped[d.tid]++; else scan.n_mapped[d.tid]++;
-            } else { unplaced.push_back(r); scan.n_no_coor++; }
-        }
-        if (!have_bai) stats = scan;
-        for (uint32_t t = 0; t < n_ref; t++) {
-            int32_t m = INT32_MIN;
-            run_max_end[t].reserve(by_tid[t].size());
-            for (auto& r : by_tid[t]) { m = std::max(m, r.end); run_max_end[t].push_back(m); }
-        }
-        on_device = true;
-        dev = ctx;
     }
+
+    // make the records of contig tid resident (ranged device ingest; a no-op otherwise)
+    void ensure_tid(uint32_t tid) const {
+        if (!ranged_ || tid >= batch_of_tid_.size()) return;
+        const int b = batch_of_tid_[tid];
+        if (b >= 0 && b != loaded_) const_cast<BamReader*>(this)->load_batch(b);
+    }
+    // the reads without coordinates live at the end of the file: the last range
+    void ensure_unplaced() const { if (ranged_ && !batches_.empty() && loaded_ != (int)batches_.size() - 1) const_cast<BamReader*>(this)->load_batch((int)batches_.size() - 1); }
+    bool ranged() const { return ranged_; }
+    size_t n_ranges() const { return ranged_ ? batches_.size() : 1; }
 
     // reads overlapping [beg,end) on tid in file order: half-open record span [pos, endpos)
     template <class F> void for_overlapping(uint32_t tid, int64_t beg, int64_t end, F&& f) const {
@@ -245,6 +280,69 @@ public:
     const uint8_t* rec(const RecRef& r) const { if (on_device) throw std::runtime_error("record bytes are on the device"); return raw.data() + r.off; }
 
 private:
+    struct Batch { uint64_t start_off = 0, stop_off = 0; size_t m0 = 0, m1 = 0; };
+    std::shared_ptr<MappedFile> file_;
+    std::vector<Member> members_;
+    std::vector<uint64_t> seeds_;             // known record starts (offsets in the whole inflated stream)
+    size_t total_ = 0;
+    uint64_t first_rec_ = 0;
+    bool have_bai_ = false, ranged_ = false;
+    std::vector<Batch> batches_;
+    std::vector<int> batch_of_tid_;
+    int loaded_ = -1;
+
+    void load_batch(int b) {
+        const Batch& bt = batches_[b];
+        for (auto& v : by_tid) v.clear();
+        for (auto& v : run_max_end) v.clear();
+        unplaced.clear();
+        load_members(bt.m0, bt.m1, bt.start_off, bt.stop_off);
+        loaded_ = b;
+    }
+
+    // inflate members [m0, m1] on the device, walk the records of [start_off, stop_off) and index them
+    void load_members(size_t m0, size_t m1, uint64_t start_off, uint64_t stop_off) {
+        const MappedFile& mf = *file_;
+        const uint32_t n_ref = (uint32_t)ref_names.size();
+        const uint64_t fbase = members_[m0].file_off, obase = members_[m0].out_off;
+        std::vector<mkp_bgzf_member> jobs;
+        jobs.reserve(m1 - m0 + 1);
+        for (size_t k = m0; k <= m1; k++) { const Member& m = members_[k]; if (m.out_len) jobs.push_back({(uint64_t)m.in_off - fbase, (uint64_t)m.out_off - obase, (uint32_t)m.in_len, m.out_len}); }
+        std::vector<uint64_t> seeds;
+        seeds.push_back(start_off - obase);
+        for (auto it = std::upper_bound(seeds_.begin(), seeds_.end(), start_off); it != seeds_.end() && *it < stop_off; ++it) seeds.push_back(*it - obase);
+        const uint64_t inflated = members_[m1].out_off + members_[m1].out_len - obase;
+        const size_t flen = (size_t)(members_[m1].in_off + members_[m1].in_len + 8 - fbase);
+        size_t n_rec = 0;
+        float ms[4] = {0, 0, 0, 0};
+        if (mkp_bam_load_range(dev, mf.data + fbase, std::min(flen, mf.size - (size_t)fbase), jobs.data(), jobs.size(), inflated, stop_off - obase,
+                               seeds.data(), seeds.size(), &n_rec, ms))
+            throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(dev));
+        for (int i = 0; i < 4; i++) ingest_ms[i] += ms[i];
+        std::vector<mkp_bam_rec> recs(n_rec);
+        if (n_rec && mkp_bam_records(dev, recs.data())) throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(dev));
+        BamIndexStats scan;
+        scan.n_mapped.assign(n_ref, 0); scan.n_unmapped.assign(n_ref, 0);
+        for (size_t i = 0; i < n_rec; i++) {
+            const mkp_bam_rec& d = recs[i];
+            RecRef r;
+            r.off = d.off + obase;      // identity of the record: offset in the whole inflated stream
+            r.size = d.size; r.pos = d.pos; r.end = d.end; r.idx = (uint32_t)i; r.l_seq = d.l_seq; r.flag = (uint16_t)d.flag;
+            if (d.tid >= 0 && (uint32_t)d.tid < n_ref) {
+                by_tid[d.tid].push_back(r);
+                if (d.flag & 4) scan.n_unmapped[d.tid]++; else scan.n_mapped[d.tid]++;
+            } else { unplaced.push_back(r); scan.n_no_coor++; }
+        }
+        if (!have_bai_) stats = scan;
+        for (uint32_t t = 0; t < n_ref; t++) {
+            if (by_tid[t].empty()) continue;
+            int32_t m = INT32_MIN;
+            run_max_end[t].clear();
+            run_max_end[t].reserve(by_tid[t].size());
+            for (auto& r : by_tid[t]) { m = std::max(m, r.end); run_max_end[t].push_back(m); }
+        }
+    }
+
     void index_records(size_t total) {
         const uint8_t* p = raw.data();
         if (total < 12 || memcmp(p, "BAM\1", 4) != 0) throw std::runtime_error("not a BAM stream");
@@ -300,7 +398,7 @@ private:
     }
 
     // BAI pseudo-bin 37450 (SAMv1 5.2): per-reference mapped/unmapped counts == hts_idx_get_stat
-    bool load_bai(const std::string& bam_path, std::vector<uint64_t>* voffs) {
+    bool load_bai(const std::string& bam_path, std::vector<uint64_t>* voffs, std::vector<uint64_t>* ref_first = nullptr) {
         std::string cand[2] = {bam_path + ".bai", bam_path.size() > 4 ? bam_path.substr(0, bam_path.size() - 4) + ".bai" : std::string()};
         for (auto& path : cand) {
             if (path.empty()) continue;
@@ -318,6 +416,8 @@ private:
             if (n_ref != ref_names.size()) continue;
             BamIndexStats s;
             s.n_mapped.assign(n_ref, 0); s.n_unmapped.assign(n_ref, 0);
+            if (ref_first) ref_first->assign(n_ref, UINT64_MAX);
+            auto note = [&](uint32_t r, uint64_t v) { if (ref_first && v && v < (*ref_first)[r]) (*ref_first)[r] = v; };
             bool ok = true;
             for (uint32_t r = 0; r < n_ref && ok; r++) {
                 if (o + 4 > b.size()) { ok = false; break; }
@@ -332,17 +432,17 @@ private:
                         s.n_mapped[r] = load_le<uint64_t>(b.data() + o + 16);
                         s.n_unmapped[r] = load_le<uint64_t>(b.data() + o + 24);
                     } else if (voffs) {
-                        for (uint32_t c = 0; c < n_chunk; c++) voffs->push_back(load_le<uint64_t>(b.data() + o + 16ull * c));
+                        for (uint32_t c = 0; c < n_chunk; c++) { const uint64_t v = load_le<uint64_t>(b.data() + o + 16ull * c); voffs->push_back(v); note(r, v); }
                     }
                     o += 16ull * n_chunk;
                 }
                 if (!ok || o + 4 > b.size()) { ok = false; break; }
                 const uint32_t n_intv = load_le<uint32_t>(b.data() + o);
                 if (o + 4 + 8ull * n_intv > b.size()) { ok = false; break; }
-                if (voffs) for (uint32_t c = 0; c < n_intv; c++) voffs->push_back(load_le<uint64_t>(b.data() + o + 4 + 8ull * c));
+                if (voffs) for (uint32_t c = 0; c < n_intv; c++) { const uint64_t v = load_le<uint64_t>(b.data() + o + 4 + 8ull * c); voffs->push_back(v); note(r, v); }
                 o += 4 + 8ull * n_intv;
             }
-            if (!ok) { if (voffs) voffs->clear(); continue; }
+            if (!ok) { if (voffs) voffs->clear(); if (ref_first) ref_first->clear(); continue; }
             if (o + 8 <= b.size()) s.n_no_coor = load_le<uint64_t>(b.data() + o);
             s.from_bai = true;
             stats = s;

@@ -31,11 +31,13 @@ int mkh_bam_open_device(const char* path, mkp_ctx* ctx, mkh_bam** out) {
 int64_t mkh_device_chunk(const mkh_bam* b, uint32_t tid, uint32_t start, uint32_t end, const uint32_t* focus_pos, const uint32_t* focus_neg) {
     try {
         std::vector<RecRef> recs;
+        b->reader.ensure_tid(tid);
         b->reader.for_overlapping(tid, start, end, [&](const RecRef& r) { recs.push_back(r); });
         return (int64_t)device_chunk(b->reader, recs, start, end, focus_pos, focus_neg);
     } catch (const std::exception& e) { fprintf(stderr, "mkh_device_chunk: %s\n", e.what()); return -1; }
 }
 void mkh_bam_ingest_ms(const mkh_bam* b, float* ms) { for (int i = 0; i < 4; i++) ms[i] = b->reader.ingest_ms[i]; }
+uint32_t mkh_bam_n_ranges(const mkh_bam* b) { return (uint32_t)b->reader.n_ranges(); }
 uint64_t mkh_bam_total_records(const mkh_bam* b) { uint64_t n = b->reader.unplaced.size(); for (auto& v : b->reader.by_tid) n += v.size(); return n; }
 // host-side helpers of --partition-tag / --bedgraph, exposed for the CPU tests
 int mkh_f32_display(float v, char* out, int cap) { const std::string s = f32_display(v); if ((int)s.size() + 1 > cap) return -1; memcpy(out, s.c_str(), s.size() + 1); return (int)s.size(); }

@@ -221,6 +221,7 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
         for (const Grp& g : todo) {
             if (cfg.include && !cfg.include->overlaps_any(g.tid, g.start, g.end)) continue;
             std::vector<RecRef> recs;
+            bam.ensure_tid(g.tid);          // ranged device ingest: the contig's byte range becomes resident
             bam.for_overlapping(g.tid, g.start, g.end, [&](const RecRef& r) { if (sampler_flag_ok(r, only_mapped || cfg.edge_on)) recs.push_back(r); });
             size_t used = 0, cursor = 0;
             while (cursor < recs.size() && (g.n < 0 || used < (size_t)g.n)) {
@@ -243,6 +244,7 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
     if (!only_mapped) {   // reads without coordinates (reads_sampler/mod.rs:85-129)
         const size_t limit = cfg.take_all ? (size_t)-1 : (cfg.num_reads > selected_ids.size() ? cfg.num_reads - selected_ids.size() : 0);
         cand.clear();
+        bam.ensure_unplaced();
         for (auto& r : bam.unplaced) if (sampler_flag_ok(r, cfg.edge_on)) add_candidate(r);
         if (!cand.recs.empty()) {
             decode_contributes(cand, 0);
@@ -476,6 +478,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             // the reads of the chunk; with --partition-tag one group per key (each an independent pileup:
             // src/pileup/mod.rs:795-830), in key order
             std::vector<RecRef> all_recs;
+            bam.ensure_tid(ivs[i0].tid);
             bam.for_overlapping(ivs[i0].tid, cs, ce, [&](const RecRef& r) { all_recs.push_back(r); });
             if (all_recs.empty()) { i0 = i1; continue; }
             std::map<std::string, std::vector<RecRef>> groups;
@@ -580,7 +583,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 fprintf(jf, "{\"positions\": %llu, \"rows\": %llu, \"reads\": %llu, \"chunks\": %llu, \"algorithmic_bytes\": %llu, \"load_s\": %.6f, \"thresholds_s\": %.6f, \"intervals_s\": %.6f, \"pack_s\": %.6f, \"gpu_s\": %.6f, \"kernel_ms\": %.6f, \"write_s\": %.6f, \"total_s\": %.6f, \"ingest\": \"%s\", \"ingest_h2d_ms\": %.3f, \"ingest_inflate_ms\": %.3f, \"ingest_walk_ms\": %.3f}\n",
                         (unsigned long long)S.positions, (unsigned long long)S.rows, (unsigned long long)S.reads_packed, (unsigned long long)S.chunks, (unsigned long long)S.algorithmic_bytes,
                         S.load_s, S.threshold_s, S.interval_s, S.pack_s, S.gpu_s, S.kernel_ms, S.write_s, S.total_s,
-                        bam.on_device ? "device" : "host", bam.ingest_ms[0], bam.ingest_ms[1], bam.ingest_ms[2]);
+                        bam.on_device ? (bam.ranged() ? "device-ranged" : "device") : "host", bam.ingest_ms[0], bam.ingest_ms[1], bam.ingest_ms[2]);
                 fclose(jf);
             }
         }

@@ -396,7 +396,13 @@ int mkp_device_memory(mkp_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
 
 int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
                  uint64_t inflated_len, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms) {
+    return mkp_bam_load_range(ctx, file, file_len, members, n_members, inflated_len, inflated_len, seeds, n_seeds, n_records, ms);
+}
+
+int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                       uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms) {
     if (!ctx || !file || !members || !seeds || !n_seeds) return -1;
+    if (walk_end > inflated_len) return fail(ctx, "walk_end lies outside the inflated range");
     if (n_members >= (1u << 24)) return fail(ctx, "too many BGZF members for one load");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -458,7 +464,7 @@ int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_b
     CK(cudaEventRecord(ctx->ev[1], ctx->stream2));
     CK(cudaEventRecord(ctx->ev[2], st));
     const int wg = (int)((n_seeds + 127) / 128);
-    k_walk<0><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), inflated_len, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
+    k_walk<0><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), walk_end, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
                                   ctx->d_seg_counts.as<uint32_t>(), nullptr, nullptr, u + 10);
     k_block_sum<<<n_blk, 1024, 0, st>>>(ctx->d_seg_counts.as<uint32_t>(), (uint32_t)n_seeds, ctx->d_block_sums.as<uint32_t>());
     k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 12);
@@ -474,7 +480,7 @@ int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_b
     }
     const size_t nrec = h[2];
     CK(ctx->d_recs.ensure(std::max<size_t>(1, nrec) * sizeof(mkp_bam_rec)));
-    k_walk<1><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), inflated_len, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
+    k_walk<1><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), walk_end, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
                                   ctx->d_seg_counts.as<uint32_t>(), ctx->d_seg_base.as<uint32_t>(), ctx->d_recs.as<mkp_bam_rec>(), u + 10);
     CK(cudaEventRecord(ctx->ev[3], st));
     CK(cudaMemcpyAsync(h, u + 10, 4, cudaMemcpyDeviceToHost, st));

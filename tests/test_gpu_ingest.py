@@ -236,3 +236,42 @@ def test_full_contig_device_vs_host_cli(native_lib, synth_exe, tmp_path):
     assert stats[0]["ingest"] == "device" and stats[1]["ingest"] == "host"
     assert stats[0]["algorithmic_bytes"] == stats[1]["algorithmic_bytes"]
     assert stats[0]["rows"] == stats[1]["rows"]
+
+
+def test_ranged_ingest_equals_whole_file(native_lib, synth_exe, tmp_path, monkeypatch):
+    """A BAM too big for the device is loaded contig range by contig range (mkp_bam_load_range). Forced here with a tiny
+    budget: slices and CLI output must equal the whole-file load and the host front end."""
+    import json
+    import subprocess
+    import modkit_b200 as mk
+    prefix = str(tmp_path / "w")
+    subprocess.check_call([synth_exe, "--out", prefix, "--contig", "syn1:400000", "--contig", "syn2:150000", "--contig", "syn3:260000", "--coverage", "15",
+                           "--mods", "hm", "--seed", "9", "--level", "1", "--odd-records"], stdout=subprocess.DEVNULL)
+    outs = {}
+    for mode, budget, extra in (("whole", None, []), ("ranged", "1", []), ("host", None, ["--host-ingest"])):
+        if budget is None:
+            monkeypatch.delenv("MODKIT_B200_INGEST_BUDGET_MB", raising=False)
+        else:
+            monkeypatch.setenv("MODKIT_B200_INGEST_BUDGET_MB", budget)
+        out, sj = str(tmp_path / (mode + ".bed")), str(tmp_path / (mode + ".json"))
+        rc, text = run_product(["--cpg", "--ref", prefix + ".fa", "--stats-json", sj, "--gpu-chunk-bp", "200000"] + extra, prefix + ".bam", out)
+        assert rc == 0
+        outs[mode] = (text, json.load(open(sj)))
+    assert outs["whole"][1]["ingest"] == "device" and outs["ranged"][1]["ingest"] == "device-ranged" and outs["host"][1]["ingest"] == "host"
+    assert outs["whole"][0] == outs["ranged"][0] == outs["host"][0] and len(outs["whole"][0]) > 10000
+    # the C-ABI view: every contig of the ranged reader slices to the host packer's bytes
+    monkeypatch.setenv("MODKIT_B200_INGEST_BUDGET_MB", "1")
+    c = mk.Context(0)
+    dev, host = mk.Bam(prefix + ".bam", ctx=c), mk.Bam(prefix + ".bam", threads=2)
+    assert dev.n_ranges == 3
+    for tid in (2, 0, 1, 2):
+        length = host.refs[tid][1]
+        pk = host.pack(tid, 1000, length - 1000)
+        assert dev.device_chunk(tid, 1000, length - 1000) == pk.n_reads > 0
+        hdrs, heap = c.fetch_chunk()
+        ref_h = pk.headers()
+        for f in ref_h.dtype.names:
+            assert np.array_equal(hdrs[f], ref_h[f]), f
+        assert heap.tobytes() == pk.heap().tobytes()
+        pk.free()
+    dev.close(); host.close(); c.close()
