@@ -99,7 +99,7 @@ typedef struct {          /* per-chunk counters, filled by mkp_pileup_* */
     uint32_t n_reads_skipped; /* admitted reads without usable mod info (skip_set)  */
     uint32_t n_states;        /* distinct (primary base, mod code) pairs seen       */
     uint32_t device_error;    /* 0, or MKP_DERR_* bits (also turned into an error)  */
-    float    kernel_ms[8];    /* CUDA-event ms: 0 parse 1 resolve 2 rank 3 (unused) 4 count_calls||count_bases 5 rows 6 host sync/alloc 7 total */
+    float    kernel_ms[8];    /* CUDA-event ms: 0 parse 1 resolve 2 rank 3 (unused) 4 counters (k_count_bases, k_count_calls beside it) 5 rows 6 host sync/alloc 7 total */
 } mkp_stats;
 
 #define MKP_DERR_TOO_MANY_STATES   1u   /* > 32 distinct (base,code) states                      */
