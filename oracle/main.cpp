@@ -5,6 +5,7 @@
 // and (b) as the `cpu_baseline` / `--impl reference` arm of bench.py (the Rust reference cannot be
 // built in this image: no cargo/rustc). Parallelised like the reference: one worker per genomic
 // interval (src/pileup/mod.rs:696-715), results written in feeder order.
+#include <filesystem>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -264,8 +265,9 @@ int main(int argc, char** argv) {
             if (!out) die("failed to make output file");
             if (header) fputs(bedmethyl_header(), out);
         } else {
-            std::string cmd = "mkdir -p '" + pos[1] + "'";
-            if (system(cmd.c_str()) != 0) die("failed to create output directory");
+            std::error_code ec;
+            std::filesystem::create_directories(pos[1], ec);
+            if (ec) die("failed to create output directory");
         }
         auto sink = [&](const std::string& fname) -> FILE* {
             auto it = files.find(fname);
