@@ -64,6 +64,9 @@ typedef struct {
     uint8_t  force_allow_implicit;
     uint8_t  edge_filter_on, edge_filter_inverted;
     uint32_t edge_filter_start, edge_filter_end;
+    uint32_t max_depth;                  /* --max-depth (src/pileup/mod.rs:755-759 -> htslib bam_plp_set_maxcnt): a read that
+                                            would make the column at its start position deeper than this is dropped from the
+                                            pileup; 0 = no limit */
 } mkp_params;
 
 /* ---- one chunk of work: reads overlapping [start,end) of one contig -------------------------
@@ -108,6 +111,10 @@ typedef struct {          /* per-chunk counters, filled by mkp_pileup_* */
 #define MKP_DERR_IMPLICIT_MODE     8u   /* reserved (implicit '.'/default-mode fill is done on the device)      */
 
 int  mkp_create(int device, mkp_ctx** out);
+/* Pin the calling host thread (threads it creates later inherit the mask) to the CPUs of the NUMA node the device hangs off,
+ * so that pinned staging buffers (first touch) and packer threads are local to the GPU's PCIe root. 0 = bound, 1 = no NUMA
+ * information (nothing changed), <0 = error. */
+int  mkp_bind_host_thread(int device);
 void mkp_destroy(mkp_ctx* ctx);
 const char* mkp_last_error(const mkp_ctx* ctx);   /* valid until the next call on ctx */
 int  mkp_set_params(mkp_ctx* ctx, const mkp_params* params);
@@ -189,6 +196,8 @@ int  mkp_fetch_chunk(mkp_ctx* ctx, mkp_read_hdr* hdrs, uint32_t* n_reads, uint8_
 /* SURVEY §8(d) algorithmic bytes of a chunk: sum over reads of 32 + 4 n_cigar + ceil(l_seq/2) + len_mm + len_ml,
  * plus 40 bytes per emitted row (roofline accounting only). */
 size_t mkp_algorithmic_bytes(const mkp_chunk* chunk, size_t n_rows);
+/* Number of kernels this context has launched since mkp_create (bench.py reports the difference over its timed region). */
+uint64_t mkp_kernel_launches(const mkp_ctx* ctx);
 
 #ifdef __cplusplus
 }

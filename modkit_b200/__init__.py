@@ -29,7 +29,7 @@ class Params(C.Structure):
                 ("n_mod_thresholds", C.c_uint32), ("mod_code", C.c_uint32 * 16), ("mod_threshold", C.c_float * 16),
                 ("numeric_mode", C.c_uint8), ("collapse_code", C.c_uint32), ("force_allow_implicit", C.c_uint8),
                 ("edge_filter_on", C.c_uint8), ("edge_filter_inverted", C.c_uint8),
-                ("edge_filter_start", C.c_uint32), ("edge_filter_end", C.c_uint32)]
+                ("edge_filter_start", C.c_uint32), ("edge_filter_end", C.c_uint32), ("max_depth", C.c_uint32)]
 
 
 class Chunk(C.Structure):
@@ -47,14 +47,17 @@ ROW_DTYPE = np.dtype([("pos", "<u4"), ("code", "<u4"), ("strand", "u1"), ("prima
                       ("n_filtered", "<u4"), ("n_diff", "<u4"), ("n_nocall", "<u4")])
 assert ROW_DTYPE.itemsize == 40
 
-MKP_SYMBOLS = ["mkp_create", "mkp_destroy", "mkp_last_error", "mkp_set_params", "mkp_upload_chunk", "mkp_pileup_resident",
-               "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_algorithmic_bytes",
+MKP_SYMBOLS = ["mkp_create", "mkp_bind_host_thread", "mkp_destroy", "mkp_last_error", "mkp_set_params", "mkp_upload_chunk", "mkp_pileup_resident",
+               "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_algorithmic_bytes", "mkp_kernel_launches",
                "mkp_device_memory", "mkp_bam_load", "mkp_bam_load_range", "mkp_bam_records", "mkp_bam_chunk", "mkp_bam_inflated", "mkp_fetch_chunk"]
 MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_refs", "mkh_bam_ref_name", "mkh_bam_ref_len",
                "mkh_bam_n_mapped", "mkh_bam_n_records", "mkh_pack_region", "mkh_packed_free", "mkh_packed_n_reads",
                "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
                "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records",
-               "mkh_f32_display", "mkh_bam_partition_key", "mkh_bam_n_ranges"]
+               "mkh_f32_display", "mkh_bam_partition_key", "mkh_bam_n_ranges", "mkh_pileup_main_sharded", "mkh_shard_plan",
+               "mkh_bam_open_device_pieces", "mkh_bam_fetch"]
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint64), C.c_size_t, C.c_void_p)
 
 
 def library_path():
@@ -73,6 +76,7 @@ def load_library(build_if_missing=True):
         _build.build()
     lib = C.CDLL(_LIB_PATH)
     lib.mkp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.mkp_bind_host_thread.argtypes = [C.c_int]
     lib.mkp_destroy.argtypes = [C.c_void_p]
     lib.mkp_destroy.restype = None
     lib.mkp_last_error.argtypes = [C.c_void_p]
@@ -85,8 +89,19 @@ def load_library(build_if_missing=True):
     lib.mkp_sample_histogram.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     lib.mkp_algorithmic_bytes.argtypes = [C.POINTER(Chunk), C.c_size_t]
     lib.mkp_algorithmic_bytes.restype = C.c_size_t
+    lib.mkp_kernel_launches.argtypes = [C.c_void_p]
+    lib.mkp_kernel_launches.restype = C.c_uint64
     lib.mkp_bam_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_size_t,
                                  C.POINTER(C.c_size_t), C.c_void_p]
+    lib.mkp_bam_load_range.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_size_t), C.c_void_p]
+    lib.mkp_device_memory.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.mkh_pileup_main_sharded.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p, C.POINTER(C.c_double)]
+    lib.mkh_shard_plan.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.mkh_shard_plan.restype = C.c_int64
+    lib.mkh_bam_open_device_pieces.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.mkh_bam_fetch.argtypes = [C.c_char_p, C.c_uint32, C.c_int64, C.c_int64, C.c_void_p, C.c_uint64]
+    lib.mkh_bam_fetch.restype = C.c_int64
     lib.mkp_bam_records.argtypes = [C.c_void_p, C.c_void_p]
     lib.mkp_bam_chunk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.mkp_bam_inflated.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
@@ -143,6 +158,77 @@ def pileup_main(args):
     return lib.mkh_pileup_main(len(args), argv)
 
 
+def bind_host_thread(device):
+    """Pin this thread (and threads started later) to the CPUs of the device's NUMA node. Returns 0 when bound."""
+    return load_library().mkp_bind_host_thread(int(device))
+
+
+def torch_allreduce(device=None):
+    """Sum-all-reduce of a u64 vector over the default torch.distributed group (NCCL when `device` is a CUDA device,
+    gloo on CPU): the transport of the two exchanges of an interval-sharded run."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(buf, n, _user):
+        try:
+            a = np.ctypeslib.as_array(buf, shape=(n,))
+            t = torch.from_numpy(a.astype(np.int64))
+            if device is not None:
+                t = t.to(device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            a[:] = t.cpu().numpy().astype(np.uint64)
+            return 0
+        except Exception as e:   # never let an exception cross the C boundary
+            import sys
+            print("allreduce failed: %r" % (e,), file=sys.stderr)
+            return -1
+    return fn
+
+
+def pileup_main_sharded(args, rank, world, allreduce):
+    """One rank of an interval-sharded `modkit pileup <args>` (every rank passes the same args plus its own --device).
+    `allreduce(buf, n, user) -> 0` sums a u64 vector over the ranks in place (see torch_allreduce).
+    Returns (exit code, stats dict)."""
+    lib = load_library()
+    argv = (C.c_char_p * len(args))(*[str(a).encode() for a in args])
+    cb = ALLREDUCE_FN(allreduce) if allreduce is not None else C.cast(None, ALLREDUCE_FN)
+    st = (C.c_double * 16)()
+    rc = lib.mkh_pileup_main_sharded(len(args), argv, rank, world, cb, None, st)
+    keys = ["total_s", "load_s", "thresholds_s", "gpu_s", "write_s", "rows_total", "positions_total", "rows_rank",
+            "threshold_A", "threshold_C", "threshold_G", "threshold_T", "sampler_fetch_s", "intervals_s", "pack_s", "kernel_ms"]
+    return rc, dict(zip(keys, [float(x) for x in st]))
+
+
+def bam_fetch(bam_path, tid, beg, end):
+    """Offsets (inflated stream) of the records overlapping [beg,end) of tid, through the index (CPU only); tid None = the
+    reads without coordinates."""
+    lib = load_library()
+    cap = 1 << 16
+    while True:
+        offs = np.zeros(cap, dtype=np.uint64)
+        n = lib.mkh_bam_fetch(str(bam_path).encode(), 0xffffffff if tid is None else tid, beg, end, offs.ctypes.data, cap)
+        if n < 0:
+            raise MkpError("bam_fetch failed (%d)" % n)
+        if n <= cap:
+            return offs[:n].copy()
+        cap = int(n)
+
+
+def shard_plan(bam_path, interval_size, world):
+    """[(rank, tid, start, end)] pieces of the interval-range shards the product uses for `world` ranks (CPU only)."""
+    lib = load_library()
+    cap = 4096
+    while True:
+        a = np.zeros(3 * cap, dtype=np.uint32)
+        e = np.zeros(cap, dtype=np.uint32)
+        n = lib.mkh_shard_plan(str(bam_path).encode(), interval_size, world, a.ctypes.data, e.ctypes.data, cap)
+        if n < 0:
+            raise MkpError("shard plan failed")
+        if n <= cap:
+            return [(int(a[3 * k]), int(a[3 * k + 1]), int(a[3 * k + 2]), int(e[k])) for k in range(n)]
+        cap = int(n)
+
+
 HDR_DTYPE = np.dtype([("ref_start", "<i4"), ("l_seq", "<u4"), ("n_cigar", "<u4"), ("flags", "<u4"), ("off", "<u8"), ("len_ml", "<u4"), ("len_mm", "<u4")])
 MEMBER_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4")])
 REC_DTYPE = np.dtype([("off", "<u8"), ("size", "<u4"), ("tid", "<i4"), ("pos", "<i4"), ("end", "<i4"), ("flag", "<u4"), ("l_seq", "<u4")])
@@ -153,11 +239,16 @@ class Bam:
     """A BAM file. With ctx=None the file is inflated and indexed on the host (zlib); with a Context the BGZF members are
     inflated, the record chain walked and the reads sliced on that GPU (mkp_bam_load / mkp_bam_chunk)."""
 
-    def __init__(self, path, threads=4, ctx=None):
+    def __init__(self, path, threads=4, ctx=None, pieces=None):
         self._lib = load_library()
         self._h = C.c_void_p()
         self._ctx = ctx
-        if ctx is None:
+        if pieces is not None:
+            # one rank of an interval-sharded run: only the byte ranges under the (tid, lo, hi) pieces go to the device
+            a = np.ascontiguousarray(np.array(pieces, dtype=np.uint32).reshape(-1, 3))
+            if self._lib.mkh_bam_open_device_pieces(str(path).encode(), ctx._h, a.ctypes.data, len(a), C.byref(self._h)):
+                raise MkpError("cannot open BAM pieces on the device " + str(path))
+        elif ctx is None:
             if self._lib.mkh_bam_open(str(path).encode(), threads, C.byref(self._h)):
                 raise MkpError("cannot open BAM " + str(path))
         elif self._lib.mkh_bam_open_device(str(path).encode(), ctx._h, C.byref(self._h)):
@@ -322,6 +413,7 @@ class Context:
     def upload(self, packed):
         ch = packed.chunk()
         self._check(self._lib.mkp_upload_chunk(self._h, C.byref(ch)))
+        self._n_reads_hint = int(packed.n_reads)
 
     def pileup_resident(self):
         st = Stats()
@@ -343,6 +435,7 @@ class Context:
         n = C.c_size_t()
         st = Stats()
         self._check(self._lib.mkp_pileup_chunk(self._h, C.byref(ch), C.byref(rows), C.byref(n), C.byref(st)))
+        self._n_reads_hint = int(packed.n_reads)
         if not n.value:
             return np.zeros(0, dtype=ROW_DTYPE), st
         buf = (C.c_uint8 * (40 * n.value)).from_address(rows.value)
@@ -365,6 +458,10 @@ class Context:
         return hist, contrib, inexact.value
 
     _n_reads_hint = 0
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.mkp_kernel_launches(self._h))
 
     # ---- device ingest (mkp_bam_*) ----
     def bam_load(self, file_bytes, members, inflated_len, seeds):

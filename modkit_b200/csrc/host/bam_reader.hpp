@@ -73,6 +73,10 @@ public:
 
     bool on_device = false;                   // records live in the inflated stream on the GPU (open_device); raw is empty
     mkp_ctx* dev = nullptr;
+    // BAI linear index (16 kb windows): smallest virtual offset of a record overlapping the window; empty without an index
+    std::vector<std::vector<uint64_t>> lin;
+    std::vector<uint64_t> ref_first_voff;     // virtual offset of the first record of every contig (UINT64_MAX: none)
+    bool have_index() const { return have_bai_ && file_ != nullptr; }
     float ingest_ms[4] = {0, 0, 0, 0};        // device ingest: H2D, inflate, record walk, total
 
     struct Member { size_t in_off, in_len, out_off; uint32_t out_len; size_t file_off; };
@@ -143,6 +147,15 @@ public:
     // A file whose bytes + inflated stream fit in the device memory is loaded once. A bigger coordinate-sorted, indexed file
     // is loaded range by range (consecutive contigs, mkp_bam_load_range): ensure_tid() switches the resident range.
     void open_device(const std::string& path, mkp_ctx* ctx) {
+        open_device_index(path, ctx);
+        load_default();
+    }
+
+    // Step 1 of the device ingest: map the file, walk the member headers, read the BAM header and the index. Nothing is
+    // copied to the device yet: callers either load everything (load_default) or only the byte ranges that hold the reads
+    // of some reference pieces (load_pieces: one rank of an interval-sharded run).
+    void open_device_index(const std::string& path, mkp_ctx* ctx) {
+        path_ = path;
         file_ = std::make_shared<MappedFile>();
         file_->open(path);
         const MappedFile& mf = *file_;
@@ -159,14 +172,7 @@ public:
             const size_t o = head.size();
             head.resize(o + m.out_len);
             if (!m.out_len) return;
-            z_stream zs;
-            memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("zlib init failed");
-            zs.next_in = (Bytef*)(mf.data + m.in_off); zs.avail_in = (uInt)m.in_len;
-            zs.next_out = head.data() + o; zs.avail_out = m.out_len;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END) throw std::runtime_error(path + ": inflate failed");
+            inflate_member(m, head.data() + o);
         };
         auto need = [&](size_t n) { while (head.size() < n) more(); };
         need(12);
@@ -189,23 +195,88 @@ public:
         stats.n_mapped.assign(n_ref, 0);
         stats.n_unmapped.assign(n_ref, 0);
         // ---- seeds: virtual offsets of the index -> offsets in the inflated stream
-        auto to_offset = [&](uint64_t v, uint64_t* x) {
-            const uint64_t coff = v >> 16, uoff = v & 0xffff;
-            auto it = std::lower_bound(members.begin(), members.end(), coff, [](const Member& m, uint64_t c) { return m.file_off < c; });
-            if (it == members.end() || it->file_off != coff) return false;
-            *x = it->out_off + uoff;
-            return true;
-        };
-        std::vector<uint64_t> voffs, ref_first;
-        have_bai_ = load_bai(path, &voffs, &ref_first);
+        std::vector<uint64_t> voffs;
+        have_bai_ = load_bai(path, &voffs, &ref_first_voff);
         seeds_.clear();
         seeds_.push_back(first_rec_);
-        for (uint64_t v : voffs) { uint64_t x; if (to_offset(v, &x) && x > first_rec_ && x + 36 <= total) seeds_.push_back(x); }
+        for (uint64_t v : voffs) { uint64_t x; if (voff_to_offset(v, &x) && x > first_rec_ && x + 36 <= total) seeds_.push_back(x); }
         std::sort(seeds_.begin(), seeds_.end());
         seeds_.erase(std::unique(seeds_.begin(), seeds_.end()), seeds_.end());
         if (first_rec_ >= total) seeds_.clear();
         dev = ctx;
         on_device = true;
+    }
+
+    // virtual offset -> offset in the inflated stream (false: the compressed offset is not a member start)
+    bool voff_to_offset(uint64_t v, uint64_t* x) const {
+        const uint64_t coff = v >> 16, uoff = v & 0xffff;
+        auto it = std::lower_bound(members_.begin(), members_.end(), coff, [](const Member& m, uint64_t c) { return m.file_off < c; });
+        if (it == members_.end() || it->file_off != coff) return false;
+        *x = it->out_off + uoff;
+        return true;
+    }
+    size_t member_of_offset(uint64_t off) const {
+        return (size_t)(std::upper_bound(members_.begin(), members_.end(), off, [](uint64_t x, const Member& m) { return x < m.out_off; }) - members_.begin()) - 1;
+    }
+    void inflate_member(const Member& m, uint8_t* dst) const {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("zlib init failed");
+        zs.next_in = (Bytef*)(file_->data + m.in_off); zs.avail_in = (uInt)m.in_len;
+        zs.next_out = dst; zs.avail_out = m.out_len;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END) throw std::runtime_error(path_ + ": inflate failed");
+    }
+
+    // Offset (inflated stream) at or before the first record that overlaps reference position `pos` of contig tid: the
+    // linear index entry of the 16 kb window holding pos (entries are non-decreasing; a zero entry means "no record":
+    // the nearest earlier entry is used). UINT64_MAX when no record of the contig can overlap [pos, ...).
+    uint64_t lower_bound_offset(uint32_t tid, uint64_t pos) const {
+        if (tid >= lin.size() || tid >= ref_first_voff.size() || ref_first_voff[tid] == UINT64_MAX) return UINT64_MAX;
+        const auto& L = lin[tid];
+        size_t w = (size_t)(pos >> 14);
+        if (w >= L.size()) return UINT64_MAX;        // beyond the last window that any record overlaps
+        uint64_t v = 0;
+        for (size_t k = w + 1; k-- > 0;) if (L[k]) { v = L[k]; break; }
+        if (!v) v = ref_first_voff[tid];
+        uint64_t x;
+        if (!voff_to_offset(v, &x)) throw std::runtime_error(path_ + ": index offset is not a BGZF member start (stale index?)");
+        return std::max<uint64_t>(x, first_rec_);
+    }
+    // compressed-file offset near the first record overlapping `pos` (shard weights only: monotone in (tid, pos))
+    uint64_t approx_file_offset(uint32_t tid, uint64_t pos) const {
+        if (tid >= lin.size() || tid >= ref_first_voff.size() || ref_first_voff[tid] == UINT64_MAX) {
+            for (size_t t = (size_t)tid + 1; t < ref_first_voff.size(); t++) if (ref_first_voff[t] != UINT64_MAX) return ref_first_voff[t] >> 16;
+            return file_ ? file_->size : 0;
+        }
+        const auto& L = lin[tid];
+        size_t w = (size_t)(pos >> 14);
+        if (w >= L.size()) {
+            for (size_t t = (size_t)tid + 1; t < ref_first_voff.size(); t++) if (ref_first_voff[t] != UINT64_MAX) return ref_first_voff[t] >> 16;
+            return file_ ? file_->size : 0;
+        }
+        for (size_t k = w + 1; k-- > 0;) if (L[k]) return L[k] >> 16;
+        return ref_first_voff[tid] >> 16;
+    }
+    // offset of the first record of the first contig after tid that has records (or of the unplaced reads / end of stream)
+    uint64_t contig_end_offset(uint32_t tid) const {
+        for (size_t t = (size_t)tid + 1; t < ref_first_voff.size(); t++) {
+            uint64_t x;
+            if (ref_first_voff[t] != UINT64_MAX && voff_to_offset(ref_first_voff[t], &x)) return x;
+        }
+        return total_;      // (the reads without coordinates, if any, travel with the last contig)
+    }
+
+    // Step 2a: everything (or, when the file does not fit, contig ranges on demand)
+    void load_default() {
+        const MappedFile& mf = *file_;
+        const size_t total = total_;
+        const std::vector<Member>& members = members_;
+        const uint32_t n_ref = (uint32_t)ref_names.size();
+        const std::vector<uint64_t>& ref_first = ref_first_voff;
+        auto to_offset = [&](uint64_t v, uint64_t* x) { return voff_to_offset(v, x); };
+        mkp_ctx* ctx = dev;
         // ---- does everything fit at once?
         size_t free_b = 0, total_b = 0;
         const bool have_mem = mkp_device_memory(ctx, &free_b, &total_b) == 0;
@@ -230,7 +301,7 @@ public:
         firsts[0].first = first_rec_;
         batch_of_tid_.assign(n_ref, -1);
         batches_.clear();
-        auto member_of = [&](uint64_t off) { return (size_t)(std::upper_bound(members.begin(), members.end(), off, [](uint64_t x, const Member& m) { return x < m.out_off; }) - members.begin()) - 1; };
+        auto member_of = [&](uint64_t off) { return member_of_offset(off); };
         for (size_t i = 0; i < firsts.size();) {
             Batch bt;
             bt.start_off = firsts[i].first;
@@ -259,6 +330,128 @@ public:
         }
     }
 
+    // Step 2b: only the reads overlapping the given reference pieces (genome order, at most one piece per contig): the shard of
+    // one rank. The byte range of a piece starts at the linear-index offset of its first window and ends where the next contig
+    // starts, or - inside a contig - at the index offset of a window `margin` past the piece end; after the load the last record
+    // must lie at or past the piece end, otherwise the margin grows and the range is loaded again. Needs the index.
+    struct Piece { uint32_t tid, lo, hi; };
+    void load_pieces(const std::vector<Piece>& pieces) {
+        if (!have_bai_) throw std::runtime_error("interval-sharded runs need a BAM index (.bai)");
+        const uint32_t n_ref = (uint32_t)ref_names.size();
+        ranged_ = true;
+        loaded_ = -1;
+        batch_of_tid_.assign(n_ref, -1);
+        batches_.clear();
+        size_t free_b = 0, total_b = 0;
+        const bool have_mem = mkp_device_memory(dev, &free_b, &total_b) == 0;
+        double budget = have_mem ? 0.55 * (double)free_b : 1e18;
+        if (const char* e = getenv("MODKIT_B200_INGEST_BUDGET_MB")) budget = atof(e) * 1048576.0;
+        auto cost = [&](uint64_t a, uint64_t b) {
+            const size_t m0 = member_of_offset(a), m1 = member_of_offset(b - 1);
+            return (double)(members_[m1].in_off + members_[m1].in_len - members_[m0].file_off) + 1.6 * (double)(members_[m1].out_off + members_[m1].out_len - members_[m0].out_off);
+        };
+        for (size_t i = 0; i < pieces.size(); i++) {
+            const Piece& pc = pieces[i];
+            const uint64_t a = lower_bound_offset(pc.tid, pc.lo);
+            if (a == UINT64_MAX) continue;                               // no record of the contig reaches the piece
+            Batch nb;
+            nb.start_off = a;
+            nb.tid_last = pc.tid; nb.hi_last = pc.hi; nb.margin = 1u << 19;
+            nb.stop_off = piece_stop(nb);
+            if (nb.stop_off <= nb.start_off) continue;
+            if (!batches_.empty() && cost(batches_.back().start_off, nb.stop_off) <= budget) {     // extend the open batch
+                Batch& bt = batches_.back();
+                bt.stop_off = std::max(bt.stop_off, nb.stop_off); bt.tid_last = nb.tid_last; bt.hi_last = nb.hi_last; bt.margin = nb.margin;
+            } else batches_.push_back(nb);
+            batch_of_tid_[pc.tid] = (int)batches_.size() - 1;
+        }
+        for (auto& bt : batches_) {
+            bt.m0 = member_of_offset(bt.start_off); bt.m1 = member_of_offset(bt.stop_off - 1);
+            if (have_mem && cost(bt.start_off, bt.stop_off) + (double)(1ull << 30) > (double)free_b)
+                throw DeviceIngestTooBig("one contig piece of the BAM does not fit on the device for the GPU ingest");
+        }
+        if (batches_.size() == 1) load_batch(0);
+    }
+
+    // ---- host-side region fetch (BAI linear index + zlib): the equivalent of IndexedReader::fetch for the few thousand
+    // records the threshold sampler looks at (src/reads_sampler/sampling_schedule.rs:683-722); independent of what is
+    // resident on the device. Records overlapping [beg,end) of tid come out in file order.
+    struct FetchCursor {
+        uint32_t tid = 0; int64_t beg = 0, end = 0;
+        size_t m_next = 0;             // next member to inflate
+        uint64_t base_off = 0;         // inflated-stream offset of buf[0]
+        std::vector<uint8_t> buf;
+        size_t p = 0;                  // parse position in buf
+        bool done = true;
+        const uint8_t* bytes(const RecRef& r) const { return buf.data() + (r.off - base_off); }   // valid until the next fetch_more
+    };
+    FetchCursor fetch_begin(uint32_t tid, int64_t beg, int64_t end) const {
+        FetchCursor c;
+        c.tid = tid; c.beg = beg; c.end = end;
+        const uint64_t x = lower_bound_offset(tid, (uint64_t)std::max<int64_t>(0, beg));
+        if (x == UINT64_MAX || x >= total_) return c;
+        c.m_next = member_of_offset(x);
+        c.base_off = members_[c.m_next].out_off;
+        c.p = (size_t)(x - c.base_off);
+        c.done = false;
+        return c;
+    }
+    // the reads without coordinates (tid -1) follow the last placed record
+    FetchCursor fetch_unplaced_begin() const {
+        FetchCursor c;
+        c.tid = 0xffffffffu; c.beg = INT64_MIN; c.end = INT64_MAX;
+        uint64_t x = first_rec_;
+        for (size_t t = ref_first_voff.size(); t-- > 0;) {
+            if (ref_first_voff[t] == UINT64_MAX || t >= lin.size() || lin[t].empty()) continue;
+            const uint64_t y = lower_bound_offset((uint32_t)t, ((uint64_t)lin[t].size() - 1) << 14);
+            if (y != UINT64_MAX) { x = y; break; }
+        }
+        if (x >= total_) return c;
+        c.m_next = member_of_offset(x);
+        c.base_off = members_[c.m_next].out_off;
+        c.p = (size_t)(x - c.base_off);
+        c.done = false;
+        return c;
+    }
+    template <class F> size_t fetch_more(FetchCursor& c, size_t n, F&& ok, std::vector<RecRef>* out) const {
+        size_t added = 0;
+        if (c.p > (1u << 20)) { c.buf.erase(c.buf.begin(), c.buf.begin() + (ptrdiff_t)c.p); c.base_off += c.p; c.p = 0; }
+        auto need = [&](size_t upto) {          // make buf hold at least `upto` bytes; false at the end of the stream
+            while (c.buf.size() < upto) {
+                if (c.m_next >= members_.size()) return false;
+                const Member& m = members_[c.m_next++];
+                const size_t o = c.buf.size();
+                c.buf.resize(o + m.out_len);
+                if (m.out_len) inflate_member(m, c.buf.data() + o);
+            }
+            return true;
+        };
+        while (!c.done && added < n) {
+            if (!need(c.p + 4)) { c.done = true; break; }
+            const uint32_t bs = load_le<uint32_t>(c.buf.data() + c.p);
+            if (bs < 32) throw std::runtime_error(path_ + ": corrupt BAM record");
+            if (!need(c.p + 4 + bs)) { c.done = true; break; }
+            const uint8_t* r = c.buf.data() + c.p + 4;
+            const int32_t tid = load_le<int32_t>(r), pos = load_le<int32_t>(r + 4);
+            if (c.tid == 0xffffffffu) { if (tid >= 0) { c.p += 4 + bs; continue; } }           // reads without coordinates: the tail of the file
+            else if (tid != (int32_t)c.tid) { if (tid >= 0 && tid < (int32_t)c.tid) { c.p += 4 + bs; continue; } c.done = true; break; }
+            else if (pos >= c.end) { c.done = true; break; }
+            const uint32_t l_name = r[8], n_cig = load_le<uint16_t>(r + 12), flag = load_le<uint16_t>(r + 14);
+            if (32ull + l_name + 4ull * n_cig > bs) throw std::runtime_error(path_ + ": corrupt BAM record");
+            int64_t span = 0;
+            if (!(flag & 4) && n_cig) {
+                const uint8_t* cg = r + 32 + l_name;
+                for (uint32_t k = 0; k < n_cig; k++) { const uint32_t v = load_le<uint32_t>(cg + 4 * k), op = v & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += v >> 4; }
+            }
+            RecRef ref;
+            ref.off = c.base_off + c.p + 4; ref.size = bs; ref.pos = pos; ref.end = (int32_t)(pos + (span ? span : 1));
+            ref.idx = 0xffffffffu; ref.l_seq = load_le<uint32_t>(r + 16); ref.flag = (uint16_t)flag;
+            c.p += 4 + bs;
+            if (ref.end > c.beg && ok(ref)) { out->push_back(ref); added++; }
+        }
+        return added;
+    }
+
     // make the records of contig tid resident (ranged device ingest; a no-op otherwise)
     void ensure_tid(uint32_t tid) const {
         if (!ranged_ || tid >= batch_of_tid_.size()) return;
@@ -280,7 +473,11 @@ public:
     const uint8_t* rec(const RecRef& r) const { if (on_device) throw std::runtime_error("record bytes are on the device"); return raw.data() + r.off; }
 
 private:
-    struct Batch { uint64_t start_off = 0, stop_off = 0; size_t m0 = 0, m1 = 0; };
+    struct Batch {
+        uint64_t start_off = 0, stop_off = 0; size_t m0 = 0, m1 = 0;
+        int64_t tid_last = -1; uint32_t hi_last = 0, margin = 0;       // load_pieces: the piece that ends the batch (end check)
+    };
+    std::string path_;
     std::shared_ptr<MappedFile> file_;
     std::vector<Member> members_;
     std::vector<uint64_t> seeds_;             // known record starts (offsets in the whole inflated stream)
@@ -291,13 +488,37 @@ private:
     std::vector<int> batch_of_tid_;
     int loaded_ = -1;
 
+    // end of the byte range of a batch that ends inside contig tid_last at hi_last (see load_pieces)
+    uint64_t piece_stop(const Batch& bt) const {
+        const uint32_t tid = (uint32_t)bt.tid_last;
+        const uint64_t cend = contig_end_offset(tid);
+        if (bt.hi_last >= ref_lens[tid]) return cend;
+        const uint64_t far = (uint64_t)bt.hi_last + bt.margin;
+        if (far >= ref_lens[tid]) return cend;
+        uint64_t x = lower_bound_offset(tid, far);
+        if (x == UINT64_MAX) return cend;
+        // the record at x may start inside a member that the walk has to see whole: ranges end on record starts, fine
+        return std::min(std::max(x, bt.start_off), cend);
+    }
+
     void load_batch(int b) {
-        const Batch& bt = batches_[b];
-        for (auto& v : by_tid) v.clear();
-        for (auto& v : run_max_end) v.clear();
-        unplaced.clear();
-        load_members(bt.m0, bt.m1, bt.start_off, bt.stop_off);
-        loaded_ = b;
+        for (;;) {
+            Batch& bt = batches_[b];
+            for (auto& v : by_tid) v.clear();
+            for (auto& v : run_max_end) v.clear();
+            unplaced.clear();
+            if (bt.stop_off > bt.start_off) load_members(bt.m0, bt.m1, bt.start_off, bt.stop_off);
+            loaded_ = b;
+            if (bt.tid_last < 0) return;
+            // a range that ends inside a contig must have seen a record starting at or past the piece end
+            const uint32_t tid = (uint32_t)bt.tid_last;
+            if (bt.stop_off >= contig_end_offset(tid)) return;
+            const auto& v = by_tid[tid];
+            if (!v.empty() && (uint32_t)std::max(0, v.back().pos) >= bt.hi_last) return;
+            if (bt.margin >= (1u << 30)) { bt.stop_off = contig_end_offset(tid); }
+            else { bt.margin <<= 2; bt.stop_off = std::max(bt.stop_off, piece_stop(bt)); }
+            bt.m1 = member_of_offset(bt.stop_off - 1);
+        }
     }
 
     // inflate members [m0, m1] on the device, walk the records of [start_off, stop_off) and index them
@@ -417,6 +638,7 @@ private:
             BamIndexStats s;
             s.n_mapped.assign(n_ref, 0); s.n_unmapped.assign(n_ref, 0);
             if (ref_first) ref_first->assign(n_ref, UINT64_MAX);
+            std::vector<std::vector<uint64_t>> lin_local(n_ref);
             auto note = [&](uint32_t r, uint64_t v) { if (ref_first && v && v < (*ref_first)[r]) (*ref_first)[r] = v; };
             bool ok = true;
             for (uint32_t r = 0; r < n_ref && ok; r++) {
@@ -439,13 +661,16 @@ private:
                 if (!ok || o + 4 > b.size()) { ok = false; break; }
                 const uint32_t n_intv = load_le<uint32_t>(b.data() + o);
                 if (o + 4 + 8ull * n_intv > b.size()) { ok = false; break; }
-                if (voffs) for (uint32_t c = 0; c < n_intv; c++) { const uint64_t v = load_le<uint64_t>(b.data() + o + 4 + 8ull * c); voffs->push_back(v); note(r, v); }
+                lin_local[r].resize(n_intv);
+                for (uint32_t c = 0; c < n_intv; c++) lin_local[r][c] = load_le<uint64_t>(b.data() + o + 4 + 8ull * c);
+                if (voffs) for (uint32_t c = 0; c < n_intv; c++) { const uint64_t v = lin_local[r][c]; voffs->push_back(v); note(r, v); }
                 o += 4 + 8ull * n_intv;
             }
             if (!ok) { if (voffs) voffs->clear(); if (ref_first) ref_first->clear(); continue; }
             if (o + 8 <= b.size()) s.n_no_coor = load_le<uint64_t>(b.data() + o);
             s.from_bai = true;
             stats = s;
+            lin.swap(lin_local);
             return true;
         }
         // no usable index: keep the counts taken while scanning the records (identical for a consistent index)

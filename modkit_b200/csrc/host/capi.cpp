@@ -14,8 +14,56 @@ int mkh_pileup_main(int argc, const char* const* argv) {
     std::string err;
     if (!parse_pileup_args(argc, argv, &o, &err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 2; }
     RunSummary s;
-    if (run_pileup(o, &s, &err)) { fprintf(stderr, "> Error! %s\n", err.c_str()); return 1; }
+    if (run_pileup_devices(o, &s, &err)) { fprintf(stderr, "> Error! %s\n", err.c_str()); return 1; }
     return 0;
+}
+
+// One rank of an interval-sharded `modkit pileup`: every rank is called with the same arguments (plus its own
+// --device); `allreduce` sums a u64 vector over the ranks in place and returns 0 (NCCL through torch.distributed in
+// bench.py / modkit_b200.pileup_main_sharded; any other transport works). It is called exactly twice per run, in the same
+// order on every rank: the sampled-probability histograms (u64[4*1025 + 2]; thresholds.rs:118-156) and the output slice
+// sizes (u64[world + 2]); with --include-unmapped a third, one-word exchange precedes them.
+// out_stats (optional, double[16]): total_s, load_s, thresholds_s, gpu_s, write_s, rows (all ranks), positions (all ranks), rows of this
+// rank, base thresholds A C G T (-1 = none), sampler fetch_s, intervals_s, pack_s, kernel_ms.
+int mkh_pileup_main_sharded(int argc, const char* const* argv, int rank, int world, int (*allreduce)(uint64_t*, size_t, void*), void* user, double* out_stats) {
+    PileupOptions o;
+    std::string err;
+    if (!parse_pileup_args(argc, argv, &o, &err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 2; }
+    if (rank < 0 || world < 1 || rank >= world || (world > 1 && !allreduce)) { fprintf(stderr, "error: bad rank/world\n"); return 2; }
+    Collective c;
+    c.rank = rank; c.world = world; c.allreduce_sum = allreduce; c.user = user;
+    RunSummary s;
+    if (run_pileup(o, &s, &err, &c)) { fprintf(stderr, "> Error! %s\n", err.c_str()); return 1; }
+    if (out_stats) { out_stats[0] = s.total_s; out_stats[1] = s.load_s; out_stats[2] = s.threshold_s; out_stats[3] = s.gpu_s; out_stats[4] = s.write_s;
+                     out_stats[5] = (double)s.rows_total; out_stats[6] = (double)s.positions_total; out_stats[7] = (double)s.rows;
+                     for (int b = 0; b < 4; b++) out_stats[8 + b] = s.threshold_set[b] ? (double)s.thresholds[b] : -1.0;
+                     out_stats[12] = s.fetch_s; out_stats[13] = s.interval_s; out_stats[14] = s.pack_s; out_stats[15] = s.kernel_ms; }
+    return 0;
+}
+
+// Shard plan of a BAM for `world` ranks (the cuts run_pileup uses; CPU only: header + index, no device): fills
+// out[3 * k .. 3 * k + 2] = (rank, tid, start), end[k] per piece; returns the number of pieces, or -1.
+int64_t mkh_shard_plan(const char* bam_path, uint32_t interval_size, int world, uint32_t* out_rank_tid_start, uint32_t* out_end, uint64_t cap) {
+    try {
+        BamReader bam;
+        bam.open_device_index(bam_path, nullptr);
+        std::vector<RefTarget> targets;
+        for (uint32_t t = 0; t < bam.ref_names.size(); t++) targets.push_back({t, 0, bam.ref_lens[t], bam.ref_names[t]});
+        std::vector<RefInterval> ivs = interval_grid(targets, interval_size, false, nullptr, nullptr);
+        const std::vector<size_t> cuts = shard_cuts(bam, ivs, world);
+        uint64_t n = 0;
+        for (int r = 0; r < world; r++) {
+            uint32_t tid = 0, lo = 0, hi = 0; bool open = false;
+            auto flush = [&]() { if (!open) return; if (n < cap) { out_rank_tid_start[3 * n] = (uint32_t)r; out_rank_tid_start[3 * n + 1] = tid; out_rank_tid_start[3 * n + 2] = lo; out_end[n] = hi; } n++; open = false; };
+            for (size_t i = cuts[r]; i < cuts[r + 1]; i++) {
+                if (open && tid == ivs[i].tid && hi == ivs[i].start) { hi = ivs[i].end; continue; }
+                flush();
+                tid = ivs[i].tid; lo = ivs[i].start; hi = ivs[i].end; open = true;
+            }
+            flush();
+        }
+        return (int64_t)n;
+    } catch (const std::exception& e) { fprintf(stderr, "mkh_shard_plan: %s\n", e.what()); return -1; }
 }
 
 int mkh_bam_open(const char* path, int threads, mkh_bam** out) {
@@ -26,6 +74,32 @@ int mkh_bam_open(const char* path, int threads, mkh_bam** out) {
 int mkh_bam_open_device(const char* path, mkp_ctx* ctx, mkh_bam** out) {
     try { mkh_bam* b = new mkh_bam(); b->reader.open_device(path, ctx); *out = b; return 0; }
     catch (const std::exception& e) { fprintf(stderr, "mkh_bam_open_device: %s\n", e.what()); return -1; }
+}
+// the same for one rank of an interval-sharded run: only the byte ranges under the pieces (tid, lo, hi)[n] are loaded
+int mkh_bam_open_device_pieces(const char* path, mkp_ctx* ctx, const uint32_t* tid_lo_hi, uint32_t n, mkh_bam** out) {
+    try {
+        mkh_bam* b = new mkh_bam();
+        b->reader.open_device_index(path, ctx);
+        std::vector<BamReader::Piece> pieces;
+        for (uint32_t i = 0; i < n; i++) pieces.push_back({tid_lo_hi[3 * i], tid_lo_hi[3 * i + 1], tid_lo_hi[3 * i + 2]});
+        b->reader.load_pieces(pieces);
+        *out = b;
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "mkh_bam_open_device_pieces: %s\n", e.what()); return -1; }
+}
+// Host-side region fetch through the index (CPU only; the sampler's candidate source): offsets (inflated stream) of the records
+// overlapping [beg,end) of tid, in file order. Returns the count (offsets beyond cap are not stored), or -1.
+int64_t mkh_bam_fetch(const char* path, uint32_t tid, int64_t beg, int64_t end, uint64_t* offs, uint64_t cap) {
+    try {
+        BamReader r;
+        r.open_device_index(path, nullptr);
+        if (!r.have_index()) return -2;
+        BamReader::FetchCursor c = tid == 0xffffffffu ? r.fetch_unplaced_begin() : r.fetch_begin(tid, beg, end);
+        std::vector<RecRef> recs;
+        while (!c.done) r.fetch_more(c, 4096, [](const RecRef&) { return true; }, &recs);
+        for (size_t i = 0; i < recs.size() && i < cap; i++) offs[i] = recs[i].off;
+        return (int64_t)recs.size();
+    } catch (const std::exception& e) { fprintf(stderr, "mkh_bam_fetch: %s\n", e.what()); return -1; }
 }
 // the reads overlapping [start,end) of tid become the resident chunk of the ingest context; returns the read count or -1
 int64_t mkh_device_chunk(const mkh_bam* b, uint32_t tid, uint32_t start, uint32_t end, const uint32_t* focus_pos, const uint32_t* focus_neg) {

@@ -317,7 +317,6 @@ inline uint32_t motif_interval(MotifContext& mc, const RefTarget& c, uint64_t st
     }
 }
 
-// ReferenceIntervalsFeeder order (src/interval_chunks.rs:563-643); `groups` = MultiChromCoordinates membership
 // optimize_reference_records (src/position_filter.rs:106-212): the targets become spans that cover runs of include-bed
 // intervals (a run is closed once it is longer than interval_size)
 inline std::vector<RefTarget> targets_from_include_bed(const IncludeBed& ib, const std::vector<RefTarget>& targets, uint32_t interval_size) {
@@ -345,16 +344,102 @@ inline std::vector<RefTarget> targets_from_include_bed(const IncludeBed& ib, con
     return out;
 }
 
-inline std::vector<RefInterval> reference_intervals(const std::vector<RefTarget>& targets, uint32_t interval_size, bool combine,
-                                                    MotifContext* mc, std::vector<std::vector<size_t>>* groups = nullptr,
-                                                    const IncludeBed* include = nullptr, int threads = 1) {
+// End of the combine-strands interval that starts at `start` with nominal end `end` (src/fasta.rs:92-226): the same loop
+// as motif_interval(combine = true), but every round only looks at the reference around the cut. The result depends on
+// the merged span that covers cut - 1, whose right end is decided by the hits at and to the right of the hits covering
+// cut - 1; those start within 2 * longest of the cut, so a window that starts 4 * longest + 8 before it sees all of them
+// (a hit straddling the window start ends well before the cut and can neither be nor extend that span's right end).
+inline uint32_t combine_interval_end(MotifContext& mc, const RefTarget& c, uint64_t start, uint64_t end) {
+    const uint64_t ref_end = c.end();
+    const uint64_t pad = mc.longest * 5, W = mc.longest * 4 + 8;
+    uint64_t cut = end, fetch_end = std::min(end + pad, ref_end);
+    std::string seq;
+    std::vector<SiteRules> sites;
+    for (;;) {
+        const uint64_t ws = cut > start + W ? cut - W : start;
+        mc.fasta.slice(c.name, ws, fetch_end, mc.keep_case, &seq);
+        sites.assign(mc.motifs.size(), SiteRules());
+        for (size_t i = 0; i < mc.motifs.size(); i++) motif_sites(seq, ws, mc.motifs[i], &sites[i]);
+        if (mc.include) for (auto& st : sites) for (auto it = st.begin(); it != st.end();) {
+            uint8_t keep = 0;
+            if ((it->second & 1) && mc.include->has(c.tid, it->first, false)) keep |= 1;
+            if ((it->second & 2) && mc.include->has(c.tid, it->first, true)) keep |= 2;
+            if (!keep) it = st.erase(it); else { it->second = keep; ++it; }
+        }
+        const uint64_t too_close = fetch_end >= mc.longest ? fetch_end - mc.longest : 0;
+        std::vector<std::pair<uint64_t, uint64_t>> spans;
+        for (size_t i = 0; i < sites.size(); i++) {
+            const uint64_t adj = mc.motifs[i].len >= mc.motifs[i].offset ? mc.motifs[i].len - mc.motifs[i].offset : mc.motifs[i].len;
+            for (auto& kv : sites[i]) spans.push_back({kv.first, kv.first + adj});
+        }
+        std::sort(spans.begin(), spans.end());
+        uint64_t search_end = cut, cur_b = 0, cur_e = 0;
+        bool open = false, found = false;
+        auto test = [&](uint64_t b, uint64_t e) { return b < cut && e > (cut ? cut - 1 : 0); };
+        for (auto& sp : spans) {
+            if (open && sp.first <= cur_e) { cur_e = std::max(cur_e, sp.second); continue; }
+            if (open && test(cur_b, cur_e)) { search_end = cur_e; found = true; break; }
+            cur_b = sp.first; cur_e = sp.second; open = true;
+        }
+        if (!found && open && test(cur_b, cur_e)) search_end = cur_e;
+        if (search_end < too_close || fetch_end >= ref_end) return (uint32_t)search_end;
+        cut = fetch_end;
+        fetch_end = std::min(fetch_end + pad, ref_end);
+    }
+}
+
+// ReferenceIntervalsFeeder order (src/interval_chunks.rs:563-643), step 1: the interval boundaries only (cheap: the
+// combine-strands chain reads a few bases around every cut). `owner[i]` = index into `targets`.
+inline std::vector<RefInterval> interval_grid(const std::vector<RefTarget>& targets, uint32_t interval_size, bool combine, MotifContext* mc,
+                                              std::vector<size_t>* owner) {
     std::vector<RefInterval> out;
-    // focus positions of one interval whose end is already fixed
+    for (size_t ti = 0; ti < targets.size(); ti++) {
+        const RefTarget& c = targets[ti];
+        if (!c.length) continue;
+        uint32_t at = c.start;
+        for (;;) {
+            RefInterval iv;
+            iv.tid = c.tid; iv.start = at;
+            uint32_t e = (uint32_t)std::min<uint64_t>((uint64_t)at + interval_size, c.end());
+            if (mc && combine) e = std::min(combine_interval_end(*mc, c, at, e), c.end());
+            iv.end = e;
+            if (owner) owner->push_back(ti);
+            out.push_back(std::move(iv));
+            if (e >= c.end()) break;
+            at = e;
+        }
+    }
+    return out;
+}
+
+// Step 2: focus positions (motif hits / include-bed positions) of the intervals [i0, i1), in parallel. Identical to what
+// motif_interval + fill_focus give interval by interval: hits are searched in [start, end + 5 * longest) (any slice that
+// reaches `longest` past the end finds every hit with a site before the end), hits that straddle the interval START are
+// not found, sites at or past the end are dropped.
+inline void fill_interval_focus(std::vector<RefInterval>& ivs, size_t i0, size_t i1, const std::vector<RefTarget>& targets, const std::vector<size_t>& owner,
+                                bool combine, MotifContext* mc, const IncludeBed* include, int threads) {
+    if (!(mc || include) || i1 <= i0) return;
     auto fill = [&](RefInterval& iv, const RefTarget& c) {
         if (mc) {
             std::vector<SiteRules> sites;
-            motif_interval(*mc, c, iv.start, iv.end, false, &sites);
-            fill_focus(&iv, sites, mc->motifs, false);
+            if (!combine) motif_interval(*mc, c, iv.start, iv.end, false, &sites);
+            else {
+                // sites of [start, end): scan a slice that reaches past the end, keep what lies before it
+                MotifContext& m = *mc;
+                std::string seq;
+                const uint64_t fe = std::min<uint64_t>((uint64_t)iv.end + m.longest * 5, c.end());
+                m.fasta.slice(c.name, iv.start, fe, m.keep_case, &seq);
+                sites.assign(m.motifs.size(), SiteRules());
+                for (size_t i = 0; i < m.motifs.size(); i++) motif_sites(seq, iv.start, m.motifs[i], &sites[i]);
+                if (m.include) for (auto& st : sites) for (auto it = st.begin(); it != st.end();) {
+                    uint8_t keep = 0;
+                    if ((it->second & 1) && m.include->has(c.tid, it->first, false)) keep |= 1;
+                    if ((it->second & 2) && m.include->has(c.tid, it->first, true)) keep |= 2;
+                    if (!keep) it = st.erase(it); else { it->second = keep; ++it; }
+                }
+                for (auto& st : sites) for (auto it = st.begin(); it != st.end();) { if (it->first > iv.end) it = st.erase(it); else ++it; }
+            }
+            fill_focus(&iv, sites, mc->motifs, combine);
         } else if (include) {   // FocusPositions::new_regions / check_position (interval_chunks.rs:299-371)
             iv.all_positions = false;
             auto paint = [&](const std::map<uint32_t, std::vector<IncludeBed::Span>>& m, uint8_t bit) {
@@ -366,43 +451,29 @@ inline std::vector<RefInterval> reference_intervals(const std::vector<RefTarget>
             paint(include->minus, 2);
         }
     };
-    std::vector<const RefTarget*> owner;
-    for (auto& c : targets) {
-        if (!c.length) continue;
-        uint32_t at = c.start;
-        for (;;) {
-            RefInterval iv;
-            iv.tid = c.tid; iv.start = at;
-            uint32_t e = (uint32_t)std::min<uint64_t>((uint64_t)at + interval_size, c.end());
-            if (mc && combine) {
-                // the interval end moves with the motif hits around it: a sequential chain
-                std::vector<SiteRules> sites;
-                e = std::min(motif_interval(*mc, c, at, e, true, &sites), c.end());
-                iv.end = e;
-                fill_focus(&iv, sites, mc->motifs, true);
-            } else iv.end = e;          // fixed grid: focus positions are filled below, in parallel
-            owner.push_back(&c);
-            out.push_back(std::move(iv));
-            if (e >= c.end()) break;
-            at = e;
-        }
-    }
-    if (!(mc && combine) && (mc || include)) {
-        const size_t n = out.size();
-        const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n));
-        std::atomic<size_t> next{0};
-        std::exception_ptr err;
-        std::mutex err_mu;
-        auto work = [&]() {
-            try { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; fill(out[i], *owner[i]); } }
-            catch (...) { std::lock_guard<std::mutex> g(err_mu); if (!err) err = std::current_exception(); }
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(work);
-        work();
-        for (auto& t : th) t.join();
-        if (err) std::rethrow_exception(err);
-    }
+    const size_t n = i1 - i0;
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n));
+    std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex err_mu;
+    auto work = [&]() {
+        try { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; fill(ivs[i0 + i], targets[owner[i0 + i]]); } }
+        catch (...) { std::lock_guard<std::mutex> g(err_mu); if (!err) err = std::current_exception(); }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (err) std::rethrow_exception(err);
+}
+
+// both steps for all intervals; `groups` = MultiChromCoordinates membership (sampling schedule)
+inline std::vector<RefInterval> reference_intervals(const std::vector<RefTarget>& targets, uint32_t interval_size, bool combine,
+                                                    MotifContext* mc, std::vector<std::vector<size_t>>* groups = nullptr,
+                                                    const IncludeBed* include = nullptr, int threads = 1) {
+    std::vector<size_t> owner;
+    std::vector<RefInterval> out = interval_grid(targets, interval_size, combine, mc, &owner);
+    fill_interval_focus(out, 0, out.size(), targets, owner, combine, mc, include, threads);
     if (groups) {
         std::vector<size_t> grp;
         uint64_t grp_len = 0;

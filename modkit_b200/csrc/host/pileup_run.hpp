@@ -3,6 +3,7 @@
 // messages where they are observable, same output ordering (feeder order, positions ascending).
 #pragma once
 #include <chrono>
+#include <condition_variable>
 #include <filesystem>
 #include <unordered_set>
 
@@ -28,6 +29,8 @@ struct PileupOptions {
     bool bedgraph = false;             // --bedgraph: out path is a directory of <code>_<strand>.bedgraph files
     std::string prefix;                // --prefix for the files of --bedgraph / --partition-tag
     bool quiet = false;
+    uint32_t max_depth = 8000;         // --max-depth (src/pileup/subcommand.rs:117-121)
+    std::vector<int> devices;          // --devices a,b,...: one interval shard per listed GPU (threads of this process)
 };
 
 struct Region { std::string name; uint32_t start = 0, end = 0; };
@@ -63,6 +66,8 @@ inline Region parse_region_arg(const std::string& raw, const BamReader& bam) {  
     if (r.end <= r.start) throw std::runtime_error("invalid region " + raw);
     return r;
 }
+
+inline double secs_between(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); }
 
 struct DeviceGuard {
     mkp_ctx* ctx = nullptr;
@@ -261,25 +266,372 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
     return selected_ids.size();
 }
 
+// ---- the same schedule on an indexed file, without the per-group device round trips -----------------------------
+// The candidates come straight from the file (BamReader::fetch_*: BAI linear index + zlib on the few members that hold
+// them), so the sampler does not depend on what is resident on the device, and the per-contig state of the schedule
+// (`so_far`) makes contigs independent: in an interval-sharded run every rank samples the contigs it owns and the
+// histograms are summed once. Per contig the schedule is first simulated under the assumption that every group
+// finds its quota (true whenever the coverage is not tiny); the candidates of all planned groups are fetched in parallel,
+// decoded in ONE device pass, and the real schedule then consumes them in order. A group that deviates from the plan, or
+// needs more candidates than were fetched, falls back to fetching and decoding on demand - the result is the same reads
+// either way: the first n contributing records of every group, in file order.
+struct Collective {          // sum over the ranks of a sharded run (in place); world == 1: nothing to do
+    int rank = 0, world = 1;
+    int (*allreduce_sum)(uint64_t* buf, size_t n, void* user) = nullptr;
+    void* user = nullptr;
+    void sum(uint64_t* buf, size_t n) const {
+        if (world <= 1) return;
+        if (!allreduce_sum || allreduce_sum(buf, n, user) != 0) throw std::runtime_error("collective (all-reduce) failed");
+    }
+};
+
+inline void append_packed(const PackedChunk& src, PackedChunk* dst) {
+    const uint64_t base = (dst->heap.size() + 15) & ~(uint64_t)15;
+    dst->heap.resize(base);
+    dst->heap.insert(dst->heap.end(), src.heap.begin(), src.heap.end());
+    for (auto h : src.hdrs) { h.off += base; dst->hdrs.push_back(h); }
+    dst->recs.insert(dst->recs.end(), src.recs.begin(), src.recs.end());
+}
+
+inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const SamplerConfig& cfg, uint64_t* hist, uint64_t* inexact,
+                                       const Collective& coll, double* fetch_s = nullptr) {
+    using clk = std::chrono::steady_clock;
+    int region_tid = -1;
+    if (cfg.region) {
+        for (size_t i = 0; i < bam.ref_names.size(); i++) if (bam.ref_names[i] == cfg.region->name) region_tid = (int)i;
+        if (region_tid < 0) throw std::runtime_error("did not find target_id for region in header");
+    }
+    uint64_t total_mapped = 0, total_unmapped = 0;
+    std::map<uint32_t, uint64_t> mapped;
+    for (uint32_t t = 0; t < bam.ref_names.size(); t++) {
+        if (cfg.region && (int)t != region_tid) continue;
+        if (!cfg.region && cfg.include && !cfg.include->has_contig(t)) continue;
+        mapped[t] = bam.stats.n_mapped[t];
+        total_mapped += bam.stats.n_mapped[t];
+        total_unmapped += bam.stats.n_unmapped[t];
+    }
+    if (!cfg.region) total_unmapped += bam.stats.n_no_coor;
+    const uint64_t total = cfg.include_unmapped ? total_mapped + total_unmapped : total_mapped;
+    if (!total) throw std::runtime_error("zero reads found in bam index");
+    std::map<uint32_t, int64_t> quota;   // -1 = all
+    for (auto& kv : mapped) {
+        if (!kv.second) continue;
+        if (cfg.take_all) { quota[kv.first] = -1; continue; }
+        const float frac = (float)kv.second / (float)total;
+        quota[kv.first] = (int64_t)std::min<uint64_t>((uint64_t)std::ceil((float)cfg.num_reads * frac), kv.second);
+    }
+    std::vector<RefTarget> contigs;
+    std::map<uint32_t, uint32_t> contig_len;
+    for (uint32_t t = 0; t < bam.ref_names.size(); t++) {
+        if (!quota.count(t)) continue;
+        RefTarget c{t, 0, bam.ref_lens[t], bam.ref_names[t]};
+        if (cfg.region) { c.start = cfg.region->start; c.length = cfg.region->end - cfg.region->start; }
+        contigs.push_back(c);
+        contig_len[t] = c.length;
+    }
+    std::vector<std::vector<size_t>> groups;
+    std::vector<RefInterval> ivs;
+    if (!contigs.empty()) ivs = reference_intervals(contigs, cfg.sampling_interval_size, false, nullptr, &groups);
+    const size_t B = std::max<size_t>(1, (size_t)std::floor((float)cfg.threads * 1.5f));
+    const bool only_mapped = !cfg.include_unmapped;
+    // super-batch structure: per super-batch and contig, the contig's intervals (position order) and their total length
+    struct SbC { std::vector<size_t> iv; uint32_t len = 0; };
+    std::vector<std::map<uint32_t, SbC>> sbs;
+    for (size_t sb = 0; sb < groups.size(); sb += B) {
+        std::vector<size_t> coords;
+        for (size_t k = sb; k < std::min(groups.size(), sb + B); k++) for (size_t i : groups[k]) coords.push_back(i);
+        std::sort(coords.begin(), coords.end(), [&](size_t a, size_t b) { return ivs[a].tid != ivs[b].tid ? ivs[a].tid < ivs[b].tid : ivs[a].start < ivs[b].start; });
+        std::map<uint32_t, SbC> m;
+        for (size_t i : coords) { SbC& c = m[ivs[i].tid]; c.iv.push_back(i); c.len += ivs[i].end - ivs[i].start; }
+        sbs.push_back(std::move(m));
+    }
+    struct Grp { uint32_t tid, start, end; int64_t n; };
+    // groups of contig t in super-batch s given the reads sampled from the contig so far (sampling_schedule.rs:171-615)
+    auto todo_for = [&](size_t s, uint32_t t, size_t done) {
+        std::vector<Grp> todo;
+        auto sc = sbs[s].find(t);
+        auto q = quota.find(t);
+        if (sc == sbs[s].end() || q == quota.end()) return todo;
+        int64_t kc;
+        if (q->second < 0) kc = -1;
+        else {
+            if ((size_t)q->second <= done) return todo;
+            const float f = (float)sc->second.len / (float)contig_len[t];
+            kc = (int64_t)std::ceil(f * (float)((size_t)q->second - done));
+        }
+        bool have = false;
+        Grp slack{};
+        for (size_t i : sc->second.iv) {
+            const RefInterval& iv = ivs[i];
+            if (kc < 0) { todo.push_back({iv.tid, iv.start, iv.end, -1}); continue; }
+            const float f = (float)(iv.end - iv.start) / (float)sc->second.len;
+            const int64_t x = (int64_t)std::ceil((float)kc * f);
+            Grp cur{iv.tid, iv.start, iv.end, x};
+            if (x < 50) {
+                if (!have) { slack = cur; have = true; }
+                else {
+                    Grp m{cur.tid, std::min(slack.start, cur.start), std::max(slack.end, cur.end), slack.n + x};
+                    if (m.n < 50) slack = m; else { todo.push_back(m); have = false; }
+                }
+            } else if (have) {
+                have = false;
+                todo.push_back({cur.tid, std::min(slack.start, cur.start), std::max(slack.end, cur.end), slack.n + x});
+            } else todo.push_back(cur);
+        }
+        if (have) todo.push_back(slack);
+        return todo;
+    };
+    // contig -> rank: largest contigs first onto the least loaded rank (identical on every rank)
+    std::map<uint32_t, int> owner;
+    {
+        std::vector<std::pair<uint64_t, uint32_t>> order;
+        for (auto& kv : quota) order.push_back({mapped[kv.first], kv.first});
+        std::sort(order.begin(), order.end(), [](auto& a, auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+        std::vector<uint64_t> load(std::max(1, coll.world), 0);
+        for (auto& o : order) { int r = 0; for (int k = 1; k < coll.world; k++) if (load[k] < load[r]) r = k; owner[o.second] = r; load[r] += o.first + 1; }
+    }
+    memset(hist, 0, 4 * 1025 * sizeof(uint64_t));
+    uint64_t inexact_local = 0, n_selected = 0;
+    std::vector<uint64_t> batch_hist(4 * 1025);
+    std::vector<uint32_t> fpos, fneg;
+    double t_fetch = 0;
+    const bool req_mapped = only_mapped || cfg.edge_on;
+
+    auto upload = [&](PackedChunk& pc, uint32_t tid) {
+        mkp_chunk ch;
+        memset(&ch, 0, sizeof ch);
+        ch.start = 0; ch.end = 32;
+        if (cfg.include) {
+            int64_t lo = INT64_MAX, hi = 0;
+            for (auto& r : pc.recs) { lo = std::min<int64_t>(lo, r.pos); hi = std::max<int64_t>(hi, r.end); }
+            if (lo < 0) lo = 0;
+            if (hi <= lo) hi = lo + 1;
+            ch.start = (uint32_t)lo; ch.end = (uint32_t)hi;
+            cfg.include->bitmaps(tid, ch.start, ch.end, &fpos, &fneg);
+            ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data();
+        }
+        ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
+        if (mkp_upload_chunk(ctx, &ch)) throw std::runtime_error(mkp_last_error(ctx));
+    };
+    auto contributes_of = [&](PackedChunk& pc, uint32_t tid, std::vector<uint8_t>* contributes) {
+        contributes->assign(pc.recs.size(), 0);
+        if (pc.recs.empty()) return;
+        upload(pc, tid);
+        if (mkp_sample_histogram(ctx, cfg.include_unmapped ? 1 : 0, nullptr, nullptr, contributes->data(), nullptr)) throw std::runtime_error(mkp_last_error(ctx));
+    };
+    auto add_taken = [&](const std::vector<uint8_t>& take) {     // histogram of the flagged reads of the resident chunk
+        bool any = false;
+        for (uint8_t t : take) any = any || t;
+        if (!any) return;
+        uint64_t inx = 0;
+        if (mkp_sample_histogram(ctx, cfg.include_unmapped ? 1 : 0, take.data(), batch_hist.data(), nullptr, &inx)) throw std::runtime_error(mkp_last_error(ctx));
+        for (int k = 0; k < 4 * 1025; k++) hist[k] += batch_hist[k];
+        inexact_local += inx;
+    };
+    auto key_of = [](const Grp& g) { return std::to_string(g.tid) + ":" + std::to_string(g.start) + "-" + std::to_string(g.end) + "/" + std::to_string(g.n); };
+
+    struct Planned { Grp g; BamReader::FetchCursor cur; PackedChunk pc; size_t lo = 0, hi = 0; bool used = false; };
+    for (auto& c : contigs) {
+        const uint32_t t = c.tid;
+        if (owner[t] != coll.rank) continue;
+        // ---- plan under "every group finds its quota"
+        std::vector<Planned> plan;
+        {
+            size_t done = 0;
+            for (size_t s = 0; s < sbs.size(); s++) for (const Grp& g : todo_for(s, t, done)) {
+                if (cfg.include && !cfg.include->overlaps_any(g.tid, g.start, g.end)) continue;
+                Planned p; p.g = g; plan.push_back(std::move(p));
+                if (g.n >= 0) done += (size_t)g.n;
+            }
+        }
+        // ---- fetch the candidates of all planned groups (parallel), then one decode pass
+        const auto tf0 = clk::now();
+        {
+            std::atomic<size_t> next{0};
+            std::exception_ptr err;
+            std::mutex mu;
+            auto work = [&]() {
+                try {
+                    std::vector<RecRef> recs;
+                    for (;;) {
+                        const size_t i = next.fetch_add(1);
+                        if (i >= plan.size()) break;
+                        Planned& p = plan[i];
+                        p.cur = bam.fetch_begin(p.g.tid, p.g.start, p.g.end);
+                        const size_t want = p.g.n < 0 ? (size_t)-1 : (size_t)p.g.n * 2 + 32;
+                        // packed right after each fetch: record bytes live in the cursor's buffer until the next fetch_more
+                        while (!p.cur.done && p.pc.recs.size() < want) {
+                            recs.clear();
+                            bam.fetch_more(p.cur, std::min<size_t>(want - p.pc.recs.size(), 4096), [&](const RecRef& r) { return sampler_flag_ok(r, req_mapped); }, &recs);
+                            for (auto& r : recs) { pack_record(p.cur.bytes(r), r.size, &p.pc); p.pc.recs.push_back(r); }
+                        }
+                    }
+                } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
+            };
+            const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, cfg.threads), plan.size()));
+            std::vector<std::thread> th;
+            for (int k = 1; k < nt; k++) th.emplace_back(work);
+            work();
+            for (auto& x : th) x.join();
+            if (err) std::rethrow_exception(err);
+        }
+        PackedChunk bulk;
+        for (auto& p : plan) { p.lo = bulk.recs.size(); append_packed(p.pc, &bulk); p.hi = bulk.recs.size(); p.pc.clear(); p.pc.heap.shrink_to_fit(); }
+        t_fetch += secs_between(tf0, clk::now());
+        std::vector<uint8_t> contributes, take(bulk.recs.size(), 0);
+        contributes_of(bulk, t, &contributes);
+        bool bulk_resident = true;
+        std::map<std::string, size_t> by_key;
+        for (size_t i = 0; i < plan.size(); i++) by_key.emplace(key_of(plan[i].g), i);
+        // ---- the real schedule
+        std::unordered_set<uint64_t> selected;
+        size_t done = 0;
+        PackedChunk extra;
+        std::vector<uint8_t> xcontrib, xtake;
+        std::vector<RecRef> recs;
+        for (size_t s = 0; s < sbs.size(); s++) for (const Grp& g : todo_for(s, t, done)) {
+            if (cfg.include && !cfg.include->overlaps_any(g.tid, g.start, g.end)) continue;
+            size_t used = 0;
+            BamReader::FetchCursor cur;
+            auto it = by_key.find(key_of(g));
+            if (it != by_key.end() && !plan[it->second].used) {
+                Planned& p = plan[it->second];
+                p.used = true;
+                for (size_t k = p.lo; k < p.hi && (g.n < 0 || used < (size_t)g.n); k++) {
+                    if (!contributes[k]) continue;
+                    used++;
+                    if (selected.insert(bulk.recs[k].off).second) take[k] = 1;
+                }
+                cur = std::move(p.cur);
+            } else cur = bam.fetch_begin(g.tid, g.start, g.end);
+            // on demand: the plan did not cover the group, or the group needs more candidates than were fetched
+            while (!cur.done && (g.n < 0 || used < (size_t)g.n)) {
+                const size_t want = g.n < 0 ? 4096 : ((size_t)g.n - used) * 2 + 32;
+                extra.clear();
+                recs.clear();
+                bam.fetch_more(cur, want, [&](const RecRef& r) { return sampler_flag_ok(r, req_mapped); }, &recs);
+                for (auto& r : recs) { pack_record(cur.bytes(r), r.size, &extra); extra.recs.push_back(r); }
+                if (extra.recs.empty()) continue;
+                contributes_of(extra, t, &xcontrib);
+                bulk_resident = false;
+                xtake.assign(extra.recs.size(), 0);
+                for (size_t k = 0; k < extra.recs.size() && (g.n < 0 || used < (size_t)g.n); k++) {
+                    if (!xcontrib[k]) continue;
+                    used++;
+                    if (selected.insert(extra.recs[k].off).second) xtake[k] = 1;
+                }
+                add_taken(xtake);
+            }
+            done += used;
+        }
+        if (!bulk.recs.empty()) {
+            bool any = false;
+            for (uint8_t x : take) any = any || x;
+            if (any) { if (!bulk_resident) upload(bulk, t); add_taken(take); }
+        }
+        n_selected += selected.size();
+    }
+    if (!only_mapped) {   // reads without coordinates (reads_sampler/mod.rs:85-129): the last rank, after the global count is known
+        uint64_t cnt[1] = {n_selected};
+        coll.sum(cnt, 1);
+        if (coll.rank == coll.world - 1) {
+            const size_t limit = cfg.take_all ? (size_t)-1 : (cfg.num_reads > cnt[0] ? cfg.num_reads - (size_t)cnt[0] : 0);
+            PackedChunk cand;
+            BamReader::FetchCursor cur = bam.fetch_unplaced_begin();
+            std::vector<RecRef> recs;
+            while (!cur.done) {
+                recs.clear();
+                bam.fetch_more(cur, 4096, [&](const RecRef& r) { return sampler_flag_ok(r, cfg.edge_on); }, &recs);
+                for (auto& r : recs) { pack_record(cur.bytes(r), r.size, &cand); cand.recs.push_back(r); }
+            }
+            if (!cand.recs.empty()) {
+                std::vector<uint8_t> contributes, take(cand.recs.size(), 0);
+                contributes_of(cand, 0, &contributes);
+                size_t used = 0;
+                for (size_t k = 0; k < cand.recs.size() && used < limit; k++) { if (!contributes[k]) continue; used++; take[k] = 1; }
+                add_taken(take);
+                n_selected += used;
+            }
+        }
+    }
+    // ---- the one exchange of a sharded run: sum of the histograms (+ the inexact-value count and the read count)
+    if (coll.world > 1) {
+        std::vector<uint64_t> buf(4 * 1025 + 2);
+        memcpy(buf.data(), hist, 4 * 1025 * sizeof(uint64_t));
+        buf[4 * 1025] = inexact_local; buf[4 * 1025 + 1] = n_selected;
+        coll.sum(buf.data(), buf.size());
+        memcpy(hist, buf.data(), 4 * 1025 * sizeof(uint64_t));
+        inexact_local = buf[4 * 1025]; n_selected = buf[4 * 1025 + 1];
+    }
+    if (inexact) *inexact = inexact_local;
+    if (fetch_s) *fetch_s = t_fetch;
+    return (size_t)n_selected;
+}
+
+// htslib bam_plp_push with maxcnt (sam.c): the engine drops the reads of its flag mask first (they never count), keeps the
+// first read of every start position, and drops a further read of the same start position when its buffer already holds
+// `maxcnt` reads. The buffer holds the kept reads whose end lies at or after the current start (a read is released when the
+// column at its end position is built). `recs`: the records fetched for ONE interval, file order; filtered in place.
+inline void depth_limit_keep(std::vector<RecRef>* recs, uint32_t maxcnt) {
+    if (!maxcnt || recs->size() <= maxcnt) return;
+    std::vector<int32_t> ends;          // min-heap of the ends of the kept reads still in the buffer
+    auto cmp = [](int32_t a, int32_t b) { return a > b; };
+    int64_t cur = INT64_MIN;
+    size_t w = 0;
+    for (size_t i = 0; i < recs->size(); i++) {
+        const RecRef& r = (*recs)[i];
+        if (r.flag & (0x4 | 0x100 | 0x200 | 0x400)) { (*recs)[w++] = r; continue; }      // masked: never enters the buffer (and is not admitted later either)
+        bool keep = true;
+        if (r.pos != cur) {
+            cur = r.pos;
+            while (!ends.empty() && ends.front() < r.pos) { std::pop_heap(ends.begin(), ends.end(), cmp); ends.pop_back(); }
+        } else if (ends.size() + 1 > maxcnt) keep = false;
+        if (keep) { ends.push_back(r.end); std::push_heap(ends.begin(), ends.end(), cmp); (*recs)[w++] = r; }
+    }
+    recs->resize(w);
+}
+
 struct RunSummary {
     uint64_t positions = 0, rows = 0, reads_packed = 0, algorithmic_bytes = 0, chunks = 0;
+    uint64_t rows_total = 0, positions_total = 0;      // over all ranks of a sharded run
+    double fetch_s = 0;                                // threshold sampler: host fetch of the candidates
     double load_s = 0, threshold_s = 0, interval_s = 0, pack_s = 0, gpu_s = 0, write_s = 0, total_s = 0, kernel_ms = 0;
     float thresholds[4] = {0, 0, 0, 0};
     bool threshold_set[4] = {false, false, false, false};
 };
 
-inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* error) {
+// Interval-sharded runs: the reference intervals (feeder order) are cut into `world` contiguous ranges of about
+// equal weight = compressed BAM bytes under the interval (BAI linear index) plus a small term for its length. Every rank
+// computes the same cuts; cuts lie on interval boundaries, so rows and focus sets do not depend on the number of ranks.
+inline std::vector<size_t> shard_cuts(const BamReader& bam, const std::vector<RefInterval>& ivs, int world) {
+    std::vector<double> cum(ivs.size() + 1, 0.0);
+    for (size_t i = 0; i < ivs.size(); i++) {
+        double w = (double)(ivs[i].end - ivs[i].start) / 64.0;
+        if (bam.have_index()) {
+            const uint64_t a = bam.approx_file_offset(ivs[i].tid, ivs[i].start), b = bam.approx_file_offset(ivs[i].tid, ivs[i].end);
+            if (b > a) w += (double)(b - a);
+        }
+        cum[i + 1] = cum[i] + w;
+    }
+    std::vector<size_t> cuts(world + 1, ivs.size());
+    cuts[0] = 0;
+    for (int r = 1; r < world; r++) {
+        const double want = cum.back() * r / world;
+        cuts[r] = (size_t)(std::lower_bound(cum.begin(), cum.end(), want) - cum.begin());
+        cuts[r] = std::min(std::max(cuts[r], cuts[r - 1]), ivs.size());
+    }
+    return cuts;
+}
+
+inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* error, const Collective* coll_in = nullptr) {
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const Collective coll = coll_in ? *coll_in : Collective();
+    const bool sharded = coll.world > 1;
     try {
         const auto t0 = clk::now();
         if (o.percentile > 1.0f) throw std::runtime_error("filter percentile must be <= 1.0");
         // the device comes first: with the device ingest (default) the BAM is inflated and sliced on the GPU
-        // reference intervals + motif focus positions: host-only work, computed beside the ingest and the threshold pass
-        std::vector<RefInterval> ivs;
-        std::exception_ptr iv_err;
-        double iv_secs = 0;
-        struct Joiner { std::thread t; void join() { if (t.joinable()) t.join(); } ~Joiner() { join(); } } iv_job;
         DeviceGuard dev;
         {
             const int rc = mkp_create(o.device, &dev.ctx);
@@ -295,18 +647,12 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         const bool to_dir = partitioned || o.bedgraph;     // the output path is a directory (writers.rs:264-381, 1005-1082)
         if (to_dir && o.header) throw std::runtime_error("the argument '--header' cannot be used with '--bedgraph' / '--partition-tag'");
         if (o.bedgraph && o.mixed) throw std::runtime_error("the argument '--mixed-delim' cannot be used with '--bedgraph'");
+        if (sharded && (to_dir || o.host_ingest)) throw std::runtime_error("multi-GPU runs write one bedMethyl file through the device ingest: --bedgraph / --partition-tag / --host-ingest need a single device");
+        if (sharded && (o.out_bed == "-" || o.out_bed == "stdout")) throw std::runtime_error("multi-GPU runs need an output file (ranks write their slices at their offsets)");
         // partition keys are read from the records' aux fields on the host: that mode uses the host front end
-        if (o.host_ingest || partitioned) bam.open(o.in_bam, o.threads);
-        else {
-            try { bam.open_device(o.in_bam, dev.ctx); }
-            catch (const DeviceIngestTooBig& e) {
-                // a front-end choice, not a compute fallback: the reads are sliced on the host and uploaded chunk by chunk
-                if (!o.quiet) fprintf(stderr, "> %s; reading the BAM on the host instead\n", e.what());
-                bam = BamReader();
-                bam.open(o.in_bam, o.threads);
-            }
-        }
-        const auto t_load = clk::now();
+        bool loaded = false;
+        if (o.host_ingest || partitioned) { bam.open(o.in_bam, o.threads); loaded = true; }
+        else bam.open_device_index(o.in_bam, dev.ctx);         // header + index; the device load follows once the shard is known
         Region region, sregion;
         const Region* rp = nullptr; const Region* srp = nullptr;
         if (!o.region.empty()) { region = parse_region_arg(o.region, bam); rp = &region; }
@@ -324,15 +670,13 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             include.read(o.include_bed, name_to_tid);
             inc = &include;
         }
-        uint64_t any_mapped = 0;
-        for (auto& t : targets) if (rp || !inc || inc->has_contig(t.tid)) any_mapped += bam.stats.n_mapped[t.tid];
-        if (!any_mapped) throw std::runtime_error("did not find any mapped reads, perform alignment first or use modkit extract and/or modkit summary to inspect unaligned modBAMs");
         bool combine_strands = o.combine_strands;
         if (combine_strands && !(o.cpg || !o.motif_parts.empty())) throw std::runtime_error("need to specify either --motif or --cpg to combine strands");
 
         mkp_params P;
         memset(&P, 0, sizeof P);
         P.force_allow_implicit = o.force_allow;
+        P.max_depth = o.max_depth;
         if (o.traditional) { P.numeric_mode = 2; P.collapse_code = 'h'; combine_strands = true; }
         else if (o.combine_mods) P.numeric_mode = 1;
         else if (!o.ignore.empty()) { uint32_t c; if (!parse_code(o.ignore, &c)) throw std::runtime_error("failed to parse mod code " + o.ignore); P.numeric_mode = 2; P.collapse_code = c; }
@@ -368,6 +712,37 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             mc.include = inc;
             for (auto& m : mc.motifs) mc.longest = std::max<uint64_t>(mc.longest, m.len);
         }
+        // ---- reference intervals: boundaries now (cheap), focus positions of this rank's range in the background
+        const auto t_iv0 = clk::now();
+        std::vector<RefTarget> iv_targets = targets;
+        if (inc) iv_targets = targets_from_include_bed(*inc, iv_targets, o.interval_size);
+        std::vector<size_t> iv_owner;
+        std::vector<RefInterval> ivs = interval_grid(iv_targets, o.interval_size, combine_strands, have_motifs ? &mc : nullptr, &iv_owner);
+        size_t my_i0 = 0, my_i1 = ivs.size();
+        if (sharded) { const std::vector<size_t> cuts = shard_cuts(bam, ivs, coll.world); my_i0 = cuts[coll.rank]; my_i1 = cuts[coll.rank + 1]; }
+        // ---- device load: everything, or the byte ranges under this rank's intervals
+        if (!loaded) {
+            if (sharded) {
+                std::vector<BamReader::Piece> pieces;
+                for (size_t i = my_i0; i < my_i1; i++) {
+                    if (!pieces.empty() && pieces.back().tid == ivs[i].tid) pieces.back().hi = std::max(pieces.back().hi, ivs[i].end);
+                    else pieces.push_back({ivs[i].tid, ivs[i].start, ivs[i].end});
+                }
+                bam.load_pieces(pieces);
+            } else {
+                try { bam.load_default(); }
+                catch (const DeviceIngestTooBig& e) {
+                    // a front-end choice, not a compute fallback: the reads are sliced on the host and uploaded chunk by chunk
+                    if (!o.quiet) fprintf(stderr, "> %s; reading the BAM on the host instead\n", e.what());
+                    bam = BamReader();
+                    bam.open(o.in_bam, o.threads);
+                }
+            }
+        }
+        const auto t_load = clk::now();
+        uint64_t any_mapped = 0;
+        for (auto& t : targets) if (rp || !inc || inc->has_contig(t.tid)) any_mapped += bam.stats.n_mapped[t.tid];
+        if (!any_mapped) throw std::runtime_error("did not find any mapped reads, perform alignment first or use modkit extract and/or modkit summary to inspect unaligned modBAMs");
         // output first, like the reference, so a bad path fails before any work
         FILE* out = nullptr;
         struct Router {          // files of the output directory, created on first use
@@ -383,7 +758,15 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             }
             ~Router() { for (auto& kv : files) fclose(kv.second); }
         } router;
-        if (!to_dir) {
+        std::string shard_text;      // sharded: this rank's slice of the output, written at its offset at the end
+        if (sharded) {
+            if (coll.rank == 0) {
+                FILE* f = fopen(o.out_bed.c_str(), "w");     // created (and truncated) by rank 0 before the first exchange
+                if (!f) throw std::runtime_error("failed to make output file");
+                fclose(f);
+                if (o.header) shard_text += bed_header_line();
+            }
+        } else if (!to_dir) {
             out = (o.out_bed == "-" || o.out_bed == "stdout") ? stdout : fopen(o.out_bed.c_str(), "w");
             if (!out) throw std::runtime_error("failed to make output file");
             if (o.header) fputs(bed_header_line(), out);
@@ -395,13 +778,14 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         }
         const std::string pfx = o.prefix.empty() ? std::string() : o.prefix + "_";
 
+        // every object the background job touches is declared above; the joiner below is destroyed (joined) first
+        std::exception_ptr iv_err;
+        double iv_secs = 0;
+        struct Joiner { std::thread t; void join() { if (t.joinable()) t.join(); } ~Joiner() { join(); } } iv_job;
         iv_job.t = std::thread([&]() {
             try {
-                const auto ta = clk::now();
-                std::vector<RefTarget> tg = targets;
-                if (inc) tg = targets_from_include_bed(*inc, tg, o.interval_size);
-                ivs = reference_intervals(tg, o.interval_size, combine_strands, have_motifs ? &mc : nullptr, nullptr, inc, std::max(1, o.threads / 2));
-                iv_secs = secs(ta, clk::now());
+                fill_interval_focus(ivs, my_i0, my_i1, iv_targets, iv_owner, combine_strands, have_motifs ? &mc : nullptr, inc, std::max(1, o.threads / 2));
+                iv_secs = secs(t_iv0, clk::now());
             } catch (...) { iv_err = std::current_exception(); }
         });
         // thresholds (subcommand.rs:615-638, command_utils.rs:49-134)
@@ -414,6 +798,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             P.mod_code[P.n_mod_thresholds] = code;
             P.mod_threshold[P.n_mod_thresholds++] = std::stof(raw.substr(c + 1));
         }
+        double fetch_s = 0;
         if (!o.filter_thresholds.empty()) {
             bool have_default = false;
             for (auto& raw : o.filter_thresholds) {
@@ -431,7 +816,9 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 }
             }
         } else if (!o.no_filtering) {
-            if (mkp_set_params(dev.ctx, &P)) throw std::runtime_error(mkp_last_error(dev.ctx));
+            mkp_params PS = P;
+            PS.max_depth = 0;           // the sampler looks at reads, not at pileup columns
+            if (mkp_set_params(dev.ctx, &PS)) throw std::runtime_error(mkp_last_error(dev.ctx));
             SamplerConfig sc;
             sc.threads = o.threads; sc.sampling_interval_size = o.sampling_interval_size;
             if (o.have_frac) { if (o.frac != 1.0) throw std::runtime_error("only --sampling-frac 1.0 is reproducible without the reference's RNG; use -n or -f 1.0"); sc.take_all = true; }
@@ -442,7 +829,11 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             sc.include = inc;
             std::vector<uint64_t> hist(4 * 1025);
             uint64_t inexact = 0;
-            sample_histogram(bam, dev.ctx, sc, hist.data(), &inexact);
+            if (bam.on_device && bam.have_index()) sample_histogram_indexed(bam, dev.ctx, sc, hist.data(), &inexact, coll, &fetch_s);
+            else {
+                if (sharded) throw std::runtime_error("interval-sharded runs need a BAM index (.bai)");
+                sample_histogram(bam, dev.ctx, sc, hist.data(), &inexact);
+            }
             if (inexact) throw std::runtime_error("sampled probabilities are not multiples of 1/1024 (" + std::to_string(inexact) + " values): exact histogram quantile impossible; pass --filter-threshold");
             for (int b = 0; b < 4; b++) {
                 float thr;
@@ -452,7 +843,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 if (!percentile_from_hist(hist.data() + b * 1025, o.percentile, &thr)) throw std::runtime_error("not enough datapoints to estimate a threshold");
                 P.base_threshold_set[b] = 1;
                 P.base_threshold[b] = thr;
-                if (!o.quiet) fprintf(stderr, "> Using filter threshold %.9g for %c.\n", thr, "ACGT"[b]);
+                if (!o.quiet && coll.rank == 0) fprintf(stderr, "> Using filter threshold %.9g for %c.\n", thr, "ACGT"[b]);
             }
         }
         if (mkp_set_params(dev.ctx, &P)) throw std::runtime_error(mkp_last_error(dev.ctx));
@@ -462,25 +853,52 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         iv_job.join();
         if (iv_err) std::rethrow_exception(iv_err);
         const auto t_iv = clk::now();
+        (void)t_iv;
         RunSummary S;
+        S.fetch_s = fetch_s;
+        if (sharded) { ivs.erase(ivs.begin() + (ptrdiff_t)my_i1, ivs.end()); ivs.erase(ivs.begin(), ivs.begin() + (ptrdiff_t)my_i0); }
         for (auto& iv : ivs) S.positions += iv.end - iv.start;
 
         PackedChunk pc;
         std::vector<uint32_t> fpos, fneg;
         std::vector<OutRow> orows;
         std::string text;
-        for (size_t i0 = 0; i0 < ivs.size();) {
+        for (size_t c0 = 0; c0 < ivs.size();) {
             // a chunk = consecutive intervals of one contig up to chunk_bp
-            size_t i1 = i0 + 1;
-            while (i1 < ivs.size() && ivs[i1].tid == ivs[i0].tid && ivs[i1].start == ivs[i1 - 1].end && ivs[i1].end - ivs[i0].start <= o.chunk_bp) i1++;
+            size_t c1 = c0 + 1;
+            while (c1 < ivs.size() && ivs[c1].tid == ivs[c0].tid && ivs[c1].start == ivs[c1 - 1].end && ivs[c1].end - ivs[c0].start <= o.chunk_bp) c1++;
+            if (ivs[c1 - 1].end <= ivs[c0].start) { c0 = c1; continue; }
+            // the reads of the chunk
+            std::vector<RecRef> chunk_recs;
+            bam.ensure_tid(ivs[c0].tid);
+            bam.for_overlapping(ivs[c0].tid, ivs[c0].start, ivs[c1 - 1].end, [&](const RecRef& r) { chunk_recs.push_back(r); });
+            if (chunk_recs.empty()) { c0 = c1; continue; }
+            // --max-depth (src/pileup/mod.rs:755-759 -> bam_plp_set_maxcnt): the pileup engine of the reference runs per interval and
+            // drops reads while its buffer is full, so the reads that count can differ from interval to interval. Only a chunk
+            // that holds more reads than the limit can be affected: it is then processed interval by interval, each with the
+            // reads its own engine would keep. (Parity unpinned by the reference's tests; rule restated in depth_limit_keep.)
+            struct Work { size_t a, b; std::vector<RecRef> recs; };
+            std::vector<Work> work;
+            bool split = false;
+            if (o.max_depth && chunk_recs.size() > o.max_depth) {
+                std::vector<Work> per_iv;
+                for (size_t k = c0; k < c1; k++) {
+                    Work w{k, k + 1, {}};
+                    for (auto& r : chunk_recs) if (r.pos < (int64_t)ivs[k].end && r.end > (int64_t)ivs[k].start) w.recs.push_back(r);
+                    const size_t before = w.recs.size();
+                    depth_limit_keep(&w.recs, o.max_depth);
+                    split = split || w.recs.size() != before;
+                    per_iv.push_back(std::move(w));
+                }
+                if (split) work.swap(per_iv);
+            }
+            if (!split) { Work w{c0, c1, {}}; w.recs.swap(chunk_recs); work.push_back(std::move(w)); }
+            for (auto& wk : work) {
+            const size_t i0 = wk.a, i1 = wk.b;
             const uint32_t cs = ivs[i0].start, ce = ivs[i1 - 1].end;
-            if (ce <= cs) { i0 = i1; continue; }
-            // the reads of the chunk; with --partition-tag one group per key (each an independent pileup:
-            // src/pileup/mod.rs:795-830), in key order
-            std::vector<RecRef> all_recs;
-            bam.ensure_tid(ivs[i0].tid);
-            bam.for_overlapping(ivs[i0].tid, cs, ce, [&](const RecRef& r) { all_recs.push_back(r); });
-            if (all_recs.empty()) { i0 = i1; continue; }
+            if (ce <= cs || wk.recs.empty()) continue;
+            std::vector<RecRef>& all_recs = wk.recs;
+            // with --partition-tag one group per key (each an independent pileup: src/pileup/mod.rs:795-830), in key order
             std::map<std::string, std::vector<RecRef>> groups;
             if (!partitioned) groups[""].swap(all_recs);
             else for (auto& r : all_recs) {
@@ -560,20 +978,44 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 for (auto& t : th) t.join();
             }
             for (int t = 0; t < nt; t++) {
-                if (out) fwrite(parts[t].data(), 1, parts[t].size(), out);
+                if (sharded) shard_text.append(parts[t]);
+                else if (out) fwrite(parts[t].data(), 1, parts[t].size(), out);
                 for (auto& kv : routed[t]) if (!kv.second.empty()) fwrite(kv.second.data(), 1, kv.second.size(), router.get(kv.first));
                 S.rows += part_rows[t];
             }
             S.write_s += secs(tc, clk::now());
             }   // partition groups
-            i0 = i1;
+            }   // work items
+            c0 = c1;
         }
         if (out) { if (out != stdout) fclose(out); else fflush(out); }
+        if (sharded) {
+            // rank-ordered concatenation (the reference's ordered collect, src/pileup/subcommand.rs:735-799): the slice sizes
+            // are exchanged (second and last collective) and every rank writes its slice at its offset
+            const auto tw = clk::now();
+            std::vector<uint64_t> sizes((size_t)coll.world + 2, 0);
+            sizes[coll.rank] = shard_text.size();
+            sizes[coll.world] = S.rows; sizes[(size_t)coll.world + 1] = S.positions;
+            coll.sum(sizes.data(), sizes.size());
+            uint64_t at = 0;
+            for (int r = 0; r < coll.rank; r++) at += sizes[r];
+            const int fd = ::open(o.out_bed.c_str(), O_WRONLY);
+            if (fd < 0) throw std::runtime_error("failed to open output file " + o.out_bed);
+            size_t done = 0;
+            while (done < shard_text.size()) {
+                const ssize_t w = pwrite(fd, shard_text.data() + done, shard_text.size() - done, (off_t)(at + done));
+                if (w <= 0) { ::close(fd); throw std::runtime_error("failed to write output file " + o.out_bed); }
+                done += (size_t)w;
+            }
+            ::close(fd);
+            S.rows_total = sizes[coll.world]; S.positions_total = sizes[(size_t)coll.world + 1];
+            S.write_s += secs(tw, clk::now());
+        } else { S.rows_total = S.rows; S.positions_total = S.positions; }
         const auto t1 = clk::now();
         S.load_s = secs(t0, t_load); S.threshold_s = secs(t_load, t_thr); S.interval_s = iv_secs;   /* runs beside ingest + thresholds; wait time = secs(t_thr, t_iv) */ S.total_s = secs(t0, t1);
         for (int b = 0; b < 4; b++) { S.thresholds[b] = P.base_threshold[b]; S.threshold_set[b] = P.base_threshold_set[b]; }
         if (summary) *summary = S;
-        if (!o.quiet)
+        if (!o.quiet && (!sharded || coll.rank == 0))
             fprintf(stderr, "> Done, processed %llu rows. positions=%llu reads=%llu chunks=%llu load=%.3fs thresholds=%.3fs intervals=%.3fs pack=%.3fs gpu=%.3fs (kernels %.3f ms) write=%.3fs total=%.3fs\n",
                     (unsigned long long)S.rows, (unsigned long long)S.positions, (unsigned long long)S.reads_packed, (unsigned long long)S.chunks,
                     S.load_s, S.threshold_s, S.interval_s, S.pack_s, S.gpu_s, S.kernel_ms, S.write_s, S.total_s);
@@ -594,6 +1036,63 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
     }
 }
 
+// ---- several GPUs from one process: `--devices a,b,...` runs one interval shard per listed device on its own host thread
+// (bound to the device's NUMA node); the two exchanges of a sharded run (histogram sum, slice sizes) are in-process sums.
+struct InProcGroup {
+    int world = 1;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint64_t> acc, result;
+    int arrived = 0, gen = 0;
+    bool aborted = false;
+    void abort() { std::lock_guard<std::mutex> g(mu); aborted = true; cv.notify_all(); }
+    int allreduce(uint64_t* buf, size_t n) {
+        std::unique_lock<std::mutex> lk(mu);
+        if (aborted) return -1;
+        if (arrived == 0) acc.assign(n, 0);
+        if (acc.size() != n) { aborted = true; cv.notify_all(); return -1; }
+        for (size_t i = 0; i < n; i++) acc[i] += buf[i];
+        const int my_gen = gen;
+        if (++arrived == world) { result = acc; arrived = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != my_gen || aborted; });
+        if (gen == my_gen) return -1;       // aborted before the round completed
+        memcpy(buf, result.data(), n * sizeof(uint64_t));
+        return 0;
+    }
+    static int thunk(uint64_t* buf, size_t n, void* user) { return ((InProcGroup*)user)->allreduce(buf, n); }
+};
+
+inline int run_pileup_devices(const PileupOptions& o, RunSummary* summary, std::string* error) {
+    const int world = (int)o.devices.size();
+    if (world <= 1) { PileupOptions o1 = o; if (world == 1) o1.device = o.devices[0]; return run_pileup(o1, summary, error); }
+    InProcGroup grp;
+    grp.world = world;
+    std::vector<RunSummary> sums(world);
+    std::vector<std::string> errs(world);
+    std::vector<int> rcs(world, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; r++) th.emplace_back([&, r]() {
+        mkp_bind_host_thread(o.devices[r]);            // NUMA-local pinned buffers and worker threads
+        PileupOptions or_ = o;
+        or_.device = o.devices[r];
+        or_.threads = std::max(1, o.threads / world);
+        if (r) or_.stats_json.clear();
+        Collective c;
+        c.rank = r; c.world = world; c.allreduce_sum = &InProcGroup::thunk; c.user = &grp;
+        rcs[r] = run_pileup(or_, &sums[r], &errs[r], &c);
+        if (rcs[r]) grp.abort();
+    });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < world; r++) if (rcs[r] && errs[r] != "collective (all-reduce) failed") { if (error) *error = errs[r]; return rcs[r]; }
+    for (int r = 0; r < world; r++) if (rcs[r]) { if (error) *error = errs[r]; return rcs[r]; }
+    if (summary) {
+        *summary = sums[0];
+        for (int r = 1; r < world; r++) { summary->reads_packed += sums[r].reads_packed; summary->chunks += sums[r].chunks; summary->algorithmic_bytes += sums[r].algorithmic_bytes; summary->kernel_ms = std::max(summary->kernel_ms, sums[r].kernel_ms); }
+        summary->rows = sums[0].rows_total; summary->positions = sums[0].positions_total;
+    }
+    return 0;
+}
+
 // clap-compatible subset of the `modkit pileup` flag surface (src/pileup/subcommand.rs:37-379)
 inline bool parse_pileup_args(int argc, const char* const* argv, PileupOptions* o, std::string* err) {
     std::vector<std::string> pos;
@@ -608,7 +1107,9 @@ inline bool parse_pileup_args(int argc, const char* const* argv, PileupOptions* 
             else if (a == "--sampling-interval-size") o->sampling_interval_size = (uint32_t)std::stoul(val());
             else if (a == "-n" || a == "--num-reads") o->num_reads = std::stoul(val());
             else if (a == "-f" || a == "--sampling-frac") { o->have_frac = true; o->frac = std::stod(val()); }
-            else if (a == "--seed" || a == "--max-depth" || a == "--queue-size" || a == "--chunk-size" || a == "--log-filepath" || a == "--log") val();
+            else if (a == "--max-depth") o->max_depth = (uint32_t)std::stoul(val());
+            else if (a == "--devices") { o->devices.clear(); std::string v = val(); for (size_t i = 0; i < v.size();) { size_t j = v.find(',', i); if (j == std::string::npos) j = v.size(); o->devices.push_back(std::stoi(v.substr(i, j - i))); i = j + 1; } if (o->devices.empty()) throw std::runtime_error("--devices needs a list of device indices"); }
+            else if (a == "--seed" || a == "--queue-size" || a == "--chunk-size" || a == "--log-filepath" || a == "--log") val();
             else if (a == "--no-filtering") o->no_filtering = true;
             else if (a == "-p" || a == "--filter-percentile") o->percentile = std::stof(val());
             else if (a == "--filter-threshold" || a == "--pass_threshold") o->filter_thresholds.push_back(val());

@@ -1,8 +1,11 @@
 // C ABI (include/mkp.h) over the sm_100a kernels in mkp_kernels.cuh.
 // One mkp_ctx per GPU: grow-only device buffers, one stream, CUDA events around every stage.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <cctype>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -59,6 +62,7 @@ struct mkp_ctx {
     bool inflate_attr_set = false;
     // results
     size_t n_rows = 0;
+    uint64_t launches = 0;       // kernels launched by this context (mkp_kernel_launches)
     std::vector<mkp_row> h_rows;
     std::vector<uint64_t> h_entry_off;
     mkp_row* h_rows_pinned = nullptr;
@@ -91,6 +95,42 @@ int mkp_create(int device, mkp_ctx** out) {
     memset(&ctx->params, 0, sizeof ctx->params);
     *out = ctx;
     return 0;
+}
+
+int mkp_bind_host_thread(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+    for (char* c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return 1;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return 1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return 1;
+    char list[4096] = {0};
+    const size_t n = fread(list, 1, sizeof list - 1, f);
+    fclose(f);
+    if (!n) return 1;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int any = 0;
+    for (char* p = list; *p;) {           // "0-31,64-95"
+        char* e;
+        long a = strtol(p, &e, 10);
+        if (e == p) break;
+        long b = a;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, &set); any = 1; }
+        p = e;
+        while (*p == ',' || *p == '\n' || *p == ' ') p++;
+    }
+    if (!any) return 1;
+    return sched_setaffinity(0, sizeof set, &set) == 0 ? 0 : -2;
 }
 
 void mkp_destroy(mkp_ctx* ctx) {
@@ -238,14 +278,14 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     CK(cudaMemsetAsync(ctx->d_small.p, 0xff, 32 * 8, st));
     CK(cudaMemsetAsync(ctx->d_small.as<uint8_t>() + 32 * 8, 0, SMALL_BYTES - 32 * 8, st));
     C.mode = MODE_PILEUP;
-    if (ctx->n_reads) k_parse<<<grid, 128, 0, st>>>(C);
+    ctx->launches += 1; if (ctx->n_reads) k_parse<<<grid, 128, 0, st>>>(C);
     CK(cudaEventRecord(ctx->ev[1], st));
-    if (ctx->n_reads) { k_resolve<MODE_PILEUP, true><<<grid, 128, 0, st>>>(C); k_resolve<MODE_PILEUP, false><<<grid, 128, 0, st>>>(C); }
+    ctx->launches += 2; if (ctx->n_reads) { k_resolve<MODE_PILEUP, true><<<grid, 128, 0, st>>>(C); k_resolve<MODE_PILEUP, false><<<grid, 128, 0, st>>>(C); }
     CK(cudaEventRecord(ctx->ev[2], st));
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);   // n_states, err, n_hot, n_rows
-    k_block_popc<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.focus_pos, C.focus_neg);
-    k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 2);
-    k_word_prefix<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.hot_prefix);
+    ctx->launches += 1; k_block_popc<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.focus_pos, C.focus_neg);
+    ctx->launches += 1; k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 2);
+    ctx->launches += 1; k_word_prefix<<<n_blk, 1024, 0, st>>>(C.hot, n_words, ctx->d_block_sums.as<uint32_t>(), C.hot_prefix);
     CK(cudaEventRecord(ctx->ev[3], st));
     uint32_t h_small[4];
     unsigned long long h_calls = 0;
@@ -273,10 +313,10 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     // latency-bound at 32 registers, so they co-reside on the SMs)
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-    if (ctx->n_reads && n_hot) k_count_calls<<<g2, 256, 0, ctx->stream2>>>(D);
+    ctx->launches += 1; if (ctx->n_reads && n_hot) k_count_calls<<<g2, 256, 0, ctx->stream2>>>(D);
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
     CK(cudaEventRecord(ctx->ev[5], st));
-    if (ctx->n_reads && n_hot) k_count_bases<<<g2, 256, 0, st>>>(D);
+    ctx->launches += 1; if (ctx->n_reads && n_hot) k_count_bases<<<g2, 256, 0, st>>>(D);
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CK(cudaEventRecord(ctx->ev[6], st));
     RowDev R;
@@ -285,10 +325,10 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     R.obs_word = D.obs_word;
     R.row_counts = ctx->d_row_counts.as<uint32_t>(); R.row_prefix = ctx->d_row_prefix.as<uint32_t>(); R.rows = nullptr;
     const int rg = (n_words + 255) / 256;
-    k_rows<false><<<rg, 256, 0, st>>>(R);
-    k_block_sum<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>());
-    k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 3);
-    k_value_prefix<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_row_prefix.as<uint32_t>());
+    ctx->launches += 1; k_rows<false><<<rg, 256, 0, st>>>(R);
+    ctx->launches += 1; k_block_sum<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>());
+    ctx->launches += 1; k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 3);
+    ctx->launches += 1; k_value_prefix<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_row_prefix.as<uint32_t>());
     CK(cudaEventRecord(ctx->ev[7], st));
     uint32_t n_rows = 0;
     CK(cudaMemcpyAsync(&n_rows, u + 3, 4, cudaMemcpyDeviceToHost, st));
@@ -296,7 +336,7 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     CK(ctx->d_rows.ensure(std::max<size_t>(1, n_rows) * sizeof(mkp_row)));
     R.rows = ctx->d_rows.as<mkp_row>();
     CK(cudaEventRecord(ctx->ev[8], st));
-    if (n_rows) k_rows<true><<<rg, 256, 0, st>>>(R);
+    ctx->launches += 1; if (n_rows) k_rows<true><<<rg, 256, 0, st>>>(R);
     CK(cudaEventRecord(ctx->ev[9], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
@@ -362,7 +402,7 @@ int mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* tak
         C.hist = ctx->d_hist.as<unsigned long long>();
     }
     C.mode = MODE_HIST;
-    if (ctx->n_reads) { k_parse<<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST, true><<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST, false><<<grid, 128, 0, st>>>(C); }
+    ctx->launches += 3; if (ctx->n_reads) { k_parse<<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST, true><<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST, false><<<grid, 128, 0, st>>>(C); }
     CK(cudaGetLastError());
     uint32_t h_small[2];
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
@@ -458,17 +498,17 @@ int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         const size_t nm = cut[sl + 1] - cut[sl];
         const int grid = (int)std::min<size_t>((nm + INF_THREADS - 1) / INF_THREADS, (size_t)ctx->sm_count * per_sm);
-        k_inflate<<<grid, INF_THREADS, smem, st>>>(ctx->d_file.as<uint8_t>(), ctx->d_members.as<mkp_bgzf_member>() + cut[sl], (uint32_t)nm,
+        ctx->launches += 1; k_inflate<<<grid, INF_THREADS, smem, st>>>(ctx->d_file.as<uint8_t>(), ctx->d_members.as<mkp_bgzf_member>() + cut[sl], (uint32_t)nm,
                                                   ctx->d_bam.as<uint8_t>(), u + 10, ctx->d_slab_work.as<uint32_t>() + sl, (uint32_t)cut[sl]);
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream2));
     CK(cudaEventRecord(ctx->ev[2], st));
     const int wg = (int)((n_seeds + 127) / 128);
-    k_walk<0><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), walk_end, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
+    ctx->launches += 1; k_walk<0><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), walk_end, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
                                   ctx->d_seg_counts.as<uint32_t>(), nullptr, nullptr, u + 10);
-    k_block_sum<<<n_blk, 1024, 0, st>>>(ctx->d_seg_counts.as<uint32_t>(), (uint32_t)n_seeds, ctx->d_block_sums.as<uint32_t>());
-    k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 12);
-    k_value_prefix<<<n_blk, 1024, 0, st>>>(ctx->d_seg_counts.as<uint32_t>(), (uint32_t)n_seeds, ctx->d_block_sums.as<uint32_t>(), ctx->d_seg_base.as<uint32_t>());
+    ctx->launches += 1; k_block_sum<<<n_blk, 1024, 0, st>>>(ctx->d_seg_counts.as<uint32_t>(), (uint32_t)n_seeds, ctx->d_block_sums.as<uint32_t>());
+    ctx->launches += 1; k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 12);
+    ctx->launches += 1; k_value_prefix<<<n_blk, 1024, 0, st>>>(ctx->d_seg_counts.as<uint32_t>(), (uint32_t)n_seeds, ctx->d_block_sums.as<uint32_t>(), ctx->d_seg_base.as<uint32_t>());
     uint32_t h[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(h, u + 10, 12, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -480,7 +520,7 @@ int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const
     }
     const size_t nrec = h[2];
     CK(ctx->d_recs.ensure(std::max<size_t>(1, nrec) * sizeof(mkp_bam_rec)));
-    k_walk<1><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), walk_end, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
+    ctx->launches += 1; k_walk<1><<<wg, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), walk_end, ctx->d_seeds.as<uint64_t>(), (uint32_t)n_seeds,
                                   ctx->d_seg_counts.as<uint32_t>(), ctx->d_seg_base.as<uint32_t>(), ctx->d_recs.as<mkp_bam_rec>(), u + 10);
     CK(cudaEventRecord(ctx->ev[3], st));
     CK(cudaMemcpyAsync(h, u + 10, 4, cudaMemcpyDeviceToHost, st));
@@ -533,15 +573,15 @@ int mkp_bam_chunk(mkp_ctx* ctx, uint32_t start, uint32_t end, const uint32_t* re
     if (n) {
         for (uint32_t i = 0; i < n; i++) if (rec_ids[i] >= ctx->n_records) return fail(ctx, "record id out of range");
         CK(cudaMemcpyAsync(ctx->d_ids.p, rec_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        k_slice_plan<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_recs.as<mkp_bam_rec>(), ctx->d_ids.as<uint32_t>(), n,
+        ctx->launches += 1; k_slice_plan<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_recs.as<mkp_bam_rec>(), ctx->d_ids.as<uint32_t>(), n,
                                                      ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_plan.as<SlicePlan>(), ctx->d_need.as<uint32_t>());
-        k_slice_scan<<<1, 1024, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_need.as<uint32_t>(), n, ctx->d_entry_off.as<uint64_t>(), ctx->d_totals.as<uint64_t>());
+        ctx->launches += 1; k_slice_scan<<<1, 1024, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_need.as<uint32_t>(), n, ctx->d_entry_off.as<uint64_t>(), ctx->d_totals.as<uint64_t>());
         CK(cudaMemcpyAsync(tot, ctx->d_totals.p, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         CK(ctx->d_heap.ensure(tot[0] + 64));
         const int grid = std::max(1, std::min(ctx->sm_count * 8, (int)((n + 7) / 8)));
-        k_slice_copy<<<grid, 256, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_plan.as<SlicePlan>(), n, ctx->d_heap.as<uint8_t>());
+        ctx->launches += 1; k_slice_copy<<<grid, 256, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_plan.as<SlicePlan>(), n, ctx->d_heap.as<uint8_t>());
     } else {
         CK(cudaMemsetAsync(ctx->d_entry_off.p, 0, 8, st));
         CK(ctx->d_heap.ensure(64));
@@ -574,6 +614,8 @@ int mkp_fetch_chunk(mkp_ctx* ctx, mkp_read_hdr* hdrs, uint32_t* n_reads, uint8_t
     if (heap_bytes) *heap_bytes = ctx->heap_bytes;
     return 0;
 }
+
+uint64_t mkp_kernel_launches(const mkp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 size_t mkp_algorithmic_bytes(const mkp_chunk* ch, size_t n_rows) {
     size_t b = 0;

@@ -90,6 +90,7 @@ int main(int argc, char** argv) {
         size_t num_reads = 10042;
         bool have_frac = false; double frac = 0;
         bool no_filtering = false, include_unmapped = false, force_allow = false, cpg = false, mask = false;
+        uint32_t max_depth = 8000;
         bool traditional = false, combine_mods = false, combine_strands = false, mixed = false, header = false, invert_edge = false;
         float percentile = 0.1f;
         std::vector<std::string> filter_thresholds, mod_thresholds, motif_parts;
@@ -106,7 +107,8 @@ int main(int argc, char** argv) {
             else if (a == "--sampling-interval-size") sampling_interval_size = (uint32_t)std::stoul(val());
             else if (a == "-n" || a == "--num-reads") num_reads = std::stoul(val());
             else if (a == "-f" || a == "--sampling-frac") { have_frac = true; frac = std::stod(val()); }
-            else if (a == "--seed" || a == "--max-depth" || a == "--queue-size" || a == "--chunk-size" || a == "--log-filepath" || a == "--log") val();
+            else if (a == "--max-depth") max_depth = (uint32_t)std::stoul(val());
+            else if (a == "--seed" || a == "--queue-size" || a == "--chunk-size" || a == "--log-filepath" || a == "--log") val();
             else if (a == "--no-filtering") no_filtering = true;
             else if (a == "-p" || a == "--filter-percentile") percentile = std::stof(val());
             else if (a == "--filter-threshold" || a == "--pass_threshold") filter_thresholds.push_back(val());
@@ -162,6 +164,7 @@ int main(int argc, char** argv) {
         if (combine_strands && !(cpg || !motif_parts.empty())) die("need to specify either --motif or --cpg to combine strands");
 
         PileupParams P;
+        P.max_depth = max_depth;
         P.force_allow_implicit = force_allow;
         bool threshold_collapse = false;
         if (traditional) {

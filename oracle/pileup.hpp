@@ -8,8 +8,9 @@
 //   combine_strand_features src/pileup/mod.rs:469-561
 //   aligned pairs           src/util.rs:122-145 (+ rust-htslib aligned_pairs: M/=/X pair, I/S query, D/N ref)
 //   htslib pileup admission flag mask UNMAP|SECONDARY|QCFAIL|DUP (htslib bam_plp_init default) plus
-//   supplementary/seq_len==0 (src/pileup/mod.rs:783-791). max-depth truncation is NOT restated
-//   (parity unpinned).
+//   supplementary/seq_len==0 (src/pileup/mod.rs:783-791). --max-depth (src/pileup/mod.rs:755-759 ->
+//   htslib bam_plp_set_maxcnt) is restated from htslib's bam_plp_push in plp_maxcnt_filter below; no reference test
+//   exercises it (parity unpinned).
 // The reference iterates htslib pileup columns; this restatement walks each read's CIGAR once and
 // scatters into dense per-interval arrays. The per-(read,position) feature rules are identical.
 #pragma once
@@ -56,6 +57,7 @@ struct PileupParams {
     bool force_allow_implicit = false;
     bool combine_strands = false;
     EdgeFilter edge;
+    uint32_t max_depth = 8000;     // 0 = no limit
 };
 
 struct Row {  // PileupFeatureCounts
@@ -210,6 +212,29 @@ inline bool admitted_for_pileup(const BamRecord& r) {
     return true;
 }
 
+// bam_plp_push (htslib sam.c) with bam_plp_set_maxcnt: `iter->tid == b->core.tid && iter->pos == b->core.pos &&
+// iter->mp->cnt > iter->maxcnt` => the read is not buffered. iter->pos only equals a read's start for the second and later
+// reads of one start position (the first one arrives while the engine still stands on an earlier column); mp->cnt is the
+// number of buffered reads plus the list's sentinel node; a buffered read is released when the column at its end position
+// is built, i.e. every read whose end lies before the current start is gone.
+inline void plp_maxcnt_filter(std::vector<const BamRecord*>* recs, uint32_t maxcnt) {
+    if (!maxcnt || recs->size() <= maxcnt) return;
+    std::multiset<int64_t> ends;
+    int64_t cur = INT64_MIN;
+    std::vector<const BamRecord*> out;
+    for (const BamRecord* r : *recs) {
+        const int64_t s = r->pos();
+        int64_t rlen = 0;
+        for (int ci = 0; ci < r->n_cigar(); ci++) { const uint32_t c = r->cigar_op(ci); const int op = c & 0xf; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4; }
+        const int64_t e = s + (rlen ? rlen : 1);
+        if (s != cur) { cur = s; ends.erase(ends.begin(), ends.lower_bound(s)); }
+        else if (ends.size() + 1 > (size_t)maxcnt) continue;
+        ends.insert(e);
+        out.push_back(r);
+    }
+    recs->swap(out);
+}
+
 // process_region: rows for one interval, sorted by position then (strand, code)
 inline void process_interval(const BamFile& bam, const Interval& iv, const PileupParams& P, StateTable& st,
                              const std::vector<Motif>* motifs, std::vector<Row>* rows_out,
@@ -221,7 +246,15 @@ inline void process_interval(const BamFile& bam, const Interval& iv, const Pileu
     std::vector<const BamRecord*> recs;
     // `keep`: the reads of one partition (--partition-tag): every partition key is an independent pileup
     // (tallies and observed-code sets are keyed by PartitionKey, src/pileup/mod.rs:767-830, 942-965)
-    bam.fetch(iv.tid, start, end, [&](const BamRecord& r) { if (admitted_for_pileup(r) && (!keep || (*keep)(r))) recs.push_back(&r); });
+    // htslib's pileup engine sees every fetched record (one engine per interval, src/pileup/mod.rs:732-759): bam_plp_push drops
+    // the reads of its flag mask, then - maxcnt - a read whose start equals the engine's current column while the buffer is
+    // full; what is left reaches the column loop, where modkit's own filter and the partition key apply.
+    {
+        std::vector<const BamRecord*> pushed;
+        bam.fetch(iv.tid, start, end, [&](const BamRecord& r) { if (!(r.flag() & (0x4 | 0x100 | 0x200 | 0x400))) pushed.push_back(&r); });
+        plp_maxcnt_filter(&pushed, P.max_depth);
+        for (const BamRecord* r : pushed) if (admitted_for_pileup(*r) && (!keep || (*keep)(*r))) recs.push_back(r);
+    }
     if (recs.empty()) return;
     static thread_local std::vector<ReadCalls> calls;
     if (calls.size() < recs.size()) calls.resize(recs.size());

@@ -69,6 +69,9 @@ SYNTH_CASES = [
     ("two_contigs_region", ["--contig", "c1:90000", "--contig", "c2:130000", "--coverage", 15, "--mods", "m", "--seed", 16], ["--region", "c2:20000-100000", "-i", "30011"]),
     ("multi_contig_motifs", ["--contig", "c1:60000", "--contig", "c2:80000", "--contig", "c3:500", "--coverage", 15, "--mods", "hma", "--seed", 17],
      ["--motif", "CG", "0", "--motif", "GATC", "1", "--motif", "A", "0", "--ref", "@FA", "--no-filtering"]),
+    ("cfg4_traditional_40x", ["--contig", "c1:120000", "--contig", "c2:70000", "--coverage", 40, "--mods", "hm", "--seed", 23], ["--preset", "traditional", "--ref", "@FA"]),
+    ("cfg5_hma_60x_cpg_combine", ["--contig", "c1:100000", "--contig", "c2:60000", "--coverage", 60, "--mods", "hma", "--seed", 24], ["--cpg", "--combine-strands", "--ref", "@FA"]),
+    ("max_depth_12", ["--contig", "syn1:120000", "--coverage", 30, "--mods", "hm", "--seed", 25, "--start-grid", 2500], ["--max-depth", "12", "--filter-threshold", "C:0.7", "-i", "30000"]),
     ("include_bed", ["--contig", "c1:150000", "--contig", "c2:90000", "--coverage", 20, "--mods", "hm", "--seed", 18], ["--include-bed", "@BED", "-i", "20000", "-n", "300"]),
     ("include_bed_cpg_combine", ["--contig", "c1:150000", "--coverage", 20, "--mods", "hm", "--seed", 19], ["--include-bed", "@BED", "--cpg", "--combine-strands", "--ref", "@FA", "-p", "0.2"]),
 ]

@@ -5,6 +5,7 @@
 //
 //   synth_modbam --out PREFIX [--contig NAME:LEN]... [--coverage 30] [--seed 20260924] [--mods m|hm|hma]
 //                [--mean-len 12000] [--level 1] [--threads 8] [--combined-hm] [--implicit] [--odd-records] [--partition-tags]
+//                [--start-grid G]  (read starts snapped to multiples of G: stacks of reads sharing a start, for --max-depth)
 //                [--region-only START-END]   (only reads overlapping the window; reference still full length)
 // Writes PREFIX.fa, PREFIX.fa.fai, PREFIX.bam, PREFIX.bam.bai and prints a JSON summary (exact algorithmic bytes,
 // read-bases, reads) on stdout.
@@ -48,6 +49,7 @@ struct Opts {
     bool combined_hm = false, implicit = false, odd = false;
     bool ptags = false;    // --partition-tags: RG:Z (A/B/C or absent), HP (C or i, or absent), XF:f on some reads
     int64_t win_start = -1, win_end = -1;
+    uint32_t start_grid = 0;   // --start-grid G: read starts snapped down to multiples of G (amplicon-like stacks of reads with one start)
 };
 
 // ---- BGZF / BAM / BAI writing ----------------------------------------------------------------------
@@ -247,6 +249,7 @@ int main(int argc, char** argv) {
         else if (a == "--implicit") o.implicit = true;
         else if (a == "--odd-records") o.odd = true;
         else if (a == "--partition-tags") o.ptags = true;
+        else if (a == "--start-grid") o.start_grid = (uint32_t)std::stoul(val());
         else if (a == "--region-only") { std::string s = val(); auto d = s.find('-'); o.win_start = std::stoll(s.substr(0, d)); o.win_end = std::stoll(s.substr(d + 1)); }
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
@@ -319,7 +322,7 @@ int main(int argc, char** argv) {
                 double expect = o.coverage * (e - b) / e_len;
                 uint32_t n = (uint32_t)expect + (rng.uni() < expect - std::floor(expect) ? 1 : 0);
                 std::vector<uint32_t> starts(n);
-                for (auto& s : starts) s = b + rng.below(e - b);
+                for (auto& s : starts) { s = b + rng.below(e - b); if (o.start_grid) s = std::max(b, s / o.start_grid * o.start_grid); }
                 std::sort(starts.begin(), starts.end());
                 uint64_t rid = ((uint64_t)tiles[k].ci << 40) | ((uint64_t)tiles[k].t << 20);
                 for (uint32_t s : starts) make_read(o, c, (int32_t)tiles[k].ci, s, rid++, rng, &outs[k]);
