@@ -386,7 +386,7 @@ def main():
         # ---- file_to_bed: the product, sharded over the N GPUs: BGZF file (page cache) -> bedMethyl text in /dev/shm.
         # In-process (CUDA context already created), twice; the second run is reported.
         out_bed = os.path.join(d, "out.bed")
-        args = PRESET + ["--ref", prefix + ".fa", "-t", str(threads), "--device", str(local_rank), "--quiet", prefix + ".bam", out_bed]
+        args = PRESET + ["--ref", prefix + ".fa", "-t", "32", "--device", str(local_rank), "--quiet", prefix + ".bam", out_bed]
         f2b = None
         for _ in range(2):
             barrier()

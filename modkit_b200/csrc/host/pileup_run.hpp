@@ -14,6 +14,7 @@ namespace mkh {
 struct PileupOptions {
     std::string in_bam, out_bed;
     int threads = 4;
+    int schedule_threads = 0;          // --threads as the user gave it (the sampling schedule depends on it); 0 = threads
     uint32_t interval_size = 100000, sampling_interval_size = 1000000;
     size_t num_reads = 10042;
     bool have_frac = false; double frac = 0;
@@ -77,6 +78,7 @@ struct DeviceGuard {
 // ---- threshold estimation: host schedule (reads_sampler/*), device decode + histogram --------------
 struct SamplerConfig {
     int threads = 4;
+    int workers = 4;                   // host threads that fetch candidates (not part of the schedule)
     uint32_t sampling_interval_size = 1000000;
     bool take_all = false;
     size_t num_reads = 10042;
@@ -468,7 +470,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
                     }
                 } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
             };
-            const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, cfg.threads), plan.size()));
+            const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, cfg.workers), plan.size()));
             std::vector<std::thread> th;
             for (int k = 1; k < nt; k++) th.emplace_back(work);
             work();
@@ -820,7 +822,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             PS.max_depth = 0;           // the sampler looks at reads, not at pileup columns
             if (mkp_set_params(dev.ctx, &PS)) throw std::runtime_error(mkp_last_error(dev.ctx));
             SamplerConfig sc;
-            sc.threads = o.threads; sc.sampling_interval_size = o.sampling_interval_size;
+            sc.threads = o.schedule_threads > 0 ? o.schedule_threads : o.threads; sc.workers = o.threads; sc.sampling_interval_size = o.sampling_interval_size;
             if (o.have_frac) { if (o.frac != 1.0) throw std::runtime_error("only --sampling-frac 1.0 is reproducible without the reference's RNG; use -n or -f 1.0"); sc.take_all = true; }
             sc.num_reads = o.num_reads;
             sc.region = srp ? srp : rp;
@@ -1075,6 +1077,7 @@ inline int run_pileup_devices(const PileupOptions& o, RunSummary* summary, std::
         mkp_bind_host_thread(o.devices[r]);            // NUMA-local pinned buffers and worker threads
         PileupOptions or_ = o;
         or_.device = o.devices[r];
+        or_.schedule_threads = o.schedule_threads > 0 ? o.schedule_threads : o.threads;
         or_.threads = std::max(1, o.threads / world);
         if (r) or_.stats_json.clear();
         Collective c;

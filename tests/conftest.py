@@ -65,3 +65,12 @@ def run_product(args, bam, out):
 def read_dir(path):
     """{file name: text} of an output directory (--bedgraph / --partition-tag)."""
     return {f: open(os.path.join(path, f)).read() for f in sorted(os.listdir(path))}
+
+
+def same_text(got, exp):
+    """Equality of two large texts with a short report (pytest's own diff of multi-megabyte strings takes minutes)."""
+    if got == exp:
+        return True
+    a, b = got.splitlines(), exp.splitlines()
+    i = next((k for k, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
+    raise AssertionError("texts differ at line %d of %d/%d:\n  got: %s\n  exp: %s" % (i, len(a), len(b), a[i][:160] if i < len(a) else "<end>", b[i][:160] if i < len(b) else "<end>"))

@@ -125,7 +125,9 @@ static void make_read(const Opts& o, const Contig& c, int32_t tid, uint32_t star
     const uint32_t ref_end = r;
     if (clip_r) { for (int i = 0; i < 20; i++) { seq.push_back(NT[rng.below(4)]); q2r.push_back(-1); } push_op(4, 20); }
     const uint32_t L = (uint32_t)seq.size();
-    if (o.win_start >= 0 && !((int64_t)start < o.win_end && (int64_t)ref_end > o.win_start)) return;
+    // a read outside the --region-only window is generated all the same (it consumes its share of the tile's random stream, so
+    // the reads of the window are the same reads as in the full file) and only not written
+    const bool emit_read = !(o.win_start >= 0 && !((int64_t)start < o.win_end && (int64_t)ref_end > o.win_start));
 
     // forward (as sequenced) view
     auto fwd = [&](uint32_t f) -> char { return rev ? comp(seq[L - 1 - f]) : seq[f]; };
@@ -197,6 +199,7 @@ static void make_read(const Opts& o, const Contig& c, int32_t tid, uint32_t star
             mm += ';';
         }
     }
+    if (!emit_read) return;
     // ---- BAM record
     char name[32];
     int l_name = snprintf(name, sizeof name, "r%010llu", (unsigned long long)read_id) + 1;
