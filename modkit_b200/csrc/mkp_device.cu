@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "mkp_kernels.cuh"
+#include "mkp_fused.cuh"
 #include "mkp_ingest.cuh"
 
 using namespace mkp;
@@ -63,6 +64,10 @@ struct mkp_ctx {
     // results
     size_t n_rows = 0;
     uint64_t launches = 0;       // kernels launched by this context (mkp_kernel_launches)
+    // fused pass (chunks with focus bitmaps): tile table, rank of the focus set (built at upload), capacities
+    DevBuf d_tiles, d_pscr;
+    uint32_t n_tiles = 0, n_hot = 0, state_cap = 4, p_stride = 0;
+    bool fused_attr_set = false, focus_ready = false;
     std::vector<mkp_row> h_rows;
     std::vector<uint64_t> h_entry_off;
     mkp_row* h_rows_pinned = nullptr;
@@ -76,6 +81,8 @@ static int fail(mkp_ctx* c, const std::string& m, int code = -1) { if (c) c->err
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 extern "C" {
+
+static int finish_upload(mkp_ctx* ctx);
 
 int mkp_create(int device, mkp_ctx** out) {
     if (!out) return -1;
@@ -141,7 +148,7 @@ void mkp_destroy(mkp_ctx* ctx) {
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
                       &ctx->d_file, &ctx->d_members, &ctx->d_bam, &ctx->d_seeds, &ctx->d_seg_counts, &ctx->d_seg_base, &ctx->d_recs, &ctx->d_ids, &ctx->d_plan,
-                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work};
+                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_tiles, &ctx->d_pscr};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -208,7 +215,7 @@ int mkp_upload_chunk(mkp_ctx* ctx, const mkp_chunk* ch) {
         CK(cudaMemcpyAsync(ctx->d_focus_neg.p, ch->focus_neg, (size_t)ctx->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return finish_upload(ctx);
 }
 
 static int decode_grid(const mkp_ctx* ctx, uint32_t n_reads) {
@@ -256,11 +263,160 @@ static std::string derr_text(uint32_t e) {
     return s;
 }
 
+// Chunks with focus bitmaps: the positions that can produce rows are known at upload, so the rank structure (counter slot of
+// every focus position) and the tile table of the fused pass are built here, once per chunk, not once per pass.
+static int finish_upload(mkp_ctx* ctx) {
+    ctx->focus_ready = false;
+    if (!ctx->have_focus) return 0;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n_words = ctx->n_words;
+    const uint32_t n_blk = (n_words + 1023) / 1024;
+    CK(ctx->d_hot.ensure((size_t)n_words * 4 + 4));
+    CK(ctx->d_hot_prefix.ensure((size_t)n_words * 4 + 4));
+    CK(ctx->d_block_sums.ensure((size_t)n_blk * 4 + 4));
+    CK(ctx->d_small.ensure(SMALL_BYTES));
+    uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
+    ctx->launches += 4;
+    k_focus_union<<<(n_words + 255) / 256, 256, 0, st>>>(ctx->d_focus_pos.as<uint32_t>(), ctx->d_focus_neg.as<uint32_t>(), ctx->d_hot.as<uint32_t>(), n_words);
+    k_block_popc<<<n_blk, 1024, 0, st>>>(ctx->d_hot.as<uint32_t>(), n_words, ctx->d_block_sums.as<uint32_t>(), nullptr, nullptr);
+    k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 2);
+    k_word_prefix<<<n_blk, 1024, 0, st>>>(ctx->d_hot.as<uint32_t>(), n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_hot_prefix.as<uint32_t>());
+    uint32_t n_hot = 0;
+    CK(cudaMemcpyAsync(&n_hot, u + 2, 4, cudaMemcpyDeviceToHost, st));
+    ctx->n_tiles = ctx->n_reads ? (uint32_t)((ctx->heap_bytes + FZ_TILE - 1) / FZ_TILE) : 0;
+    if (ctx->n_tiles == 0 && ctx->n_reads) ctx->n_tiles = 1;
+    CK(ctx->d_tiles.ensure(((size_t)ctx->n_tiles + 1) * sizeof(TileInfo)));
+    ctx->launches += 1;
+    k_tiles<<<(ctx->n_tiles + 1 + 255) / 256, 256, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->n_reads, ctx->heap_bytes, ctx->d_tiles.as<TileInfo>(), ctx->n_tiles);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    ctx->n_hot = n_hot;
+    ctx->focus_ready = true;
+    return 0;
+}
+
+// The pass for chunks with focus bitmaps: k_pileup_fused, the generic kernels over the reads it left, the row kernels. Everything
+// is enqueued at once; the host reads the counters once, at the end (capacities that turn out too small - distinct
+// (base, code) states per slot, rows - grow and the affected part runs again).
+static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t n_words = ctx->n_words, n_hot = ctx->n_hot;
+    const uint32_t n_blk = (n_words + 1023) / 1024;
+    ChunkDev C;
+    const int g_slow = std::max(1, std::min(ctx->sm_count * 2, (int)((ctx->n_reads + 3) / 4)));
+    if (int rc = prepare_decode(ctx, &C, g_slow)) return rc;
+    CK(ctx->d_block_sums.ensure((size_t)n_blk * 4 + 4));
+    CK(ctx->d_row_counts.ensure((size_t)n_words * 4 + 4));
+    CK(ctx->d_row_prefix.ensure((size_t)n_words * 4 + 4));
+    CK(ctx->d_obs_word.ensure((size_t)n_words * 8 + 8));
+    const int grid = ctx->sm_count;
+    ctx->p_stride = std::min<uint32_t>(65536u, std::max<uint32_t>(1024u, 2u * ctx->max_blocks * 32u));
+    CK(ctx->d_pscr.ensure((size_t)grid * FZ_WARPS * ctx->p_stride * 4));
+    if (!ctx->fused_attr_set) {
+        CK(cudaFuncSetAttribute(k_pileup_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzShared)));
+        ctx->fused_attr_set = true;
+    }
+    uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);   // n_states, err, n_hot, n_rows, work[0..5] = u+4.., tile counter u+12
+    uint32_t h_small[4] = {0, 0, 0, 0};
+    unsigned long long h_calls = 0;
+    uint32_t h_slow = 0;
+    for (int attempt = 0;; attempt++) {
+        const uint32_t S_cap = ctx->state_cap;
+        const uint32_t stride = SL_MOD + 2 * S_cap;
+        CK(ctx->d_slots.ensure(std::max<size_t>(1, n_hot) * stride * 4));
+        if (!ctx->d_rows.p) CK(ctx->d_rows.ensure(std::max<size_t>(1024, (size_t)n_hot * 3) * sizeof(mkp_row)));
+        CK(cudaEventRecord(ctx->ev[0], st));
+        CK(cudaMemsetAsync(ctx->d_small.p, 0xff, 32 * 8, st));
+        CK(cudaMemsetAsync(ctx->d_small.as<uint8_t>() + 32 * 8, 0, SMALL_BYTES - 32 * 8, st));
+        CK(cudaMemsetAsync(ctx->d_slots.p, 0, (size_t)n_hot * stride * 4, st));
+        CK(cudaMemsetAsync(ctx->d_obs_word.p, 0, (size_t)n_words * 8, st));
+        FusedDev F;
+        memset(&F, 0, sizeof F);
+        F.hdrs = C.hdrs; F.heap = C.heap; F.n_reads = C.n_reads; F.cs = C.cs; F.ce = C.ce;
+        F.tiles = ctx->d_tiles.as<TileInfo>(); F.n_tiles = ctx->n_tiles; F.tile_counter = u + 12;
+        F.focus_pos = C.focus_pos; F.focus_neg = C.focus_neg; F.hot = C.hot; F.hot_prefix = C.hot_prefix;
+        F.slots = ctx->d_slots.as<uint32_t>(); F.stride = stride; F.n_states = S_cap; F.n_words = n_words;
+        F.obs_word = ctx->d_obs_word.as<uint32_t>();
+        F.states = C.states; F.n_states_seen = C.n_states; F.err = C.err;
+        F.slow_list = C.slow_list; F.slow_count = C.work + 4; F.total_calls = C.total_calls;
+        F.p_scratch = ctx->d_pscr.as<uint32_t>(); F.p_stride = ctx->p_stride;
+        if (ctx->n_reads && ctx->n_tiles) { ctx->launches += 1; k_pileup_fused<<<grid, FZ_THREADS, sizeof(FzShared), st>>>(F); }
+        CK(cudaEventRecord(ctx->ev[1], st));
+        // the reads the fused kernel left to the generic path (list mode); both add into the same slots
+        C.mode = MODE_PILEUP; C.list_mode = 1;
+        CountDev D;
+        D.hdrs = C.hdrs; D.heap = C.heap; D.meta = C.meta; D.calls = C.calls; D.n_reads = C.n_reads; D.cs = C.cs; D.ce = C.ce;
+        D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
+        D.slots = F.slots; D.stride = stride; D.n_states = S_cap; D.n_words = n_words; D.obs_word = F.obs_word; D.work = u + 6;
+        D.list = C.slow_list; D.list_count = C.work + 4;
+        if (ctx->n_reads) {
+            ctx->launches += 4;
+            k_parse<<<g_slow, 128, 0, st>>>(C);
+            k_resolve<MODE_PILEUP, false><<<g_slow, 128, 0, st>>>(C);
+            const int g2 = std::max(1, std::min(ctx->sm_count * 2, (int)((ctx->n_reads + 7) / 8)));
+            k_count_calls<<<g2, 256, 0, st>>>(D);
+            k_count_bases<<<g2, 256, 0, st>>>(D);
+        }
+        CK(cudaEventRecord(ctx->ev[2], st));
+        RowDev R;
+        R.hot = C.hot; R.hot_prefix = C.hot_prefix; R.n_words = n_words; R.cs = C.cs; R.ce = C.ce;
+        R.slots = F.slots; R.stride = stride; R.n_states = S_cap; R.states = C.states; R.numeric_mode = ctx->params.numeric_mode;
+        R.obs_word = F.obs_word;
+        R.row_counts = ctx->d_row_counts.as<uint32_t>(); R.row_prefix = ctx->d_row_prefix.as<uint32_t>();
+        R.rows = ctx->d_rows.as<mkp_row>(); R.rows_cap = (uint32_t)std::min<size_t>(0xffffffffu, ctx->d_rows.cap / sizeof(mkp_row));
+        const int rg = (n_words + 255) / 256;
+        ctx->launches += 5;
+        k_rows<false><<<rg, 256, 0, st>>>(R);
+        k_block_sum<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>());
+        k_scan_blocks<<<1, 1024, 0, st>>>(ctx->d_block_sums.as<uint32_t>(), n_blk, u + 3);
+        k_value_prefix<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_row_prefix.as<uint32_t>());
+        k_rows<true><<<rg, 256, 0, st>>>(R);
+        CK(cudaEventRecord(ctx->ev[3], st));
+        CK(cudaMemcpyAsync(h_small, u, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_slow, u + 8, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_calls, C.total_calls, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (h_small[1]) {
+            if (stats) { memset(stats, 0, sizeof *stats); stats->device_error = h_small[1]; }
+            return fail(ctx, "device decode error: " + derr_text(h_small[1]), -10);
+        }
+        if (h_small[0] > S_cap) {                       // more distinct states than the slot layout holds: widen it, run again
+            uint32_t c = S_cap;
+            while (c < h_small[0]) c *= 2;
+            ctx->state_cap = std::min<uint32_t>(c, MAX_STATES);
+            if (attempt > 4) return fail(ctx, "state capacity did not converge");
+            continue;
+        }
+        if (h_small[3] > R.rows_cap) {                  // more rows than the buffer holds: grow it, emit again
+            CK(ctx->d_rows.ensure((size_t)h_small[3] * sizeof(mkp_row)));
+            R.rows = ctx->d_rows.as<mkp_row>(); R.rows_cap = (uint32_t)std::min<size_t>(0xffffffffu, ctx->d_rows.cap / sizeof(mkp_row));
+            ctx->launches += 1;
+            k_rows<true><<<rg, 256, 0, st>>>(R);
+            CK(cudaEventRecord(ctx->ev[3], st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+        }
+        break;
+    }
+    ctx->n_rows = h_small[3];
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_rows = h_small[3]; stats->n_hot = n_hot; stats->n_calls = h_calls; stats->n_states = h_small[0];
+        stats->n_reads_skipped = h_slow;            // reads that went through the generic kernels
+        auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
+        // kernel_ms: 0 fused pass (incl. the clearing of the slots), 1 generic kernels over the listed reads, 5 rows, 7 total
+        stats->kernel_ms[0] = el(0, 1); stats->kernel_ms[1] = el(1, 2); stats->kernel_ms[5] = el(2, 3); stats->kernel_ms[7] = el(0, 3);
+    }
+    return 0;
+}
+
 int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     if (!ctx) return -1;
     if (!ctx->have_params) return fail(ctx, "mkp_set_params was not called");
     if (ctx->ce <= ctx->cs) return fail(ctx, "no resident chunk");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->have_focus && ctx->focus_ready && !getenv("MKP_NO_FUSED")) return pileup_fused(ctx, stats);
     cudaStream_t st = ctx->stream;
     ChunkDev C;
     const int grid = decode_grid(ctx, ctx->n_reads);
@@ -307,6 +463,7 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
     D.slots = ctx->d_slots.as<uint32_t>(); D.stride = stride; D.n_states = std::max<uint32_t>(n_states, 1);
     D.n_words = n_words; D.obs_word = ctx->d_obs_word.as<uint32_t>(); D.work = u + 6;
+    D.list = nullptr; D.list_count = nullptr;
     CK(cudaEventRecord(ctx->ev[4], st));
     const int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
     // the two counting kernels only meet in commutative atomics on the slots: run them side by side (both are
@@ -334,7 +491,7 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     CK(cudaMemcpyAsync(&n_rows, u + 3, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(ctx->d_rows.ensure(std::max<size_t>(1, n_rows) * sizeof(mkp_row)));
-    R.rows = ctx->d_rows.as<mkp_row>();
+    R.rows = ctx->d_rows.as<mkp_row>(); R.rows_cap = 0xffffffffu;
     CK(cudaEventRecord(ctx->ev[8], st));
     ctx->launches += 1; if (n_rows) k_rows<true><<<rg, 256, 0, st>>>(R);
     CK(cudaEventRecord(ctx->ev[9], st));
@@ -599,7 +756,7 @@ int mkp_bam_chunk(mkp_ctx* ctx, uint32_t start, uint32_t end, const uint32_t* re
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    return 0;
+    return finish_upload(ctx);
 }
 
 int mkp_fetch_chunk(mkp_ctx* ctx, mkp_read_hdr* hdrs, uint32_t* n_reads, uint8_t* heap, uint64_t* heap_bytes) {

@@ -94,6 +94,9 @@ struct ChunkDev {
     uint32_t hist_include_unaligned;
     uint32_t mode;              // MODE_PILEUP / MODE_HIST (admission rules of k_parse)
     struct ReadLists* rl;
+    // list mode (chunks with focus bitmaps: the reads k_pileup_fused left to the generic kernels): k_parse walks
+    // slow_list[0 .. *(work + 4)) instead of all reads, and the hot bitmap (= the focus set, ranked at upload) is not written
+    uint32_t list_mode;
 };
 
 __constant__ DevParams c_par;
@@ -386,7 +389,10 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
     for (;;) {
         // dynamic work distribution: reads differ in length by 2-3 orders of magnitude
         uint32_t ri = 0;
-        if (lane == 0) ri = atomicAdd(C.work, 1u);
+        if (lane == 0) {
+            ri = atomicAdd(C.work, 1u);
+            if (C.list_mode) ri = ri < C.work[4] ? C.slow_list[ri] : 0xffffffffu;
+        }
         ri = __shfl_sync(FULL, ri, 0);
         if (ri >= C.n_reads) break;
         const mkp_read_hdr h = C.hdrs[ri];
@@ -1239,7 +1245,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                             calls[n_calls + __popc(em & ((1u << lane) - 1u))] = make_uint2(rpos, info);
                             // marks of a read that fails later stay behind: a hot position without calls yields no rows
                             const uint32_t x = rpos - C.cs;
-                            atomicOr(&C.hot[x >> 5], 1u << (x & 31));
+                            if (!C.list_mode) atomicOr(&C.hot[x >> 5], 1u << (x & 31));
                         }
                         n_calls += __popc(em);
                     } else {
@@ -1349,7 +1355,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                 meta.pos_mask = pos_mask; meta.neg_mask = neg_mask; meta.n_calls = n_calls;
                 meta.imp[0] = imp_meta[0]; meta.imp[1] = imp_meta[1];
                 if (lane == 0 && n_calls) atomicAdd(C.total_calls, (unsigned long long)n_calls);
-                if (!FAST_ONLY && (imp_meta[0] | imp_meta[1])) {
+                if (!FAST_ONLY && (imp_meta[0] | imp_meta[1]) && !C.list_mode) {
                     // every aligned occurrence of an implicit table's base is a call position
                     uint32_t qc2 = 0, rc2 = (uint32_t)h.ref_start;
                     for (uint32_t i = 0; i < h.n_cigar; i++) {
@@ -1462,6 +1468,8 @@ struct CountDev {
     uint32_t n_words;
     uint32_t* obs_word;   // [2][n_words] observed-code masks of fully covered bitmap words
     uint32_t* work;       // dynamic read counter
+    const uint32_t* list; // list mode: the reads to count (k_pileup_fused counted the others) and their number
+    const uint32_t* list_count;
 };
 
 __device__ __forceinline__ uint32_t slot_of(const CountDev& D, uint32_t x) {
@@ -1482,7 +1490,7 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
     const uint32_t lane = lane_id();
     for (;;) {
         uint32_t ri = 0;
-        if (lane == 0) ri = atomicAdd(D.work + 1, 1u);
+        if (lane == 0) { ri = atomicAdd(D.work + 1, 1u); if (D.list) ri = ri < *D.list_count ? D.list[ri] : 0xffffffffu; }
         ri = __shfl_sync(FULL, ri, 0);
         if (ri >= D.n_reads) break;
         const ReadMeta m = D.meta[ri];
@@ -1525,7 +1533,7 @@ __global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D)
     const uint32_t wib = threadIdx.x >> 5;
     for (;;) {
         uint32_t ri = 0;
-        if (lane == 0) ri = atomicAdd(D.work, 1u);
+        if (lane == 0) { ri = atomicAdd(D.work, 1u); if (D.list) ri = ri < *D.list_count ? D.list[ri] : 0xffffffffu; }
         ri = __shfl_sync(FULL, ri, 0);
         if (ri >= D.n_reads) break;
         const ReadMeta m = D.meta[ri];
@@ -1705,6 +1713,7 @@ struct RowDev {
     uint32_t* row_counts;     // per hot-bitmap word
     const uint32_t* row_prefix;
     mkp_row* rows;
+    uint32_t rows_cap;        // emit pass: a word whose rows do not fit is skipped (the host grows the buffer and emits again)
 };
 
 // rows of one slot, in output order. emit == nullptr => count only
@@ -1758,6 +1767,7 @@ __global__ void __launch_bounds__(256) k_rows(RowDev R) {
     if (!bits) { if (!EMIT) R.row_counts[w] = 0; return; }
     uint32_t slot = R.hot_prefix[w];
     uint32_t n = 0;
+    if (EMIT && (unsigned long long)R.row_prefix[w] + R.row_counts[w] > (unsigned long long)R.rows_cap) return;
     mkp_row* out = EMIT ? R.rows + R.row_prefix[w] : nullptr;
     while (bits) {
         uint32_t bit = __ffs(bits) - 1;
