@@ -303,7 +303,11 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
     const uint32_t n_words = ctx->n_words, n_hot = ctx->n_hot;
     const uint32_t n_blk = (n_words + 1023) / 1024;
     ChunkDev C;
-    const int g_slow = std::max(1, std::min(ctx->sm_count * 2, (int)((ctx->n_reads + 3) / 4)));
+    // MKP_FUSED=1: the TMA-staged single-traversal kernel (k_pileup_fused); default: the per-stage kernels (see DESIGN.md 4:
+    // the pass is bound by instruction issue, and the per-stage kernels keep 2-3x more warps per SM in flight)
+    const char* fz = getenv("MKP_FUSED");
+    const bool use_fused = fz && fz[0] == '1';
+    const int g_slow = use_fused ? std::max(1, std::min(ctx->sm_count * 2, (int)((ctx->n_reads + 3) / 4))) : decode_grid(ctx, ctx->n_reads);
     if (int rc = prepare_decode(ctx, &C, g_slow)) return rc;
     CK(ctx->d_block_sums.ensure((size_t)n_blk * 4 + 4));
     CK(ctx->d_row_counts.ensure((size_t)n_words * 4 + 4));
@@ -320,6 +324,7 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
     uint32_t h_small[4] = {0, 0, 0, 0};
     unsigned long long h_calls = 0;
     uint32_t h_slow = 0;
+    bool fused_ran = false;
     for (int attempt = 0;; attempt++) {
         const uint32_t S_cap = ctx->state_cap;
         const uint32_t stride = SL_MOD + 2 * S_cap;
@@ -340,24 +345,50 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         F.states = C.states; F.n_states_seen = C.n_states; F.err = C.err;
         F.slow_list = C.slow_list; F.slow_count = C.work + 4; F.total_calls = C.total_calls;
         F.p_scratch = ctx->d_pscr.as<uint32_t>(); F.p_stride = ctx->p_stride;
-        if (ctx->n_reads && ctx->n_tiles) { ctx->launches += 1; k_pileup_fused<<<grid, FZ_THREADS, sizeof(FzShared), st>>>(F); }
-        CK(cudaEventRecord(ctx->ev[1], st));
-        // the reads the fused kernel left to the generic path (list mode); both add into the same slots
-        C.mode = MODE_PILEUP; C.list_mode = 1;
+        C.mode = MODE_PILEUP;
         CountDev D;
         D.hdrs = C.hdrs; D.heap = C.heap; D.meta = C.meta; D.calls = C.calls; D.n_reads = C.n_reads; D.cs = C.cs; D.ce = C.ce;
         D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
         D.slots = F.slots; D.stride = stride; D.n_states = S_cap; D.n_words = n_words; D.obs_word = F.obs_word; D.work = u + 6;
-        D.list = C.slow_list; D.list_count = C.work + 4;
-        if (ctx->n_reads) {
-            ctx->launches += 4;
-            k_parse<<<g_slow, 128, 0, st>>>(C);
-            k_resolve<MODE_PILEUP, false><<<g_slow, 128, 0, st>>>(C);
-            const int g2 = std::max(1, std::min(ctx->sm_count * 2, (int)((ctx->n_reads + 7) / 8)));
-            k_count_calls<<<g2, 256, 0, st>>>(D);
-            k_count_bases<<<g2, 256, 0, st>>>(D);
+        if (use_fused) {
+            if (ctx->n_reads && ctx->n_tiles) { ctx->launches += 1; k_pileup_fused<<<grid, FZ_THREADS, sizeof(FzShared), st>>>(F); }
+            CK(cudaEventRecord(ctx->ev[1], st));
+            // the reads the fused kernel left to the generic path (list mode); both add into the same slots
+            C.list_mode = 1;
+            D.list = C.slow_list; D.list_count = C.work + 4;
+            if (ctx->n_reads) {
+                ctx->launches += 4;
+                k_parse<<<g_slow, 128, 0, st>>>(C);
+                k_resolve<MODE_PILEUP, false><<<g_slow, 128, 0, st>>>(C);
+                const int g2 = std::max(1, std::min(ctx->sm_count * 2, (int)((ctx->n_reads + 7) / 8)));
+                k_count_calls<<<g2, 256, 0, st>>>(D);
+                k_count_bases<<<g2, 256, 0, st>>>(D);
+            }
+            CK(cudaEventRecord(ctx->ev[2], st));
+            CK(cudaEventRecord(ctx->ev[4], st));
+        } else {
+            // the per-stage kernels at full occupancy (every read), counters addressed by the rank of the focus bit: no hot
+            // marks, no rank pass, no host round trip between the stages
+            C.list_mode = 2;
+            D.list = nullptr; D.list_count = nullptr;
+            const int gd = decode_grid(ctx, ctx->n_reads);
+            if (ctx->n_reads) {
+                ctx->launches += 5;
+                k_parse<<<gd, 128, 0, st>>>(C);
+                CK(cudaEventRecord(ctx->ev[1], st));
+                k_resolve<MODE_PILEUP, true><<<gd, 128, 0, st>>>(C);
+                k_resolve<MODE_PILEUP, false><<<gd, 128, 0, st>>>(C);
+                CK(cudaEventRecord(ctx->ev[2], st));
+                const int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
+                CK(cudaEventRecord(ctx->ev_fork, st));
+                CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                k_count_calls<<<g2, 256, 0, ctx->stream2>>>(D);
+                CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                k_count_bases<<<g2, 256, 0, st>>>(D);
+                CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+            } else { CK(cudaEventRecord(ctx->ev[1], st)); CK(cudaEventRecord(ctx->ev[2], st)); }
+            CK(cudaEventRecord(ctx->ev[4], st));
         }
-        CK(cudaEventRecord(ctx->ev[2], st));
         RowDev R;
         R.hot = C.hot; R.hot_prefix = C.hot_prefix; R.n_words = n_words; R.cs = C.cs; R.ce = C.ce;
         R.slots = F.slots; R.stride = stride; R.n_states = S_cap; R.states = C.states; R.numeric_mode = ctx->params.numeric_mode;
@@ -372,6 +403,7 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         k_value_prefix<<<n_blk, 1024, 0, st>>>(R.row_counts, n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_row_prefix.as<uint32_t>());
         k_rows<true><<<rg, 256, 0, st>>>(R);
         CK(cudaEventRecord(ctx->ev[3], st));
+        fused_ran = use_fused;
         CK(cudaMemcpyAsync(h_small, u, 16, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_slow, u + 8, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_calls, C.total_calls, 8, cudaMemcpyDeviceToHost, st));
@@ -405,8 +437,10 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         stats->n_rows = h_small[3]; stats->n_hot = n_hot; stats->n_calls = h_calls; stats->n_states = h_small[0];
         stats->n_reads_skipped = h_slow;            // reads that went through the generic kernels
         auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
-        // kernel_ms: 0 fused pass (incl. the clearing of the slots), 1 generic kernels over the listed reads, 5 rows, 7 total
-        stats->kernel_ms[0] = el(0, 1); stats->kernel_ms[1] = el(1, 2); stats->kernel_ms[5] = el(2, 3); stats->kernel_ms[7] = el(0, 3);
+        // kernel_ms: 0 parse (fused: the fused pass), incl. the clearing of the slots; 1 resolve (fused: generic kernels over the listed
+        // reads); 4 counters; 5 rows; 6 host syncs (none on this path); 7 total
+        stats->kernel_ms[0] = el(0, 1); stats->kernel_ms[1] = el(1, 2); stats->kernel_ms[4] = el(2, 4); stats->kernel_ms[5] = el(4, 3); stats->kernel_ms[7] = el(0, 3);
+        if (!fused_ran) stats->n_reads_skipped = 0;
     }
     return 0;
 }
@@ -416,7 +450,7 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     if (!ctx->have_params) return fail(ctx, "mkp_set_params was not called");
     if (ctx->ce <= ctx->cs) return fail(ctx, "no resident chunk");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->have_focus && ctx->focus_ready && !getenv("MKP_NO_FUSED")) return pileup_fused(ctx, stats);
+    if (ctx->have_focus && ctx->focus_ready && !getenv("MKP_NO_FOCUS_RANK")) return pileup_fused(ctx, stats);
     cudaStream_t st = ctx->stream;
     ChunkDev C;
     const int grid = decode_grid(ctx, ctx->n_reads);

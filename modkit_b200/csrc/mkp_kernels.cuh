@@ -94,8 +94,9 @@ struct ChunkDev {
     uint32_t hist_include_unaligned;
     uint32_t mode;              // MODE_PILEUP / MODE_HIST (admission rules of k_parse)
     struct ReadLists* rl;
-    // list mode (chunks with focus bitmaps: the reads k_pileup_fused left to the generic kernels): k_parse walks
-    // slow_list[0 .. *(work + 4)) instead of all reads, and the hot bitmap (= the focus set, ranked at upload) is not written
+    // chunks with focus bitmaps (the hot bitmap is the focus set, ranked at upload, and is not written):
+    // 1 = list mode: the reads k_pileup_fused left to the generic kernels; k_parse walks slow_list[0 .. *(work + 4));
+    // 2 = every read through the per-stage kernels
     uint32_t list_mode;
 };
 
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
         uint32_t ri = 0;
         if (lane == 0) {
             ri = atomicAdd(C.work, 1u);
-            if (C.list_mode) ri = ri < C.work[4] ? C.slow_list[ri] : 0xffffffffu;
+            if (C.list_mode == 1) ri = ri < C.work[4] ? C.slow_list[ri] : 0xffffffffu;
         }
         ri = __shfl_sync(FULL, ri, 0);
         if (ri >= C.n_reads) break;
