@@ -418,7 +418,7 @@ def main():
                 pass
             peak = float(peaks.get("hbm_gbs", 6650.0))
             alg = alg_in + 40 * rows_all
-            names = ["parse", "resolve", "rank", "unused", "count_calls+count_bases", "rows", "host_sync_alloc"]
+            names = ["parse", "resolve", "rank", "unused", "count_calls+count_bases", "rows", "host_sync_alloc"]     # rank / host_sync_alloc are 0 on the focus-rank pass
             dom = int(np.argmax(stage_sum[:6]))
             # per-GPU rate of the dominant kernel: the bytes all GPUs' launches of it processed / the time they spent in it
             ach = alg / (stage_sum[dom] * 1e-3) / 1e9

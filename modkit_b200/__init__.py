@@ -192,10 +192,10 @@ def pileup_main_sharded(args, rank, world, allreduce):
     lib = load_library()
     argv = (C.c_char_p * len(args))(*[str(a).encode() for a in args])
     cb = ALLREDUCE_FN(allreduce) if allreduce is not None else C.cast(None, ALLREDUCE_FN)
-    st = (C.c_double * 16)()
+    st = (C.c_double * 20)()
     rc = lib.mkh_pileup_main_sharded(len(args), argv, rank, world, cb, None, st)
     keys = ["total_s", "load_s", "thresholds_s", "gpu_s", "write_s", "rows_total", "positions_total", "rows_rank",
-            "threshold_A", "threshold_C", "threshold_G", "threshold_T", "sampler_fetch_s", "intervals_s", "pack_s", "kernel_ms"]
+            "threshold_A", "threshold_C", "threshold_G", "threshold_T", "sampler_fetch_s", "intervals_s", "pack_s", "kernel_ms", "slice_s", "pass_s", "rowcopy_s"]
     return rc, dict(zip(keys, [float(x) for x in st]))
 
 

@@ -23,8 +23,8 @@ int mkh_pileup_main(int argc, const char* const* argv) {
 // bench.py / modkit_b200.pileup_main_sharded; any other transport works). It is called exactly twice per run, in the same
 // order on every rank: the sampled-probability histograms (u64[4*1025 + 2]; thresholds.rs:118-156) and the output slice
 // sizes (u64[world + 2]); with --include-unmapped a third, one-word exchange precedes them.
-// out_stats (optional, double[16]): total_s, load_s, thresholds_s, gpu_s, write_s, rows (all ranks), positions (all ranks), rows of this
-// rank, base thresholds A C G T (-1 = none), sampler fetch_s, intervals_s, pack_s, kernel_ms.
+// out_stats (optional, double[20]): total_s, load_s, thresholds_s, gpu_s, write_s, rows (all ranks), positions (all ranks), rows of this
+// rank, base thresholds A C G T (-1 = none), sampler fetch_s, intervals_s, pack_s, kernel_ms, slice_s, pass_s, rowcopy_s.
 int mkh_pileup_main_sharded(int argc, const char* const* argv, int rank, int world, int (*allreduce)(uint64_t*, size_t, void*), void* user, double* out_stats) {
     PileupOptions o;
     std::string err;
@@ -37,7 +37,8 @@ int mkh_pileup_main_sharded(int argc, const char* const* argv, int rank, int wor
     if (out_stats) { out_stats[0] = s.total_s; out_stats[1] = s.load_s; out_stats[2] = s.threshold_s; out_stats[3] = s.gpu_s; out_stats[4] = s.write_s;
                      out_stats[5] = (double)s.rows_total; out_stats[6] = (double)s.positions_total; out_stats[7] = (double)s.rows;
                      for (int b = 0; b < 4; b++) out_stats[8 + b] = s.threshold_set[b] ? (double)s.thresholds[b] : -1.0;
-                     out_stats[12] = s.fetch_s; out_stats[13] = s.interval_s; out_stats[14] = s.pack_s; out_stats[15] = s.kernel_ms; }
+                     out_stats[12] = s.fetch_s; out_stats[13] = s.interval_s; out_stats[14] = s.pack_s; out_stats[15] = s.kernel_ms;
+                     out_stats[16] = s.slice_s; out_stats[17] = s.pass_s; out_stats[18] = s.rowcopy_s; }
     return 0;
 }
 

@@ -215,6 +215,14 @@ struct RefInterval {
     bool all_positions = true;
     SiteRules rule;                                      // focus positions
     std::map<uint32_t, std::vector<int>> plus_ids, minus_ids;   // motif ids per strand
+    // single palindromic two-base motif such as CG (the common case): the same information as a flat, position-sorted list
+    // (position, StrandRule bits); motif id 0 on the strand(s) of the bits. rule / plus_ids / minus_ids stay empty.
+    bool flat_valid = false;
+    std::vector<std::pair<uint32_t, uint8_t>> flat;
+    uint8_t flat_rule(uint32_t p) const {
+        auto it = std::lower_bound(flat.begin(), flat.end(), std::make_pair(p, (uint8_t)0));
+        return it != flat.end() && it->first == p ? it->second : 0;
+    }
 };
 
 struct MotifContext {
@@ -419,7 +427,31 @@ inline std::vector<RefInterval> interval_grid(const std::vector<RefTarget>& targ
 inline void fill_interval_focus(std::vector<RefInterval>& ivs, size_t i0, size_t i1, const std::vector<RefTarget>& targets, const std::vector<size_t>& owner,
                                 bool combine, MotifContext* mc, const IncludeBed* include, int threads) {
     if (!(mc || include) || i1 <= i0) return;
+    // one palindromic two-base motif at offset 0 (CG): hits cannot share a position, so the focus set is a flat sorted list
+    const bool flat_ok = mc && mc->motifs.size() == 1 && mc->motifs[0].len == 2 && mc->motifs[0].palindromic && mc->motifs[0].offset == 0 &&
+                         mc->motifs[0].fwd[0] != mc->motifs[0].fwd[1] && __builtin_popcount(mc->motifs[0].fwd[0]) == 1 && __builtin_popcount(mc->motifs[0].fwd[1]) == 1;
     auto fill = [&](RefInterval& iv, const RefTarget& c) {
+        if (flat_ok) {
+            MotifContext& m = *mc;
+            std::string seq;
+            // hits are searched in [start, fe): without --combine-strands fe is the interval end (a hit straddling the end is not
+            // found, src/fasta.rs:207-227); with it the slice reaches past the end and sites at or past the end are dropped
+            const uint64_t fe = combine ? std::min<uint64_t>((uint64_t)iv.end + m.longest * 5, c.end()) : iv.end;
+            m.fasta.slice(c.name, iv.start, fe, m.keep_case, &seq);
+            const uint8_t b0 = m.motifs[0].fwd[0], b1 = m.motifs[0].fwd[1];
+            iv.all_positions = false;
+            iv.flat_valid = true;
+            iv.flat.clear();
+            for (size_t i = 0; i + 1 < seq.size(); i++) {
+                if (!(base_bit(seq[i]) & b0) || !(base_bit(seq[i + 1]) & b1)) continue;
+                const uint32_t p = (uint32_t)(iv.start + i);
+                uint8_t k0 = 1, k1 = 2;
+                if (m.include) { if (!m.include->has(c.tid, p, false)) k0 = 0; if (!m.include->has(c.tid, p + 1, true)) k1 = 0; }
+                if (k0 && p < iv.end) iv.flat.push_back({p, k0});
+                if (k1 && p + 1 < iv.end) iv.flat.push_back({p + 1, k1});
+            }
+            return;
+        }
         if (mc) {
             std::vector<SiteRules> sites;
             if (!combine) motif_interval(*mc, c, iv.start, iv.end, false, &sites);
@@ -500,7 +532,9 @@ inline void finish_interval_rows(const RefInterval& iv, const mkp_row* rows, siz
     for (size_t i = 0; i < n; i++) {
         const mkp_row& r = rows[i];
         const std::vector<int>* ids = nullptr;
-        if (!iv.all_positions) {
+        static const std::vector<int> id0{0};
+        if (iv.flat_valid) { if (iv.flat_rule(r.pos) & (r.strand == '+' ? 1 : 2)) ids = &id0; }
+        else if (!iv.all_positions) {
             const auto& m = r.strand == '+' ? iv.plus_ids : iv.minus_ids;
             auto it = m.find(r.pos);
             if (it != m.end()) ids = &it->second;
@@ -511,9 +545,13 @@ inline void finish_interval_rows(const RefInterval& iv, const mkp_row* rows, siz
     // rows are position sorted: index by position
     std::map<uint32_t, std::pair<size_t, size_t>> span;
     for (size_t i = 0; i < tmp.size();) { size_t j = i; while (j < tmp.size() && tmp[j].r.pos == tmp[i].r.pos) j++; span[tmp[i].r.pos] = {i, j}; i = j; }
-    for (auto& kv : iv.plus_ids) {
+    static const std::vector<int> id0v{0};
+    std::vector<std::pair<uint32_t, const std::vector<int>*>> plus_sites;
+    if (iv.flat_valid) { for (auto& e : iv.flat) if (e.second & 1) plus_sites.push_back({e.first, &id0v}); }
+    else for (auto& kv : iv.plus_ids) plus_sites.push_back({kv.first, &kv.second});
+    for (auto& kv : plus_sites) {
         const uint32_t p = kv.first;
-        for (int id : kv.second) {
+        for (int id : *kv.second) {
             const MotifSpec& m = (*motifs)[id];
             if (!m.palindromic) continue;
             const int64_t partner = (int64_t)p + (m.rc_offset - m.offset);
@@ -602,7 +640,12 @@ inline void focus_bitmaps(const std::vector<RefInterval>& ivs, size_t i0, size_t
                           std::vector<uint32_t>* fpos, std::vector<uint32_t>* fneg) {
     const size_t nw = (ce - cs + 31) / 32;
     fpos->assign(nw, 0); fneg->assign(nw, 0);
-    for (size_t i = i0; i < i1; i++) for (auto& kv : ivs[i].rule) {
+    for (size_t i = i0; i < i1; i++) if (ivs[i].flat_valid) for (auto& kv : ivs[i].flat) {
+        const uint32_t x = kv.first - cs;
+        if (kv.second & 1) (*fpos)[x >> 5] |= 1u << (x & 31);
+        if (kv.second & 2) (*fneg)[x >> 5] |= 1u << (x & 31);
+    }
+    for (size_t i = i0; i < i1; i++) if (!ivs[i].flat_valid) for (auto& kv : ivs[i].rule) {
         const uint32_t x = kv.first - cs;
         if (kv.second & 1) (*fpos)[x >> 5] |= 1u << (x & 31);
         if (kv.second & 2) (*fneg)[x >> 5] |= 1u << (x & 31);

@@ -4,6 +4,7 @@
 #pragma once
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <filesystem>
 #include <unordered_set>
 
@@ -433,59 +434,74 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
     auto key_of = [](const Grp& g) { return std::to_string(g.tid) + ":" + std::to_string(g.start) + "-" + std::to_string(g.end) + "/" + std::to_string(g.n); };
 
     struct Planned { Grp g; BamReader::FetchCursor cur; PackedChunk pc; size_t lo = 0, hi = 0; bool used = false; };
+    struct ContigPlan { uint32_t tid = 0; std::vector<Planned> plan; size_t bulk = 0; };
+    struct Bulk { PackedChunk pc; std::vector<uint8_t> contributes, take; uint32_t tid = 0; };
+    std::vector<ContigPlan> cps;
+    // ---- plan every owned contig under "every group finds its quota"
     for (auto& c : contigs) {
         const uint32_t t = c.tid;
         if (owner[t] != coll.rank) continue;
-        // ---- plan under "every group finds its quota"
-        std::vector<Planned> plan;
-        {
-            size_t done = 0;
-            for (size_t s = 0; s < sbs.size(); s++) for (const Grp& g : todo_for(s, t, done)) {
-                if (cfg.include && !cfg.include->overlaps_any(g.tid, g.start, g.end)) continue;
-                Planned p; p.g = g; plan.push_back(std::move(p));
-                if (g.n >= 0) done += (size_t)g.n;
-            }
+        ContigPlan cp;
+        cp.tid = t;
+        size_t done = 0;
+        for (size_t s = 0; s < sbs.size(); s++) for (const Grp& g : todo_for(s, t, done)) {
+            if (cfg.include && !cfg.include->overlaps_any(g.tid, g.start, g.end)) continue;
+            Planned p; p.g = g; cp.plan.push_back(std::move(p));
+            if (g.n >= 0) done += (size_t)g.n;
         }
-        // ---- fetch the candidates of all planned groups (parallel), then one decode pass
-        const auto tf0 = clk::now();
-        {
-            std::atomic<size_t> next{0};
-            std::exception_ptr err;
-            std::mutex mu;
-            auto work = [&]() {
-                try {
-                    std::vector<RecRef> recs;
-                    for (;;) {
-                        const size_t i = next.fetch_add(1);
-                        if (i >= plan.size()) break;
-                        Planned& p = plan[i];
-                        p.cur = bam.fetch_begin(p.g.tid, p.g.start, p.g.end);
-                        const size_t want = p.g.n < 0 ? (size_t)-1 : (size_t)p.g.n * 2 + 32;
-                        // packed right after each fetch: record bytes live in the cursor's buffer until the next fetch_more
-                        while (!p.cur.done && p.pc.recs.size() < want) {
-                            recs.clear();
-                            bam.fetch_more(p.cur, std::min<size_t>(want - p.pc.recs.size(), 4096), [&](const RecRef& r) { return sampler_flag_ok(r, req_mapped); }, &recs);
-                            for (auto& r : recs) { pack_record(p.cur.bytes(r), r.size, &p.pc); p.pc.recs.push_back(r); }
-                        }
+        cps.push_back(std::move(cp));
+    }
+    // ---- fetch the candidates of all planned groups of all contigs (parallel over groups)
+    const auto tf0 = clk::now();
+    {
+        std::vector<Planned*> all;
+        for (auto& cp : cps) for (auto& p : cp.plan) all.push_back(&p);
+        std::atomic<size_t> next{0};
+        std::exception_ptr err;
+        std::mutex mu;
+        auto work = [&]() {
+            try {
+                std::vector<RecRef> recs;
+                for (;;) {
+                    const size_t i = next.fetch_add(1);
+                    if (i >= all.size()) break;
+                    Planned& p = *all[i];
+                    p.cur = bam.fetch_begin(p.g.tid, p.g.start, p.g.end);
+                    const size_t want = p.g.n < 0 ? (size_t)-1 : (size_t)p.g.n * 2 + 32;
+                    // packed right after each fetch: record bytes live in the cursor's buffer until the next fetch_more
+                    while (!p.cur.done && p.pc.recs.size() < want) {
+                        recs.clear();
+                        bam.fetch_more(p.cur, std::min<size_t>(want - p.pc.recs.size(), 4096), [&](const RecRef& r) { return sampler_flag_ok(r, req_mapped); }, &recs);
+                        for (auto& r : recs) { pack_record(p.cur.bytes(r), r.size, &p.pc); p.pc.recs.push_back(r); }
                     }
-                } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
-            };
-            const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, cfg.workers), plan.size()));
-            std::vector<std::thread> th;
-            for (int k = 1; k < nt; k++) th.emplace_back(work);
-            work();
-            for (auto& x : th) x.join();
-            if (err) std::rethrow_exception(err);
-        }
-        PackedChunk bulk;
-        for (auto& p : plan) { p.lo = bulk.recs.size(); append_packed(p.pc, &bulk); p.hi = bulk.recs.size(); p.pc.clear(); p.pc.heap.shrink_to_fit(); }
-        t_fetch += secs_between(tf0, clk::now());
-        std::vector<uint8_t> contributes, take(bulk.recs.size(), 0);
-        contributes_of(bulk, t, &contributes);
-        bool bulk_resident = true;
+                }
+            } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
+        };
+        const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, cfg.workers), all.size()));
+        std::vector<std::thread> th;
+        for (int k = 1; k < nt; k++) th.emplace_back(work);
+        work();
+        for (auto& x : th) x.join();
+        if (err) std::rethrow_exception(err);
+    }
+    // ---- one resident chunk for all of them (one per contig with --include-bed: its bitmaps are per contig), one decode pass each
+    std::vector<Bulk> bulks;
+    for (auto& cp : cps) {
+        if (bulks.empty() || cfg.include) { bulks.emplace_back(); bulks.back().tid = cp.tid; }
+        cp.bulk = bulks.size() - 1;
+        Bulk& B = bulks.back();
+        for (auto& p : cp.plan) { p.lo = B.pc.recs.size(); append_packed(p.pc, &B.pc); p.hi = B.pc.recs.size(); p.pc.clear(); p.pc.heap.shrink_to_fit(); p.pc.hdrs.shrink_to_fit(); }
+    }
+    t_fetch += secs_between(tf0, clk::now());
+    size_t resident_bulk = (size_t)-1;
+    for (size_t bi = 0; bi < bulks.size(); bi++) { bulks[bi].take.assign(bulks[bi].pc.recs.size(), 0); contributes_of(bulks[bi].pc, bulks[bi].tid, &bulks[bi].contributes); resident_bulk = bi; }
+    // ---- the real schedule, contig by contig
+    for (auto& cp : cps) {
+        const uint32_t t = cp.tid;
+        std::vector<Planned>& plan = cp.plan;
+        Bulk& B = bulks[cp.bulk];
         std::map<std::string, size_t> by_key;
         for (size_t i = 0; i < plan.size(); i++) by_key.emplace(key_of(plan[i].g), i);
-        // ---- the real schedule
         std::unordered_set<uint64_t> selected;
         size_t done = 0;
         PackedChunk extra;
@@ -500,9 +516,9 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
                 Planned& p = plan[it->second];
                 p.used = true;
                 for (size_t k = p.lo; k < p.hi && (g.n < 0 || used < (size_t)g.n); k++) {
-                    if (!contributes[k]) continue;
+                    if (!B.contributes[k]) continue;
                     used++;
-                    if (selected.insert(bulk.recs[k].off).second) take[k] = 1;
+                    if (selected.insert(B.pc.recs[k].off).second) B.take[k] = 1;
                 }
                 cur = std::move(p.cur);
             } else cur = bam.fetch_begin(g.tid, g.start, g.end);
@@ -515,7 +531,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
                 for (auto& r : recs) { pack_record(cur.bytes(r), r.size, &extra); extra.recs.push_back(r); }
                 if (extra.recs.empty()) continue;
                 contributes_of(extra, t, &xcontrib);
-                bulk_resident = false;
+                resident_bulk = (size_t)-1;
                 xtake.assign(extra.recs.size(), 0);
                 for (size_t k = 0; k < extra.recs.size() && (g.n < 0 || used < (size_t)g.n); k++) {
                     if (!xcontrib[k]) continue;
@@ -526,12 +542,16 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
             }
             done += used;
         }
-        if (!bulk.recs.empty()) {
-            bool any = false;
-            for (uint8_t x : take) any = any || x;
-            if (any) { if (!bulk_resident) upload(bulk, t); add_taken(take); }
-        }
         n_selected += selected.size();
+    }
+    // ---- histogram of the selected reads of every bulk chunk
+    for (size_t bi = 0; bi < bulks.size(); bi++) {
+        Bulk& B = bulks[bi];
+        bool any = false;
+        for (uint8_t x : B.take) any = any || x;
+        if (!any) continue;
+        if (resident_bulk != bi) { upload(B.pc, B.tid); resident_bulk = bi; }
+        add_taken(B.take);
     }
     if (!only_mapped) {   // reads without coordinates (reads_sampler/mod.rs:85-129): the last rank, after the global count is known
         uint64_t cnt[1] = {n_selected};
@@ -597,6 +617,7 @@ struct RunSummary {
     uint64_t positions = 0, rows = 0, reads_packed = 0, algorithmic_bytes = 0, chunks = 0;
     uint64_t rows_total = 0, positions_total = 0;      // over all ranks of a sharded run
     double fetch_s = 0;                                // threshold sampler: host fetch of the candidates
+    double slice_s = 0, pass_s = 0, rowcopy_s = 0;     // parts of gpu_s: GPU slicing + upload of focus, kernels, rows to the host
     double load_s = 0, threshold_s = 0, interval_s = 0, pack_s = 0, gpu_s = 0, write_s = 0, total_s = 0, kernel_ms = 0;
     float thresholds[4] = {0, 0, 0, 0};
     bool threshold_set[4] = {false, false, false, false};
@@ -861,84 +882,139 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         if (sharded) { ivs.erase(ivs.begin() + (ptrdiff_t)my_i1, ivs.end()); ivs.erase(ivs.begin(), ivs.begin() + (ptrdiff_t)my_i0); }
         for (auto& iv : ivs) S.positions += iv.end - iv.start;
 
-        PackedChunk pc;
-        std::vector<uint32_t> fpos, fneg;
-        std::vector<OutRow> orows;
-        std::string text;
-        for (size_t c0 = 0; c0 < ivs.size();) {
-            // a chunk = consecutive intervals of one contig up to chunk_bp
-            size_t c1 = c0 + 1;
-            while (c1 < ivs.size() && ivs[c1].tid == ivs[c0].tid && ivs[c1].start == ivs[c1 - 1].end && ivs[c1].end - ivs[c0].start <= o.chunk_bp) c1++;
-            if (ivs[c1 - 1].end <= ivs[c0].start) { c0 = c1; continue; }
-            // the reads of the chunk
-            std::vector<RecRef> chunk_recs;
-            bam.ensure_tid(ivs[c0].tid);
-            bam.for_overlapping(ivs[c0].tid, ivs[c0].start, ivs[c1 - 1].end, [&](const RecRef& r) { chunk_recs.push_back(r); });
-            if (chunk_recs.empty()) { c0 = c1; continue; }
-            // --max-depth (src/pileup/mod.rs:755-759 -> bam_plp_set_maxcnt): the pileup engine of the reference runs per interval and
-            // drops reads while its buffer is full, so the reads that count can differ from interval to interval. Only a chunk
-            // that holds more reads than the limit can be affected: it is then processed interval by interval, each with the
-            // reads its own engine would keep. (Parity unpinned by the reference's tests; rule restated in depth_limit_keep.)
-            struct Work { size_t a, b; std::vector<RecRef> recs; };
-            std::vector<Work> work;
-            bool split = false;
-            if (o.max_depth && chunk_recs.size() > o.max_depth) {
-                std::vector<Work> per_iv;
-                for (size_t k = c0; k < c1; k++) {
-                    Work w{k, k + 1, {}};
-                    for (auto& r : chunk_recs) if (r.pos < (int64_t)ivs[k].end && r.end > (int64_t)ivs[k].start) w.recs.push_back(r);
-                    const size_t before = w.recs.size();
-                    depth_limit_keep(&w.recs, o.max_depth);
-                    split = split || w.recs.size() != before;
-                    per_iv.push_back(std::move(w));
+        // ---- two stages: a device thread selects the reads of chunk after chunk, slices them on the GPU, runs the pass and takes
+        // the rows; this thread turns finished chunks into text (strand combining, formatting: parallel over intervals) and
+        // writes them in order. The device works on chunk k + 1 while chunk k is being formatted.
+        struct ChunkOut { size_t i0 = 0, i1 = 0; std::string key_name; std::vector<mkp_row> rows; bool last = false; };
+        std::mutex q_mu;
+        std::condition_variable q_cv;
+        std::deque<ChunkOut> queue;
+        std::exception_ptr dev_err;
+        bool consumer_gone = false;
+        const bool want_alg_bytes = !o.stats_json.empty();
+        auto push_out = [&](ChunkOut&& co) {
+            std::unique_lock<std::mutex> lk(q_mu);
+            q_cv.wait(lk, [&] { return queue.size() < 2 || consumer_gone; });
+            queue.push_back(std::move(co));
+            q_cv.notify_all();
+        };
+        auto device_stage = [&]() {
+            try {
+                PackedChunk pc;
+                std::vector<uint32_t> fpos, fneg;
+                for (size_t c0 = 0; c0 < ivs.size();) {
+                    // a chunk = consecutive intervals of one contig up to chunk_bp
+                    size_t c1 = c0 + 1;
+                    while (c1 < ivs.size() && ivs[c1].tid == ivs[c0].tid && ivs[c1].start == ivs[c1 - 1].end && ivs[c1].end - ivs[c0].start <= o.chunk_bp) c1++;
+                    if (ivs[c1 - 1].end <= ivs[c0].start) { c0 = c1; continue; }
+                    // the reads of the chunk
+                    std::vector<RecRef> chunk_recs;
+                    bam.ensure_tid(ivs[c0].tid);
+                    bam.for_overlapping(ivs[c0].tid, ivs[c0].start, ivs[c1 - 1].end, [&](const RecRef& r) { chunk_recs.push_back(r); });
+                    if (chunk_recs.empty()) { c0 = c1; continue; }
+                    // --max-depth (src/pileup/mod.rs:755-759 -> bam_plp_set_maxcnt): the pileup engine of the reference runs per interval
+                    // and drops reads while its buffer is full, so the reads that count can differ from interval to interval. Only a
+                    // chunk that holds more reads than the limit can be affected: it is then processed interval by interval, each with
+                    // the reads its own engine would keep. (Parity unpinned by the reference's tests; rule restated in depth_limit_keep.)
+                    struct Work { size_t a, b; std::vector<RecRef> recs; };
+                    std::vector<Work> work;
+                    bool split = false;
+                    if (o.max_depth && chunk_recs.size() > o.max_depth) {
+                        std::vector<Work> per_iv;
+                        for (size_t k = c0; k < c1; k++) {
+                            Work w{k, k + 1, {}};
+                            for (auto& r : chunk_recs) if (r.pos < (int64_t)ivs[k].end && r.end > (int64_t)ivs[k].start) w.recs.push_back(r);
+                            const size_t before = w.recs.size();
+                            depth_limit_keep(&w.recs, o.max_depth);
+                            split = split || w.recs.size() != before;
+                            per_iv.push_back(std::move(w));
+                        }
+                        if (split) work.swap(per_iv);
+                    }
+                    if (!split) { Work w{c0, c1, {}}; w.recs.swap(chunk_recs); work.push_back(std::move(w)); }
+                    for (auto& wk : work) {
+                        const size_t i0 = wk.a, i1 = wk.b;
+                        const uint32_t cs = ivs[i0].start, ce = ivs[i1 - 1].end;
+                        if (ce <= cs || wk.recs.empty()) continue;
+                        std::vector<RecRef>& all_recs = wk.recs;
+                        // with --partition-tag one group per key (each an independent pileup: src/pileup/mod.rs:795-830), in key order
+                        std::map<std::string, std::vector<RecRef>> groups;
+                        if (!partitioned) groups[""].swap(all_recs);
+                        else for (auto& r : all_recs) {
+                            // only alignments the pileup admits create a key (flag filter of the pileup engine, pileup/mod.rs:783-791)
+                            if ((r.flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) || r.l_seq == 0) continue;
+                            std::string k;
+                            groups[partition_key_of(bam.rec(r), r.size, o.partition_tags, &k) ? k : std::string("\1")].push_back(r);
+                        }
+                        bool focus_done = false;
+                        for (auto& grp : groups) {
+                            const auto ta = clk::now();
+                            pc.clear();
+                            if (bam.on_device) pc.recs = grp.second;
+                            else pack_records_mt(bam, grp.second, o.threads, &pc);
+                            if (pc.recs.empty()) continue;
+                            mkp_chunk ch;
+                            memset(&ch, 0, sizeof ch);
+                            ch.start = cs; ch.end = ce; ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
+                            if (have_motifs || inc) { if (!focus_done) { focus_bitmaps(ivs, i0, i1, cs, ce, &fpos, &fneg); focus_done = true; } ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data(); }
+                            const auto tb = clk::now();
+                            S.pack_s += secs(ta, tb);
+                            const mkp_row* rows = nullptr;
+                            size_t n_rows = 0;
+                            mkp_stats st;
+                            if (bam.on_device) {
+                                // slice on the GPU (no packed chunk in host memory), then the same kernels
+                                device_chunk(bam, pc.recs, cs, ce, ch.focus_pos, ch.focus_neg);
+                                const auto t_s = clk::now();
+                                S.slice_s += secs(tb, t_s);
+                                if (mkp_pileup_resident(dev.ctx, &st)) throw std::runtime_error(mkp_last_error(dev.ctx));
+                                const auto t_k = clk::now();
+                                S.pass_s += secs(t_s, t_k);
+                                if (mkp_fetch_rows(dev.ctx, &rows, &n_rows)) throw std::runtime_error(mkp_last_error(dev.ctx));
+                                S.rowcopy_s += secs(t_k, clk::now());
+                                if (want_alg_bytes) {
+                                    pc.hdrs.resize(pc.recs.size());
+                                    uint32_t nr = 0;
+                                    if (mkp_fetch_chunk(dev.ctx, pc.hdrs.data(), &nr, nullptr, nullptr)) throw std::runtime_error(mkp_last_error(dev.ctx));
+                                }
+                            } else if (mkp_pileup_chunk(dev.ctx, &ch, &rows, &n_rows, &st)) throw std::runtime_error(mkp_last_error(dev.ctx));
+                            ChunkOut co;
+                            co.i0 = i0; co.i1 = i1;
+                            co.key_name = !partitioned ? std::string() : (grp.first == "\1" ? std::string("ungrouped") : grp.first);
+                            co.rows.assign(rows, rows + n_rows);          // the context's row buffer is reused by the next chunk
+                            S.gpu_s += secs(tb, clk::now());
+                            S.kernel_ms += st.kernel_ms[7];
+                            S.reads_packed += pc.recs.size();
+                            S.algorithmic_bytes += (want_alg_bytes || !bam.on_device ? pc.algorithmic_bytes() : 0) + 40 * n_rows;
+                            S.chunks++;
+                            push_out(std::move(co));
+                        }
+                    }
+                    c0 = c1;
                 }
-                if (split) work.swap(per_iv);
+            } catch (...) { dev_err = std::current_exception(); }
+            ChunkOut fin;
+            fin.last = true;
+            push_out(std::move(fin));
+        };
+        struct DevJoiner { std::thread t; std::mutex* mu; std::condition_variable* cv; bool* gone;
+                           ~DevJoiner() { { std::lock_guard<std::mutex> g(*mu); *gone = true; } cv->notify_all(); if (t.joinable()) t.join(); } } dev_job{std::thread(), &q_mu, &q_cv, &consumer_gone};
+        dev_job.t = std::thread(device_stage);
+        for (;;) {
+            ChunkOut co;
+            {
+                std::unique_lock<std::mutex> lk(q_mu);
+                q_cv.wait(lk, [&] { return !queue.empty(); });
+                co = std::move(queue.front());
+                queue.pop_front();
+                q_cv.notify_all();
             }
-            if (!split) { Work w{c0, c1, {}}; w.recs.swap(chunk_recs); work.push_back(std::move(w)); }
-            for (auto& wk : work) {
-            const size_t i0 = wk.a, i1 = wk.b;
-            const uint32_t cs = ivs[i0].start, ce = ivs[i1 - 1].end;
-            if (ce <= cs || wk.recs.empty()) continue;
-            std::vector<RecRef>& all_recs = wk.recs;
-            // with --partition-tag one group per key (each an independent pileup: src/pileup/mod.rs:795-830), in key order
-            std::map<std::string, std::vector<RecRef>> groups;
-            if (!partitioned) groups[""].swap(all_recs);
-            else for (auto& r : all_recs) {
-                // only alignments the pileup admits create a key (flag filter of the pileup engine, pileup/mod.rs:783-791)
-                if ((r.flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) || r.l_seq == 0) continue;
-                std::string k;
-                groups[partition_key_of(bam.rec(r), r.size, o.partition_tags, &k) ? k : std::string("\1")].push_back(r);
-            }
-            for (auto& grp : groups) {
-            const std::string key_name = !partitioned ? std::string() : (grp.first == "\1" ? std::string("ungrouped") : grp.first);
-            const auto ta = clk::now();
-            pc.clear();
-            if (bam.on_device) pc.recs = grp.second;
-            else pack_records_mt(bam, grp.second, o.threads, &pc);
-            if (pc.recs.empty()) continue;
-            mkp_chunk ch;
-            memset(&ch, 0, sizeof ch);
-            ch.start = cs; ch.end = ce; ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
-            if (have_motifs || inc) { focus_bitmaps(ivs, i0, i1, cs, ce, &fpos, &fneg); ch.focus_pos = fpos.data(); ch.focus_neg = fneg.data(); }
-            const auto tb = clk::now();
-            S.pack_s += secs(ta, tb);
-            const mkp_row* rows = nullptr;
-            size_t n_rows = 0;
-            mkp_stats st;
-            if (bam.on_device) {
-                // slice on the GPU (no packed chunk in host memory), then the same kernels
-                device_chunk(bam, pc.recs, cs, ce, ch.focus_pos, ch.focus_neg);
-                if (mkp_pileup_resident(dev.ctx, &st) || mkp_fetch_rows(dev.ctx, &rows, &n_rows)) throw std::runtime_error(mkp_last_error(dev.ctx));
-                pc.hdrs.resize(pc.recs.size());
-                uint32_t nr = 0;
-                if (mkp_fetch_chunk(dev.ctx, pc.hdrs.data(), &nr, nullptr, nullptr)) throw std::runtime_error(mkp_last_error(dev.ctx));
-            } else if (mkp_pileup_chunk(dev.ctx, &ch, &rows, &n_rows, &st)) throw std::runtime_error(mkp_last_error(dev.ctx));
+            if (co.last) break;
             const auto tc = clk::now();
-            S.gpu_s += secs(tb, tc);
-            S.kernel_ms += st.kernel_ms[7];
-            S.reads_packed += pc.recs.size();
-            S.algorithmic_bytes += pc.algorithmic_bytes() + 40 * n_rows;
-            S.chunks++;
+            const size_t i0 = co.i0, i1 = co.i1;
+            const mkp_row* rows = co.rows.data();
+            const size_t n_rows = co.rows.size();
+            const std::string& key_name = co.key_name;
             // rows are position sorted: every interval gets its slice; intervals are finished and formatted in parallel
             const std::string& chrom = bam.ref_names[ivs[i0].tid];
             const size_t n_iv = i1 - i0;
@@ -986,10 +1062,9 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 S.rows += part_rows[t];
             }
             S.write_s += secs(tc, clk::now());
-            }   // partition groups
-            }   // work items
-            c0 = c1;
         }
+        if (dev_job.t.joinable()) dev_job.t.join();
+        if (dev_err) std::rethrow_exception(dev_err);
         if (out) { if (out != stdout) fclose(out); else fflush(out); }
         if (sharded) {
             // rank-ordered concatenation (the reference's ordered collect, src/pileup/subcommand.rs:735-799): the slice sizes
@@ -1024,10 +1099,10 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         if (!o.stats_json.empty()) {
             FILE* jf = fopen(o.stats_json.c_str(), "w");
             if (jf) {
-                fprintf(jf, "{\"positions\": %llu, \"rows\": %llu, \"reads\": %llu, \"chunks\": %llu, \"algorithmic_bytes\": %llu, \"load_s\": %.6f, \"thresholds_s\": %.6f, \"intervals_s\": %.6f, \"pack_s\": %.6f, \"gpu_s\": %.6f, \"kernel_ms\": %.6f, \"write_s\": %.6f, \"total_s\": %.6f, \"ingest\": \"%s\", \"ingest_h2d_ms\": %.3f, \"ingest_inflate_ms\": %.3f, \"ingest_walk_ms\": %.3f}\n",
+                fprintf(jf, "{\"positions\": %llu, \"rows\": %llu, \"reads\": %llu, \"chunks\": %llu, \"algorithmic_bytes\": %llu, \"load_s\": %.6f, \"thresholds_s\": %.6f, \"intervals_s\": %.6f, \"pack_s\": %.6f, \"gpu_s\": %.6f, \"kernel_ms\": %.6f, \"write_s\": %.6f, \"total_s\": %.6f, \"ingest\": \"%s\", \"ingest_h2d_ms\": %.3f, \"ingest_inflate_ms\": %.3f, \"ingest_walk_ms\": %.3f, \"sampler_fetch_s\": %.6f, \"slice_s\": %.6f, \"pass_s\": %.6f, \"rowcopy_s\": %.6f}\n",
                         (unsigned long long)S.positions, (unsigned long long)S.rows, (unsigned long long)S.reads_packed, (unsigned long long)S.chunks, (unsigned long long)S.algorithmic_bytes,
                         S.load_s, S.threshold_s, S.interval_s, S.pack_s, S.gpu_s, S.kernel_ms, S.write_s, S.total_s,
-                        bam.on_device ? (bam.ranged() ? "device-ranged" : "device") : "host", bam.ingest_ms[0], bam.ingest_ms[1], bam.ingest_ms[2]);
+                        bam.on_device ? (bam.ranged() ? "device-ranged" : "device") : "host", bam.ingest_ms[0], bam.ingest_ms[1], bam.ingest_ms[2], S.fetch_s, S.slice_s, S.pass_s, S.rowcopy_s);
                 fclose(jf);
             }
         }
