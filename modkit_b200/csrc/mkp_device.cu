@@ -65,8 +65,8 @@ struct mkp_ctx {
     size_t n_rows = 0;
     uint64_t launches = 0;       // kernels launched by this context (mkp_kernel_launches)
     // fused pass (chunks with focus bitmaps): tile table, rank of the focus set (built at upload), capacities
-    DevBuf d_tiles, d_pscr;
-    uint32_t n_tiles = 0, n_hot = 0, state_cap = 4, p_stride = 0;
+    DevBuf d_pscr;
+    uint32_t n_hot = 0, state_cap = 4, p_stride = 0;
     bool fused_attr_set = false, focus_ready = false;
     std::vector<mkp_row> h_rows;
     std::vector<uint64_t> h_entry_off;
@@ -148,7 +148,7 @@ void mkp_destroy(mkp_ctx* ctx) {
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
                       &ctx->d_file, &ctx->d_members, &ctx->d_bam, &ctx->d_seeds, &ctx->d_seg_counts, &ctx->d_seg_base, &ctx->d_recs, &ctx->d_ids, &ctx->d_plan,
-                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_tiles, &ctx->d_pscr};
+                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -283,11 +283,6 @@ static int finish_upload(mkp_ctx* ctx) {
     k_word_prefix<<<n_blk, 1024, 0, st>>>(ctx->d_hot.as<uint32_t>(), n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_hot_prefix.as<uint32_t>());
     uint32_t n_hot = 0;
     CK(cudaMemcpyAsync(&n_hot, u + 2, 4, cudaMemcpyDeviceToHost, st));
-    ctx->n_tiles = ctx->n_reads ? (uint32_t)((ctx->heap_bytes + FZ_TILE - 1) / FZ_TILE) : 0;
-    if (ctx->n_tiles == 0 && ctx->n_reads) ctx->n_tiles = 1;
-    CK(ctx->d_tiles.ensure(((size_t)ctx->n_tiles + 1) * sizeof(TileInfo)));
-    ctx->launches += 1;
-    k_tiles<<<(ctx->n_tiles + 1 + 255) / 256, 256, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->n_reads, ctx->heap_bytes, ctx->d_tiles.as<TileInfo>(), ctx->n_tiles);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     ctx->n_hot = n_hot;
@@ -338,7 +333,7 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         FusedDev F;
         memset(&F, 0, sizeof F);
         F.hdrs = C.hdrs; F.heap = C.heap; F.n_reads = C.n_reads; F.cs = C.cs; F.ce = C.ce;
-        F.tiles = ctx->d_tiles.as<TileInfo>(); F.n_tiles = ctx->n_tiles; F.tile_counter = u + 12;
+        F.read_counter = u + 12;
         F.focus_pos = C.focus_pos; F.focus_neg = C.focus_neg; F.hot = C.hot; F.hot_prefix = C.hot_prefix;
         F.slots = ctx->d_slots.as<uint32_t>(); F.stride = stride; F.n_states = S_cap; F.n_words = n_words;
         F.obs_word = ctx->d_obs_word.as<uint32_t>();
@@ -351,7 +346,7 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
         D.slots = F.slots; D.stride = stride; D.n_states = S_cap; D.n_words = n_words; D.obs_word = F.obs_word; D.work = u + 6;
         if (use_fused) {
-            if (ctx->n_reads && ctx->n_tiles) { ctx->launches += 1; k_pileup_fused<<<grid, FZ_THREADS, sizeof(FzShared), st>>>(F); }
+            if (ctx->n_reads) { ctx->launches += 1; k_pileup_fused<<<grid, FZ_THREADS, sizeof(FzShared), st>>>(F); }
             CK(cudaEventRecord(ctx->ev[1], st));
             // the reads the fused kernel left to the generic path (list mode); both add into the same slots
             C.list_mode = 1;

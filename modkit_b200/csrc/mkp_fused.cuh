@@ -6,13 +6,13 @@
 // src/pileup/mod.rs:718-1020; per-read work: src/mod_bam.rs:900-1577, src/read_cache.rs:69-211,
 // src/threshold_mod_caller.rs:28-63, src/util.rs:122-145, src/pileup/mod.rs:238-281, 831-937).
 //
-// Data movement. The heap of packed read blocks (`CIGAR | SEQ | ML | MM`, 16-byte aligned, contiguous: include/mkp.h) is cut
-// into tiles = the reads whose block starts in one FZ_TILE-byte window. One producer thread per CTA streams tiles through a
-// ring of FZ_STAGES shared-memory stages with `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` (one copy
-// for the tile's bytes, one for its read headers), FZ_WARPS consumer warps take the reads of a landed tile from a
-// shared-memory counter (reads differ in length by two orders of magnitude), and a stage is handed back through an `empty`
-// mbarrier when every consumer warp is done with it. A read whose block does not end inside the staged bytes (longer than
-// FZ_CAP - its start offset) is read straight from global memory by the same code (generic pointers).
+// Data movement. A read's block (`CIGAR | SEQ | ML | MM`, 16-byte aligned, contiguous: include/mkp.h) is the unit. One
+// producer warp per CTA takes reads in runs of 32 (one coalesced load of their headers), and places every read in a
+// FZ_RING-byte shared-memory ring with one `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` per read,
+// signalled on the read's own `full` mbarrier (FZ_SLOTS reads in flight). FZ_WARPS consumer warps take reads in placement
+// order (a shared-memory ticket) - reads differ in length by two orders of magnitude, so no warp ever waits for another - and
+// hand a read's slot back through its `empty` mbarrier; the producer reclaims ring bytes in placement order. A block longer
+// than FZ_MAXBLK is not staged: that read goes to the generic kernels (`slow_list`).
 //
 // Per read (warp): MM header scan -> tokens -> occurrence select on the 4-bit SEQ (forward positions stay in shared
 // memory) -> one walk over the CIGAR in batches of 32 ops; under every batch the read's calls are resolved (ML -> probability,
@@ -27,38 +27,34 @@
 
 namespace mkp {
 
-#ifndef MKP_FZ_STAGES
-#define MKP_FZ_STAGES 3
+#ifndef MKP_FZ_RING
+#define MKP_FZ_RING (160 * 1024)
 #endif
-#ifndef MKP_FZ_TILE
-#define MKP_FZ_TILE (24 * 1024)
+#ifndef MKP_FZ_MAXBLK
+#define MKP_FZ_MAXBLK (32 * 1024)
 #endif
-#ifndef MKP_FZ_CAP
-#define MKP_FZ_CAP (40 * 1024)
+#ifndef MKP_FZ_SLOTS
+#define MKP_FZ_SLOTS 64
 #endif
 #ifndef MKP_FZ_WARPS
-#define MKP_FZ_WARPS 12
+#define MKP_FZ_WARPS 16
 #endif
 #ifndef MKP_FZ_PCAP
 #define MKP_FZ_PCAP 384
 #endif
-constexpr int FZ_STAGES = MKP_FZ_STAGES;
-constexpr int FZ_TILE = MKP_FZ_TILE;       // heap bytes per tile window
-constexpr int FZ_CAP = MKP_FZ_CAP;         // bytes staged per tile
-constexpr int FZ_HDRS = 32;                // read headers staged per tile
+constexpr int FZ_RING = MKP_FZ_RING;       // bytes of read blocks resident per CTA
+constexpr int FZ_MAXBLK = MKP_FZ_MAXBLK;   // a longer block is not staged: the read goes to the generic kernels
+constexpr int FZ_SLOTS = MKP_FZ_SLOTS;     // reads in flight per CTA (staged or being staged); > FZ_WARPS
 constexpr int FZ_WARPS = MKP_FZ_WARPS;     // consumer warps per CTA (+ 1 producer warp)
 constexpr int FZ_PCAP = MKP_FZ_PCAP;       // forward positions per warp kept in shared memory
 constexpr int FZ_THREADS = (FZ_WARPS + 1) * 32;
-
-struct TileInfo { unsigned long long base; uint32_t first; uint32_t pad; };   // entry n_tiles = (heap end, n_reads)
+static_assert(FZ_SLOTS > FZ_WARPS + 1 && FZ_MAXBLK * 4 <= FZ_RING, "ring geometry");
 
 struct FusedDev {
     const mkp_read_hdr* hdrs;
     const uint8_t* heap;
     uint32_t n_reads, cs, ce;
-    const TileInfo* tiles;
-    uint32_t n_tiles;
-    uint32_t* tile_counter;
+    uint32_t* read_counter;                                 // reads are handed to the CTAs in runs of 32
     const uint32_t* focus_pos; const uint32_t* focus_neg;
     const uint32_t* hot; const uint32_t* hot_prefix;        // hot = focus_pos | focus_neg, rank structure built at upload
     uint32_t* slots; uint32_t stride, n_states;             // n_states = state capacity of the slot layout
@@ -70,11 +66,7 @@ struct FusedDev {
     uint32_t* p_scratch; uint32_t p_stride;                 // per-warp global scratch for reads with more than FZ_PCAP entries
 };
 
-struct __align__(16) FzStage {
-    uint8_t data[FZ_CAP];
-    mkp_read_hdr hdrs[FZ_HDRS];
-};
-struct FzStageMeta { unsigned long long base; uint32_t first, n, bytes, next; };
+struct FzSlot { mkp_read_hdr hdr; uint32_t ring_off, ri, kind, bytes; };       // kind: 0 read, 2 end of work
 struct __align__(16) FzWarp {
     ListTab tab;
     union {
@@ -84,10 +76,11 @@ struct __align__(16) FzWarp {
     uint32_t P[FZ_PCAP];
 };
 struct FzShared {
-    FzStage stage[FZ_STAGES];
+    __align__(128) uint8_t ring[FZ_RING];
     FzWarp warp[FZ_WARPS];
-    FzStageMeta meta[FZ_STAGES];
-    __align__(8) unsigned long long full[FZ_STAGES], empty[FZ_STAGES];
+    FzSlot slot[FZ_SLOTS];
+    __align__(8) unsigned long long full[FZ_SLOTS], empty[FZ_SLOTS];
+    uint32_t ticket;
 };
 
 // ---- mbarrier / bulk copy (PTX ISA 8.x, sm_90+; on sm_100a the copy is a UBLKCP) ------------------------------------
@@ -107,22 +100,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// tile table: tiles[t] = first read whose block starts at or after t * FZ_TILE, and that block's offset
-__global__ void k_tiles(const mkp_read_hdr* __restrict__ hdrs, uint32_t n_reads, unsigned long long heap_end, TileInfo* __restrict__ tiles, uint32_t n_tiles) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    TileInfo ti;
-    ti.pad = 0;
-    if (t == n_tiles) { ti.first = n_reads; ti.base = (heap_end + 15ull) & ~15ull; }
-    else {
-        const unsigned long long want = (unsigned long long)t * FZ_TILE;
-        uint32_t lo = 0, hi = n_reads;
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (hdrs[mid].off < want) lo = mid + 1; else hi = mid; }
-        ti.first = lo;
-        ti.base = lo < n_reads ? hdrs[lo].off : ((heap_end + 15ull) & ~15ull);
-    }
-    tiles[t] = ti;
-}
 __global__ void k_focus_union(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ o, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = a[i] | b[i];
@@ -778,63 +755,96 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_pileup_fused(const FusedDev F
     const uint32_t lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < FZ_STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], FZ_WARPS); }
+        for (int s = 0; s < FZ_SLOTS; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+        S.ticket = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (wib == FZ_WARPS) {
-        // ---- producer: one thread streams tiles through the ring
-        if (lane == 0) {
-            for (uint32_t it = 0;; it++) {
-                const uint32_t s = it % FZ_STAGES, ph = (it / FZ_STAGES) & 1u;
-                mbar_wait(&S.empty[s], ph ^ 1u);
-                uint32_t t, n = 0;
-                TileInfo ta, tb;
-                for (;;) {                               // next tile that holds reads (a long read leaves the windows under it empty)
-                    t = atomicAdd(F.tile_counter, 1u);
-                    if (t >= F.n_tiles) break;
-                    ta = F.tiles[t]; tb = F.tiles[t + 1];
-                    n = tb.first - ta.first;
-                    if (n) break;
+        // ---- producer warp: takes runs of 32 reads, loads their headers (one coalesced load), and lane 0 places every read in
+        // the ring: slot k % FZ_SLOTS for the k-th read of this CTA, bytes from the ring's tail. Ring bytes are reclaimed in order
+        // (`oldest` = first read not yet known to be released; its consumer arrives on empty[slot] when done).
+        uint32_t seq = 0, oldest = 0;          // reads placed / reads known released
+        uint32_t tail = 0;                     // next free ring byte
+        auto release_oldest = [&]() {          // lane 0
+            mbar_wait(&S.empty[oldest % FZ_SLOTS], (oldest / FZ_SLOTS) & 1u);
+            oldest++;
+        };
+        auto place = [&](const mkp_read_hdr& h, uint32_t ri, uint32_t kind) {     // lane 0
+            while (seq - oldest >= (uint32_t)FZ_SLOTS) release_oldest();              // the slot's previous read is done
+            const unsigned long long size = 4ull * h.n_cigar + ((h.l_seq + 1) >> 1) + h.len_ml + h.len_mm;
+            const uint32_t sz = kind == 0 ? (uint32_t)((size + 15ull) & ~15ull) : 0u;
+            uint32_t at = tail;
+            if (sz) {
+                // bytes in use: [head, tail) or, after a wrap, [head, end) + [0, tail); a placement never makes tail meet head
+                for (;;) {
+                    if (oldest == seq) { at = 0; break; }                            // nothing resident
+                    const uint32_t head = S.slot[oldest % FZ_SLOTS].ring_off;        // first byte still in use
+                    if (tail > head) {
+                        if (tail + sz <= (uint32_t)FZ_RING) { at = tail; break; }
+                        if (sz < head) { at = 0; break; }                            // wrap: the bytes up to the ring's end stay unused
+                    } else if (tail + sz < head) { at = tail; break; }
+                    release_oldest();
                 }
-                FzStageMeta& M = S.meta[s];
-                if (t >= F.n_tiles) { M.n = 0xffffffffu; mbar_arrive(&S.full[s]); break; }
-                const unsigned long long span = tb.base - ta.base;
-                const uint32_t bytes = span > (unsigned long long)FZ_CAP ? (uint32_t)FZ_CAP : (uint32_t)span;
-                const uint32_t nh = n < (uint32_t)FZ_HDRS ? n : (uint32_t)FZ_HDRS;
-                M.base = ta.base; M.first = ta.first; M.n = n; M.bytes = bytes; M.next = 0;
-                mbar_arrive_expect_tx(&S.full[s], bytes + nh * (uint32_t)sizeof(mkp_read_hdr));
-                if (bytes) bulk_g2s(S.stage[s].data, F.heap + ta.base, bytes, &S.full[s]);
-                bulk_g2s(S.stage[s].hdrs, F.hdrs + ta.first, nh * (uint32_t)sizeof(mkp_read_hdr), &S.full[s]);
             }
+            FzSlot& sl = S.slot[seq % FZ_SLOTS];
+            sl.hdr = h; sl.ring_off = at; sl.ri = ri; sl.kind = kind; sl.bytes = sz;
+            unsigned long long* fb = &S.full[seq % FZ_SLOTS];
+            if (sz) {
+                mbar_arrive_expect_tx(fb, sz);
+                bulk_g2s(S.ring + at, F.heap + h.off, sz, fb);
+                tail = at + sz;
+            } else mbar_arrive(fb);
+            seq++;
+        };
+        for (;;) {
+            uint32_t r0 = 0;
+            if (lane == 0) r0 = atomicAdd(F.read_counter, 32u);
+            r0 = __shfl_sync(FULL, r0, 0);
+            if (r0 >= F.n_reads) break;
+            mkp_read_hdr h;
+            memset(&h, 0, sizeof h);
+            const uint32_t mine = r0 + lane;
+            if (mine < F.n_reads) h = F.hdrs[mine];
+            const uint32_t cnt = F.n_reads - r0 < 32u ? F.n_reads - r0 : 32u;
+            for (uint32_t k = 0; k < cnt; k++) {
+                mkp_read_hdr hk;
+                hk.ref_start = __shfl_sync(FULL, h.ref_start, k); hk.l_seq = __shfl_sync(FULL, h.l_seq, k); hk.n_cigar = __shfl_sync(FULL, h.n_cigar, k);
+                hk.flags = __shfl_sync(FULL, h.flags, k); hk.off = __shfl_sync(FULL, h.off, k); hk.len_ml = __shfl_sync(FULL, h.len_ml, k); hk.len_mm = __shfl_sync(FULL, h.len_mm, k);
+                if (lane == 0) {
+                    const unsigned long long size = 4ull * hk.n_cigar + ((hk.l_seq + 1) >> 1) + hk.len_ml + hk.len_mm;
+                    if (size > (unsigned long long)FZ_MAXBLK) F.slow_list[atomicAdd(F.slow_count, 1u)] = r0 + k;     // too long for the ring
+                    else if (size) place(hk, r0 + k, 0u);                            // (a read without bytes has no sequence: not admitted)
+                }
+            }
+        }
+        if (lane == 0) {
+            mkp_read_hdr z;
+            memset(&z, 0, sizeof z);
+            for (int w = 0; w < FZ_WARPS; w++) place(z, 0xffffffffu, 2u);           // one end marker per consumer warp
         }
         return;
     }
-    // ---- consumers
+    // ---- consumers: the k-th ticket of the CTA is the k-th read the producer placed
     FzWarp& W = S.warp[wib];
     StateCache scache;
     scache.init();
     uint32_t* Pg = F.p_scratch + (size_t)(blockIdx.x * FZ_WARPS + wib) * F.p_stride;
-    for (uint32_t it = 0;; it++) {
-        const uint32_t s = it % FZ_STAGES, ph = (it / FZ_STAGES) & 1u;
-        mbar_wait(&S.full[s], ph);
-        const FzStageMeta M = S.meta[s];
-        if (M.n == 0xffffffffu) break;
-        for (;;) {
-            uint32_t idx = 0;
-            if (lane == 0) idx = atomicAdd(&S.meta[s].next, 1u);
-            idx = __shfl_sync(FULL, idx, 0);
-            if (idx >= M.n) break;
-            const uint32_t ri = M.first + idx;
-            const mkp_read_hdr h = idx < (uint32_t)FZ_HDRS ? S.stage[s].hdrs[idx] : F.hdrs[ri];
-            const unsigned long long size = 4ull * h.n_cigar + ((h.l_seq + 1) >> 1) + h.len_ml + h.len_mm;
-            const unsigned long long rel = h.off - M.base;
-            const uint8_t* blk = rel + size <= (unsigned long long)M.bytes ? S.stage[s].data + rel : F.heap + h.off;
-            fused_read(F, W, scache, ri, h, blk, Pg);
-            __syncwarp();
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&S.ticket, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        const uint32_t sidx = k % FZ_SLOTS;
+        mbar_wait(&S.full[sidx], (k / FZ_SLOTS) & 1u);
+        const FzSlot& sl = S.slot[sidx];
+        const uint32_t kind = sl.kind;
+        if (kind == 0) {
+            const mkp_read_hdr h = sl.hdr;
+            fused_read(F, W, scache, sl.ri, h, S.ring + sl.ring_off, Pg);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.empty[s]);
+        if (lane == 0) mbar_arrive(&S.empty[sidx]);
+        if (kind == 2) break;
     }
 }
 

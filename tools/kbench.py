@@ -58,6 +58,7 @@ def main():
         elif v == "fused":
             env["MKP_FUSED"] = "1"             # k_pileup_fused
         elif v != "cur":
+            env["MKP_FUSED"] = "1"
             env["MODKIT_B200_LIB"] = os.path.join(ROOT, "modkit_b200", "_build", "variants", v + ".so")
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "--len", str(length), "--coverage", str(cov), "--steps", str(steps), "--flags", flags, "--child", prefix],
                            env=env, capture_output=True, text=True, timeout=600)
