@@ -143,6 +143,15 @@ int  mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* ta
                           uint64_t* hist, uint8_t* contributes, uint64_t* inexact);
 
 
+/* `modkit summary` support (src/summarize.rs:117-252): every base-modification call of the reads selected by `take`
+ * (as in mkp_sample_histogram) is classed with the thresholds of mkp_set_params: a call that passes is counted under its
+ * thresholded call, a call that fails under its arg-max call. Adds to table (u64[4][2][33]: canonical base A C G T, 0 pass / 1 fail,
+ * 0 = canonical or 1 + state id) and reads_with (u64[4]: reads with calls on that base); obs (u32[4]) receives the state ids seen per
+ * base (codes that were never the called state still get a row), states (u64[32]) the key of every state id of THIS call
+ * (primary base << 32 | code; ~0 = unused) - state ids are only meaningful together with that array. */
+int  mkp_sample_summary(mkp_ctx* ctx, int include_unaligned, const uint8_t* take, uint64_t* table, uint64_t* reads_with,
+                        uint32_t* obs, uint64_t* states);
+
 /* ---- BGZF / BAM ingest on the device (the on-disk format step directly before the path) ----------
  * Replaces, for the records the path consumes, htslib's bgzf_read_block + inflate + bam_read1 behind
  * rust-htslib's bam::IndexedReader::{from_path, fetch} (src/pileup/mod.rs:732-743) and the tag lookup of

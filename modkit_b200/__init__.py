@@ -48,14 +48,14 @@ ROW_DTYPE = np.dtype([("pos", "<u4"), ("code", "<u4"), ("strand", "u1"), ("prima
 assert ROW_DTYPE.itemsize == 40
 
 MKP_SYMBOLS = ["mkp_create", "mkp_bind_host_thread", "mkp_destroy", "mkp_last_error", "mkp_set_params", "mkp_upload_chunk", "mkp_pileup_resident",
-               "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_algorithmic_bytes", "mkp_kernel_launches",
+               "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_sample_summary", "mkp_algorithmic_bytes", "mkp_kernel_launches",
                "mkp_device_memory", "mkp_bam_load", "mkp_bam_load_range", "mkp_bam_records", "mkp_bam_chunk", "mkp_bam_inflated", "mkp_fetch_chunk"]
 MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_refs", "mkh_bam_ref_name", "mkh_bam_ref_len",
                "mkh_bam_n_mapped", "mkh_bam_n_records", "mkh_pack_region", "mkh_packed_free", "mkh_packed_n_reads",
                "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
                "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records",
                "mkh_f32_display", "mkh_bam_partition_key", "mkh_bam_n_ranges", "mkh_pileup_main_sharded", "mkh_shard_plan",
-               "mkh_bam_open_device_pieces", "mkh_bam_fetch"]
+               "mkh_bam_open_device_pieces", "mkh_bam_fetch", "mkh_summary_main", "mkh_sample_probs_main"]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint64), C.c_size_t, C.c_void_p)
 
@@ -87,6 +87,7 @@ def load_library(build_if_missing=True):
     lib.mkp_fetch_rows.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.mkp_pileup_chunk.argtypes = [C.c_void_p, C.POINTER(Chunk), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(Stats)]
     lib.mkp_sample_histogram.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.mkp_sample_summary.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mkp_algorithmic_bytes.argtypes = [C.POINTER(Chunk), C.c_size_t]
     lib.mkp_algorithmic_bytes.restype = C.c_size_t
     lib.mkp_kernel_launches.argtypes = [C.c_void_p]
@@ -118,6 +119,8 @@ def load_library(build_if_missing=True):
     lib.mkh_bam_total_records.argtypes = [C.c_void_p]
     lib.mkh_bam_total_records.restype = C.c_uint64
     lib.mkh_pileup_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    lib.mkh_summary_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    lib.mkh_sample_probs_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     lib.mkh_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.mkh_bam_close.argtypes = [C.c_void_p]
     lib.mkh_bam_close.restype = None
@@ -227,6 +230,20 @@ def shard_plan(bam_path, interval_size, world):
         if n <= cap:
             return [(int(a[3 * k]), int(a[3 * k + 1]), int(a[3 * k + 2]), int(e[k])) for k in range(n)]
         cap = int(n)
+
+
+def summary_main(args):
+    """In-process `modkit summary <args>` (pass --out FILE to get the report in a file); returns the exit code."""
+    lib = load_library()
+    argv = (C.c_char_p * len(args))(*[str(a).encode() for a in args])
+    return lib.mkh_summary_main(len(args), argv)
+
+
+def sample_probs_main(args):
+    """In-process `modkit sample-probs <args>`; returns the exit code."""
+    lib = load_library()
+    argv = (C.c_char_p * len(args))(*[str(a).encode() for a in args])
+    return lib.mkh_sample_probs_main(len(args), argv)
 
 
 HDR_DTYPE = np.dtype([("ref_start", "<i4"), ("l_seq", "<u4"), ("n_cigar", "<u4"), ("flags", "<u4"), ("off", "<u8"), ("len_ml", "<u4"), ("len_mm", "<u4")])

@@ -111,6 +111,12 @@ public:
         mf.open(path);
         size_t total = 0;
         std::vector<Member> members = scan_members(mf, path, &total);
+        {   // this front end keeps the whole inflated stream in host memory: say so instead of being killed by the OOM killer
+            const long pages = sysconf(_SC_AVPHYS_PAGES), psz = sysconf(_SC_PAGESIZE);
+            if (pages > 0 && psz > 0 && (double)total > 0.9 * (double)pages * (double)psz)
+                throw std::runtime_error(path + ": the host front end (--host-ingest / --partition-tag) inflates the whole file into memory (" + std::to_string(total >> 20) +
+                                         " MiB) and only " + std::to_string(((uint64_t)pages * (uint64_t)psz) >> 20) + " MiB are available; use the GPU ingest (indexed BAM) or --region");
+        }
         raw.resize(total + 16);
         std::atomic<size_t> next{0};
         std::atomic<bool> bad{false};
@@ -437,7 +443,8 @@ public:
             else if (tid != (int32_t)c.tid) { if (tid >= 0 && tid < (int32_t)c.tid) { c.p += 4 + bs; continue; } c.done = true; break; }
             else if (pos >= c.end) { c.done = true; break; }
             const uint32_t l_name = r[8], n_cig = load_le<uint16_t>(r + 12), flag = load_le<uint16_t>(r + 14);
-            if (32ull + l_name + 4ull * n_cig > bs) throw std::runtime_error(path_ + ": corrupt BAM record");
+            { const int32_t ls = load_le<int32_t>(r + 16); const uint64_t lq = ls > 0 ? (uint64_t)ls : 0;
+              if (32ull + l_name + 4ull * n_cig + (lq + 1) / 2 + lq > bs) throw std::runtime_error(path_ + ": corrupt BAM record"); }
             int64_t span = 0;
             if (!(flag & 4) && n_cig) {
                 const uint8_t* cg = r + 32 + l_name;
@@ -592,6 +599,8 @@ private:
             const uint16_t flag = load_le<uint16_t>(r + 14);
             ref.idx = n_seen++; ref.flag = flag; ref.l_seq = load_le<uint32_t>(r + 16);
             const uint16_t n_cig = load_le<uint16_t>(r + 12);
+            { const int32_t ls = load_le<int32_t>(r + 16); const uint64_t lq = ls > 0 ? (uint64_t)ls : 0;
+              if (32ull + r[8] + 4ull * n_cig + (lq + 1) / 2 + lq > bs) throw std::runtime_error("corrupt BAM record (fields exceed the record size)"); }
             int64_t span = 0;
             if (!(flag & 4) && n_cig) {
                 const uint8_t* c = r + 32 + r[8];

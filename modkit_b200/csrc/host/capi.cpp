@@ -18,6 +18,19 @@ int mkh_pileup_main(int argc, const char* const* argv) {
     return 0;
 }
 
+// In-process `modkit summary` / `modkit sample-probs`: the report goes to stdout, or to --out FILE.
+static int sample_main(int argc, const char* const* argv, bool summary) {
+    SampleOptions o;
+    std::string err, out_path, text;
+    if (!parse_sample_args(argc, argv, summary, &o, &out_path, &err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 2; }
+    if ((summary ? run_summary(o, &text, &err) : run_sample_probs(o, &text, &err))) { fprintf(stderr, "> Error! %s\n", err.c_str()); return 1; }
+    if (out_path.empty()) fwrite(text.data(), 1, text.size(), stdout);
+    else { FILE* f = fopen(out_path.c_str(), "w"); if (!f) { fprintf(stderr, "> Error! failed to make output file\n"); return 1; } fwrite(text.data(), 1, text.size(), f); fclose(f); }
+    return 0;
+}
+int mkh_summary_main(int argc, const char* const* argv) { return sample_main(argc, argv, true); }
+int mkh_sample_probs_main(int argc, const char* const* argv) { return sample_main(argc, argv, false); }
+
 // One rank of an interval-sharded `modkit pileup`: every rank is called with the same arguments (plus its own
 // --device); `allreduce` sums a u64 vector over the ranks in place and returns 0 (NCCL through torch.distributed in
 // bench.py / modkit_b200.pileup_main_sharded; any other transport works). It is called exactly twice per run, in the same

@@ -58,6 +58,7 @@ public:
             if (r <= 0) break;
             got += (size_t)r;
         }
+        if (got < buf.size()) throw std::runtime_error("short read from the reference FASTA (truncated file or stale .fai?) for contig " + contig);
         out->reserve(e - b);
         for (size_t i = 0; i < got; i++) { char c = buf[i]; if (c == '\n' || c == '\r') continue; out->push_back(keep_case ? c : (char)toupper((unsigned char)c)); }
     }

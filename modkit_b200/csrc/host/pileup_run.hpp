@@ -6,6 +6,7 @@
 #include <condition_variable>
 #include <deque>
 #include <filesystem>
+#include <set>
 #include <unordered_set>
 
 #include "pileup_host.hpp"
@@ -60,8 +61,10 @@ inline Region parse_region_arg(const std::string& raw, const BamReader& bam) {  
         throw std::runtime_error("invalid region " + raw);
     auto num = [&](std::string s) {
         s.erase(std::remove(s.begin(), s.end(), ','), s.end());
-        if (s.empty() || s.find_first_not_of("0123456789") != std::string::npos) throw std::runtime_error("invalid region " + raw);
-        return (uint32_t)std::stoull(s);
+        if (s.empty() || s.size() > 12 || s.find_first_not_of("0123456789") != std::string::npos) throw std::runtime_error("invalid region " + raw);
+        const unsigned long long v = std::stoull(s);
+        if (v > 0xffffffffull) throw std::runtime_error("invalid region " + raw + " (coordinate does not fit 32 bits)");
+        return (uint32_t)v;
     };
     r.start = num(rest.substr(0, dash));
     r.end = num(rest.substr(dash + 1));
@@ -97,8 +100,29 @@ inline bool sampler_flag_ok(const RecRef& r, bool require_mapped) {
     return true;
 }
 
+// the sampled reads themselves (summary: a second device pass over them once the thresholds are known)
+struct SampledChunk { PackedChunk pc; std::vector<uint8_t> take; uint32_t tid = 0; };
+
+// resident chunk of sampled reads: without coordinates of its own, except with --include-bed (bitmaps of the contig)
+inline void upload_sample_chunk(mkp_ctx* ctx, const PackedChunk& pc, uint32_t tid, const IncludeBed* include, std::vector<uint32_t>* fpos, std::vector<uint32_t>* fneg) {
+    mkp_chunk ch;
+    memset(&ch, 0, sizeof ch);
+    ch.start = 0; ch.end = 32;
+    if (include) {
+        int64_t lo = INT64_MAX, hi = 0;
+        for (auto& r : pc.recs) { lo = std::min<int64_t>(lo, r.pos); hi = std::max<int64_t>(hi, r.end); }
+        if (lo < 0) lo = 0;
+        if (hi <= lo) hi = lo + 1;
+        ch.start = (uint32_t)lo; ch.end = (uint32_t)hi;
+        include->bitmaps(tid, ch.start, ch.end, fpos, fneg);
+        ch.focus_pos = fpos->data(); ch.focus_neg = fneg->data();
+    }
+    ch.hdrs = pc.hdrs.data(); ch.n_reads = (uint32_t)pc.hdrs.size(); ch.heap = pc.heap.data(); ch.heap_bytes = pc.heap.size();
+    if (mkp_upload_chunk(ctx, &ch)) throw std::runtime_error(mkp_last_error(ctx));
+}
+
 // Fills hist[4][1025]; returns number of reads selected
-inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const SamplerConfig& cfg, uint64_t* hist, uint64_t* inexact) {
+inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const SamplerConfig& cfg, uint64_t* hist, uint64_t* inexact, std::vector<SampledChunk>* keep = nullptr) {
     int region_tid = -1;
     if (cfg.region) {
         for (size_t i = 0; i < bam.ref_names.size(); i++) if (bam.ref_names[i] == cfg.region->name) region_tid = (int)i;
@@ -244,6 +268,7 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
                     if (selected_ids.insert(cand.recs[k].off).second) take[k] = 1;
                 }
                 add_selected();
+                if (keep && !bam.on_device) { bool any = false; for (uint8_t x : take) any = any || x; if (any) keep->push_back({cand, take, g.tid}); }
                 cursor = want;
             }
             so_far[g.tid] += used;
@@ -264,6 +289,7 @@ inline size_t sample_histogram(const BamReader& bam, mkp_ctx* ctx, const Sampler
                 if (selected_ids.insert(cand.recs[k].off).second) take[k] = 1;
             }
             add_selected();
+            if (keep && !bam.on_device) keep->push_back({cand, take, 0});
         }
     }
     return selected_ids.size();
@@ -297,7 +323,7 @@ inline void append_packed(const PackedChunk& src, PackedChunk* dst) {
 }
 
 inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const SamplerConfig& cfg, uint64_t* hist, uint64_t* inexact,
-                                       const Collective& coll, double* fetch_s = nullptr) {
+                                       const Collective& coll, double* fetch_s = nullptr, std::vector<SampledChunk>* keep = nullptr) {
     using clk = std::chrono::steady_clock;
     int region_tid = -1;
     if (cfg.region) {
@@ -539,6 +565,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
                     if (selected.insert(extra.recs[k].off).second) xtake[k] = 1;
                 }
                 add_taken(xtake);
+                if (keep) { bool any = false; for (uint8_t x : xtake) any = any || x; if (any) keep->push_back({extra, xtake, t}); }
             }
             done += used;
         }
@@ -552,6 +579,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
         if (!any) continue;
         if (resident_bulk != bi) { upload(B.pc, B.tid); resident_bulk = bi; }
         add_taken(B.take);
+        if (keep) keep->push_back({std::move(B.pc), std::move(B.take), B.tid});
     }
     if (!only_mapped) {   // reads without coordinates (reads_sampler/mod.rs:85-129): the last rank, after the global count is known
         uint64_t cnt[1] = {n_selected};
@@ -573,6 +601,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
                 for (size_t k = 0; k < cand.recs.size() && used < limit; k++) { if (!contributes[k]) continue; used++; take[k] = 1; }
                 add_taken(take);
                 n_selected += used;
+                if (keep && used) keep->push_back({std::move(cand), std::move(take), 0});
             }
         }
     }
@@ -1222,6 +1251,295 @@ inline bool parse_pileup_args(int argc, const char* const* argv, PileupOptions* 
     }
     if (pos.size() != 2) { *err = "the following required arguments were not provided: <IN_BAM> <OUT_BED>"; return false; }
     o->in_bam = pos[0]; o->out_bed = pos[1];
+    return true;
+}
+
+
+// ================================================================================================================
+// `modkit summary` and `modkit sample-probs` (src/commands.rs:549-1190, src/summarize.rs:117-252,
+// src/writers.rs:394-684, 692-790): the reads come from the same sampling schedule as the pileup's threshold estimation, the
+// decode runs on the GPU (mkp_sample_histogram / mkp_sample_summary). The reference prints its maps in hash order; here rows
+// are ordered: canonical bases A C G T, then canonical before modified states, codes in ModCodeRepr order.
+// ================================================================================================================
+struct SampleOptions {
+    std::string in_bam, region, include_bed, ignore, edge, percentiles = "0.1,0.5,0.9";
+    std::vector<std::string> filter_thresholds, mod_thresholds;
+    int threads = 4, device = 0;
+    uint32_t interval_size = 1000000;
+    size_t num_reads = 10042;
+    bool have_frac = false, no_sampling = false, no_filtering = false, only_mapped = false, invert_edge = false, tsv = false;
+    double frac = 0;
+    float percentile = 0.1f;
+};
+
+struct ModSummaryOut {
+    uint64_t reads_with[4] = {0, 0, 0, 0};
+    std::map<uint64_t, uint64_t> pass[4], fail[4];     // key: 0 = canonical, else 1 + (code ordering key)
+    std::set<uint64_t> observed[4];
+    uint64_t total_reads = 0;
+    float thresholds[4] = {0, 0, 0, 0};
+    bool threshold_set[4] = {false, false, false, false};
+};
+
+inline uint64_t state_order_key(uint32_t code) { return 1ull + ((code & 0x80000000u) ? (1ull << 32) + (code & 0x7fffffffu) : (uint64_t)code); }
+inline std::string state_label_of_key(uint64_t k) { return k > (1ull << 32) ? std::to_string(k - 1 - (1ull << 32)) : std::string(1, (char)(k - 1)); }
+inline std::string f64_display(double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+    char buf[400];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+}
+
+// sampling + thresholds shared by both commands; fills the kept chunks when `keep` is given
+inline void sample_for_summary(const SampleOptions& o, mkp_ctx* ctx, BamReader& bam, mkp_params* P, Region* region_out, bool* have_region, IncludeBed* include, bool* have_include,
+                               std::vector<uint64_t>* hist, std::vector<SampledChunk>* keep, size_t* n_selected) {
+    try { bam.open_device_index(o.in_bam, ctx); }
+    catch (...) { throw; }
+    if (!bam.have_index()) { bam = BamReader(); bam.open(o.in_bam, o.threads); }       // no index: the (small) file is read on the host
+    *have_region = false;
+    if (!o.region.empty()) { *region_out = parse_region_arg(o.region, bam); *have_region = true; }
+    *have_include = false;
+    if (!o.include_bed.empty()) {
+        std::map<std::string, uint32_t> name_to_tid;
+        for (uint32_t t = 0; t < bam.ref_names.size(); t++) if (!*have_region || bam.ref_names[t] == region_out->name) name_to_tid[bam.ref_names[t]] = t;
+        include->read(o.include_bed, name_to_tid);
+        *have_include = true;
+    }
+    memset(P, 0, sizeof *P);
+    if (!o.ignore.empty()) { uint32_t c; if (!parse_code(o.ignore, &c)) throw std::runtime_error("failed to parse mod code " + o.ignore); P->numeric_mode = 2; P->collapse_code = c; }
+    if (!o.edge.empty()) {
+        P->edge_filter_on = 1; P->edge_filter_inverted = o.invert_edge;
+        auto c = o.edge.find(',');
+        if (c == std::string::npos) P->edge_filter_start = P->edge_filter_end = (uint32_t)std::stoul(o.edge);
+        else { P->edge_filter_start = (uint32_t)std::stoul(o.edge.substr(0, c)); P->edge_filter_end = (uint32_t)std::stoul(o.edge.substr(c + 1)); }
+    }
+    P->force_allow_implicit = 1;     // the sampler takes implicit lists as they are (no InvalidImplicitMode check outside the pileup)
+    if (mkp_set_params(ctx, P)) throw std::runtime_error(mkp_last_error(ctx));
+    SamplerConfig sc;
+    sc.threads = o.threads; sc.workers = o.threads; sc.sampling_interval_size = o.interval_size;
+    if (o.no_sampling) sc.take_all = true;
+    else if (o.have_frac) { if (o.frac != 1.0) throw std::runtime_error("only --sampling-frac 1.0 is reproducible without the reference's RNG; use -n, -f 1.0 or --no-sampling"); sc.take_all = true; }
+    sc.num_reads = o.num_reads;
+    sc.region = *have_region ? region_out : nullptr;
+    sc.include_unmapped = !(o.only_mapped || *have_include);
+    sc.edge_on = P->edge_filter_on;
+    sc.include = *have_include ? include : nullptr;
+    hist->assign(4 * 1025, 0);
+    uint64_t inexact = 0;
+    Collective solo;
+    if (bam.on_device && bam.have_index()) *n_selected = sample_histogram_indexed(bam, ctx, sc, hist->data(), &inexact, solo, nullptr, keep);
+    else *n_selected = sample_histogram(bam, ctx, sc, hist->data(), &inexact, keep);
+    if (inexact) throw std::runtime_error("sampled probabilities are not multiples of 1/1024 (" + std::to_string(inexact) + " values): exact quantiles impossible");
+}
+
+inline int run_summary(const SampleOptions& o, std::string* text, std::string* error) {
+    try {
+        DeviceGuard dev;
+        { const int rc = mkp_create(o.device, &dev.ctx); if (rc) throw std::runtime_error("no usable CUDA device (mkp_create returned " + std::to_string(rc) + "); this build has no CPU fallback"); }
+        if (o.percentile > 1.0f) throw std::runtime_error("filter percentile must be <= 1.0");
+        BamReader bam;
+        mkp_params P;
+        Region region; bool have_region = false;
+        IncludeBed include; bool have_include = false;
+        std::vector<uint64_t> hist;
+        std::vector<SampledChunk> keep;
+        size_t n_selected = 0;
+        sample_for_summary(o, dev.ctx, bam, &P, &region, &have_region, &include, &have_include, &hist, &keep, &n_selected);
+        ModSummaryOut S;
+        // thresholds (src/commands.rs:1086-1098, 1147-1160)
+        for (auto& raw : o.mod_thresholds) {
+            auto c = raw.find(':');
+            uint32_t code;
+            if (c == std::string::npos || raw.find(':', c + 1) != std::string::npos || !parse_code(raw.substr(0, c), &code))
+                throw std::runtime_error("encountered illegal per-mod threshold: " + raw + ". Should be mod_code:threshold e.g. h:0.8");
+            if (P.n_mod_thresholds >= MKP_MAX_MOD_THRESHOLDS) throw std::runtime_error("too many per-mod thresholds");
+            P.mod_code[P.n_mod_thresholds] = code;
+            P.mod_threshold[P.n_mod_thresholds++] = std::stof(raw.substr(c + 1));
+        }
+        if (!o.filter_thresholds.empty()) {
+            bool have_default = false;
+            for (auto& raw : o.filter_thresholds) {
+                auto c = raw.find(':');
+                if (c == std::string::npos) { if (have_default) throw std::runtime_error("default threshold encountered more than once"); P.default_threshold = std::stof(raw); have_default = true; }
+                else {
+                    const char* B = "ACGT";
+                    const char* f = raw.empty() ? nullptr : strchr(B, raw[0]);
+                    if (!f || !raw[0]) throw std::runtime_error("failed to parse base " + raw);
+                    P.base_threshold_set[f - B] = 1;
+                    P.base_threshold[f - B] = std::stof(raw.substr(c + 1));
+                }
+            }
+        } else if (!o.no_filtering) {
+            for (int b = 0; b < 4; b++) {
+                uint64_t n = 0;
+                for (int k = 0; k <= 1024; k++) n += hist[b * 1025 + k];
+                if (!n) continue;
+                float thr;
+                if (!percentile_from_hist(hist.data() + b * 1025, o.percentile, &thr)) throw std::runtime_error("not enough datapoints to estimate a threshold");
+                P.base_threshold_set[b] = 1; P.base_threshold[b] = thr;
+            }
+        }
+        for (int b = 0; b < 4; b++) { S.thresholds[b] = P.base_threshold[b]; S.threshold_set[b] = P.base_threshold_set[b]; }
+        if (mkp_set_params(dev.ctx, &P)) throw std::runtime_error(mkp_last_error(dev.ctx));
+        // ---- second pass over the sampled reads: counts per (base, state, pass / fail)
+        std::vector<uint32_t> fpos, fneg;
+        const int incl_unal = !(o.only_mapped || have_include) ? 1 : 0;
+        for (auto& kc : keep) {
+            if (kc.pc.recs.empty()) continue;
+            upload_sample_chunk(dev.ctx, kc.pc, kc.tid, have_include ? &include : nullptr, &fpos, &fneg);
+            std::vector<uint64_t> table(4 * 2 * 33, 0), states(32, ~0ull);
+            uint64_t rw[4] = {0, 0, 0, 0};
+            uint32_t obs[4] = {0, 0, 0, 0};
+            if (mkp_sample_summary(dev.ctx, incl_unal, kc.take.data(), table.data(), rw, obs, states.data())) throw std::runtime_error(mkp_last_error(dev.ctx));
+            for (int b = 0; b < 4; b++) {
+                S.reads_with[b] += rw[b];
+                for (int f = 0; f < 2; f++) for (int k = 0; k < 33; k++) {
+                    const uint64_t n = table[(b * 2 + f) * 33 + k];
+                    if (!n) continue;
+                    const uint64_t key = k == 0 ? 0 : state_order_key((uint32_t)states[k - 1]);
+                    (f == 0 ? S.pass[b] : S.fail[b])[key] += n;
+                }
+                for (int id = 0; id < 32; id++) if ((obs[b] >> id) & 1u) S.observed[b].insert(state_order_key((uint32_t)states[id]));
+            }
+            for (uint8_t t : kc.take) S.total_reads += t;
+        }
+        // ---- text
+        std::string& out = *text;
+        out.clear();
+        std::string bases;
+        for (int b = 0; b < 4; b++) if (!S.pass[b].empty() || S.reads_with[b]) { if (!bases.empty()) bases += ","; bases += "ACGT"[b]; }
+        if (o.tsv) {
+            // TsvWriter<ModSummary> (src/writers.rs:609-684), keys in a fixed order
+            out += "mod_bases\t" + bases + "\n";
+            for (int b = 0; b < 4; b++) if (S.reads_with[b]) out += std::string("count_reads_") + "ACGT"[b] + "\t" + std::to_string(S.reads_with[b]) + "\n";
+            for (int b = 0; b < 4; b++) {
+                if (S.pass[b].empty() && !S.reads_with[b]) continue;
+                uint64_t total = 0, total_f = 0;
+                for (auto& kv : S.pass[b]) total += kv.second;
+                for (auto& kv : S.fail[b]) total_f += kv.second;
+                const std::string B(1, "ACGT"[b]);
+                for (auto& kv : S.pass[b]) {
+                    const std::string label = kv.first == 0 ? std::string("unmodified") : "modified_" + state_label_of_key(kv.first);
+                    auto fi = S.fail[b].find(kv.first);
+                    out += B + "_pass_calls_" + label + "\t" + std::to_string(kv.second) + "\n";
+                    out += B + "_pass_frac_" + label + "\t" + f64_display((double)kv.second / (double)total) + "\n";
+                    out += B + "_fail_calls_" + label + "\t" + std::to_string(fi == S.fail[b].end() ? 0 : fi->second) + "\n";
+                }
+                out += B + "_total_mod_calls\t" + std::to_string(total) + "\n";
+                out += B + "_total_fail_mod_calls\t" + std::to_string(total_f) + "\n";
+            }
+            out += "total_reads_used\t" + std::to_string(S.total_reads) + "\n";
+        } else {
+            // TableWriter<ModSummary> (src/writers.rs:394-560): '#'-prefixed metadata, then base / code / pass_count / pass_frac / all_count / all_frac
+            out += "# bases             " + bases + "\n";
+            out += "# total_reads_used  " + std::to_string(S.total_reads) + "\n";
+            for (int b = 0; b < 4; b++) if (S.reads_with[b]) out += std::string("# count_reads_") + "ACGT"[b] + "     " + std::to_string(S.reads_with[b]) + "\n";
+            for (int b = 0; b < 4; b++) if (S.threshold_set[b]) out += std::string("# pass_threshold_") + "ACGT"[b] + "  " + f32_display(S.thresholds[b]) + "\n";
+            if (have_region) out += "# region            " + region.name + ":" + std::to_string(region.start) + "-" + std::to_string(region.end) + "\n";
+            std::vector<std::vector<std::string>> rows;
+            rows.push_back({"base", "code", "pass_count", "pass_frac", "all_count", "all_frac"});
+            for (int b = 0; b < 4; b++) {
+                uint64_t total_p = 0, total_f = 0;
+                for (auto& kv : S.pass[b]) total_p += kv.second;
+                for (auto& kv : S.fail[b]) total_f += kv.second;
+                const uint64_t total = total_p + total_f;
+                std::set<uint64_t> keys;
+                for (auto& kv : S.pass[b]) keys.insert(kv.first);
+                for (uint64_t k : S.observed[b]) keys.insert(k);
+                if (!S.pass[b].empty() || !S.fail[b].empty()) keys.insert(0);           // the canonical row is always shown
+                for (uint64_t k : keys) {
+                    auto pi = S.pass[b].find(k); auto fi = S.fail[b].find(k);
+                    const uint64_t pc = pi == S.pass[b].end() ? 0 : pi->second, fc = fi == S.fail[b].end() ? 0 : fi->second;
+                    rows.push_back({std::string(1, "ACGT"[b]), k == 0 ? std::string("-") : state_label_of_key(k), std::to_string(pc),
+                                    f32_display((float)pc / (float)total_p), std::to_string(pc + fc), f32_display((float)(pc + fc) / (float)total)});
+                }
+            }
+            std::vector<size_t> w(6, 0);
+            for (auto& r : rows) for (size_t i = 0; i < 6; i++) w[i] = std::max(w[i], r[i].size());
+            for (auto& r : rows) { for (size_t i = 0; i < 6; i++) { out += " " + r[i] + std::string(w[i] - r[i].size(), ' ') + " "; } out += "\n"; }
+        }
+        return 0;
+    } catch (const std::exception& e) { if (error) *error = e.what(); return 1; }
+}
+
+// `modkit sample-probs`: percentiles of the arg-max probabilities per canonical base (thresholds table, src/writers.rs:779-790)
+inline int run_sample_probs(const SampleOptions& o, std::string* text, std::string* error) {
+    try {
+        DeviceGuard dev;
+        { const int rc = mkp_create(o.device, &dev.ctx); if (rc) throw std::runtime_error("no usable CUDA device (mkp_create returned " + std::to_string(rc) + "); this build has no CPU fallback"); }
+        std::vector<float> qs;
+        for (size_t i = 0; i < o.percentiles.size();) {
+            size_t j = o.percentiles.find(',', i); if (j == std::string::npos) j = o.percentiles.size();
+            const float q = std::stof(o.percentiles.substr(i, j - i));
+            if (q > 1.0f || q < 0.0f) throw std::runtime_error("percentiles must be between 0 and 1.0");
+            qs.push_back(q);
+            i = j + 1;
+        }
+        BamReader bam;
+        mkp_params P;
+        Region region; bool have_region = false;
+        IncludeBed include; bool have_include = false;
+        std::vector<uint64_t> hist;
+        size_t n_selected = 0;
+        sample_for_summary(o, dev.ctx, bam, &P, &region, &have_region, &include, &have_include, &hist, nullptr, &n_selected);
+        std::vector<std::vector<std::string>> rows;
+        rows.push_back({"base", "percentile", "threshold"});
+        for (int b = 0; b < 4; b++) {
+            uint64_t n = 0;
+            for (int k = 0; k <= 1024; k++) n += hist[b * 1025 + k];
+            if (!n) continue;
+            for (float q : qs) {
+                float v;
+                if (!percentile_from_hist(hist.data() + b * 1025, q, &v)) throw std::runtime_error("not enough datapoints to calculate percentiles");
+                volatile float pct = q * 100.0f;
+                rows.push_back({std::string(1, "ACGT"[b]), f32_display(pct), f32_display(v)});
+            }
+        }
+        std::vector<size_t> w(3, 0);
+        for (auto& r : rows) for (size_t i = 0; i < 3; i++) w[i] = std::max(w[i], r[i].size());
+        text->clear();
+        for (auto& r : rows) { for (size_t i = 0; i < 3; i++) { *text += " " + r[i] + std::string(w[i] - r[i].size(), ' ') + " "; } *text += "\n"; }
+        return 0;
+    } catch (const std::exception& e) { if (error) *error = e.what(); return 1; }
+}
+
+inline bool parse_sample_args(int argc, const char* const* argv, bool summary, SampleOptions* o, std::string* out_path, std::string* err) {
+    std::vector<std::string> pos;
+    for (int i = 0; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) throw std::runtime_error("a value is required for '" + a + "' but none was supplied"); return argv[++i]; };
+        try {
+            if (a == "-t" || a == "--threads") o->threads = std::stoi(val());
+            else if (a == "--region") o->region = val();
+            else if (a == "-n" || a == "--num-reads") o->num_reads = std::stoul(val());
+            else if (a == "-f" || a == "--sampling-frac") { o->have_frac = true; o->frac = std::stod(val()); }
+            else if (a == "--no-sampling") o->no_sampling = true;
+            else if (a == "-i" || a == "--interval-size") o->interval_size = (uint32_t)std::stoul(val());
+            else if (a == "--include-bed" || a == "--include-positions") o->include_bed = val();
+            else if (a == "--only-mapped") o->only_mapped = true;
+            else if (a == "--ignore") o->ignore = val();
+            else if (a == "--edge-filter") o->edge = val();
+            else if (a == "--invert-edge-filter") o->invert_edge = true;
+            else if (a == "--seed" || a == "--log-filepath" || a == "--log") val();
+            else if (a == "--suppress-progress") {}
+            else if (a == "--device") o->device = std::stoi(val());
+            else if (a == "--out") *out_path = val();                 // (this build: write the report to a file instead of stdout)
+            else if (summary && (a == "--filter-threshold" || a == "--pass_threshold")) o->filter_thresholds.push_back(val());
+            else if (summary && (a == "--mod-thresholds" || a == "--mod-threshold")) o->mod_thresholds.push_back(val());
+            else if (summary && a == "--no-filtering") o->no_filtering = true;
+            else if (summary && (a == "-p" || a == "--filter-percentile")) o->percentile = std::stof(val());
+            else if (summary && a == "--tsv") o->tsv = true;
+            else if (summary && a == "--table") o->tsv = false;
+            else if (!summary && (a == "-p" || a == "--percentiles")) o->percentiles = val();
+            else if (!summary && (a == "--hist" || a == "-o" || a == "--out-dir" || a == "--prefix" || a == "--force" || a == "--dna-color" || a == "--mod-color"))
+                throw std::runtime_error("histogram / file outputs of sample-probs (" + a + ") are not provided by this build: the percentile table goes to stdout");
+            else if (a.size() > 1 && a[0] == '-') { *err = "unexpected argument '" + a + "' found"; return false; }
+            else pos.push_back(a);
+        } catch (const std::exception& e) { *err = e.what(); return false; }
+    }
+    if (pos.size() != 1) { *err = "the following required arguments were not provided: <IN_BAM>"; return false; }
+    o->in_bam = pos[0];
     return true;
 }
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mkp_kernels.cuh"
@@ -68,6 +69,12 @@ struct mkp_ctx {
     DevBuf d_pscr;
     uint32_t n_hot = 0, state_cap = 4, p_stride = 0;
     bool fused_attr_set = false, focus_ready = false;
+    // pinned staging buffers for host -> device copies of pageable memory (the mapped BAM file): one per copy thread
+    static constexpr int N_PIN = 6;
+    static constexpr size_t PIN_BYTES = (size_t)16 << 20;
+    void* pin[N_PIN] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pin_ev[N_PIN];
+    bool pin_ready = false;
     std::vector<mkp_row> h_rows;
     std::vector<uint64_t> h_entry_off;
     mkp_row* h_rows_pinned = nullptr;
@@ -151,6 +158,7 @@ void mkp_destroy(mkp_ctx* ctx) {
                       &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
+    if (ctx->pin_ready) for (int i = 0; i < mkp_ctx::N_PIN; i++) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_ev[i]); }
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->stream2);
@@ -609,6 +617,49 @@ int mkp_sample_histogram(mkp_ctx* ctx, int include_unaligned, const uint8_t* tak
 }
 
 
+// `modkit summary` support: the calls of the reads flagged in `take`, classed with the thresholds of mkp_set_params
+// (src/summarize.rs:117-252). Adds to table[4][2][33] (base, pass/fail, 0 canonical | 1 + state), reads_with[4], obs[4];
+// states[32] receives the (base << 32 | code) key of every state id (~0 = unused).
+int mkp_sample_summary(mkp_ctx* ctx, int include_unaligned, const uint8_t* take, uint64_t* table, uint64_t* reads_with, uint32_t* obs, uint64_t* states) {
+    if (!ctx || !table || !reads_with || !obs || !states) return -1;
+    if (!ctx->have_params) return fail(ctx, "mkp_set_params was not called");
+    if (ctx->ce <= ctx->cs) return fail(ctx, "no resident chunk");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ChunkDev C;
+    const int grid = decode_grid(ctx, ctx->n_reads);
+    if (int rc = prepare_decode(ctx, &C, grid)) return rc;
+    CK(cudaMemsetAsync(ctx->d_small.p, 0xff, 32 * 8, st));
+    CK(cudaMemsetAsync(ctx->d_small.as<uint8_t>() + 32 * 8, 0, SMALL_BYTES - 32 * 8, st));
+    C.hist_include_unaligned = include_unaligned ? 1 : 0;
+    if (take) {
+        CK(ctx->d_take.ensure(std::max<size_t>(1, ctx->n_reads)));
+        CK(cudaMemcpyAsync(ctx->d_take.p, take, ctx->n_reads, cudaMemcpyHostToDevice, st));
+        C.take = ctx->d_take.as<uint8_t>();
+    }
+    const size_t words = 4 * 2 * 33 + 4 + 2;
+    CK(ctx->d_hist.ensure(std::max<size_t>(4 * 1025, words) * 8));
+    CK(cudaMemsetAsync(ctx->d_hist.p, 0, words * 8, st));
+    C.summ = ctx->d_hist.as<unsigned long long>();
+    C.mode = MODE_HIST;
+    ctx->launches += 3;
+    if (ctx->n_reads) { k_parse<<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST, true><<<grid, 128, 0, st>>>(C); k_resolve<MODE_HIST, false><<<grid, 128, 0, st>>>(C); }
+    CK(cudaGetLastError());
+    std::vector<uint64_t> h(words);
+    uint32_t h_small[2];
+    uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
+    CK(cudaMemcpyAsync(h_small, u, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h.data(), ctx->d_hist.p, words * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(states, ctx->d_small.p, 32 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_small[1]) return fail(ctx, "device decode error: " + derr_text(h_small[1]), -10);
+    for (int i = 0; i < 4 * 2 * 33; i++) table[i] += h[i];
+    for (int b = 0; b < 4; b++) reads_with[b] += h[4 * 2 * 33 + b];
+    const uint32_t* o32 = (const uint32_t*)(h.data() + 4 * 2 * 33 + 4);
+    for (int b = 0; b < 4; b++) obs[b] = o32[b];
+    return 0;
+}
+
 // ---- BGZF / BAM ingest on the device (mkp_ingest.cuh) -----------------------------------------------------
 int mkp_device_memory(mkp_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
     if (!ctx) return -1;
@@ -617,6 +668,38 @@ int mkp_device_memory(mkp_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
     CK(cudaMemGetInfo(&f, &t));
     if (free_bytes) *free_bytes = f;
     if (total_bytes) *total_bytes = t;
+    return 0;
+}
+
+// Pageable host memory -> device at link speed: N_PIN host threads copy 16 MB pieces into their own pinned buffer and enqueue the
+// transfer (a plain cudaMemcpyAsync from pageable memory is staged by the driver at ~10 GB/s). All transfers go to `st`.
+static int copy_pageable_h2d(mkp_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t n, cudaStream_t st) {
+    if (n < ((size_t)8 << 20)) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st)); return 0; }
+    if (!ctx->pin_ready) {
+        for (int i = 0; i < mkp_ctx::N_PIN; i++) { CK(cudaMallocHost(&ctx->pin[i], mkp_ctx::PIN_BYTES)); CK(cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming)); }
+        ctx->pin_ready = true;
+    }
+    const size_t piece = mkp_ctx::PIN_BYTES;
+    const size_t n_piece = (n + piece - 1) / piece;
+    const int nt = (int)std::min<size_t>(mkp_ctx::N_PIN, n_piece);
+    std::vector<cudaError_t> errs(nt, cudaSuccess);
+    auto work = [&](int t) {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        for (size_t k = t; k < n_piece && e == cudaSuccess; k += nt) {
+            const size_t off = k * piece, len = std::min(piece, n - off);
+            e = cudaEventSynchronize(ctx->pin_ev[t]);              // the previous transfer out of this buffer is done
+            if (e != cudaSuccess) break;
+            memcpy(ctx->pin[t], src + off, len);
+            e = cudaMemcpyAsync(dst + off, ctx->pin[t], len, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->pin_ev[t], st);
+        }
+        errs[t] = e;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (cudaError_t e : errs) if (e != cudaSuccess) return fail(ctx, std::string("host to device copy: ") + cudaGetErrorString(e));
     return 0;
 }
 
@@ -679,7 +762,7 @@ int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const
     for (size_t sl = 0; sl < n_slabs; sl++) {
         const size_t a = sl == 0 ? 0 : (size_t)members[cut[sl]].in_off;
         const size_t b = sl + 1 == n_slabs ? file_len : (size_t)members[cut[sl + 1]].in_off;
-        CK(cudaMemcpyAsync(ctx->d_file.as<uint8_t>() + a, file + a, b - a, cudaMemcpyHostToDevice, ctx->stream2));
+        if (int rc = copy_pageable_h2d(ctx, ctx->d_file.as<uint8_t>() + a, file + a, b - a, ctx->stream2)) return rc;
         CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         const size_t nm = cut[sl + 1] - cut[sl];

@@ -349,6 +349,9 @@ __global__ void k_walk(const uint8_t* __restrict__ bam, uint64_t total, const ui
             rec.tid = (int32_t)ld_u32(r); rec.pos = (int32_t)ld_u32(r + 4);
             const uint32_t l_name = r[8], n_cig = ld_u16(r + 12), flag = ld_u16(r + 14);
             rec.flag = flag; rec.l_seq = ld_u32(r + 16);
+            // the fixed fields must fit the record (a corrupt or hostile file must not send the slicer out of bounds)
+            { const int32_t ls = (int32_t)rec.l_seq; const unsigned long long lq = ls > 0 ? (unsigned long long)ls : 0ull;
+              if (32ull + l_name + 4ull * n_cig + (lq + 1) / 2 + lq > bs) { atomicCAS(status, 0u, 0x80000000u | 1u); break; } }
             // htslib bam_endpos: pos + reference length of the CIGAR (1 when unmapped or without CIGAR)
             unsigned long long span = 0;
             if (!(flag & 4) && n_cig && 32ull + l_name + 4ull * n_cig <= bs) {

@@ -92,6 +92,10 @@ struct ChunkDev {
     unsigned long long* hist_inexact;
     const uint8_t* take;
     uint32_t hist_include_unaligned;
+    // `modkit summary` (src/summarize.rs:117-252): with the caller's thresholds in c_par, every value of MODE_HIST is also classed
+    // by (thresholded call, arg-max call): summ[((base * 2 + fail) * 33) + s], s = 0 canonical, 1 + state id; then reads per base
+    // [4] and, as u32, the states observed per base [4]. nullptr = off.
+    unsigned long long* summ;
     uint32_t mode;              // MODE_PILEUP / MODE_HIST (admission rules of k_parse)
     struct ReadLists* rl;
     // chunks with focus bitmaps (the hot bitmap is the focus set, ranked at upload, and is not written):
@@ -986,6 +990,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
         uint32_t pos_mask = 0, neg_mask = 0;
         bool table_survived = false;
         uint32_t imp_explicit[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // HIST: explicit values on implicit tables (per lane)
+        uint32_t sum_obs[4] = {0, 0, 0, 0};                    // summary: states seen per canonical base (per lane)
         uint2* calls = C.calls + meta.entry_off;
         if (!err && any_entries) {
             const bool trim_ok = !c_par.edge_on || !(L <= c_par.edge_start || L <= c_par.edge_end);
@@ -1128,6 +1133,33 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                                         if (n2c >= 1) { mp = p0; hm2 = true; }
                                         if (n2c == 2 && p1 >= mp) mp = p1;
                                         hv = (hm2 && mp > cp) ? mp : cp;
+                                        if (C.summ) {
+                                            // thresholded call (as in the pileup) and arg-max call (last maximum wins, mod_bam.rs:489-505)
+                                            uint32_t s0 = 0, s1 = 0;
+                                            if (n2c >= 1) { s0 = (uint32_t)state_id(C, scache, tb, c0); mask |= 1u << s0; }
+                                            if (n2c == 2) { s1 = (uint32_t)state_id(C, scache, tb, c1); mask |= 1u << s1; }
+                                            const float base_thr = c_par.base_set[tb] ? c_par.base_thr[tb] : c_par.default_thr;
+                                            bool have = false;
+                                            float best = 0.f;
+                                            uint32_t tk = 0, ts = 0;
+                                            for (int k2 = 0; k2 < n2c; k2++) {
+                                                const uint32_t cc = k2 == 0 ? c0 : c1;
+                                                const float pp = k2 == 0 ? p0 : p1;
+                                                float thr = base_thr;
+                                                if (c_par.n_mod_thr) {
+                                                    const uint32_t any_code = (uint32_t)("ACGT"[tb]);
+                                                    bool fnd = false;
+                                                    for (uint32_t t = 0; t < c_par.n_mod_thr && !fnd; t++) if (c_par.mod_code[t] == cc) { thr = c_par.mod_thr[t]; fnd = true; }
+                                                    for (uint32_t t = 0; t < c_par.n_mod_thr && !fnd; t++) if (c_par.mod_code[t] == any_code) { thr = c_par.mod_thr[t]; fnd = true; }
+                                                }
+                                                if (pp >= thr && (!have || pp >= best)) { have = true; best = pp; tk = 2; ts = k2 == 0 ? s0 : s1; }
+                                            }
+                                            if (cp >= base_thr && (!have || cp >= best)) { have = true; tk = 1; }
+                                            if (!have) tk = 0;
+                                            const uint32_t as = (n2c == 2 && p1 >= p0) ? s1 : s0;
+                                            const uint32_t ak = (hm2 && mp > cp) ? 2u : 1u;
+                                            ccode = tk | (ts << 2) | (ak << 8) | (as << 10);     // summary record of this value
+                                        }
                                     }
                                 }
                             } else {
@@ -1176,7 +1208,27 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                                 if (MODE == MODE_PILEUP) {
                                     for (int k2 = 0; k2 < use->n; k2++) mask |= 1u << state_id(C, scache, tb, use->code[k2]);
                                     kind = make_call_items(*use, ord, tb, &ccode);
-                                } else hv = argmax_items(*use, ord);
+                                } else {
+                                    hv = argmax_items(*use, ord);
+                                    if (C.summ) {
+                                        uint32_t tcode = 0;
+                                        const int tkind = make_call_items(*use, ord, tb, &tcode);
+                                        uint32_t ts = 0, as = 0;
+                                        if (tkind == 2) ts = (uint32_t)state_id(C, scache, tb, tcode);
+                                        const float cp2 = __fsub_rn(1.0f, items_sum(*use, ord));
+                                        bool hm = false;
+                                        float mp2 = 0.f;
+                                        uint32_t acode = 0;
+                                        for (int k2 = 0; k2 < use->n; k2++) {
+                                            mask |= 1u << state_id(C, scache, tb, use->code[k2]);
+                                            const float v = use->p[ord[k2]];
+                                            if (!hm || v >= mp2) { hm = true; mp2 = v; acode = use->code[ord[k2]]; }
+                                        }
+                                        const uint32_t ak = (hm && mp2 > cp2) ? 2u : 1u;
+                                        if (ak == 2) as = (uint32_t)state_id(C, scache, tb, acode);
+                                        ccode = (uint32_t)tkind | (ts << 2) | (ak << 8) | (as << 10);
+                                    }
+                                }
                             }
                             }
                             if (!e2) {
@@ -1231,6 +1283,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                                         }
                                         if (pass) {
                                             hist_ok = true; hist_v = hv; hist_base = tb;
+                                            if (C.summ) { hist_v = __uint_as_float(ccode); sum_obs[tb] |= mask; }
                                             if (!FAST_ONLY && imp_lists[st][b]) imp_explicit[st * 4 + b]++;
                                         }
                                     }
@@ -1253,7 +1306,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                         uint32_t hm = __ballot_sync(FULL, hist_ok);
                         if (hist_ok) {
                             // stash (bin | base<<16 | inexact<<20) in the call buffer; committed after validation
-                            float sc = __fmul_rn(hist_v, 1024.0f);
+                            float sc = __fmul_rn(C.summ ? 0.f : hist_v, 1024.0f);
                             int bin = (int)rintf(sc);
                             uint32_t inexact = ((float)bin != sc || bin < 0 || bin > 1024) ? 1u : 0u;
                             if (bin < 0) bin = 0;
@@ -1305,6 +1358,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                     const uint32_t state = kind == 0 ? 0u : kind == 1 ? 1u : 2u + (uint32_t)state_id(C, scache, tb, code);
                     imp_meta[s] |= (0x80u | state) << (8 * b);
                 } else {
+                    if (C.summ) for (int k = 0; k < use->n; k++) sum_obs[tb] |= 1u << state_id(C, scache, tb, use->code[k]);
                     // values: argmax of an all-zero map = canonical probability 1.0 for every passing inferred position
                     unsigned long long n_pass = 0;
                     if (C.hist_include_unaligned && !C.focus_pos) {
@@ -1386,6 +1440,35 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
                 unsigned long long extra = 0;
                 for (int sb = 0; sb < 8; sb++) extra += imp_hist[sb];
                 meta.n_hist = n_hist + (uint32_t)(extra < 0x7fffffffull ? extra : 0x7fffffffull);
+                if (C.summ) {
+                    uint32_t seen = 0;
+                    for (uint32_t k = lane; k < n_hist; k += 32) {
+                        const uint2 v = calls[k];
+                        const uint32_t tb = (v.x >> 16) & 3u, tk = v.y & 3u, ts = (v.y >> 2) & 63u, ak = (v.y >> 8) & 3u, as = (v.y >> 10) & 63u;
+                        seen |= 1u << tb;
+                        // pass: the thresholded call; fail: filed under the arg-max call (src/summarize.rs:186-214)
+                        if (tk == 1) atomicAdd(&C.summ[(tb * 2 + 0) * 33 + 0], 1ull);
+                        else if (tk == 2) atomicAdd(&C.summ[(tb * 2 + 0) * 33 + 1 + ts], 1ull);
+                        else if (ak == 1) atomicAdd(&C.summ[(tb * 2 + 1) * 33 + 0], 1ull);
+                        else atomicAdd(&C.summ[(tb * 2 + 1) * 33 + 1 + as], 1ull);
+                    }
+                    seen = __reduce_or_sync(FULL, seen);
+                    uint32_t obs[4];
+                    for (int b = 0; b < 4; b++) obs[b] = __reduce_or_sync(FULL, sum_obs[b]);
+                    if (lane == 0) {
+                        for (int sb = 0; sb < 8; sb++) if (imp_hist[sb]) {
+                            const int tb = (sb >> 2) == 0 ? (sb & 3) : 3 - (sb & 3);
+                            // an inferred entry is the all-zero map: canonical with probability 1.0
+                            const float base_thr = c_par.base_set[tb] ? c_par.base_thr[tb] : c_par.default_thr;
+                            atomicAdd(&C.summ[(tb * 2 + (1.0f >= base_thr ? 0 : 1)) * 33 + 0], imp_hist[sb]);
+                            seen |= 1u << tb;
+                        }
+                        for (int b = 0; b < 4; b++) {
+                            if ((seen >> b) & 1u) atomicAdd(&C.summ[4 * 2 * 33 + b], 1ull);
+                            if (obs[b]) atomicOr((uint32_t*)(C.summ + 4 * 2 * 33 + 4) + b, obs[b]);
+                        }
+                    }
+                }
                 if (C.hist) {
                     for (uint32_t k = lane; k < n_hist; k += 32) {
                         uint32_t v = calls[k].x;

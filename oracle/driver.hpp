@@ -8,6 +8,9 @@
 //                          src/reads_sampler/record_sampler.rs, src/read_ids_to_base_mod_probs.rs:223-362,965-1069
 //   bedMethyl writer       src/writers.rs:43-183
 #pragma once
+#include <set>
+#include <charconv>
+#include <cmath>
 #include <charconv>
 #include <cmath>
 #include <functional>
@@ -337,7 +340,7 @@ struct SampleOptions {
 };
 
 // values (argmax probabilities) per canonical base from one record; false when the record contributes nothing
-inline bool sample_record(const BamRecord& r, const SampleOptions& o, std::vector<float> vals[4]) {
+inline bool sample_record(const BamRecord& r, const SampleOptions& o, std::vector<float> vals[4], std::vector<BaseModProbs>* probs = nullptr) {
     ModBaseInfo info;
     std::string fwd;
     if (!decode_mod_base_info(r, &info, &fwd) || info.is_empty()) return false;
@@ -364,6 +367,7 @@ inline bool sample_record(const BamRecord& r, const SampleOptions& o, std::vecto
             }
             BaseModProbs bmp = o.collapse ? redistribute(kv.second, o.collapse_code) : kv.second;
             vals[cb].push_back(argmax_prob(bmp));
+            if (probs) probs[cb].push_back(bmp);
             kept++;
         }
         if (kept) added = true;
@@ -381,7 +385,7 @@ inline bool sampler_admits(const BamRecord& r, bool only_mapped_or_edge) {
 
 // Returns per-base thresholds (base_set / base_thr of the Caller)
 inline void estimate_thresholds(const BamFile& bam, const SampleOptions& o, float percentile, Caller* caller,
-                                std::vector<float> all_vals_out[4] = nullptr) {
+                                std::vector<float> all_vals_out[4] = nullptr, std::vector<const BamRecord*>* selected_out = nullptr) {
     // 1. index stats restricted to the region's contig
     int region_tid = o.region ? bam.tid_of(o.region->name) : -1;
     if (o.region && region_tid < 0) throw std::runtime_error("did not find target_id for region in header");
@@ -488,7 +492,7 @@ inline void estimate_thresholds(const BamFile& bam, const SampleOptions& o, floa
                     seen_here.insert(r.data);
                     returned++;
                     used++;
-                    if (seen.insert(r.data).second) for (int b = 0; b < 4; b++) vals[b].insert(vals[b].end(), v[b].begin(), v[b].end());
+                    if (seen.insert(r.data).second) { for (int b = 0; b < 4; b++) vals[b].insert(vals[b].end(), v[b].begin(), v[b].end()); if (selected_out) selected_out->push_back(&r); }
                 }
             }
             sampled_so_far[g.tid] += returned;
@@ -509,7 +513,7 @@ inline void estimate_thresholds(const BamFile& bam, const SampleOptions& o, floa
             std::vector<float> v[4];
             if (sample_record(r, o, v)) {
                 used++;
-                if (seen.insert(r.data).second) for (int b = 0; b < 4; b++) vals[b].insert(vals[b].end(), v[b].begin(), v[b].end());
+                if (seen.insert(r.data).second) { for (int b = 0; b < 4; b++) vals[b].insert(vals[b].end(), v[b].begin(), v[b].end()); if (selected_out) selected_out->push_back(&r); }
             }
         }
     }
@@ -520,6 +524,107 @@ inline void estimate_thresholds(const BamFile& bam, const SampleOptions& o, floa
         caller->base_thr[b] = percentile_linear_interp(vals[b], percentile);
         if (all_vals_out) all_vals_out[b] = vals[b];
     }
+}
+
+// --- `modkit summary` (src/summarize.rs:117-252) and the two report formats (src/writers.rs:394-684) ------------------------
+// The reference prints hash maps in their iteration order; rows here are ordered: bases A C G T, canonical before modified
+// states, codes in ModCodeRepr order (the same order the product prints).
+struct ModSummaryOut {
+    uint64_t reads_with[4] = {0, 0, 0, 0};
+    std::map<uint64_t, uint64_t> pass[4], fail[4];      // key 0 = canonical, else 1 + code order key
+    std::set<uint64_t> observed[4];
+    uint64_t total_reads = 0;
+};
+inline uint64_t state_order_key(ModCode c) { return 1ull + ((c & 0x80000000u) ? (1ull << 32) + (c & 0x7fffffffu) : (uint64_t)c); }
+inline std::string state_label_of_key(uint64_t k) { return k > (1ull << 32) ? std::to_string(k - 1 - (1ull << 32)) : std::string(1, (char)(k - 1)); }
+
+inline void summarize_reads(const std::vector<const BamRecord*>& selected, const SampleOptions& o, const Caller& caller, ModSummaryOut* S) {
+    for (const BamRecord* rp : selected) {
+        std::vector<float> v[4];
+        std::vector<BaseModProbs> probs[4];
+        if (!sample_record(*rp, o, v, probs)) continue;
+        S->total_reads++;
+        for (int b = 0; b < 4; b++) {
+            if (probs[b].empty()) continue;
+            S->reads_with[b]++;
+            for (const BaseModProbs& bmp : probs[b]) {
+                bmp.probs.for_each([&](ModCode c, float) { S->observed[b].insert(state_order_key(c)); });
+                const Call tc = make_call(caller, b, bmp);
+                // arg-max call (mod_bam.rs:489-505), last maximum wins
+                const float cp = bmp.canonical_prob();
+                bool have = false; float mp = 0.f; ModCode mc = 0;
+                bmp.probs.for_each([&](ModCode c, float p) { if (!have || p >= mp) { have = true; mp = p; mc = c; } });
+                const bool arg_mod = have && mp > cp;
+                if (tc.kind == CALL_CANONICAL) S->pass[b][0]++;
+                else if (tc.kind == CALL_MODIFIED) S->pass[b][state_order_key(tc.code)]++;
+                else if (arg_mod) S->fail[b][state_order_key(mc)]++;
+                else S->fail[b][0]++;
+            }
+        }
+    }
+}
+
+inline std::string f64_display(double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+    char buf[400];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+}
+inline std::string f32_display(float v);
+
+inline std::string summary_text(const ModSummaryOut& S, const Caller& caller, bool tsv, const std::string& region_text) {
+    std::string out, bases;
+    for (int b = 0; b < 4; b++) if (!S.pass[b].empty() || S.reads_with[b]) { if (!bases.empty()) bases += ","; bases += BASES[b]; }
+    if (tsv) {
+        out += "mod_bases\t" + bases + "\n";
+        for (int b = 0; b < 4; b++) if (S.reads_with[b]) out += std::string("count_reads_") + BASES[b] + "\t" + std::to_string(S.reads_with[b]) + "\n";
+        for (int b = 0; b < 4; b++) {
+            if (S.pass[b].empty() && !S.reads_with[b]) continue;
+            uint64_t total = 0, total_f = 0;
+            for (auto& kv : S.pass[b]) total += kv.second;
+            for (auto& kv : S.fail[b]) total_f += kv.second;
+            const std::string B(1, BASES[b]);
+            for (auto& kv : S.pass[b]) {
+                const std::string label = kv.first == 0 ? std::string("unmodified") : "modified_" + state_label_of_key(kv.first);
+                auto fi = S.fail[b].find(kv.first);
+                out += B + "_pass_calls_" + label + "\t" + std::to_string(kv.second) + "\n";
+                out += B + "_pass_frac_" + label + "\t" + f64_display((double)kv.second / (double)total) + "\n";
+                out += B + "_fail_calls_" + label + "\t" + std::to_string(fi == S.fail[b].end() ? 0 : fi->second) + "\n";
+            }
+            out += B + "_total_mod_calls\t" + std::to_string(total) + "\n";
+            out += B + "_total_fail_mod_calls\t" + std::to_string(total_f) + "\n";
+        }
+        out += "total_reads_used\t" + std::to_string(S.total_reads) + "\n";
+        return out;
+    }
+    out += "# bases             " + bases + "\n";
+    out += "# total_reads_used  " + std::to_string(S.total_reads) + "\n";
+    for (int b = 0; b < 4; b++) if (S.reads_with[b]) out += std::string("# count_reads_") + BASES[b] + "     " + std::to_string(S.reads_with[b]) + "\n";
+    for (int b = 0; b < 4; b++) if (caller.base_set[b]) out += std::string("# pass_threshold_") + BASES[b] + "  " + f32_display(caller.base_thr[b]) + "\n";
+    if (!region_text.empty()) out += "# region            " + region_text + "\n";
+    std::vector<std::vector<std::string>> rows;
+    rows.push_back({"base", "code", "pass_count", "pass_frac", "all_count", "all_frac"});
+    for (int b = 0; b < 4; b++) {
+        uint64_t total_p = 0, total_f = 0;
+        for (auto& kv : S.pass[b]) total_p += kv.second;
+        for (auto& kv : S.fail[b]) total_f += kv.second;
+        const uint64_t total = total_p + total_f;
+        std::set<uint64_t> keys;
+        for (auto& kv : S.pass[b]) keys.insert(kv.first);
+        for (uint64_t k : S.observed[b]) keys.insert(k);
+        if (!S.pass[b].empty() || !S.fail[b].empty()) keys.insert(0);
+        for (uint64_t k : keys) {
+            auto pi = S.pass[b].find(k); auto fi = S.fail[b].find(k);
+            const uint64_t pc = pi == S.pass[b].end() ? 0 : pi->second, fc = fi == S.fail[b].end() ? 0 : fi->second;
+            rows.push_back({std::string(1, BASES[b]), k == 0 ? std::string("-") : state_label_of_key(k), std::to_string(pc),
+                            f32_display((float)pc / (float)total_p), std::to_string(pc + fc), f32_display((float)(pc + fc) / (float)total)});
+        }
+    }
+    std::vector<size_t> w(6, 0);
+    for (auto& r : rows) for (size_t i = 0; i < 6; i++) w[i] = std::max(w[i], r[i].size());
+    for (auto& r : rows) { for (size_t i = 0; i < 6; i++) { out += " " + r[i] + std::string(w[i] - r[i].size(), ' ') + " "; } out += "\n"; }
+    return out;
 }
 
 // --- bedMethyl writer (writers.rs:87-156) ---------------------------------------------------------

@@ -80,9 +80,115 @@ static int kat_main(int argc, char** argv) {
     return 2;
 }
 
+// modkit_oracle summary|sample-probs [flags] <in.bam>  (src/commands.rs:549-1190): report on stdout
+static int sample_main(int argc, char** argv) {
+    const bool summary = std::string(argv[1]) == "summary";
+    std::vector<std::string> pos, filter_thresholds, mod_thresholds;
+    int threads = 4;
+    uint32_t interval_size = 1000000;
+    size_t num_reads = 10042;
+    bool have_frac = false, no_sampling = false, no_filtering = false, only_mapped = false, invert_edge = false, tsv = false;
+    double frac = 0;
+    float percentile = 0.1f;
+    std::string region_s, include_bed, ignore_s, edge_s, percentiles = "0.1,0.5,0.9";
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) die("missing value for " + a); return argv[++i]; };
+        if (a == "-t" || a == "--threads") threads = std::stoi(val());
+        else if (a == "--region") region_s = val();
+        else if (a == "-n" || a == "--num-reads") num_reads = std::stoul(val());
+        else if (a == "-f" || a == "--sampling-frac") { have_frac = true; frac = std::stod(val()); }
+        else if (a == "--no-sampling") no_sampling = true;
+        else if (a == "-i" || a == "--interval-size") interval_size = (uint32_t)std::stoul(val());
+        else if (a == "--include-bed") include_bed = val();
+        else if (a == "--only-mapped") only_mapped = true;
+        else if (a == "--ignore") ignore_s = val();
+        else if (a == "--edge-filter") edge_s = val();
+        else if (a == "--invert-edge-filter") invert_edge = true;
+        else if (summary && a == "--filter-threshold") filter_thresholds.push_back(val());
+        else if (summary && a == "--mod-thresholds") mod_thresholds.push_back(val());
+        else if (summary && a == "--no-filtering") no_filtering = true;
+        else if (summary && (a == "-p" || a == "--filter-percentile")) percentile = std::stof(val());
+        else if (summary && a == "--tsv") tsv = true;
+        else if (!summary && (a == "-p" || a == "--percentiles")) percentiles = val();
+        else if (a.size() > 1 && a[0] == '-') die("unexpected argument " + a);
+        else pos.push_back(a);
+    }
+    if (pos.size() != 1) die("usage: modkit_oracle " + std::string(argv[1]) + " [flags] <in.bam>");
+    BamFile bam;
+    bam.load(pos[0], threads);
+    Region region;
+    const Region* rp = nullptr;
+    if (!region_s.empty()) { region = parse_region(region_s, bam); rp = &region; }
+    PositionFilter pfilter;
+    const PositionFilter* pf = nullptr;
+    if (!include_bed.empty()) {
+        std::map<std::string, uint32_t> name_to_tid;
+        for (auto& c : get_targets(bam, rp)) name_to_tid[c.name] = c.tid;
+        pfilter.load(include_bed, name_to_tid);
+        pf = &pfilter;
+    }
+    SampleOptions so;
+    so.threads = threads; so.sampling_interval_size = interval_size;
+    if (no_sampling) so.frac_all = true;
+    else if (have_frac) { if (frac != 1.0) die("oracle supports only -f 1.0"); so.frac_all = true; }
+    so.num_reads = num_reads;
+    so.region = rp;
+    so.include_unmapped = !(only_mapped || pf);
+    if (!ignore_s.empty()) { so.collapse = true; if (!parse_mod_code(ignore_s, &so.collapse_code)) die("failed to parse mod code " + ignore_s); }
+    if (!edge_s.empty()) {
+        so.edge.on = true; so.edge.inverted = invert_edge;
+        auto c = edge_s.find(',');
+        if (c == std::string::npos) so.edge.start = so.edge.end = std::stoul(edge_s);
+        else { so.edge.start = std::stoul(edge_s.substr(0, c)); so.edge.end = std::stoul(edge_s.substr(c + 1)); }
+    }
+    so.pf = pf;
+    Caller est;
+    std::vector<float> vals[4];
+    std::vector<const BamRecord*> selected;
+    estimate_thresholds(bam, so, percentile, &est, vals, &selected);
+    std::string text;
+    if (!summary) {
+        std::vector<std::vector<std::string>> rows;
+        rows.push_back({"base", "percentile", "threshold"});
+        std::vector<float> qs;
+        for (size_t i = 0; i < percentiles.size();) { size_t j = percentiles.find(',', i); if (j == std::string::npos) j = percentiles.size(); qs.push_back(std::stof(percentiles.substr(i, j - i))); i = j + 1; }
+        for (int b = 0; b < 4; b++) {
+            if (vals[b].empty()) continue;
+            for (float q : qs) { volatile float pct = q * 100.0f; rows.push_back({std::string(1, BASES[b]), f32_display(pct), f32_display(percentile_linear_interp(vals[b], q))}); }
+        }
+        std::vector<size_t> w(3, 0);
+        for (auto& r : rows) for (size_t i = 0; i < 3; i++) w[i] = std::max(w[i], r[i].size());
+        for (auto& r : rows) { for (size_t i = 0; i < 3; i++) text += " " + r[i] + std::string(w[i] - r[i].size(), ' ') + " "; text += "\n"; }
+    } else {
+        Caller caller;
+        for (auto& raw : mod_thresholds) {
+            auto c = raw.find(':');
+            ModCode code;
+            if (c == std::string::npos || !parse_mod_code(raw.substr(0, c), &code)) die("encountered illegal per-mod threshold: " + raw);
+            caller.mod_thr.push_back({code, std::stof(raw.substr(c + 1))});
+        }
+        if (!filter_thresholds.empty()) {
+            for (auto& raw : filter_thresholds) {
+                auto c = raw.find(':');
+                if (c == std::string::npos) caller.default_thr = std::stof(raw);
+                else { const char* f = strchr(BASES, raw[0]); if (!f || !raw[0]) die("failed to parse base " + raw); caller.base_set[f - BASES] = true; caller.base_thr[f - BASES] = std::stof(raw.substr(c + 1)); }
+            }
+        } else if (!no_filtering) {
+            for (int b = 0; b < 4; b++) { caller.base_set[b] = est.base_set[b]; caller.base_thr[b] = est.base_thr[b]; }
+        }
+        ModSummaryOut S;
+        summarize_reads(selected, so, caller, &S);
+        text = summary_text(S, caller, tsv, rp ? rp->name + ":" + std::to_string(rp->start) + "-" + std::to_string(rp->end) : std::string());
+    }
+    fwrite(text.data(), 1, text.size(), stdout);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     try {
         if (argc >= 2 && (std::string(argv[1]) == "decode" || std::string(argv[1]) == "call" || std::string(argv[1]) == "percentile")) return kat_main(argc, argv);
+        if (argc >= 2 && (std::string(argv[1]) == "summary" || std::string(argv[1]) == "sample-probs")) return sample_main(argc, argv);
         if (argc < 2 || std::string(argv[1]) != "pileup") die("usage: modkit_oracle pileup [flags] <in.bam> <out.bed>");
         std::vector<std::string> pos;
         int threads = 4;

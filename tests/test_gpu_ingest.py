@@ -107,6 +107,8 @@ def fake_bam(payloads):
     out = [b"BAM\x01", struct.pack("<I", 0), struct.pack("<I", 0)]
     for p in payloads:
         assert len(p) >= 32
+        # consistent fixed fields (l_read_name = n_cigar = l_seq = 0): the record walk rejects records whose fields exceed them
+        p = p[:8] + b"\x00" + p[9:12] + b"\x00\x00" + p[14:16] + b"\x00\x00\x00\x00" + p[20:]
         out.append(struct.pack("<I", len(p)) + p)
     return b"".join(out)
 
