@@ -529,6 +529,37 @@ inline std::string code_text(uint32_t code) { return (code & 0x80000000u) ? std:
 // strand combination (pileup/mod.rs:469-561).
 inline void finish_interval_rows(const RefInterval& iv, const mkp_row* rows, size_t n, const std::vector<MotifSpec>* motifs,
                                  bool combine_strands, std::vector<OutRow>* out) {
+    if (iv.flat_valid && combine_strands && motifs) {
+        // one two-base palindromic motif (CG): the '+' rows at a site and the '-' rows at site + 1 are summed per code, in code
+        // order (the BTreeMap of combine_strand_features); rows are position sorted, so one forward walk does it
+        size_t i = 0;
+        for (const auto& site : iv.flat) {
+            if (!(site.second & 1)) continue;
+            const uint32_t p = site.first;
+            while (i < n && rows[i].pos < p) i++;
+            mkp_row acc[40];             // (the device knows at most 32 (base, code) states)
+            int na = 0;
+            const bool minus_ok = (iv.flat_rule(p + 1) & 2) != 0;
+            for (size_t j = i; j < n && rows[j].pos <= p + 1; j++) {
+                const mkp_row& r = rows[j];
+                if (!((r.pos == p && r.strand == '+') || (r.pos == p + 1 && r.strand == '-' && minus_ok))) continue;
+                int k = 0;
+                while (k < na && acc[k].code != r.code) k++;
+                if (k == na) {
+                    if (na == 40) break;
+                    memset(&acc[na], 0, sizeof(mkp_row));
+                    acc[na].pos = p; acc[na].code = r.code; acc[na].strand = '.'; acc[na].primary_base = r.primary_base;
+                    na++;
+                }
+                mkp_row& A = acc[k];
+                A.n_mod += r.n_mod; A.n_canon += r.n_canon; A.n_other += r.n_other; A.n_delete += r.n_delete;
+                A.n_filtered += r.n_filtered; A.n_diff += r.n_diff; A.n_nocall += r.n_nocall;
+            }
+            for (int a = 1; a < na; a++) { const mkp_row key = acc[a]; int b = a; while (b > 0 && acc[b - 1].code > key.code) { acc[b] = acc[b - 1]; b--; } acc[b] = key; }
+            for (int a = 0; a < na; a++) out->push_back({acc[a], 0, '.'});
+        }
+        return;
+    }
     std::vector<OutRow> tmp;
     for (size_t i = 0; i < n; i++) {
         const mkp_row& r = rows[i];

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <future>
 #include <filesystem>
 #include <set>
 #include <unordered_set>
@@ -83,6 +84,8 @@ struct DeviceGuard {
 struct SamplerConfig {
     int threads = 4;
     int workers = 4;                   // host threads that fetch candidates (not part of the schedule)
+    std::shared_future<void>* device_ready = nullptr;    // indexed sampler: the candidates are fetched from the file first (host only); the
+                                                         // decode passes wait for this (the device is busy loading the BAM until then)
     uint32_t sampling_interval_size = 1000000;
     bool take_all = false;
     size_t num_reads = 10042;
@@ -519,6 +522,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
         for (auto& p : cp.plan) { p.lo = B.pc.recs.size(); append_packed(p.pc, &B.pc); p.hi = B.pc.recs.size(); p.pc.clear(); p.pc.heap.shrink_to_fit(); p.pc.hdrs.shrink_to_fit(); }
     }
     t_fetch += secs_between(tf0, clk::now());
+    if (cfg.device_ready) cfg.device_ready->wait();
     size_t resident_bulk = (size_t)-1;
     for (size_t bi = 0; bi < bulks.size(); bi++) { bulks[bi].take.assign(bulks[bi].pc.recs.size(), 0); contributes_of(bulks[bi].pc, bulks[bi].tid, &bulks[bi].contributes); resident_bulk = bi; }
     // ---- the real schedule, contig by contig
@@ -772,6 +776,37 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         std::vector<RefInterval> ivs = interval_grid(iv_targets, o.interval_size, combine_strands, have_motifs ? &mc : nullptr, &iv_owner);
         size_t my_i0 = 0, my_i1 = ivs.size();
         if (sharded) { const std::vector<size_t> cuts = shard_cuts(bam, ivs, coll.world); my_i0 = cuts[coll.rank]; my_i1 = cuts[coll.rank + 1]; }
+        // ---- threshold estimation starts now when it can run beside the load: its candidates come straight from the file (host
+        // fetch through the index), only its decode passes need the device and wait for `dev_ready`
+        const bool estimate = o.filter_thresholds.empty() && !o.no_filtering;
+        std::vector<uint64_t> bg_hist(4 * 1025);
+        uint64_t bg_inexact = 0;
+        double bg_fetch_s = 0;
+        std::exception_ptr bg_err;
+        std::promise<void> dev_ready_p;
+        std::shared_future<void> dev_ready_f = dev_ready_p.get_future().share();
+        bool dev_ready_set = false;
+        SamplerConfig bg_sc;
+        struct BgJoin { std::thread t; std::promise<void>* p; bool* set; ~BgJoin() { if (!*set) { try { p->set_value(); } catch (...) {} *set = true; } if (t.joinable()) t.join(); } } bg_job{std::thread(), &dev_ready_p, &dev_ready_set};
+        const bool sampler_bg = estimate && !loaded && bam.have_index();
+        if (sampler_bg) {
+            if (o.have_frac && o.frac != 1.0) throw std::runtime_error("only --sampling-frac 1.0 is reproducible without the reference's RNG; use -n or -f 1.0");
+            mkp_params PS = P;
+            PS.max_depth = 0;           // the sampler looks at reads, not at pileup columns
+            if (mkp_set_params(dev.ctx, &PS)) throw std::runtime_error(mkp_last_error(dev.ctx));
+            bg_sc.threads = o.schedule_threads > 0 ? o.schedule_threads : o.threads; bg_sc.workers = o.threads; bg_sc.sampling_interval_size = o.sampling_interval_size;
+            bg_sc.take_all = o.have_frac;
+            bg_sc.num_reads = o.num_reads;
+            bg_sc.region = srp ? srp : rp;
+            bg_sc.include_unmapped = o.include_unmapped;
+            bg_sc.edge_on = P.edge_filter_on;
+            bg_sc.include = inc;
+            bg_sc.device_ready = &dev_ready_f;
+            bg_job.t = std::thread([&]() {
+                try { sample_histogram_indexed(bam, dev.ctx, bg_sc, bg_hist.data(), &bg_inexact, coll, &bg_fetch_s); }
+                catch (...) { bg_err = std::current_exception(); }
+            });
+        }
         // ---- device load: everything, or the byte ranges under this rank's intervals
         if (!loaded) {
             if (sharded) {
@@ -791,6 +826,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 }
             }
         }
+        if (!dev_ready_set) { dev_ready_p.set_value(); dev_ready_set = true; }
         const auto t_load = clk::now();
         uint64_t any_mapped = 0;
         for (auto& t : targets) if (rp || !inc || inc->has_contig(t.tid)) any_mapped += bam.stats.n_mapped[t.tid];
@@ -866,6 +902,21 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                     P.base_threshold_set[f - B] = 1;
                     P.base_threshold[f - B] = std::stof(raw.substr(c + 1));
                 }
+            }
+        } else if (!o.no_filtering && sampler_bg) {
+            if (bg_job.t.joinable()) bg_job.t.join();
+            if (bg_err) std::rethrow_exception(bg_err);
+            fetch_s = bg_fetch_s;
+            if (bg_inexact) throw std::runtime_error("sampled probabilities are not multiples of 1/1024 (" + std::to_string(bg_inexact) + " values): exact histogram quantile impossible; pass --filter-threshold");
+            for (int b = 0; b < 4; b++) {
+                float thr;
+                uint64_t n = 0;
+                for (int k = 0; k <= 1024; k++) n += bg_hist[b * 1025 + k];
+                if (!n) continue;
+                if (!percentile_from_hist(bg_hist.data() + b * 1025, o.percentile, &thr)) throw std::runtime_error("not enough datapoints to estimate a threshold");
+                P.base_threshold_set[b] = 1;
+                P.base_threshold[b] = thr;
+                if (!o.quiet && coll.rank == 0) fprintf(stderr, "> Using filter threshold %.9g for %c.\n", thr, "ACGT"[b]);
             }
         } else if (!o.no_filtering) {
             mkp_params PS = P;

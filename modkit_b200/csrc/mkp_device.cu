@@ -66,7 +66,7 @@ struct mkp_ctx {
     size_t n_rows = 0;
     uint64_t launches = 0;       // kernels launched by this context (mkp_kernel_launches)
     // fused pass (chunks with focus bitmaps): tile table, rank of the focus set (built at upload), capacities
-    DevBuf d_pscr;
+    DevBuf d_pscr, d_inftab;
     uint32_t n_hot = 0, state_cap = 4, p_stride = 0;
     bool fused_attr_set = false, focus_ready = false;
     // pinned staging buffers for host -> device copies of pageable memory (the mapped BAM file): one per copy thread
@@ -155,7 +155,7 @@ void mkp_destroy(mkp_ctx* ctx) {
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
                       &ctx->d_file, &ctx->d_members, &ctx->d_bam, &ctx->d_seeds, &ctx->d_seg_counts, &ctx->d_seg_base, &ctx->d_recs, &ctx->d_ids, &ctx->d_plan,
-                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr};
+                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr, &ctx->d_inftab};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     if (ctx->pin_ready) for (int i = 0; i < mkp_ctx::N_PIN; i++) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_ev[i]); }
@@ -729,12 +729,21 @@ int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const
     CK(cudaMemcpyAsync(ctx->d_members.p, members, n_members * sizeof(mkp_bgzf_member), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_seeds.p, seeds, n_seeds * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(u + 10, 0, 12, st));
-    const size_t smem = (size_t)INF_THREADS * INF_STRIDE * 2;
-    if (!ctx->inflate_attr_set) {      // per device: the opt-in to > 48 KB of dynamic shared memory
+    // decoder tables in shared memory (MKP_INFLATE_SMEM=1) or in an L2-resident global scratch (default): see k_inflate
+    static const bool tab_global = !(getenv("MKP_INFLATE_SMEM") && getenv("MKP_INFLATE_SMEM")[0] == '1');
+    int warps_sm = 28;
+    if (const char* e = getenv("MKP_INFLATE_WARPS")) warps_sm = std::max(1, std::min(32, atoi(e)));
+    const size_t smem = tab_global ? 0 : (size_t)INF_THREADS * INF_STRIDE * 2;
+    if (!tab_global && !ctx->inflate_attr_set) {      // per device: the opt-in to > 48 KB of dynamic shared memory
         CK(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->inflate_attr_set = true;
     }
-    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    const int per_sm = tab_global ? warps_sm : std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    uint16_t* gtab = nullptr;
+    if (tab_global) {
+        CK(ctx->d_inftab.ensure((size_t)ctx->sm_count * per_sm * INF_THREADS * INF_STRIDE * 2));
+        gtab = ctx->d_inftab.as<uint16_t>();
+    }
     const size_t resident = (size_t)ctx->sm_count * per_sm * INF_THREADS;      // decoders in flight
     // The file goes over in slabs (copy stream); the members of a slab are inflated (compute stream) while the next slab
     // is on the wire. A slab holds at least one round of resident decoders and 128 MB, so small files are a single slab.
@@ -768,7 +777,7 @@ int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const
         const size_t nm = cut[sl + 1] - cut[sl];
         const int grid = (int)std::min<size_t>((nm + INF_THREADS - 1) / INF_THREADS, (size_t)ctx->sm_count * per_sm);
         ctx->launches += 1; k_inflate<<<grid, INF_THREADS, smem, st>>>(ctx->d_file.as<uint8_t>(), ctx->d_members.as<mkp_bgzf_member>() + cut[sl], (uint32_t)nm,
-                                                  ctx->d_bam.as<uint8_t>(), u + 10, ctx->d_slab_work.as<uint32_t>() + sl, (uint32_t)cut[sl]);
+                                                  ctx->d_bam.as<uint8_t>(), u + 10, ctx->d_slab_work.as<uint32_t>() + sl, (uint32_t)cut[sl], gtab);
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream2));
     CK(cudaEventRecord(ctx->ev[2], st));

@@ -126,10 +126,15 @@ constexpr int INF_COPY_STEP = 64;
 #define INF_SYMS_PER_STEP 4
 #endif
 
-__global__ void __launch_bounds__(INF_THREADS) k_inflate(const uint8_t* __restrict__ in, const mkp_bgzf_member* __restrict__ jobs, uint32_t n_jobs,
-                                                        uint8_t* out, uint32_t* status, uint32_t* work, uint32_t job_base) {
+#ifndef MKP_INF_MINB
+#define MKP_INF_MINB 28
+#endif
+__global__ void __launch_bounds__(INF_THREADS, MKP_INF_MINB) k_inflate(const uint8_t* __restrict__ in, const mkp_bgzf_member* __restrict__ jobs, uint32_t n_jobs,
+                                                        uint8_t* out, uint32_t* status, uint32_t* work, uint32_t job_base, uint16_t* gtab) {
     extern __shared__ uint16_t inf_smem[];
-    uint16_t* const my = inf_smem + (size_t)threadIdx.x * INF_STRIDE;
+    // decoder tables: shared memory (1.4 KB per decoder: 5 warps of decoders per SM), or - gtab - a per-decoder global scratch that
+    // stays in L2: a lookup costs more, but four times as many decoders are resident and the kernel is latency bound
+    uint16_t* const my = gtab ? gtab + ((size_t)blockIdx.x * INF_THREADS + threadIdx.x) * INF_STRIDE : inf_smem + (size_t)threadIdx.x * INF_STRIDE;
     uint16_t lsym[288], dsym[32];
     uint16_t* const lcnt = my + INF_LCNT;
     uint16_t* const dcnt = my + INF_DCNT; uint16_t* const offs = my + INF_OFFS; uint16_t* const ltab = my + INF_LTAB;
