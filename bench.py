@@ -423,11 +423,16 @@ def main():
             # per-GPU rate of the dominant kernel: the bytes all GPUs' launches of it processed / the time they spent in it
             ach = alg / (stage_sum[dom] * 1e-3) / 1e9
             whole = alg / (stage_sum[7] * 1e-3) / 1e9
-            traffic, traffic_src = None, None
+            # DRAM traffic per step (all launches of the kernel over the genome): one ncu capture of this workload, committed under
+            # profiles/ (tools/profile_r02.sh); null for any other workload
+            traffic, traffic_src, traffic_whole = None, None, None
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_full.json")))
-                if tj.get("genome_bp") == total_bp and tj.get("coverage") == a.coverage:
-                    traffic, traffic_src = int(tj["whole_pass"]["dram_bytes"]), "profiles/r02_traffic_full.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum over the launches of one pass)"
+                kname = {"parse": "k_parse", "resolve": "k_resolve<0, 1>", "count_calls+count_bases": "k_count_bases", "rows": "k_rows<1>"}.get(names[dom])
+                if tj.get("genome_bp") == total_bp and tj.get("coverage") == a.coverage and kname in tj["kernels"]:
+                    traffic = int(tj["kernels"][kname]["dram_bytes_read"] + tj["kernels"][kname]["dram_bytes_write"])
+                    traffic_whole = int(tj["whole_pass"]["dram_bytes"])
+                    traffic_src = "profiles/r02_traffic_full.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the kernel's launches of one pass over the genome)"
             except Exception:
                 pass
             # ---- CPU baseline + parity of the bench's own output: the oracle on the first CPU_WINDOW bp of contig 1, same flags,
@@ -480,7 +485,7 @@ def main():
                     "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                  "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s", "traffic": traffic, "traffic_source": traffic_src,
                                  "algorithmic_bytes_per_step": int(alg), "kernel_ms_all_gpus": float(stage_sum[dom]),
-                                 "whole_path": {"achieved": whole, "frac": whole / peak, "ms_all_gpus": float(stage_sum[7])}},
+                                 "whole_path": {"achieved": whole, "frac": whole / peak, "ms_all_gpus": float(stage_sum[7]), "traffic": traffic_whole}},
                     "stage_ms": {n: float(stage_sum[i]) for i, n in enumerate(names)},
                     "cpu_baseline": cpu,
                     "clocks": clocks.summary(),

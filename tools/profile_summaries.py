@@ -27,7 +27,7 @@ for row in r[1:]:
 tot = sum(v[1] for v in agg.values())
 unit = r[1][h.index("Metric Unit")] if len(r) > 1 else "ns"
 with open("profiles/%s_launch_shares.txt" % out, "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, all launches of `bench.py --contig-len 8000000 --steps 2 --warmup 3`\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, the pass kernels of `python bench.py --steps 2 --warmup 3 --skip-cpu` (tools/profile_r02.sh)\n")
     f.write("# (cold-cache, serialised launches: shares of device time, not bench values). unit of sums: %s\n" % unit)
     for name in sorted(agg, key=lambda n: -agg[n][1]):
         f.write("%6.2f%%  %5d launches  %14.1f  %s\n" % (100 * agg[name][1] / tot, agg[name][0], agg[name][1], name))
@@ -39,8 +39,8 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
 with open("profiles/%s_ncu_kernels.txt" % out, "w") as f:
-    f.write("# selected metrics of one `ncu --set full --clock-control none` capture per kernel (8 Mb workload; see tools/profile.sh)\n")
-    for rep in (tag + "_pileup.ncu-rep", tag + "_ingest.ncu-rep"):
+    f.write("# selected metrics of one `ncu --set full --clock-control none` capture per kernel (16 Mb chunk of the bench workload, tools/kbench.py; see tools/profile_r02.sh)\n")
+    for rep in (tag + "_pileup.ncu-rep", tag + "_fused.ncu-rep", tag + "_ingest.ncu-rep"):
         p = os.path.join(G, rep)
         if not os.path.exists(p): continue
         raw = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
