@@ -14,6 +14,7 @@
 
 #include "mkp_kernels.cuh"
 #include "mkp_fused.cuh"
+#include "mkp_tile.cuh"
 #include "mkp_ingest.cuh"
 
 using namespace mkp;
@@ -66,7 +67,9 @@ struct mkp_ctx {
     size_t n_rows = 0;
     uint64_t launches = 0;       // kernels launched by this context (mkp_kernel_launches)
     // fused pass (chunks with focus bitmaps): tile table, rank of the focus set (built at upload), capacities
-    DevBuf d_pscr, d_inftab;
+    DevBuf d_pscr, d_inftab, d_tiles;
+    uint32_t n_tiles = 0;
+    bool tile_attr_set = false;
     uint32_t n_hot = 0, state_cap = 4, p_stride = 0;
     bool fused_attr_set = false, focus_ready = false;
     // pinned staging buffers for host -> device copies of pageable memory (the mapped BAM file): one per copy thread
@@ -155,7 +158,7 @@ void mkp_destroy(mkp_ctx* ctx) {
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
                       &ctx->d_file, &ctx->d_members, &ctx->d_bam, &ctx->d_seeds, &ctx->d_seg_counts, &ctx->d_seg_base, &ctx->d_recs, &ctx->d_ids, &ctx->d_plan,
-                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr, &ctx->d_inftab};
+                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr, &ctx->d_inftab, &ctx->d_tiles};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     if (ctx->pin_ready) for (int i = 0; i < mkp_ctx::N_PIN; i++) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_ev[i]); }
@@ -291,6 +294,11 @@ static int finish_upload(mkp_ctx* ctx) {
     k_word_prefix<<<n_blk, 1024, 0, st>>>(ctx->d_hot.as<uint32_t>(), n_words, ctx->d_block_sums.as<uint32_t>(), ctx->d_hot_prefix.as<uint32_t>());
     uint32_t n_hot = 0;
     CK(cudaMemcpyAsync(&n_hot, u + 2, 4, cudaMemcpyDeviceToHost, st));
+    ctx->n_tiles = ctx->n_reads ? (uint32_t)((ctx->heap_bytes + TL_WIN - 1) / TL_WIN) : 0;
+    if (ctx->n_tiles == 0 && ctx->n_reads) ctx->n_tiles = 1;
+    CK(ctx->d_tiles.ensure(((size_t)ctx->n_tiles + 1) * sizeof(TileInfo)));
+    ctx->launches += 1;
+    k_tiles<<<(ctx->n_tiles + 1 + 255) / 256, 256, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->n_reads, ctx->heap_bytes, ctx->d_tiles.as<TileInfo>(), ctx->n_tiles);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     ctx->n_hot = n_hot;
@@ -309,7 +317,9 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
     // MKP_FUSED=1: the TMA-staged single-traversal kernel (k_pileup_fused); default: the per-stage kernels (see DESIGN.md 4:
     // the pass is bound by instruction issue, and the per-stage kernels keep 2-3x more warps per SM in flight)
     const char* fz = getenv("MKP_FUSED");
-    const bool use_fused = fz && fz[0] == '1';
+    const char* tl = getenv("MKP_TILE");
+    const bool use_tile = tl && tl[0] == '1';                  // k_pileup_tile: CTA-cooperative phases over TMA-staged tiles
+    const bool use_fused = use_tile || (fz && fz[0] == '1');
     const int g_slow = use_fused ? std::max(1, std::min(ctx->sm_count * 2, (int)((ctx->n_reads + 3) / 4))) : decode_grid(ctx, ctx->n_reads);
     if (int rc = prepare_decode(ctx, &C, g_slow)) return rc;
     CK(ctx->d_block_sums.ensure((size_t)n_blk * 4 + 4));
@@ -354,7 +364,13 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
         D.slots = F.slots; D.stride = stride; D.n_states = S_cap; D.n_words = n_words; D.obs_word = F.obs_word; D.work = u + 6;
         if (use_fused) {
-            if (ctx->n_reads) { ctx->launches += 1; k_pileup_fused<<<grid, FZ_THREADS, sizeof(FzShared), st>>>(F); }
+            if (ctx->n_reads && use_tile) {
+                if (!ctx->tile_attr_set) { CK(cudaFuncSetAttribute(k_pileup_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TlShared))); ctx->tile_attr_set = true; }
+                TileDev Tl;
+                Tl.F = F; Tl.tiles = ctx->d_tiles.as<TileInfo>(); Tl.n_tiles = ctx->n_tiles; Tl.tile_counter = u + 13;
+                ctx->launches += 1;
+                k_pileup_tile<<<grid, TL_THREADS, sizeof(TlShared), st>>>(Tl);
+            } else if (ctx->n_reads) { ctx->launches += 1; k_pileup_fused<<<grid, FZ_THREADS, sizeof(FzShared), st>>>(F); }
             CK(cudaEventRecord(ctx->ev[1], st));
             // the reads the fused kernel left to the generic path (list mode); both add into the same slots
             C.list_mode = 1;

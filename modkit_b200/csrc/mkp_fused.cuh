@@ -120,18 +120,17 @@ __device__ __forceinline__ bool edge_keep(uint32_t f, uint32_t L) {
 }
 
 // one read, one warp
-__device__ __forceinline__ void fused_read(const FusedDev& F, FzWarp& W, StateCache& scache, uint32_t ri, const mkp_read_hdr& h, const uint8_t* blk, uint32_t* Pg) {
+// MM list discovery (src/mod_bam.rs:900-1000), shape classification and tokens -> occurrence indices (src/mod_bam.rs:667-767) of one
+// read by one warp. P receives the 0-based occurrence index of every token (per list at T.ent_off[l]); `slow` = the read goes to
+// the generic kernels; `err` = the read has no usable mod info (it still counts as bases).
+__device__ __forceinline__ void fz_lists_and_tokens(uint32_t* err_flags, FzWarp& W, const mkp_read_hdr& h, const uint8_t* mm, uint32_t* P,
+                                                    bool& err, uint32_t& nl, int (&gp)[4], int (&ga)[4], bool& slow, uint32_t& need, uint32_t& ent, uint32_t& alias_mask) {
     const uint32_t lane = lane_id();
     ListTab& T = W.tab;
-    const uint32_t flag = h.flags & 0xffffu;
     const uint32_t L = h.l_seq;
-    const bool rev = flag & 0x10;
-    if ((flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) || L == 0) return;          // not admitted (pileup/mod.rs:783-791 + htslib mask)
-    const uint32_t* cig = (const uint32_t*)blk;
-    const uint8_t* seq = blk + 4ull * h.n_cigar;
-    const uint8_t* ml = seq + ((L + 1) >> 1);
-    const uint8_t* mm = ml + h.len_ml;
-    bool err = (h.flags & MKP_RF_TAGS_INVALID) != 0;
+    const bool rev = (h.flags & 0x10u) != 0;
+    struct { uint32_t* err; } F{err_flags};
+    err = (h.flags & MKP_RF_TAGS_INVALID) != 0;
     // ---- list discovery (src/mod_bam.rs:900-1000): warp scan for ';' and the first ',' of each part, lane 0 parses the headers
     {
         const uint32_t M = h.len_mm;
@@ -212,12 +211,12 @@ __device__ __forceinline__ void fused_read(const FusedDev& F, FzWarp& W, StateCa
     }
     __syncwarp();
     if (T.n == 0xffffffffu) err = true;
-    const uint32_t nl = err ? 0 : T.n;
+    nl = err ? 0 : T.n;
     // ---- shape of the read: per base one list (<= 2 codes) or one list + its byte-identical copy (one code each), '+' strand,
     //      '?' mode. Everything else goes to the generic kernels.
-    int gp[4] = {-1, -1, -1, -1}, ga[4] = {-1, -1, -1, -1};
-    bool slow = false;
-    uint32_t need = 0;
+    for (int b = 0; b < 4; b++) { gp[b] = -1; ga[b] = -1; }
+    slow = false;
+    need = 0;
     for (uint32_t l = 0; l < nl; l++) {
         const uint8_t fb = T.base[l];
         if (fb == 'N' || T.strand[l] || T.mode[l] != 0) { slow = true; break; }
@@ -233,12 +232,10 @@ __device__ __forceinline__ void fused_read(const FusedDev& F, FzWarp& W, StateCa
         if (ga[b] >= 0) { if (n0 != 1 || T.ncodes[ga[b]] != 1 || T.code[gp[b]][0] == T.code[ga[b]][0]) slow = true; }
         else if (n0 > 2 || (n0 == 2 && T.code[gp[b]][0] == T.code[gp[b]][1])) slow = true;
     }
-    if (slow) { if (lane == 0) F.slow_list[atomicAdd(F.slow_count, 1u)] = ri; return; }
-    const uint32_t nblk = (L + 31) >> 5;
-    uint32_t* P = h.len_ml <= (uint32_t)FZ_PCAP ? W.P : Pg;
+    if (slow) return;
     // ---- tokens -> occurrence indices (src/mod_bam.rs:667-767); same code as k_parse, positions stay on chip
-    uint32_t ent = 0, mlp = 0;
-    uint32_t alias_mask = 0;
+    ent = 0; alias_mask = 0;
+    uint32_t mlp = 0;
     for (uint32_t l = 0; l < nl && !err; l++) {
         const uint32_t ds = T.d_start[l], de = T.d_end[l];
         const bool must = T.n_delta[l] == 0xffffffffu;
@@ -272,7 +269,7 @@ __device__ __forceinline__ void fused_read(const FusedDev& F, FzWarp& W, StateCa
             bool bad = false;
             if (mine) {
                 const unsigned long long k = carry + pre - 1ull;
-                if (k >= (unsigned long long)L) bad = true;
+                if (k >= (unsigned long long)L || ent + idx >= h.len_ml) bad = true;     // (more tokens than ML entries is an error anyway)
                 else P[ent + idx] = (uint32_t)k;
             }
             if (__any_sync(FULL, bad)) err = true;
@@ -403,7 +400,25 @@ __device__ __forceinline__ void fused_read(const FusedDev& F, FzWarp& W, StateCa
     }
     // the second list of a base must be the byte-identical copy of the first (its entries then sit at the same positions)
     if (!err) for (int b = 0; b < 4; b++) if (ga[b] >= 0 && !((alias_mask >> ga[b]) & 1u)) slow = true;
+    if (slow) return;
+}
+
+__device__ __forceinline__ void fused_read(const FusedDev& F, FzWarp& W, StateCache& scache, uint32_t ri, const mkp_read_hdr& h, const uint8_t* blk, uint32_t* Pg) {
+    const uint32_t lane = lane_id();
+    ListTab& T = W.tab;
+    const uint32_t flag = h.flags & 0xffffu;
+    const uint32_t L = h.l_seq;
+    const bool rev = flag & 0x10;
+    if ((flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) || L == 0) return;          // not admitted (pileup/mod.rs:783-791 + htslib mask)
+    const uint32_t* cig = (const uint32_t*)blk;
+    const uint8_t* seq = blk + 4ull * h.n_cigar;
+    const uint8_t* ml = seq + ((L + 1) >> 1);
+    const uint8_t* mm = ml + h.len_ml;
+    bool err; uint32_t nl, need, ent, alias_mask; int gp[4], ga[4]; bool slow;
+    uint32_t* P = h.len_ml <= (uint32_t)FZ_PCAP ? W.P : Pg;
+    fz_lists_and_tokens(F.err, W, h, mm, P, err, nl, gp, ga, slow, need, ent, alias_mask);
     if (slow) { if (lane == 0) F.slow_list[atomicAdd(F.slow_count, 1u)] = ri; return; }
+    const uint32_t nblk = (L + 31) >> 5;
     // ---- streaming select: occurrence index -> forward position, one pass over the SEQ per needed base
     if (!err && need) {
         const uint32_t* seqw = (const uint32_t*)seq;

@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
                 bool bad = false;
                 if (mine) {
                     const unsigned long long k = carry + pre - 1ull;
-                    if (k >= (unsigned long long)L) bad = true;          // past the last base whatever the base is
+                    if (k >= (unsigned long long)L || ent + idx >= h.len_ml) bad = true;   // past the last base whatever the base is; more tokens than ML entries is an error anyway (and P has len_ml slots)
                     else P[ent + idx] = (uint32_t)k;
                 }
                 if (__any_sync(FULL, bad)) err = true;

@@ -1,5 +1,5 @@
-"""k_pileup_fused (MKP_FUSED=1: the TMA-staged single-traversal kernel for chunks with focus bitmaps) against the oracle and
-against the default per-stage kernels: same bytes."""
+"""The TMA-staged single-traversal kernels for chunks with focus bitmaps - k_pileup_fused (MKP_FUSED=1, warp per read over a ring)
+and k_pileup_tile (MKP_TILE=1, CTA-cooperative phases over tiles) - against the oracle: same bytes as the per-stage kernels."""
 import os
 
 import pytest
@@ -10,11 +10,11 @@ from test_gpu_parity import SYNTH_CASES, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def fused_env():
-    os.environ["MKP_FUSED"] = "1"
+@pytest.fixture(params=["MKP_FUSED", "MKP_TILE"])
+def fused_env(request):
+    os.environ[request.param] = "1"
     yield
-    os.environ.pop("MKP_FUSED", None)
+    os.environ.pop(request.param, None)
 
 
 FOCUS_GOLDENS = [c for c in golden_cases() if any(a in ("--cpg", "--motif", "--include-bed", "--preset") for a in c["args"])]

@@ -57,6 +57,8 @@ def main():
             env["MKP_NO_FOCUS_RANK"] = "1"     # round-1 pass: hot marks + rank + two host round trips
         elif v == "fused":
             env["MKP_FUSED"] = "1"             # k_pileup_fused
+        elif v == "tile":
+            env["MKP_TILE"] = "1"              # k_pileup_tile
         elif v != "cur":
             env["MKP_FUSED"] = "1"
             env["MODKIT_B200_LIB"] = os.path.join(ROOT, "modkit_b200", "_build", "variants", v + ".so")
