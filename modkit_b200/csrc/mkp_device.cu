@@ -67,7 +67,8 @@ struct mkp_ctx {
     size_t n_rows = 0;
     uint64_t launches = 0;       // kernels launched by this context (mkp_kernel_launches)
     // fused pass (chunks with focus bitmaps): tile table, rank of the focus set (built at upload), capacities
-    DevBuf d_pscr, d_inftab, d_tiles;
+    DevBuf d_pscr, d_inftab, d_tiles, d_order;
+    bool order_ready = false;
     uint32_t n_tiles = 0;
     bool tile_attr_set = false;
     uint32_t n_hot = 0, state_cap = 4, p_stride = 0;
@@ -158,7 +159,7 @@ void mkp_destroy(mkp_ctx* ctx) {
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
                       &ctx->d_file, &ctx->d_members, &ctx->d_bam, &ctx->d_seeds, &ctx->d_seg_counts, &ctx->d_seg_base, &ctx->d_recs, &ctx->d_ids, &ctx->d_plan,
-                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr, &ctx->d_inftab, &ctx->d_tiles};
+                      &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr, &ctx->d_inftab, &ctx->d_tiles, &ctx->d_order};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
     if (ctx->pin_ready) for (int i = 0; i < mkp_ctx::N_PIN; i++) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_ev[i]); }
@@ -263,6 +264,7 @@ static int prepare_decode(mkp_ctx* ctx, ChunkDev* C, int grid) {
     C->rl = ctx->d_rl.as<ReadLists>();
     CK(ctx->d_slow.ensure((size_t)ctx->n_reads * 4 + 4));
     C->slow_list = ctx->d_slow.as<uint32_t>();
+    C->order = ctx->order_ready ? ctx->d_order.as<uint32_t>() : nullptr;
     return 0;
 }
 
@@ -278,8 +280,20 @@ static std::string derr_text(uint32_t e) {
 // every focus position) and the tile table of the fused pass are built here, once per chunk, not once per pass.
 static int finish_upload(mkp_ctx* ctx) {
     ctx->focus_ready = false;
-    if (!ctx->have_focus) return 0;
+    ctx->order_ready = false;
     cudaStream_t st = ctx->stream;
+    if (ctx->n_reads >= 4096 && !getenv("MKP_NO_ORDER")) {            // processing order of the read queues: longest reads first
+        CK(ctx->d_order.ensure((size_t)ctx->n_reads * 4 + 32 * 4));
+        uint32_t* hist = ctx->d_order.as<uint32_t>() + ctx->n_reads;
+        CK(cudaMemsetAsync(hist, 0, 32 * 4, st));
+        const int g = (int)((ctx->n_reads + 255) / 256);
+        ctx->launches += 3;
+        k_order_hist<<<g, 256, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->n_reads, hist);
+        k_order_scan<<<1, 1, 0, st>>>(hist);
+        k_order_scatter<<<g, 256, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->n_reads, hist, ctx->d_order.as<uint32_t>());
+        ctx->order_ready = true;
+    }
+    if (!ctx->have_focus) { CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); return 0; }
     const uint32_t n_words = ctx->n_words;
     const uint32_t n_blk = (n_words + 1023) / 1024;
     CK(ctx->d_hot.ensure((size_t)n_words * 4 + 4));
@@ -363,6 +377,7 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         D.hdrs = C.hdrs; D.heap = C.heap; D.meta = C.meta; D.calls = C.calls; D.n_reads = C.n_reads; D.cs = C.cs; D.ce = C.ce;
         D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
         D.slots = F.slots; D.stride = stride; D.n_states = S_cap; D.n_words = n_words; D.obs_word = F.obs_word; D.work = u + 6;
+        D.order = nullptr;          // (the counting kernels keep the coordinate order: neighbouring reads update neighbouring slots)
         if (use_fused) {
             if (ctx->n_reads && use_tile) {
                 if (!ctx->tile_attr_set) { CK(cudaFuncSetAttribute(k_pileup_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TlShared))); ctx->tile_attr_set = true; }
@@ -516,7 +531,7 @@ int mkp_pileup_resident(mkp_ctx* ctx, mkp_stats* stats) {
     D.focus_pos = C.focus_pos; D.focus_neg = C.focus_neg; D.hot = C.hot; D.hot_prefix = C.hot_prefix;
     D.slots = ctx->d_slots.as<uint32_t>(); D.stride = stride; D.n_states = std::max<uint32_t>(n_states, 1);
     D.n_words = n_words; D.obs_word = ctx->d_obs_word.as<uint32_t>(); D.work = u + 6;
-    D.list = nullptr; D.list_count = nullptr;
+    D.list = nullptr; D.list_count = nullptr; D.order = nullptr;      // (the counting kernels keep the coordinate order: neighbouring reads update neighbouring slots)
     CK(cudaEventRecord(ctx->ev[4], st));
     const int g2 = std::max(1, std::min(ctx->sm_count * 8, (int)((ctx->n_reads + 7) / 8)));
     // the two counting kernels only meet in commutative atomics on the slots: run them side by side (both are

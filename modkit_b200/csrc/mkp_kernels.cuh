@@ -102,6 +102,8 @@ struct ChunkDev {
     // 1 = list mode: the reads k_pileup_fused left to the generic kernels; k_parse walks slow_list[0 .. *(work + 4));
     // 2 = every read through the per-stage kernels
     uint32_t list_mode;
+    // processing order of the dynamic read queue: longest reads first (a 200 kb read that starts last is the kernel's tail); null = index order
+    const uint32_t* order;
 };
 
 __constant__ DevParams c_par;
@@ -397,6 +399,7 @@ __global__ void __launch_bounds__(128, MKP_MINB_PARSE) k_parse(ChunkDev C) {
         if (lane == 0) {
             ri = atomicAdd(C.work, 1u);
             if (C.list_mode == 1) ri = ri < C.work[4] ? C.slow_list[ri] : 0xffffffffu;
+            else if (C.order && ri < C.n_reads) ri = C.order[ri];
         }
         ri = __shfl_sync(FULL, ri, 0);
         if (ri >= C.n_reads) break;
@@ -876,7 +879,7 @@ __global__ void __launch_bounds__(128, FAST_ONLY ? MKP_MINB_RESOLVE_FAST : MKP_M
     for (;;) {
         uint32_t ri = 0;
         if (FAST_ONLY) {
-            if (lane == 0) ri = atomicAdd(C.work + 1, 1u);
+            if (lane == 0) { ri = atomicAdd(C.work + 1, 1u); if (C.order && ri < C.n_reads) ri = C.order[ri]; }
             ri = __shfl_sync(FULL, ri, 0);
             if (ri >= C.n_reads) break;
         } else {
@@ -1554,6 +1557,7 @@ struct CountDev {
     uint32_t* work;       // dynamic read counter
     const uint32_t* list; // list mode: the reads to count (k_pileup_fused counted the others) and their number
     const uint32_t* list_count;
+    const uint32_t* order; // else: processing order (longest reads first), or null
 };
 
 __device__ __forceinline__ uint32_t slot_of(const CountDev& D, uint32_t x) {
@@ -1574,7 +1578,7 @@ __global__ void __launch_bounds__(256) k_count_calls(CountDev D) {
     const uint32_t lane = lane_id();
     for (;;) {
         uint32_t ri = 0;
-        if (lane == 0) { ri = atomicAdd(D.work + 1, 1u); if (D.list) ri = ri < *D.list_count ? D.list[ri] : 0xffffffffu; }
+        if (lane == 0) { ri = atomicAdd(D.work + 1, 1u); if (D.list) ri = ri < *D.list_count ? D.list[ri] : 0xffffffffu; else if (D.order && ri < D.n_reads) ri = D.order[ri]; }
         ri = __shfl_sync(FULL, ri, 0);
         if (ri >= D.n_reads) break;
         const ReadMeta m = D.meta[ri];
@@ -1617,7 +1621,7 @@ __global__ void __launch_bounds__(256, MKP_MINB_BASES) k_count_bases(CountDev D)
     const uint32_t wib = threadIdx.x >> 5;
     for (;;) {
         uint32_t ri = 0;
-        if (lane == 0) { ri = atomicAdd(D.work, 1u); if (D.list) ri = ri < *D.list_count ? D.list[ri] : 0xffffffffu; }
+        if (lane == 0) { ri = atomicAdd(D.work, 1u); if (D.list) ri = ri < *D.list_count ? D.list[ri] : 0xffffffffu; else if (D.order && ri < D.n_reads) ri = D.order[ri]; }
         ri = __shfl_sync(FULL, ri, 0);
         if (ri >= D.n_reads) break;
         const ReadMeta m = D.meta[ri];
@@ -1882,6 +1886,21 @@ __global__ void k_value_prefix(const uint32_t* __restrict__ v, uint32_t n, const
     if (threadIdx.x < 32) { uint32_t t = s_w[threadIdx.x]; uint32_t ti = warp_incl_scan(t); s_w[threadIdx.x] = ti - t; }
     __syncthreads();
     if (i < n) prefix[i] = block_sums[blockIdx.x] + s_w[threadIdx.x >> 5] + inc - x;
+}
+
+// ---- processing order: reads by descending length class (32 classes by the position of the top bit of l_seq); a counting sort,
+//      the order inside a class does not matter (all updates are commutative integer atomics)
+__global__ void k_order_hist(const mkp_read_hdr* __restrict__ hdrs, uint32_t n, uint32_t* __restrict__ hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&hist[31 - (hdrs[i].l_seq ? 31 - __clz(hdrs[i].l_seq) : 0)], 1u);
+}
+__global__ void k_order_scan(uint32_t* hist) {
+    uint32_t acc = 0;
+    for (int b = 0; b < 32; b++) { const uint32_t v = hist[b]; hist[b] = acc; acc += v; }
+}
+__global__ void k_order_scatter(const mkp_read_hdr* __restrict__ hdrs, uint32_t n, uint32_t* __restrict__ hist, uint32_t* __restrict__ order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[atomicAdd(&hist[31 - (hdrs[i].l_seq ? 31 - __clz(hdrs[i].l_seq) : 0)], 1u)] = i;
 }
 
 }  // namespace mkp

@@ -57,6 +57,8 @@ def main():
             env["MKP_NO_FOCUS_RANK"] = "1"     # round-1 pass: hot marks + rank + two host round trips
         elif v == "fused":
             env["MKP_FUSED"] = "1"             # k_pileup_fused
+        elif v == "noorder":
+            env["MKP_NO_ORDER"] = "1"          # read queues in index order
         elif v == "tile":
             env["MKP_TILE"] = "1"              # k_pileup_tile
         elif v != "cur":
