@@ -49,13 +49,13 @@ assert ROW_DTYPE.itemsize == 40
 
 MKP_SYMBOLS = ["mkp_create", "mkp_bind_host_thread", "mkp_destroy", "mkp_last_error", "mkp_set_params", "mkp_upload_chunk", "mkp_pileup_resident",
                "mkp_fetch_rows", "mkp_pileup_chunk", "mkp_sample_histogram", "mkp_sample_summary", "mkp_algorithmic_bytes", "mkp_kernel_launches",
-               "mkp_device_memory", "mkp_bam_load", "mkp_bam_load_range", "mkp_bam_records", "mkp_bam_chunk", "mkp_bam_inflated", "mkp_fetch_chunk"]
+               "mkp_device_memory", "mkp_bam_load", "mkp_bam_load_range", "mkp_bam_records", "mkp_bam_chunk", "mkp_bam_tags", "mkp_bam_inflated", "mkp_fetch_chunk"]
 MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_refs", "mkh_bam_ref_name", "mkh_bam_ref_len",
                "mkh_bam_n_mapped", "mkh_bam_n_records", "mkh_pack_region", "mkh_packed_free", "mkh_packed_n_reads",
                "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
                "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records",
                "mkh_f32_display", "mkh_bam_partition_key", "mkh_bam_n_ranges", "mkh_pileup_main_sharded", "mkh_shard_plan",
-               "mkh_bam_open_device_pieces", "mkh_bam_fetch", "mkh_summary_main", "mkh_sample_probs_main"]
+               "mkh_bam_open_device_pieces", "mkh_bam_fetch", "mkh_summary_main", "mkh_sample_probs_main", "mkh_partition_key_of_cells"]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint64), C.c_size_t, C.c_void_p)
 
@@ -105,6 +105,7 @@ def load_library(build_if_missing=True):
     lib.mkh_bam_fetch.restype = C.c_int64
     lib.mkp_bam_records.argtypes = [C.c_void_p, C.c_void_p]
     lib.mkp_bam_chunk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.mkp_bam_tags.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p]
     lib.mkp_bam_inflated.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
     lib.mkp_fetch_chunk.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint64)]
     lib.mkh_bam_open_device.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -114,6 +115,7 @@ def load_library(build_if_missing=True):
     lib.mkh_bam_ingest_ms.restype = None
     lib.mkh_f32_display.argtypes = [C.c_float, C.c_char_p, C.c_int]
     lib.mkh_bam_partition_key.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int]
+    lib.mkh_partition_key_of_cells.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_int]
     lib.mkh_bam_n_ranges.argtypes = [C.c_void_p]
     lib.mkh_bam_n_ranges.restype = C.c_uint32
     lib.mkh_bam_total_records.argtypes = [C.c_void_p]
@@ -304,6 +306,9 @@ class Bam:
     @property
     def total_records(self):
         return int(self._lib.mkh_bam_total_records(self._h))
+
+    def n_records(self, tid):
+        return int(self._lib.mkh_bam_n_records(self._h, tid))
 
     def close(self):
         if self._h:
@@ -512,6 +517,19 @@ class Context:
         self._check(self._lib.mkp_bam_chunk(self._h, start, end, ids.ctypes.data, len(ids), fp.ctypes.data if fp is not None else None,
                                             fn.ctypes.data if fn is not None else None))
         self._n_reads_hint = len(ids)
+
+    def bam_partition_keys(self, rec_ids, tags):
+        """--partition-tag keys of device-resident records (mkp_bam_tags + the host's key rule): list of str | None."""
+        ids = np.ascontiguousarray(rec_ids, dtype=np.uint32)
+        cells = np.zeros((len(ids), len(tags), 64), dtype=np.uint8)
+        self._check(self._lib.mkp_bam_tags(self._h, ids.ctypes.data, len(ids), "".join(tags).encode(), len(tags), cells.ctypes.data))
+        out, buf = [], C.create_string_buffer(4096)
+        for i in range(len(ids)):
+            rc = self._lib.mkh_partition_key_of_cells(cells[i].ctypes.data, len(tags), buf, 4096)
+            if rc < 0:
+                raise RuntimeError("partition key too long")
+            out.append(buf.value.decode() if rc == 1 else None)
+        return out
 
     def fetch_chunk(self):
         """(headers, heap) of the resident chunk, copied back from the device (tests)."""

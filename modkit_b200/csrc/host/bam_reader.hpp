@@ -761,6 +761,36 @@ inline bool partition_key_of(const uint8_t* r, uint32_t size, const std::vector<
     return any;
 }
 
+// the same key from the 64-byte (type, length, value) cells of mkp_bam_tags (device front end)
+inline bool partition_key_of_cells(const uint8_t* cells, size_t n_tags, std::string* key) {
+    bool any = false;
+    std::string k;
+    for (size_t i = 0; i < n_tags; i++) {
+        const uint8_t* c = cells + 64 * i;
+        const char ty = (char)c[0];
+        const uint8_t* p = c + 2;
+        std::string v;
+        bool have = ty != 0;
+        if (have) switch (ty) {
+            case 'Z': case 'H': v.assign((const char*)p, c[1]); break;
+            case 'A': v.assign(1, (char)p[0]); break;
+            case 'c': v = std::to_string((int)(int8_t)p[0]); break;
+            case 'C': v = std::to_string((unsigned)p[0]); break;
+            case 's': v = std::to_string(load_le<int16_t>(p)); break;
+            case 'S': v = std::to_string(load_le<uint16_t>(p)); break;
+            case 'i': v = std::to_string(load_le<int32_t>(p)); break;
+            case 'I': v = std::to_string(load_le<uint32_t>(p)); break;
+            case 'f': v = f32_display(load_le<float>(p)); break;
+            default: have = false;
+        }
+        any = any || have;
+        if (i) k += "_";
+        k += have ? v : std::string("missing");
+    }
+    if (any) *key = k;
+    return any;
+}
+
 struct PackedChunk {
     std::vector<mkp_read_hdr> hdrs;
     std::vector<uint8_t> heap;

@@ -47,6 +47,7 @@ int mkh_pileup_main_sharded(int argc, const char* const* argv, int rank, int wor
     c.rank = rank; c.world = world; c.allreduce_sum = allreduce; c.user = user;
     RunSummary s;
     if (run_pileup(o, &s, &err, &c)) { fprintf(stderr, "> Error! %s\n", err.c_str()); return 1; }
+    trace_clock().mark(rank, "run returned (device + host buffers released)");
     if (out_stats) { out_stats[0] = s.total_s; out_stats[1] = s.load_s; out_stats[2] = s.threshold_s; out_stats[3] = s.gpu_s; out_stats[4] = s.write_s;
                      out_stats[5] = (double)s.rows_total; out_stats[6] = (double)s.positions_total; out_stats[7] = (double)s.rows;
                      for (int b = 0; b < 4; b++) out_stats[8 + b] = s.threshold_set[b] ? (double)s.thresholds[b] : -1.0;
@@ -141,6 +142,14 @@ int mkh_bam_partition_key(const mkh_bam* b, uint32_t tid, uint64_t i, const char
         memcpy(out, k.c_str(), k.size() + 1);
         return have ? 1 : 0;
     } catch (const std::exception&) { return -1; }
+}
+// the key built from mkp_bam_tags cells (device front end): same return convention
+int mkh_partition_key_of_cells(const uint8_t* cells, uint32_t n_tags, char* out, int cap) {
+    std::string k;
+    const bool have = partition_key_of_cells(cells, n_tags, &k);
+    if ((int)k.size() + 1 > cap) return -1;
+    memcpy(out, k.c_str(), k.size() + 1);
+    return have ? 1 : 0;
 }
 void mkh_bam_close(mkh_bam* b) { delete b; }
 uint32_t mkh_bam_n_refs(const mkh_bam* b) { return (uint32_t)b->reader.ref_names.size(); }

@@ -81,6 +81,14 @@ struct DeviceGuard {
 };
 
 // ---- threshold estimation: host schedule (reads_sampler/*), device decode + histogram --------------
+// MKH_TRACE=1: wall-clock marks of a run's stages on stderr (development); the epoch is set where run_pileup starts
+struct TraceClock {
+    std::chrono::steady_clock::time_point epoch = std::chrono::steady_clock::now();
+    bool on = getenv("MKH_TRACE") != nullptr;
+    void mark(int rank, const char* what) const { if (on) fprintf(stderr, "[mkh r%d] %8.3f s  %s\n", rank, std::chrono::duration<double>(std::chrono::steady_clock::now() - epoch).count(), what); }
+};
+inline TraceClock& trace_clock() { static TraceClock t; return t; }
+
 struct SamplerConfig {
     int threads = 4;
     int workers = 4;                   // host threads that fetch candidates (not part of the schedule)
@@ -522,9 +530,11 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
         for (auto& p : cp.plan) { p.lo = B.pc.recs.size(); append_packed(p.pc, &B.pc); p.hi = B.pc.recs.size(); p.pc.clear(); p.pc.heap.shrink_to_fit(); p.pc.hdrs.shrink_to_fit(); }
     }
     t_fetch += secs_between(tf0, clk::now());
+    trace_clock().mark(coll.rank, "sampler: candidates fetched + packed");
     if (cfg.device_ready) cfg.device_ready->wait();
     size_t resident_bulk = (size_t)-1;
     for (size_t bi = 0; bi < bulks.size(); bi++) { bulks[bi].take.assign(bulks[bi].pc.recs.size(), 0); contributes_of(bulks[bi].pc, bulks[bi].tid, &bulks[bi].contributes); resident_bulk = bi; }
+    trace_clock().mark(coll.rank, "sampler: candidates decoded on the device");
     // ---- the real schedule, contig by contig
     for (auto& cp : cps) {
         const uint32_t t = cp.tid;
@@ -575,6 +585,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
         }
         n_selected += selected.size();
     }
+    trace_clock().mark(coll.rank, "sampler: schedule replayed");
     // ---- histogram of the selected reads of every bulk chunk
     for (size_t bi = 0; bi < bulks.size(); bi++) {
         Bulk& B = bulks[bi];
@@ -585,6 +596,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
         add_taken(B.take);
         if (keep) keep->push_back({std::move(B.pc), std::move(B.take), B.tid});
     }
+    trace_clock().mark(coll.rank, "sampler: histogram of the selection");
     if (!only_mapped) {   // reads without coordinates (reads_sampler/mod.rs:85-129): the last rank, after the global count is known
         uint64_t cnt[1] = {n_selected};
         coll.sum(cnt, 1);
@@ -686,6 +698,8 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
     const bool sharded = coll.world > 1;
     try {
         const auto t0 = clk::now();
+        trace_clock().epoch = t0;
+        auto trace = [&](const char* what) { trace_clock().mark(coll.rank, what); };
         if (o.percentile > 1.0f) throw std::runtime_error("filter percentile must be <= 1.0");
         // the device comes first: with the device ingest (default) the BAM is inflated and sliced on the GPU
         DeviceGuard dev;
@@ -693,6 +707,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             const int rc = mkp_create(o.device, &dev.ctx);
             if (rc) throw std::runtime_error("no usable CUDA device (mkp_create returned " + std::to_string(rc) + "); this build has no CPU fallback");
         }
+        trace("device context created");
         BamReader bam;
         // util.rs:690-712
         for (size_t i = 0; i < o.partition_tags.size(); i++) {
@@ -705,9 +720,10 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         if (o.bedgraph && o.mixed) throw std::runtime_error("the argument '--mixed-delim' cannot be used with '--bedgraph'");
         if (sharded && (to_dir || o.host_ingest)) throw std::runtime_error("multi-GPU runs write one bedMethyl file through the device ingest: --bedgraph / --partition-tag / --host-ingest need a single device");
         if (sharded && (o.out_bed == "-" || o.out_bed == "stdout")) throw std::runtime_error("multi-GPU runs need an output file (ranks write their slices at their offsets)");
-        // partition keys are read from the records' aux fields on the host: that mode uses the host front end
+        // (partition keys: the tag values come from the device-resident records, mkp_bam_tags; --host-ingest reads them on the host)
+        if (partitioned && o.partition_tags.size() > 4 && !o.host_ingest) throw std::runtime_error("more than 4 partition tags need --host-ingest");
         bool loaded = false;
-        if (o.host_ingest || partitioned) { bam.open(o.in_bam, o.threads); loaded = true; }
+        if (o.host_ingest) { bam.open(o.in_bam, o.threads); loaded = true; }
         else bam.open_device_index(o.in_bam, dev.ctx);         // header + index; the device load follows once the shard is known
         Region region, sregion;
         const Region* rp = nullptr; const Region* srp = nullptr;
@@ -769,6 +785,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             for (auto& m : mc.motifs) mc.longest = std::max<uint64_t>(mc.longest, m.len);
         }
         // ---- reference intervals: boundaries now (cheap), focus positions of this rank's range in the background
+        trace("index + fasta opened");
         const auto t_iv0 = clk::now();
         std::vector<RefTarget> iv_targets = targets;
         if (inc) iv_targets = targets_from_include_bed(*inc, iv_targets, o.interval_size);
@@ -788,6 +805,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         bool dev_ready_set = false;
         SamplerConfig bg_sc;
         struct BgJoin { std::thread t; std::promise<void>* p; bool* set; ~BgJoin() { if (!*set) { try { p->set_value(); } catch (...) {} *set = true; } if (t.joinable()) t.join(); } } bg_job{std::thread(), &dev_ready_p, &dev_ready_set};
+        trace("interval grid + shard cuts");
         const bool sampler_bg = estimate && !loaded && bam.have_index();
         if (sampler_bg) {
             if (o.have_frac && o.frac != 1.0) throw std::runtime_error("only --sampling-frac 1.0 is reproducible without the reference's RNG; use -n or -f 1.0");
@@ -828,6 +846,8 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         }
         if (!dev_ready_set) { dev_ready_p.set_value(); dev_ready_set = true; }
         const auto t_load = clk::now();
+        trace("device load done");
+        if (trace_clock().on) fprintf(stderr, "[mkh r%d]             ingest: h2d %.1f ms, inflate %.1f ms, record walk %.1f ms, total %.1f ms\n", coll.rank, bam.ingest_ms[0], bam.ingest_ms[1], bam.ingest_ms[2], bam.ingest_ms[3]);
         uint64_t any_mapped = 0;
         for (auto& t : targets) if (rp || !inc || inc->has_contig(t.tid)) any_mapped += bam.stats.n_mapped[t.tid];
         if (!any_mapped) throw std::runtime_error("did not find any mapped reads, perform alignment first or use modkit extract and/or modkit summary to inspect unaligned modBAMs");
@@ -874,6 +894,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             try {
                 fill_interval_focus(ivs, my_i0, my_i1, iv_targets, iv_owner, combine_strands, have_motifs ? &mc : nullptr, inc, std::max(1, o.threads / 2));
                 iv_secs = secs(t_iv0, clk::now());
+                trace("interval focus filled (background)");
             } catch (...) { iv_err = std::current_exception(); }
         });
         // thresholds (subcommand.rs:615-638, command_utils.rs:49-134)
@@ -952,6 +973,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         if (mkp_set_params(dev.ctx, &P)) throw std::runtime_error(mkp_last_error(dev.ctx));
         if (summary) for (int b = 0; b < 4; b++) { summary->thresholds[b] = P.base_threshold[b]; summary->threshold_set[b] = P.base_threshold_set[b]; }
         const auto t_thr = clk::now();
+        trace("thresholds done");
 
         iv_job.join();
         if (iv_err) std::rethrow_exception(iv_err);
@@ -1020,11 +1042,25 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                         // with --partition-tag one group per key (each an independent pileup: src/pileup/mod.rs:795-830), in key order
                         std::map<std::string, std::vector<RecRef>> groups;
                         if (!partitioned) groups[""].swap(all_recs);
-                        else for (auto& r : all_recs) {
+                        else {
                             // only alignments the pileup admits create a key (flag filter of the pileup engine, pileup/mod.rs:783-791)
-                            if ((r.flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) || r.l_seq == 0) continue;
-                            std::string k;
-                            groups[partition_key_of(bam.rec(r), r.size, o.partition_tags, &k) ? k : std::string("\1")].push_back(r);
+                            std::vector<RecRef> adm;
+                            for (auto& r : all_recs) if (!((r.flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) || r.l_seq == 0)) adm.push_back(r);
+                            std::vector<uint8_t> cells;
+                            if (bam.on_device && !adm.empty()) {
+                                std::vector<uint32_t> ids(adm.size());
+                                for (size_t k = 0; k < adm.size(); k++) ids[k] = adm[k].idx;
+                                std::string tg;
+                                for (auto& t : o.partition_tags) tg += t;
+                                cells.resize(adm.size() * o.partition_tags.size() * 64);
+                                if (mkp_bam_tags(dev.ctx, ids.data(), (uint32_t)ids.size(), tg.c_str(), (uint32_t)o.partition_tags.size(), cells.data())) throw std::runtime_error(mkp_last_error(dev.ctx));
+                            }
+                            for (size_t k = 0; k < adm.size(); k++) {
+                                std::string key;
+                                const bool have = bam.on_device ? partition_key_of_cells(cells.data() + k * o.partition_tags.size() * 64, o.partition_tags.size(), &key)
+                                                                : partition_key_of(bam.rec(adm[k]), adm[k].size, o.partition_tags, &key);
+                                groups[have ? key : std::string("\1")].push_back(adm[k]);
+                            }
                         }
                         bool focus_done = false;
                         for (auto& grp : groups) {
@@ -1073,6 +1109,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                     c0 = c1;
                 }
             } catch (...) { dev_err = std::current_exception(); }
+            trace("device stage done");
             ChunkOut fin;
             fin.last = true;
             push_out(std::move(fin));
@@ -1143,6 +1180,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             }
             S.write_s += secs(tc, clk::now());
         }
+        trace("last chunk formatted");
         if (dev_job.t.joinable()) dev_job.t.join();
         if (dev_err) std::rethrow_exception(dev_err);
         if (out) { if (out != stdout) fclose(out); else fflush(out); }
@@ -1169,6 +1207,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             S.write_s += secs(tw, clk::now());
         } else { S.rows_total = S.rows; S.positions_total = S.positions; }
         const auto t1 = clk::now();
+        trace("output written");
         S.load_s = secs(t0, t_load); S.threshold_s = secs(t_load, t_thr); S.interval_s = iv_secs;   /* runs beside ingest + thresholds; wait time = secs(t_thr, t_iv) */ S.total_s = secs(t0, t1);
         for (int b = 0; b < 4; b++) { S.thresholds[b] = P.base_threshold[b]; S.threshold_set[b] = P.base_threshold_set[b]; }
         if (summary) *summary = S;

@@ -1,6 +1,7 @@
 // C ABI (include/mkp.h) over the sm_100a kernels in mkp_kernels.cuh.
 // One mkp_ctx per GPU: grow-only device buffers, one stream, CUDA events around every stage.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <sched.h>
 
 #include <algorithm>
@@ -66,6 +67,7 @@ struct mkp_ctx {
     // results
     size_t n_rows = 0;
     uint64_t launches = 0;       // kernels launched by this context (mkp_kernel_launches)
+    double slice_prof[6] = {0, 0, 0, 0, 0, 0};   // MKP_TRACE_SLICE=1: host seconds in the phases of mkp_bam_chunk, printed by mkp_destroy
     // fused pass (chunks with focus bitmaps): tile table, rank of the focus set (built at upload), capacities
     DevBuf d_pscr, d_inftab, d_tiles, d_order;
     bool order_ready = false;
@@ -155,6 +157,8 @@ void mkp_destroy(mkp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (getenv("MKP_TRACE_SLICE")) fprintf(stderr, "[mkp] slice phases (s): buffers %.4f plan+scan %.4f heap alloc %.4f copy+focus %.4f finish_upload %.4f calls %.0f\n",
+                                           ctx->slice_prof[0], ctx->slice_prof[1], ctx->slice_prof[2], ctx->slice_prof[3], ctx->slice_prof[4], ctx->slice_prof[5]);
     DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_rl, &ctx->d_meta, &ctx->d_P,
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
@@ -870,6 +874,9 @@ int mkp_bam_chunk(mkp_ctx* ctx, uint32_t start, uint32_t end, const uint32_t* re
     if (!ctx->bam_len) return fail(ctx, "mkp_bam_load was not called");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(now() - t).count(); };
+    auto t0 = now();
     ctx->n_reads = n; ctx->cs = start; ctx->ce = end;
     ctx->n_words = (end - start + 31) / 32;
     CK(ctx->d_hdrs.ensure(std::max<size_t>(1, n) * sizeof(mkp_read_hdr)));
@@ -879,16 +886,19 @@ int mkp_bam_chunk(mkp_ctx* ctx, uint32_t start, uint32_t end, const uint32_t* re
     CK(ctx->d_need.ensure(std::max<size_t>(1, n) * 4));
     CK(ctx->d_totals.ensure(4 * 8));
     uint64_t tot[4] = {0, 0, 1, 1};
+    ctx->slice_prof[0] += since(t0); t0 = now();
     if (n) {
         for (uint32_t i = 0; i < n; i++) if (rec_ids[i] >= ctx->n_records) return fail(ctx, "record id out of range");
         CK(cudaMemcpyAsync(ctx->d_ids.p, rec_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        ctx->launches += 1; k_slice_plan<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_recs.as<mkp_bam_rec>(), ctx->d_ids.as<uint32_t>(), n,
+        ctx->launches += 1; k_slice_plan<<<(n + 7) / 8, 256, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_recs.as<mkp_bam_rec>(), ctx->d_ids.as<uint32_t>(), n,
                                                      ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_plan.as<SlicePlan>(), ctx->d_need.as<uint32_t>());
         ctx->launches += 1; k_slice_scan<<<1, 1024, 0, st>>>(ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_need.as<uint32_t>(), n, ctx->d_entry_off.as<uint64_t>(), ctx->d_totals.as<uint64_t>());
         CK(cudaMemcpyAsync(tot, ctx->d_totals.p, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
+        ctx->slice_prof[1] += since(t0); t0 = now();
         CK(ctx->d_heap.ensure(tot[0] + 64));
+        ctx->slice_prof[2] += since(t0); t0 = now();
         const int grid = std::max(1, std::min(ctx->sm_count * 8, (int)((n + 7) / 8)));
         ctx->launches += 1; k_slice_copy<<<grid, 256, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_hdrs.as<mkp_read_hdr>(), ctx->d_plan.as<SlicePlan>(), n, ctx->d_heap.as<uint8_t>());
     } else {
@@ -908,7 +918,37 @@ int mkp_bam_chunk(mkp_ctx* ctx, uint32_t start, uint32_t end, const uint32_t* re
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    return finish_upload(ctx);
+    ctx->slice_prof[3] += since(t0); t0 = now();
+    const int rc = finish_upload(ctx);
+    ctx->slice_prof[4] += since(t0); ctx->slice_prof[5] += 1;
+    return rc;
+}
+
+int mkp_bam_tags(mkp_ctx* ctx, const uint32_t* rec_ids, uint32_t n, const char* tags, uint32_t n_tags, uint8_t* out) {
+    if (!ctx || (n && !rec_ids) || !tags || !out || n_tags == 0 || n_tags > 4) return -1;
+    if (!ctx->bam_len) return fail(ctx, "mkp_bam_load was not called");
+    CK(cudaSetDevice(ctx->device));
+    if (!n) return 0;
+    cudaStream_t st = ctx->stream;
+    for (uint32_t i = 0; i < n; i++) if (rec_ids[i] >= ctx->n_records) return fail(ctx, "record id out of range");
+    CK(ctx->d_ids.ensure((size_t)n * 4));
+    CK(ctx->d_plan.ensure(std::max<size_t>(sizeof(SlicePlan), (size_t)n * n_tags * 64)));       // (scratch shared with the slicer)
+    CK(ctx->d_small.ensure(SMALL_BYTES));
+    uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
+    uint32_t pk[4] = {0, 0, 0, 0};
+    for (uint32_t t = 0; t < n_tags; t++) pk[t] = (uint32_t)(uint8_t)tags[2 * t] | ((uint32_t)(uint8_t)tags[2 * t + 1] << 8);
+    CK(cudaMemcpyAsync(ctx->d_ids.p, rec_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(u + 14, 0, 4, st));
+    ctx->launches += 1;
+    k_tag_values<<<(n + 7) / 8, 256, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_recs.as<mkp_bam_rec>(), ctx->d_ids.as<uint32_t>(), n,
+                                                 pk[0] | (pk[1] << 16), pk[2] | (pk[3] << 16), n_tags, ctx->d_plan.as<uint8_t>(), u + 14);
+    uint32_t ovf = 0;
+    CK(cudaMemcpyAsync(out, ctx->d_plan.p, (size_t)n * n_tags * 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ovf, u + 14, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (ovf) return fail(ctx, "a partition tag value is longer than 61 bytes: use --host-ingest for this file");
+    return 0;
 }
 
 int mkp_fetch_chunk(mkp_ctx* ctx, mkp_read_hdr* hdrs, uint32_t* n_reads, uint8_t* heap, uint64_t* heap_bytes) {

@@ -412,10 +412,68 @@ __device__ AuxHitDev aux_find_dev(const uint8_t* bam, uint64_t aux, uint64_t end
     return h;
 }
 
-// thread per selected record: header fields, source offsets, bytes needed
-__global__ void k_slice_plan(const uint8_t* __restrict__ bam, const mkp_bam_rec* __restrict__ recs, const uint32_t* __restrict__ ids, uint32_t n,
-                             mkp_read_hdr* hdrs, SlicePlan* plan, uint32_t* need) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- one pass over the aux area by a whole warp: the first occurrence of each of K tags, with the same stop rule as aux_find_dev
+//      (malformed data ends the walk; what was found before stays found). All lanes follow the same cursor and return the same
+//      result; the end of a Z / H value - the MM text is several KB - is searched by the 32 lanes together, 1 KB per round.
+//      (reads whole aligned 8-byte words: the inflated stream has 64 bytes of slack behind it, mkp_bam_load)
+__device__ __forceinline__ uint64_t warp_find_nul(const uint8_t* bam, uint64_t q, uint64_t end, uint32_t lane) {
+    for (uint64_t base = q & ~7ull; base < end; base += 1024) {
+        uint64_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const uint64_t a = base + 256u * k + 8u * lane; w[k] = a < end ? *(const uint64_t*)(bam + a) : ~0ull; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t a = base + 256u * k + 8u * lane;
+            uint64_t v = w[k];
+            if (a < q) v |= q - a >= 8 ? ~0ull : (1ull << (8 * (q - a))) - 1ull;                  // bytes in front of the value
+            if (a < end && a + 8 > end) v |= ~0ull << (8 * (end - a));                             // bytes behind the record
+            const uint64_t z = (v - 0x0101010101010101ull) & ~v & 0x8080808080808080ull;         // lowest set bit = first zero byte
+            const uint32_t m = __ballot_sync(0xffffffffu, z != 0);
+            if (m) {
+                const int src = __ffs(m) - 1;
+                const uint64_t zz = __shfl_sync(0xffffffffu, z, src);
+                return base + 256u * k + 8u * src + ((__ffsll((long long)zz) - 1) >> 3);
+            }
+        }
+    }
+    return end;
+}
+
+template <int K>
+__device__ __forceinline__ void aux_scan_warp(const uint8_t* bam, uint64_t aux, uint64_t end, const uint16_t (&want)[K], AuxHitDev (&hit)[K], uint32_t lane) {
+#pragma unroll
+    for (int k = 0; k < K; k++) { hit[k].found = false; hit[k].type = hit[k].sub = hit[k].n = 0; hit[k].p = 0; }
+    uint64_t p = aux;
+    while (p + 3 <= end) {
+        const uint32_t tg = (uint32_t)bam[p] | ((uint32_t)bam[p + 1] << 8), ty = bam[p + 2];
+        p += 3;
+        uint64_t sz; uint32_t n = 0, sub = 0; uint64_t vp = p;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': { const uint64_t q = warp_find_nul(bam, p, end, lane); if (q >= end) return; n = (uint32_t)(q - p); sz = (uint64_t)n + 1; break; }
+            case 'B': {
+                if (p + 5 > end) return;
+                sub = bam[p]; n = ld_u32(bam + p + 1);
+                const uint64_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                vp = p + 5; sz = 5 + es * (uint64_t)n;
+                break;
+            }
+            default: return;
+        }
+        if (p + sz > end) return;
+#pragma unroll
+        for (int k = 0; k < K; k++) if (tg == want[k] && !hit[k].found) { hit[k].found = true; hit[k].type = ty; hit[k].sub = sub; hit[k].n = n; hit[k].p = vp; }
+        p += sz;
+    }
+}
+#define MKP_TAG2(a, b) ((uint16_t)((uint8_t)(a) | ((uint8_t)(b) << 8)))
+
+// warp per selected record: header fields, source offsets, bytes needed
+__global__ void __launch_bounds__(256) k_slice_plan(const uint8_t* __restrict__ bam, const mkp_bam_rec* __restrict__ recs, const uint32_t* __restrict__ ids, uint32_t n,
+                                                    mkp_read_hdr* hdrs, SlicePlan* plan, uint32_t* need) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
     const mkp_bam_rec rc = recs[ids[i]];
     const uint8_t* r = bam + rc.off;
@@ -430,25 +488,26 @@ __global__ void k_slice_plan(const uint8_t* __restrict__ bam, const mkp_bam_rec*
     uint64_t cigar = r0 + 32 + l_name;
     const uint64_t seq = cigar + 4ull * n_cigar;
     const uint64_t aux = seq + (h.l_seq + 1) / 2 + h.l_seq;
+    const uint16_t want[6] = {MKP_TAG2('C', 'G'), MKP_TAG2('M', 'M'), MKP_TAG2('M', 'm'), MKP_TAG2('M', 'L'), MKP_TAG2('M', 'l'), MKP_TAG2('M', 'N')};
+    AuxHitDev hit[6];
+    aux_scan_warp<6>(bam, aux, rend, want, hit, lane);
     // long CIGARs (> 65535 ops) live in the CG:B,I tag (SAMv1 4.2.2)
     if (n_cigar == 2) {
-        const AuxHitDev cg = aux_find_dev(bam, aux, rend, 'C', 'G');
+        const AuxHitDev cg = hit[0];
         if (cg.found && cg.type == 'B' && cg.sub == 'I') {
             const uint32_t c0 = ld_u32(bam + cigar);
             if ((c0 & 15) == 4 && (c0 >> 4) == h.l_seq) { cigar = cg.p; n_cigar = cg.n; }
         }
     }
-    AuxHitDev mm = aux_find_dev(bam, aux, rend, 'M', 'M');
-    if (!mm.found) mm = aux_find_dev(bam, aux, rend, 'M', 'm');
+    const AuxHitDev mm = hit[1].found ? hit[1] : hit[2];
     bool ok = mm.found && mm.type == 'Z';
     AuxHitDev ml; ml.found = false; ml.n = 0; ml.p = 0; ml.type = ml.sub = 0;
     if (ok) {
-        ml = aux_find_dev(bam, aux, rend, 'M', 'L');
-        if (!ml.found) ml = aux_find_dev(bam, aux, rend, 'M', 'l');
+        ml = hit[3].found ? hit[3] : hit[4];
         ok = ml.found && ml.type == 'B' && ml.sub == 'C';
     }
     if (ok) {
-        const AuxHitDev mn = aux_find_dev(bam, aux, rend, 'M', 'N');
+        const AuxHitDev mn = hit[5];
         if (mn.found) {
             long long v = -1;
             const uint8_t* q = bam + mn.p;
@@ -461,6 +520,7 @@ __global__ void k_slice_plan(const uint8_t* __restrict__ bam, const mkp_bam_rec*
             if (ok && (unsigned long long)v != (unsigned long long)h.l_seq) ok = false;
         }
     }
+    if (lane) return;
     h.n_cigar = n_cigar;
     h.flags = flag | (ok ? 0u : MKP_RF_TAGS_INVALID);
     h.len_ml = ok ? ml.n : 0;
@@ -555,6 +615,44 @@ __global__ void __launch_bounds__(256) k_slice_copy(const uint8_t* __restrict__ 
             }
             *(uint32_t*)(d + k) = word;
         }
+    }
+}
+
+// ---- --partition-tag on the device front end: the values of up to 4 aux tags of the selected records (src/util.rs:670-688,
+//      src/pileup/mod.rs:629-646). Per (record, tag) 64 bytes: [0] = aux type (0: tag absent or not stringable), [1] = value length,
+//      [2..] = value bytes (Z/H text, or the raw little-endian scalar); a text longer than 61 bytes sets the overflow flag.
+__global__ void __launch_bounds__(256) k_tag_values(const uint8_t* __restrict__ bam, const mkp_bam_rec* __restrict__ recs, const uint32_t* __restrict__ ids, uint32_t n,
+                                                    uint32_t tags_packed_lo, uint32_t tags_packed_hi, uint32_t n_tags, uint8_t* __restrict__ out, uint32_t* overflow) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const mkp_bam_rec rc = recs[ids[i]];
+    const uint8_t* r = bam + rc.off;
+    const uint32_t l_name = r[8], n_cigar = ld_u16(r + 12);
+    const int32_t ls = (int32_t)ld_u32(r + 16);
+    const uint64_t l_seq = ls > 0 ? (uint64_t)ls : 0;
+    const uint64_t aux = rc.off + 32 + l_name + 4ull * n_cigar + (l_seq + 1) / 2 + l_seq, rend = rc.off + rc.size;
+    // (unused slots ask for a tag no file can hold: 0xffff)
+    const uint16_t want[4] = {(uint16_t)(tags_packed_lo & 0xffffu), (uint16_t)(n_tags > 1 ? tags_packed_lo >> 16 : 0xffffu),
+                              (uint16_t)(n_tags > 2 ? tags_packed_hi & 0xffffu : 0xffffu), (uint16_t)(n_tags > 3 ? tags_packed_hi >> 16 : 0xffffu)};
+    AuxHitDev hit[4];
+    aux_scan_warp<4>(bam, aux < rend ? aux : rend, rend, want, hit, lane);
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++) {
+        if (t >= n_tags) break;
+        uint8_t* o = out + ((size_t)i * n_tags + t) * 64;
+        const AuxHitDev h = hit[t];
+        uint32_t len = 0;
+        bool have = h.found;
+        if (have) switch (h.type) {
+            case 'Z': case 'H': len = h.n; break;
+            case 'A': case 'c': case 'C': len = 1; break;
+            case 's': case 'S': len = 2; break;
+            case 'i': case 'I': case 'f': len = 4; break;
+            default: have = false;                               // B arrays are not stringable: the tag counts as missing
+        }
+        if (len > 61) { if (lane == 0) atomicOr(overflow, 1u); len = 61; }
+        if (lane == 0) { o[0] = have ? (uint8_t)h.type : 0; o[1] = have ? (uint8_t)len : 0; }
+        for (uint32_t k = lane; have && k < len; k += 32) o[2 + k] = bam[h.p + k];
     }
 }
 

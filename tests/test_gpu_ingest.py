@@ -277,3 +277,26 @@ def test_ranged_ingest_equals_whole_file(native_lib, synth_exe, tmp_path, monkey
         assert heap.tobytes() == pk.heap().tobytes()
         pk.free()
     dev.close(); host.close(); c.close()
+
+
+@pytest.mark.gpu
+def test_device_partition_keys_equal_host(native_lib, synth_exe, tmp_path):
+    """mkp_bam_tags (device-resident records) vs the host's aux reader (src/util.rs:670-688, src/pileup/mod.rs:629-646): the same key for
+    every record — RG:Z or none, HP as C / i or none, XF:f on some, missing tags, records with no tag at all."""
+    import subprocess
+    import modkit_b200 as mk
+    prefix = str(tmp_path / "pk")
+    subprocess.check_call([synth_exe, "--out", prefix, "--contig", "syn1:200000", "--coverage", "15", "--mods", "hm", "--seed", "33",
+                           "--partition-tags", "--odd-records"], stdout=subprocess.DEVNULL)
+    for path in (prefix + ".bam", os.path.join(FIX, "bc_anchored_10_reads.haplotyped.sorted.bam")):
+        host = mk.Bam(path, threads=2)
+        c = mk.Context(0)
+        dev = mk.Bam(path, ctx=c)
+        n = host.n_records(0)
+        assert n > 0
+        for tags in (["RG", "HP"], ["XF"], ["HP", "XX", "RG", "XF"], ["XX", "YY"]):
+            got = c.bam_partition_keys(np.arange(n, dtype=np.uint32), tags)
+            exp = [host.partition_key(0, i, tags) for i in range(n)]
+            assert got == exp, tags
+        assert len(set(c.bam_partition_keys(np.arange(n, dtype=np.uint32), ["RG", "HP"]))) > 3
+        dev.close(); host.close(); c.close()
