@@ -106,6 +106,79 @@ public:
         return members;
     }
 
+    // The same chain walked in parallel: `hints` are compressed offsets that should be member starts (the BAI's virtual offsets).
+    // A segment starts at a hint and must end exactly on the next segment's start; then the pieces are the chain from offset 0.
+    // Anything else (a stale index, a malformed member) falls back to the serial walk, which also produces the error text.
+    static std::vector<Member> scan_members_parallel(const MappedFile& mf, const std::string& path, std::vector<uint64_t> hints, int threads, size_t* total_out) {
+        std::sort(hints.begin(), hints.end());
+        hints.erase(std::unique(hints.begin(), hints.end()), hints.end());
+        const size_t n_seg_want = (size_t)std::max(1, threads) * 8;
+        std::vector<size_t> starts;
+        starts.push_back(0);
+        for (size_t k = 1; k < n_seg_want && !hints.empty(); k++) {
+            const uint64_t want = (uint64_t)((double)mf.size * (double)k / (double)n_seg_want);
+            auto it = std::lower_bound(hints.begin(), hints.end(), want);
+            if (it == hints.end()) break;
+            if (*it > starts.back() && *it + 28 <= mf.size) starts.push_back((size_t)*it);
+        }
+        size_t min_bytes = 64u << 20;                     // small files: the serial walk is faster than starting threads
+        if (const char* e = getenv("MKH_PARALLEL_SCAN_MIN_BYTES")) min_bytes = (size_t)strtoull(e, nullptr, 10);     // (tests)
+        if (starts.size() < 2 || mf.size < min_bytes) return scan_members(mf, path, total_out);
+        const size_t n_seg = starts.size();
+        std::vector<std::vector<Member>> seg(n_seg);
+        std::vector<size_t> seg_total(n_seg, 0);
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        auto work = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n_seg || bad) break;
+                const size_t stop = i + 1 < n_seg ? starts[i + 1] : mf.size;
+                size_t off = starts[i], total = 0;
+                std::vector<Member>& out = seg[i];
+                while (off + 28 <= mf.size && off < stop) {
+                    const uint8_t* p = mf.data + off;
+                    if (p[0] != 0x1f || p[1] != 0x8b || !(p[3] & 4)) { bad = true; return; }
+                    const uint16_t xlen = load_le<uint16_t>(p + 10);
+                    if (off + 12 + xlen > mf.size) { bad = true; return; }
+                    int bsize = -1;
+                    for (size_t x = 12; x + 4 <= 12u + xlen;) {
+                        const uint16_t sl = load_le<uint16_t>(p + x + 2);
+                        if (p[x] == 'B' && p[x + 1] == 'C' && sl == 2 && x + 6 <= 12u + xlen) bsize = load_le<uint16_t>(p + x + 4);
+                        x += 4 + sl;
+                    }
+                    const size_t mlen = (size_t)bsize + 1;
+                    if (bsize < 0 || mlen < 20u + xlen || off + mlen > mf.size) { bad = true; return; }
+                    const uint32_t isize = load_le<uint32_t>(p + mlen - 4);
+                    out.push_back({off + 12 + xlen, mlen - 20 - xlen, total, isize, off});
+                    total += isize;
+                    off += mlen;
+                }
+                if (i + 1 < n_seg && off != stop) { bad = true; return; }
+                seg_total[i] = total;
+            }
+        };
+        {
+            std::vector<std::thread> th;
+            const int nt = (int)std::min<size_t>((size_t)std::max(1, threads), n_seg);
+            for (int t = 1; t < nt; t++) th.emplace_back(work);
+            work();
+            for (auto& t : th) t.join();
+        }
+        if (getenv("MKH_SCAN_DEBUG")) fprintf(stderr, "[scan] segments %zu bad %d\n", n_seg, (int)bad.load());
+        if (bad) return scan_members(mf, path, total_out);
+        size_t n = 0, total = 0;
+        for (auto& v : seg) n += v.size();
+        std::vector<Member> members;
+        members.reserve(n);
+        for (size_t i = 0; i < n_seg; i++) {
+            for (Member m : seg[i]) { m.out_off += total; members.push_back(m); }
+            total += seg_total[i];
+        }
+        *total_out = total;
+        return members;
+    }
+
     void open(const std::string& path, int threads) {
         MappedFile mf;
         mf.open(path);
@@ -166,15 +239,25 @@ public:
         file_->open(path);
         const MappedFile& mf = *file_;
         total_ = 0;
-        members_ = scan_members(mf, path, &total_);
-        const size_t total = total_;
-        const std::vector<Member>& members = members_;
-        // ---- BAM header: inflate leading members until it is complete
+        // ---- BAM header: inflate leading members until it is complete (a short serial walk of the member chain)
         std::vector<uint8_t> head;
-        size_t m_done = 0;
+        size_t h_off = 0;
         auto more = [&]() {
-            if (m_done >= members.size()) throw std::runtime_error(path + ": truncated BAM header");
-            const Member& m = members[m_done++];
+            if (h_off + 28 > mf.size) throw std::runtime_error(path + ": truncated BAM header");
+            const uint8_t* p = mf.data + h_off;
+            if (p[0] != 0x1f || p[1] != 0x8b || !(p[3] & 4)) throw std::runtime_error(path + ": not a BGZF file");
+            const uint16_t xlen = load_le<uint16_t>(p + 10);
+            int bsize = -1;
+            for (size_t x = 12; x + 4 <= 12u + xlen && h_off + x + 6 <= mf.size;) {
+                const uint16_t sl = load_le<uint16_t>(p + x + 2);
+                if (p[x] == 'B' && p[x + 1] == 'C' && sl == 2) bsize = load_le<uint16_t>(p + x + 4);
+                x += 4 + sl;
+            }
+            if (bsize < 0) throw std::runtime_error(path + ": BGZF member without BSIZE");
+            const size_t mlen = (size_t)bsize + 1;
+            if (mlen < 20u + xlen || h_off + mlen > mf.size) throw std::runtime_error(path + ": truncated BGZF member");
+            Member m{h_off + 12 + xlen, mlen - 20 - xlen, 0, load_le<uint32_t>(p + mlen - 4), h_off};
+            h_off += mlen;
             const size_t o = head.size();
             head.resize(o + m.out_len);
             if (!m.out_len) return;
@@ -195,14 +278,22 @@ public:
             ref_lens.push_back(load_le<uint32_t>(head.data() + o + 4 + ln));
             o += 8 + ln;
         }
+        // ---- index, then the member table (walked in parallel from the index's compressed offsets when there is one)
+        std::vector<uint64_t> voffs;
+        have_bai_ = load_bai(path, &voffs, &ref_first_voff);
+        {
+            std::vector<uint64_t> hints;
+            hints.reserve(voffs.size());
+            for (uint64_t v : voffs) hints.push_back(v >> 16);
+            members_ = have_bai_ ? scan_members_parallel(mf, path, std::move(hints), 16, &total_) : scan_members(mf, path, &total_);
+        }
+        const size_t total = total_;
         first_rec_ = o;
         by_tid.assign(n_ref, {});
         run_max_end.assign(n_ref, {});
         stats.n_mapped.assign(n_ref, 0);
         stats.n_unmapped.assign(n_ref, 0);
         // ---- seeds: virtual offsets of the index -> offsets in the inflated stream
-        std::vector<uint64_t> voffs;
-        have_bai_ = load_bai(path, &voffs, &ref_first_voff);
         seeds_.clear();
         seeds_.push_back(first_rec_);
         for (uint64_t v : voffs) { uint64_t x; if (voff_to_offset(v, &x) && x > first_rec_ && x + 36 <= total) seeds_.push_back(x); }

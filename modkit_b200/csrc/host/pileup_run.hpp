@@ -2,10 +2,15 @@
 // Mirrors ModBamPileup::run (src/pileup/subcommand.rs:381-817): same flags, same defaults, same error
 // messages where they are observable, same output ordering (feeder order, positions ascending).
 #pragma once
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <future>
+#include <memory>
 #include <filesystem>
 #include <set>
 #include <unordered_set>
@@ -75,9 +80,10 @@ inline Region parse_region_arg(const std::string& raw, const BamReader& bam) {  
 
 inline double secs_between(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); }
 
+inline void trace_mark0(const char* what);
 struct DeviceGuard {
     mkp_ctx* ctx = nullptr;
-    ~DeviceGuard() { if (ctx) mkp_destroy(ctx); }
+    ~DeviceGuard() { if (ctx) { trace_mark0("host objects released"); mkp_destroy(ctx); trace_mark0("device context destroyed"); } }
 };
 
 // ---- threshold estimation: host schedule (reads_sampler/*), device decode + histogram --------------
@@ -88,6 +94,7 @@ struct TraceClock {
     void mark(int rank, const char* what) const { if (on) fprintf(stderr, "[mkh r%d] %8.3f s  %s\n", rank, std::chrono::duration<double>(std::chrono::steady_clock::now() - epoch).count(), what); }
 };
 inline TraceClock& trace_clock() { static TraceClock t; return t; }
+inline void trace_mark0(const char* what) { trace_clock().mark(0, what); }
 
 struct SamplerConfig {
     int threads = 4;
@@ -535,6 +542,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
     size_t resident_bulk = (size_t)-1;
     for (size_t bi = 0; bi < bulks.size(); bi++) { bulks[bi].take.assign(bulks[bi].pc.recs.size(), 0); contributes_of(bulks[bi].pc, bulks[bi].tid, &bulks[bi].contributes); resident_bulk = bi; }
     trace_clock().mark(coll.rank, "sampler: candidates decoded on the device");
+    size_t n_on_demand = 0;
     // ---- the real schedule, contig by contig
     for (auto& cp : cps) {
         const uint32_t t = cp.tid;
@@ -564,6 +572,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
             } else cur = bam.fetch_begin(g.tid, g.start, g.end);
             // on demand: the plan did not cover the group, or the group needs more candidates than were fetched
             while (!cur.done && (g.n < 0 || used < (size_t)g.n)) {
+                n_on_demand++;
                 const size_t want = g.n < 0 ? 4096 : ((size_t)g.n - used) * 2 + 32;
                 extra.clear();
                 recs.clear();
@@ -585,6 +594,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
         }
         n_selected += selected.size();
     }
+    if (trace_clock().on) fprintf(stderr, "[mkh r%d]             sampler: %zu on-demand fetches during the replay\n", coll.rank, n_on_demand);
     trace_clock().mark(coll.rank, "sampler: schedule replayed");
     // ---- histogram of the selected reads of every bulk chunk
     for (size_t bi = 0; bi < bulks.size(); bi++) {
@@ -825,6 +835,18 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 catch (...) { bg_err = std::current_exception(); }
             });
         }
+        // ---- focus positions of this rank's intervals (reference motif scan), beside the load and the sampler. Every object the
+        // job touches is declared above; its joiner is declared after them, so it is destroyed (joined) before they are.
+        std::exception_ptr iv_err;
+        double iv_secs = 0;
+        struct Joiner { std::thread t; void join() { if (t.joinable()) t.join(); } ~Joiner() { join(); } } iv_job;
+        iv_job.t = std::thread([&]() {
+            try {
+                fill_interval_focus(ivs, my_i0, my_i1, iv_targets, iv_owner, combine_strands, have_motifs ? &mc : nullptr, inc, std::max(1, o.threads / 2));
+                iv_secs = secs(t_iv0, clk::now());
+                trace("interval focus filled (background)");
+            } catch (...) { iv_err = std::current_exception(); }
+        });
         // ---- device load: everything, or the byte ranges under this rank's intervals
         if (!loaded) {
             if (sharded) {
@@ -866,7 +888,10 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             }
             ~Router() { for (auto& kv : files) fclose(kv.second); }
         } router;
-        std::string shard_text;      // sharded: this rank's slice of the output, written at its offset at the end
+        std::string shard_text;      // sharded: this rank's slice of the output (header; the formatted parts follow in shard_parts), written at its offset at the end
+        std::vector<std::string> shard_parts;
+        int out_fd = -1;             // single regular output file: the formatting workers write their text at its offset (pwrite)
+        uint64_t file_pos = 0;
         if (sharded) {
             if (coll.rank == 0) {
                 FILE* f = fopen(o.out_bed.c_str(), "w");     // created (and truncated) by rank 0 before the first exchange
@@ -878,6 +903,12 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             out = (o.out_bed == "-" || o.out_bed == "stdout") ? stdout : fopen(o.out_bed.c_str(), "w");
             if (!out) throw std::runtime_error("failed to make output file");
             if (o.header) fputs(bed_header_line(), out);
+            if (out != stdout) {
+                fflush(out);
+                struct stat sb;
+                const off_t at = ftello(out);
+                if (at >= 0 && fstat(fileno(out), &sb) == 0 && S_ISREG(sb.st_mode)) { out_fd = fileno(out); file_pos = (uint64_t)at; }
+            }
         } else {
             std::error_code ec;
             std::filesystem::create_directories(o.out_bed, ec);
@@ -886,17 +917,6 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         }
         const std::string pfx = o.prefix.empty() ? std::string() : o.prefix + "_";
 
-        // every object the background job touches is declared above; the joiner below is destroyed (joined) first
-        std::exception_ptr iv_err;
-        double iv_secs = 0;
-        struct Joiner { std::thread t; void join() { if (t.joinable()) t.join(); } ~Joiner() { join(); } } iv_job;
-        iv_job.t = std::thread([&]() {
-            try {
-                fill_interval_focus(ivs, my_i0, my_i1, iv_targets, iv_owner, combine_strands, have_motifs ? &mc : nullptr, inc, std::max(1, o.threads / 2));
-                iv_secs = secs(t_iv0, clk::now());
-                trace("interval focus filled (background)");
-            } catch (...) { iv_err = std::current_exception(); }
-        });
         // thresholds (subcommand.rs:615-638, command_utils.rs:49-134)
         for (auto& raw : o.mod_thresholds) {
             auto c = raw.find(':');
@@ -926,6 +946,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             }
         } else if (!o.no_filtering && sampler_bg) {
             if (bg_job.t.joinable()) bg_job.t.join();
+            trace("sampler joined");
             if (bg_err) std::rethrow_exception(bg_err);
             fetch_s = bg_fetch_s;
             if (bg_inexact) throw std::runtime_error("sampled probabilities are not multiples of 1/1024 (" + std::to_string(bg_inexact) + " values): exact histogram quantile impossible; pass --filter-threshold");
@@ -1147,8 +1168,13 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             std::vector<std::string> parts(nt);
             std::vector<std::map<std::string, std::string>> routed(nt);      // to_dir: file name -> text, per worker
             std::vector<uint64_t> part_rows(nt, 0);
+            const bool direct = out_fd >= 0 && !to_dir && !sharded;
+            std::unique_ptr<std::atomic<uint64_t>[]> psize(new std::atomic<uint64_t>[nt]);
+            for (int t = 0; t < nt; t++) psize[t].store(UINT64_MAX);
+            std::atomic<bool> write_failed{false};
             {
                 auto work = [&](int t) {
+                    struct Publish { std::atomic<uint64_t>* a; ~Publish() { if (a->load() == UINT64_MAX) a->store(0); } } guard{&psize[t]};      // (a worker that leaves early must not block the others)
                     std::vector<OutRow> local;
                     const size_t a = n_iv * t / nt, b = n_iv * (t + 1) / nt;
                     for (size_t k = a; k < b; k++) {
@@ -1166,14 +1192,28 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                         }
                         part_rows[t] += local.size();
                     }
+                    if (direct) {
+                        // the text of worker t follows the text of the workers before it: wait for their sizes, then write in place
+                        psize[t].store(parts[t].size(), std::memory_order_release);
+                        uint64_t at = file_pos;
+                        for (int q = 0; q < t; q++) { uint64_t v; while ((v = psize[q].load(std::memory_order_acquire)) == UINT64_MAX) std::this_thread::yield(); at += v; }
+                        size_t done = 0;
+                        while (done < parts[t].size()) {
+                            const ssize_t w = pwrite(out_fd, parts[t].data() + done, parts[t].size() - done, (off_t)(at + done));
+                            if (w <= 0) { write_failed = true; break; }
+                            done += (size_t)w;
+                        }
+                    }
                 };
                 std::vector<std::thread> th;
                 for (int t = 1; t < nt; t++) th.emplace_back(work, t);
                 work(0);
                 for (auto& t : th) t.join();
             }
+            if (write_failed) throw std::runtime_error("failed to write output file " + o.out_bed);
             for (int t = 0; t < nt; t++) {
-                if (sharded) shard_text.append(parts[t]);
+                if (sharded) { if (!parts[t].empty()) shard_parts.push_back(std::move(parts[t])); }
+                else if (direct) file_pos += parts[t].size();
                 else if (out) fwrite(parts[t].data(), 1, parts[t].size(), out);
                 for (auto& kv : routed[t]) if (!kv.second.empty()) fwrite(kv.second.data(), 1, kv.second.size(), router.get(kv.first));
                 S.rows += part_rows[t];
@@ -1189,20 +1229,43 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             // are exchanged (second and last collective) and every rank writes its slice at its offset
             const auto tw = clk::now();
             std::vector<uint64_t> sizes((size_t)coll.world + 2, 0);
-            sizes[coll.rank] = shard_text.size();
+            uint64_t my_bytes = shard_text.size();
+            for (auto& sp : shard_parts) my_bytes += sp.size();
+            sizes[coll.rank] = my_bytes;
             sizes[coll.world] = S.rows; sizes[(size_t)coll.world + 1] = S.positions;
             coll.sum(sizes.data(), sizes.size());
             uint64_t at = 0;
             for (int r = 0; r < coll.rank; r++) at += sizes[r];
             const int fd = ::open(o.out_bed.c_str(), O_WRONLY);
             if (fd < 0) throw std::runtime_error("failed to open output file " + o.out_bed);
-            size_t done = 0;
-            while (done < shard_text.size()) {
-                const ssize_t w = pwrite(fd, shard_text.data() + done, shard_text.size() - done, (off_t)(at + done));
-                if (w <= 0) { ::close(fd); throw std::runtime_error("failed to write output file " + o.out_bed); }
-                done += (size_t)w;
+            // the pieces (header, then the formatted parts in order) go to their offsets from several threads
+            std::vector<std::pair<const std::string*, uint64_t>> pieces;
+            pieces.push_back({&shard_text, at});
+            { uint64_t q = at + shard_text.size(); for (auto& sp : shard_parts) { pieces.push_back({&sp, q}); q += sp.size(); } }
+            std::atomic<size_t> next_piece{0};
+            std::atomic<bool> failed{false};
+            auto put = [&]() {
+                for (;;) {
+                    const size_t k = next_piece.fetch_add(1);
+                    if (k >= pieces.size() || failed) break;
+                    const std::string& txt = *pieces[k].first;
+                    size_t done = 0;
+                    while (done < txt.size()) {
+                        const ssize_t w = pwrite(fd, txt.data() + done, txt.size() - done, (off_t)(pieces[k].second + done));
+                        if (w <= 0) { failed = true; break; }
+                        done += (size_t)w;
+                    }
+                }
+            };
+            {
+                std::vector<std::thread> th;
+                const int nw = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, o.threads), pieces.size()));
+                for (int t = 1; t < nw; t++) th.emplace_back(put);
+                put();
+                for (auto& t : th) t.join();
             }
             ::close(fd);
+            if (failed) throw std::runtime_error("failed to write output file " + o.out_bed);
             S.rows_total = sizes[coll.world]; S.positions_total = sizes[(size_t)coll.world + 1];
             S.write_s += secs(tw, clk::now());
         } else { S.rows_total = S.rows; S.positions_total = S.positions; }

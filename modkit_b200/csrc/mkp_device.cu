@@ -67,6 +67,7 @@ struct mkp_ctx {
     // results
     size_t n_rows = 0;
     uint64_t launches = 0;       // kernels launched by this context (mkp_kernel_launches)
+    double pass_prof[4] = {0, 0, 0, 0};          // same for the pileup pass: buffers, launches, wait, calls
     double slice_prof[6] = {0, 0, 0, 0, 0, 0};   // MKP_TRACE_SLICE=1: host seconds in the phases of mkp_bam_chunk, printed by mkp_destroy
     // fused pass (chunks with focus bitmaps): tile table, rank of the focus set (built at upload), capacities
     DevBuf d_pscr, d_inftab, d_tiles, d_order;
@@ -159,6 +160,7 @@ void mkp_destroy(mkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (getenv("MKP_TRACE_SLICE")) fprintf(stderr, "[mkp] slice phases (s): buffers %.4f plan+scan %.4f heap alloc %.4f copy+focus %.4f finish_upload %.4f calls %.0f\n",
                                            ctx->slice_prof[0], ctx->slice_prof[1], ctx->slice_prof[2], ctx->slice_prof[3], ctx->slice_prof[4], ctx->slice_prof[5]);
+    if (getenv("MKP_TRACE_SLICE")) fprintf(stderr, "[mkp] pass phases (s): buffers %.4f launches %.4f wait %.4f calls %.0f\n", ctx->pass_prof[0], ctx->pass_prof[1], ctx->pass_prof[2], ctx->pass_prof[3]);
     DevBuf* bufs[] = {&ctx->d_hdrs, &ctx->d_heap, &ctx->d_entry_off, &ctx->d_focus_pos, &ctx->d_focus_neg, &ctx->d_rl, &ctx->d_meta, &ctx->d_P,
                       &ctx->d_calls, &ctx->d_hot, &ctx->d_hot_prefix, &ctx->d_block_sums, &ctx->d_small, &ctx->d_scr_cq, &ctx->d_scr_cr, &ctx->d_slow,
                       &ctx->d_obs_word, &ctx->d_slots, &ctx->d_row_counts, &ctx->d_row_prefix, &ctx->d_rows, &ctx->d_hist, &ctx->d_take,
@@ -329,6 +331,9 @@ static int finish_upload(mkp_ctx* ctx) {
 // (base, code) states per slot, rows - grow and the affected part runs again).
 static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
     cudaStream_t st = ctx->stream;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(now() - t).count(); };
+    auto tp = now();
     const uint32_t n_words = ctx->n_words, n_hot = ctx->n_hot;
     const uint32_t n_blk = (n_words + 1023) / 1024;
     ChunkDev C;
@@ -361,6 +366,7 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         const uint32_t stride = SL_MOD + 2 * S_cap;
         CK(ctx->d_slots.ensure(std::max<size_t>(1, n_hot) * stride * 4));
         if (!ctx->d_rows.p) CK(ctx->d_rows.ensure(std::max<size_t>(1024, (size_t)n_hot * 3) * sizeof(mkp_row)));
+        ctx->pass_prof[0] += since(tp); tp = now();
         CK(cudaEventRecord(ctx->ev[0], st));
         CK(cudaMemsetAsync(ctx->d_small.p, 0xff, 32 * 8, st));
         CK(cudaMemsetAsync(ctx->d_small.as<uint8_t>() + 32 * 8, 0, SMALL_BYTES - 32 * 8, st));
@@ -445,8 +451,10 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         CK(cudaMemcpyAsync(h_small, u, 16, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_slow, u + 8, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_calls, C.total_calls, 8, cudaMemcpyDeviceToHost, st));
+        ctx->pass_prof[1] += since(tp); tp = now();
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
+        ctx->pass_prof[2] += since(tp); tp = now();
         if (h_small[1]) {
             if (stats) { memset(stats, 0, sizeof *stats); stats->device_error = h_small[1]; }
             return fail(ctx, "device decode error: " + derr_text(h_small[1]), -10);
@@ -470,6 +478,7 @@ static int pileup_fused(mkp_ctx* ctx, mkp_stats* stats) {
         break;
     }
     ctx->n_rows = h_small[3];
+    ctx->pass_prof[3] += 1;
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->n_rows = h_small[3]; stats->n_hot = n_hot; stats->n_calls = h_calls; stats->n_states = h_small[0];

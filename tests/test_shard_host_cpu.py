@@ -72,6 +72,41 @@ def test_index_fetch_matches_a_full_scan(synth_exe, native_lib, tmp_path):
         assert list(modkit_b200.bam_fetch(path, None, 0, 0)) == _overlapping(Bam(path), None, 0, 0)
 
 
+def test_parallel_member_scan_equals_serial_walk(synth_exe, native_lib, tmp_path, monkeypatch):
+    """The BGZF member table walked in parallel from the index's compressed offsets (large files) is the table of the serial walk:
+    same shard plan (weights = member offsets), same fetch results; a stale index (hints that are not member starts) falls back."""
+    prefix = _genome(synth_exe, tmp_path, "--odd-records")
+    bam = Bam(prefix + ".bam")
+    queries = ((0, 0, 100000), (0, 512345, 530000), (1, 16384, 16385), (3, 650000, 800000))
+    serial_plan = modkit_b200.shard_plan(prefix + ".bam", 100000, 5)
+    monkeypatch.setenv("MKH_PARALLEL_SCAN_MIN_BYTES", "0")
+    assert modkit_b200.shard_plan(prefix + ".bam", 100000, 5) == serial_plan
+    for tid, beg, end in queries:
+        assert list(modkit_b200.bam_fetch(prefix + ".bam", tid, beg, end)) == _overlapping(bam, tid, beg, end)
+    assert list(modkit_b200.bam_fetch(prefix + ".bam", None, 0, 0)) == _overlapping(bam, None, 0, 0)
+    # an index whose compressed offsets are shifted: no segment chain lands on the next start -> serial walk, same table
+    bai = bytearray(open(prefix + ".bam.bai", "rb").read())
+    n_ref = struct.unpack_from("<I", bai, 4)[0]
+    o = 8
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<I", bai, o)[0]; o += 4
+        for _ in range(n_bin):
+            n_chunk = struct.unpack_from("<I", bai, o + 4)[0]; o += 8 + 16 * n_chunk
+        n_intv = struct.unpack_from("<I", bai, o)[0]; o += 4
+        for k in range(n_intv):
+            v = struct.unpack_from("<Q", bai, o + 8 * k)[0]
+            if v:
+                struct.pack_into("<Q", bai, o + 8 * k, v + (3 << 16))
+        o += 8 * n_intv
+    import shutil
+    shutil.copy(prefix + ".bam", str(tmp_path / "stale.bam"))
+    open(str(tmp_path / "stale.bam.bai"), "wb").write(bytes(bai))
+    monkeypatch.delenv("MKH_PARALLEL_SCAN_MIN_BYTES")
+    want = modkit_b200.shard_plan(str(tmp_path / "stale.bam"), 100000, 5)
+    monkeypatch.setenv("MKH_PARALLEL_SCAN_MIN_BYTES", "0")
+    assert modkit_b200.shard_plan(str(tmp_path / "stale.bam"), 100000, 5) == want
+
+
 def test_oracle_max_depth_limits_reads_per_start_column(oracle_exe, synth_exe, tmp_path):
     # the depth limit only bites where more reads than the limit are buffered: outputs with a limit above the depth are
     # unchanged, a small limit lowers counts but never raises them, and --max-depth 0... is not a value the reference accepts
