@@ -55,7 +55,7 @@ MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_re
                "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
                "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records",
                "mkh_f32_display", "mkh_bam_partition_key", "mkh_bam_n_ranges", "mkh_pileup_main_sharded", "mkh_shard_plan",
-               "mkh_bam_open_device_pieces", "mkh_bam_fetch", "mkh_summary_main", "mkh_sample_probs_main", "mkh_partition_key_of_cells"]
+               "mkh_bam_open_device_pieces", "mkh_bam_fetch", "mkh_summary_main", "mkh_sample_probs_main", "mkh_partition_key_of_cells", "mkh_bam_index_n_mapped"]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint64), C.c_size_t, C.c_void_p)
 
@@ -115,6 +115,8 @@ def load_library(build_if_missing=True):
     lib.mkh_bam_ingest_ms.restype = None
     lib.mkh_f32_display.argtypes = [C.c_float, C.c_char_p, C.c_int]
     lib.mkh_bam_partition_key.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int]
+    lib.mkh_bam_index_n_mapped.argtypes = [C.c_char_p, C.c_uint32]
+    lib.mkh_bam_index_n_mapped.restype = C.c_int64
     lib.mkh_partition_key_of_cells.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_int]
     lib.mkh_bam_n_ranges.argtypes = [C.c_void_p]
     lib.mkh_bam_n_ranges.restype = C.c_uint32
@@ -217,6 +219,11 @@ def bam_fetch(bam_path, tid, beg, end):
         if n <= cap:
             return offs[:n].copy()
         cap = int(n)
+
+
+def bam_index_n_mapped(bam_path, tid):
+    """Mapped reads of contig tid according to the index, as the device front end's index-only open reads it (CPU only)."""
+    return int(load_library().mkh_bam_index_n_mapped(str(bam_path).encode(), tid))
 
 
 def shard_plan(bam_path, interval_size, world):

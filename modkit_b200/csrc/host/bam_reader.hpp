@@ -278,7 +278,12 @@ public:
             ref_lens.push_back(load_le<uint32_t>(head.data() + o + 4 + ln));
             o += 8 + ln;
         }
-        // ---- index, then the member table (walked in parallel from the index's compressed offsets when there is one)
+        by_tid.assign(n_ref, {});
+        run_max_end.assign(n_ref, {});
+        stats.n_mapped.assign(n_ref, 0);
+        stats.n_unmapped.assign(n_ref, 0);
+        // ---- index (also the per-contig read counts), then the member table (walked in parallel from the index's compressed
+        // offsets when there is one)
         std::vector<uint64_t> voffs;
         have_bai_ = load_bai(path, &voffs, &ref_first_voff);
         {
@@ -289,10 +294,6 @@ public:
         }
         const size_t total = total_;
         first_rec_ = o;
-        by_tid.assign(n_ref, {});
-        run_max_end.assign(n_ref, {});
-        stats.n_mapped.assign(n_ref, 0);
-        stats.n_unmapped.assign(n_ref, 0);
         // ---- seeds: virtual offsets of the index -> offsets in the inflated stream
         seeds_.clear();
         seeds_.push_back(first_rec_);

@@ -143,6 +143,15 @@ int mkh_bam_partition_key(const mkh_bam* b, uint32_t tid, uint64_t i, const char
         return have ? 1 : 0;
     } catch (const std::exception&) { return -1; }
 }
+// mapped-read count of a contig as the index-only open of the device front end sees it (BAI pseudo-bin; CPU only): -1 on error
+int64_t mkh_bam_index_n_mapped(const char* bam_path, uint32_t tid) {
+    try {
+        BamReader bam;
+        bam.open_device_index(bam_path, nullptr);
+        if (!bam.have_index() || tid >= bam.stats.n_mapped.size()) return -1;
+        return (int64_t)bam.stats.n_mapped[tid];
+    } catch (const std::exception&) { return -1; }
+}
 // the key built from mkp_bam_tags cells (device front end): same return convention
 int mkh_partition_key_of_cells(const uint8_t* cells, uint32_t n_tags, char* out, int cap) {
     std::string k;

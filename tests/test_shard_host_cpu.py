@@ -40,6 +40,11 @@ def test_shard_plan_covers_the_genome_on_the_interval_grid(synth_exe, native_lib
         sizes = [sum(hi - lo for r, _, lo, hi in plan if r == k) for k in range(world)]
         assert max(sizes) - min(sizes) <= 300000, sizes
     assert modkit_b200.shard_plan(prefix + ".bam", 100000, 1) == [(0, t, 0, n) for t, (_, n) in enumerate(refs)]
+    # the index-only open keeps the index's per-contig read counts (run_pileup refuses files without mapped reads)
+    host = modkit_b200.Bam(prefix + ".bam", threads=2)
+    for tid in range(len(refs)):
+        assert modkit_b200.bam_index_n_mapped(prefix + ".bam", tid) == host.n_mapped(tid) > 0
+    host.close()
 
 
 def _overlapping(bam, tid, beg, end):
