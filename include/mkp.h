@@ -191,6 +191,10 @@ int  mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_
  * record that belongs to the next range; the last members of a range may hold its first bytes). */
 int  mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
                         uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms);
+/* The same, with the file range [file_off, file_off + file_len) read from the descriptor fd (pread into pinned staging buffers: no
+ * page of the file is mapped into the caller; member offsets are relative to file_off). */
+int  mkp_bam_load_range_fd(mkp_ctx* ctx, int fd, uint64_t file_off, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                           uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms);
 /* Record table in file order (n_records entries, host memory). */
 int  mkp_bam_records(mkp_ctx* ctx, mkp_bam_rec* out);
 /* Make the records rec_ids[0..n) (indices into the record table, file order) the resident chunk for [start,end):

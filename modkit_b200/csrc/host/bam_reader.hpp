@@ -635,8 +635,9 @@ private:
         const size_t flen = (size_t)(members_[m1].in_off + members_[m1].in_len + 8 - fbase);
         size_t n_rec = 0;
         float ms[4] = {0, 0, 0, 0};
-        if (mkp_bam_load_range(dev, mf.data + fbase, std::min(flen, mf.size - (size_t)fbase), jobs.data(), jobs.size(), inflated, stop_off - obase,
-                               seeds.data(), seeds.size(), &n_rec, ms))
+        // (the file bytes are read with pread into the device layer's pinned staging buffers, not through the mapping)
+        if (mkp_bam_load_range_fd(dev, mf.fd, fbase, std::min(flen, mf.size - (size_t)fbase), jobs.data(), jobs.size(), inflated, stop_off - obase,
+                                  seeds.data(), seeds.size(), &n_rec, ms))
             throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(dev));
         for (int i = 0; i < 4; i++) ingest_ms[i] += ms[i];
         std::vector<mkp_bam_rec> recs(n_rec);

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <future>
 #include <memory>
 #include <filesystem>
@@ -80,6 +81,48 @@ inline Region parse_region_arg(const std::string& raw, const BamReader& bam) {  
 
 inline double secs_between(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); }
 
+// A fixed set of worker threads for the per-chunk formatting (threads are not created per chunk). Tasks are handed out in increasing
+// index order; run() returns when all of them are done; the caller takes part.
+class WorkerPool {
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int n_tasks_ = 0, next_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+    void drain(uint64_t g) {
+        for (;;) {
+            int i;
+            { std::lock_guard<std::mutex> lk(mu_); if (gen_ != g || next_ >= n_tasks_) return; i = next_++; }
+            (*fn_)(i);
+            { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) done_cv_.notify_all(); }
+        }
+    }
+public:
+    explicit WorkerPool(int n_threads) {
+        for (int t = 1; t < n_threads; t++) th_.emplace_back([this]() {
+            uint64_t seen = 0;
+            for (;;) {
+                uint64_t g;
+                { std::unique_lock<std::mutex> lk(mu_); cv_.wait(lk, [&] { return stop_ || gen_ != seen; }); if (stop_) return; g = seen = gen_; }
+                drain(g);
+            }
+        });
+    }
+    ~WorkerPool() { { std::lock_guard<std::mutex> lk(mu_); stop_ = true; } cv_.notify_all(); for (auto& t : th_) t.join(); }
+    int size() const { return (int)th_.size() + 1; }
+    void run(int n_tasks, const std::function<void(int)>& fn) {
+        if (n_tasks <= 0) return;
+        uint64_t g;
+        { std::lock_guard<std::mutex> lk(mu_); fn_ = &fn; n_tasks_ = n_tasks; next_ = 0; pending_ = n_tasks; g = ++gen_; }
+        cv_.notify_all();
+        drain(g);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+};
+
 inline void trace_mark0(const char* what);
 struct DeviceGuard {
     mkp_ctx* ctx = nullptr;
@@ -99,6 +142,8 @@ inline void trace_mark0(const char* what) { trace_clock().mark(0, what); }
 struct SamplerConfig {
     int threads = 4;
     int workers = 4;                   // host threads that fetch candidates (not part of the schedule)
+    std::shared_ptr<void>* defer_free = nullptr;         // indexed sampler: its candidate buffers (hundreds of MB) are handed over instead of being
+                                                         // released before the result is returned; the caller drops them when convenient
     std::shared_future<void>* device_ready = nullptr;    // indexed sampler: the candidates are fetched from the file first (host only); the
                                                          // decode passes wait for this (the device is busy loading the BAM until then)
     uint32_t sampling_interval_size = 1000000;
@@ -480,7 +525,9 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
     struct Planned { Grp g; BamReader::FetchCursor cur; PackedChunk pc; size_t lo = 0, hi = 0; bool used = false; };
     struct ContigPlan { uint32_t tid = 0; std::vector<Planned> plan; size_t bulk = 0; };
     struct Bulk { PackedChunk pc; std::vector<uint8_t> contributes, take; uint32_t tid = 0; };
-    std::vector<ContigPlan> cps;
+    struct Heavy { std::vector<ContigPlan> cps; std::vector<Bulk> bulks; };
+    auto heavy = std::make_shared<Heavy>();
+    std::vector<ContigPlan>& cps = heavy->cps;
     // ---- plan every owned contig under "every group finds its quota"
     for (auto& c : contigs) {
         const uint32_t t = c.tid;
@@ -529,7 +576,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
         if (err) std::rethrow_exception(err);
     }
     // ---- one resident chunk for all of them (one per contig with --include-bed: its bitmaps are per contig), one decode pass each
-    std::vector<Bulk> bulks;
+    std::vector<Bulk>& bulks = heavy->bulks;
     for (auto& cp : cps) {
         if (bulks.empty() || cfg.include) { bulks.emplace_back(); bulks.back().tid = cp.tid; }
         cp.bulk = bulks.size() - 1;
@@ -558,7 +605,8 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
         for (size_t s = 0; s < sbs.size(); s++) for (const Grp& g : todo_for(s, t, done)) {
             if (cfg.include && !cfg.include->overlaps_any(g.tid, g.start, g.end)) continue;
             size_t used = 0;
-            BamReader::FetchCursor cur;
+            BamReader::FetchCursor own;
+            BamReader::FetchCursor* curp = &own;
             auto it = by_key.find(key_of(g));
             if (it != by_key.end() && !plan[it->second].used) {
                 Planned& p = plan[it->second];
@@ -568,8 +616,9 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
                     used++;
                     if (selected.insert(B.pc.recs[k].off).second) B.take[k] = 1;
                 }
-                cur = std::move(p.cur);
-            } else cur = bam.fetch_begin(g.tid, g.start, g.end);
+                curp = &p.cur;             // (stays with the plan: its buffers are released with the rest, see defer_free)
+            } else own = bam.fetch_begin(g.tid, g.start, g.end);
+            BamReader::FetchCursor& cur = *curp;
             // on demand: the plan did not cover the group, or the group needs more candidates than were fetched
             while (!cur.done && (g.n < 0 || used < (size_t)g.n)) {
                 n_on_demand++;
@@ -642,6 +691,7 @@ inline size_t sample_histogram_indexed(const BamReader& bam, mkp_ctx* ctx, const
     }
     if (inexact) *inexact = inexact_local;
     if (fetch_s) *fetch_s = t_fetch;
+    if (cfg.defer_free) *cfg.defer_free = heavy;
     return (size_t)n_selected;
 }
 
@@ -814,6 +864,9 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         std::shared_future<void> dev_ready_f = dev_ready_p.get_future().share();
         bool dev_ready_set = false;
         SamplerConfig bg_sc;
+        std::shared_ptr<void> bg_garbage;
+        std::promise<void> bg_result_p;
+        std::future<void> bg_result_f = bg_result_p.get_future();
         struct BgJoin { std::thread t; std::promise<void>* p; bool* set; ~BgJoin() { if (!*set) { try { p->set_value(); } catch (...) {} *set = true; } if (t.joinable()) t.join(); } } bg_job{std::thread(), &dev_ready_p, &dev_ready_set};
         trace("interval grid + shard cuts");
         const bool sampler_bg = estimate && !loaded && bam.have_index();
@@ -830,9 +883,12 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
             bg_sc.edge_on = P.edge_filter_on;
             bg_sc.include = inc;
             bg_sc.device_ready = &dev_ready_f;
+            bg_sc.defer_free = &bg_garbage;
             bg_job.t = std::thread([&]() {
                 try { sample_histogram_indexed(bam, dev.ctx, bg_sc, bg_hist.data(), &bg_inexact, coll, &bg_fetch_s); }
                 catch (...) { bg_err = std::current_exception(); }
+                bg_result_p.set_value();           // the result is out; the candidate buffers are released after that, beside the pileup
+                bg_garbage.reset();
             });
         }
         // ---- focus positions of this rank's intervals (reference motif scan), beside the load and the sampler. Every object the
@@ -945,8 +1001,8 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 }
             }
         } else if (!o.no_filtering && sampler_bg) {
-            if (bg_job.t.joinable()) bg_job.t.join();
-            trace("sampler joined");
+            bg_result_f.wait();
+            trace("sampler result");
             if (bg_err) std::rethrow_exception(bg_err);
             fetch_s = bg_fetch_s;
             if (bg_inexact) throw std::runtime_error("sampled probabilities are not multiples of 1/1024 (" + std::to_string(bg_inexact) + " values): exact histogram quantile impossible; pass --filter-threshold");
@@ -1012,6 +1068,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         std::mutex q_mu;
         std::condition_variable q_cv;
         std::deque<ChunkOut> queue;
+        std::vector<std::vector<mkp_row>> spare_rows;       // row buffers travel back to the device stage (no fresh pages per chunk)
         std::exception_ptr dev_err;
         bool consumer_gone = false;
         const bool want_alg_bytes = !o.stats_json.empty();
@@ -1118,6 +1175,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                             ChunkOut co;
                             co.i0 = i0; co.i1 = i1;
                             co.key_name = !partitioned ? std::string() : (grp.first == "\1" ? std::string("ungrouped") : grp.first);
+                            { std::lock_guard<std::mutex> lk(q_mu); if (!spare_rows.empty()) { co.rows.swap(spare_rows.back()); spare_rows.pop_back(); } }
                             co.rows.assign(rows, rows + n_rows);          // the context's row buffer is reused by the next chunk
                             S.gpu_s += secs(tb, clk::now());
                             S.kernel_ms += st.kernel_ms[7];
@@ -1138,6 +1196,8 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         struct DevJoiner { std::thread t; std::mutex* mu; std::condition_variable* cv; bool* gone;
                            ~DevJoiner() { { std::lock_guard<std::mutex> g(*mu); *gone = true; } cv->notify_all(); if (t.joinable()) t.join(); } } dev_job{std::thread(), &q_mu, &q_cv, &consumer_gone};
         dev_job.t = std::thread(device_stage);
+        WorkerPool pool(std::max(1, o.threads));
+        std::vector<std::string> part_pool;
         for (;;) {
             ChunkOut co;
             {
@@ -1165,7 +1225,9 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 rlo[n_iv] = r1;
             }
             const int nt = std::max(1, std::min<int>(o.threads, (int)n_iv));
-            std::vector<std::string> parts(nt);
+            std::vector<std::string>& parts = part_pool;
+            if ((int)parts.size() < nt) parts.resize(nt);
+            for (auto& ps : parts) ps.clear();                               // (capacity kept from the chunks before)
             std::vector<std::map<std::string, std::string>> routed(nt);      // to_dir: file name -> text, per worker
             std::vector<uint64_t> part_rows(nt, 0);
             const bool direct = out_fd >= 0 && !to_dir && !sharded;
@@ -1205,10 +1267,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                         }
                     }
                 };
-                std::vector<std::thread> th;
-                for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-                work(0);
-                for (auto& t : th) t.join();
+                pool.run(nt, work);
             }
             if (write_failed) throw std::runtime_error("failed to write output file " + o.out_bed);
             for (int t = 0; t < nt; t++) {
@@ -1218,6 +1277,7 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 for (auto& kv : routed[t]) if (!kv.second.empty()) fwrite(kv.second.data(), 1, kv.second.size(), router.get(kv.first));
                 S.rows += part_rows[t];
             }
+            { std::lock_guard<std::mutex> lk(q_mu); co.rows.clear(); if (spare_rows.size() < 4) spare_rows.push_back(std::move(co.rows)); }
             S.write_s += secs(tc, clk::now());
         }
         trace("last chunk formatted");

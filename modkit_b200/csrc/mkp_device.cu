@@ -1,6 +1,8 @@
 // C ABI (include/mkp.h) over the sm_100a kernels in mkp_kernels.cuh.
 // One mkp_ctx per GPU: grow-only device buffers, one stream, CUDA events around every stage.
 #include <cuda_runtime.h>
+#include <atomic>
+#include <unistd.h>
 #include <chrono>
 #include <sched.h>
 
@@ -29,7 +31,9 @@ struct DevBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        // slack: chunk buffers grow with the largest chunk seen so far; a quarter on top keeps the regrowth (free + malloc of
+        // GB-sized buffers, a device synchronisation each) to one or two per run. The file / inflated-stream buffers get less.
+        size_t want = bytes + (bytes < ((size_t)4 << 30) ? bytes / 4 : bytes / 8) + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -717,8 +721,27 @@ int mkp_device_memory(mkp_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
 
 // Pageable host memory -> device at link speed: N_PIN host threads copy 16 MB pieces into their own pinned buffer and enqueue the
 // transfer (a plain cudaMemcpyAsync from pageable memory is staged by the driver at ~10 GB/s). All transfers go to `st`.
-static int copy_pageable_h2d(mkp_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t n, cudaStream_t st) {
-    if (n < ((size_t)8 << 20)) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st)); return 0; }
+// Source of a host -> device copy: bytes in memory, or - fd >= 0 - a file range read with pread() straight into the pinned staging
+// buffers (no page of the file is mapped into the process: no page faults on the way in, nothing to unmap afterwards).
+struct HostSrc { const uint8_t* mem; int fd; uint64_t fd_off; };
+static bool read_fully(int fd, uint8_t* dst, size_t n, uint64_t off) {
+    size_t got = 0;
+    while (got < n) {
+        const ssize_t r = pread(fd, dst + got, n - got, (off_t)(off + got));
+        if (r <= 0) return false;
+        got += (size_t)r;
+    }
+    return true;
+}
+static int copy_pageable_h2d(mkp_ctx* ctx, uint8_t* dst, HostSrc hs, size_t src_off, size_t n, cudaStream_t st) {
+    const uint8_t* src = hs.mem ? hs.mem + src_off : nullptr;
+    if (n < ((size_t)8 << 20)) {
+        if (src) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st)); return 0; }
+        std::vector<uint8_t> tmp(n);
+        if (!read_fully(hs.fd, tmp.data(), n, hs.fd_off + src_off)) return fail(ctx, "short read from the BAM file");
+        CK(cudaMemcpyAsync(dst, tmp.data(), n, cudaMemcpyHostToDevice, st));      // (pageable source: returns after the bytes are staged)
+        return 0;
+    }
     if (!ctx->pin_ready) {
         for (int i = 0; i < mkp_ctx::N_PIN; i++) { CK(cudaMallocHost(&ctx->pin[i], mkp_ctx::PIN_BYTES)); CK(cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming)); }
         ctx->pin_ready = true;
@@ -727,13 +750,15 @@ static int copy_pageable_h2d(mkp_ctx* ctx, uint8_t* dst, const uint8_t* src, siz
     const size_t n_piece = (n + piece - 1) / piece;
     const int nt = (int)std::min<size_t>(mkp_ctx::N_PIN, n_piece);
     std::vector<cudaError_t> errs(nt, cudaSuccess);
+    std::atomic<bool> read_failed{false};
     auto work = [&](int t) {
         cudaError_t e = cudaSetDevice(ctx->device);
         for (size_t k = t; k < n_piece && e == cudaSuccess; k += nt) {
             const size_t off = k * piece, len = std::min(piece, n - off);
             e = cudaEventSynchronize(ctx->pin_ev[t]);              // the previous transfer out of this buffer is done
             if (e != cudaSuccess) break;
-            memcpy(ctx->pin[t], src + off, len);
+            if (src) memcpy(ctx->pin[t], src + off, len);
+            else if (!read_fully(hs.fd, (uint8_t*)ctx->pin[t], len, hs.fd_off + src_off + off)) { read_failed = true; break; }
             e = cudaMemcpyAsync(dst + off, ctx->pin[t], len, cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) e = cudaEventRecord(ctx->pin_ev[t], st);
         }
@@ -744,7 +769,23 @@ static int copy_pageable_h2d(mkp_ctx* ctx, uint8_t* dst, const uint8_t* src, siz
     work(0);
     for (auto& x : th) x.join();
     for (cudaError_t e : errs) if (e != cudaSuccess) return fail(ctx, std::string("host to device copy: ") + cudaGetErrorString(e));
+    if (read_failed) return fail(ctx, "short read from the BAM file");
     return 0;
+}
+
+static int bam_load_range_impl(mkp_ctx* ctx, HostSrc hs, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                               uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms);
+
+int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                       uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms) {
+    if (!file) return -1;
+    return bam_load_range_impl(ctx, HostSrc{file, -1, 0}, file_len, members, n_members, inflated_len, walk_end, seeds, n_seeds, n_records, ms);
+}
+
+int mkp_bam_load_range_fd(mkp_ctx* ctx, int fd, uint64_t file_off, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                          uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms) {
+    if (fd < 0) return -1;
+    return bam_load_range_impl(ctx, HostSrc{nullptr, fd, file_off}, file_len, members, n_members, inflated_len, walk_end, seeds, n_seeds, n_records, ms);
 }
 
 int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
@@ -752,9 +793,9 @@ int mkp_bam_load(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_b
     return mkp_bam_load_range(ctx, file, file_len, members, n_members, inflated_len, inflated_len, seeds, n_seeds, n_records, ms);
 }
 
-int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
-                       uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms) {
-    if (!ctx || !file || !members || !seeds || !n_seeds) return -1;
+static int bam_load_range_impl(mkp_ctx* ctx, HostSrc hs, size_t file_len, const mkp_bgzf_member* members, size_t n_members,
+                               uint64_t inflated_len, uint64_t walk_end, const uint64_t* seeds, size_t n_seeds, size_t* n_records, float* ms) {
+    if (!ctx || !members || !seeds || !n_seeds) return -1;
     if (walk_end > inflated_len) return fail(ctx, "walk_end lies outside the inflated range");
     if (n_members >= (1u << 24)) return fail(ctx, "too many BGZF members for one load");
     CK(cudaSetDevice(ctx->device));
@@ -815,7 +856,7 @@ int mkp_bam_load_range(mkp_ctx* ctx, const uint8_t* file, size_t file_len, const
     for (size_t sl = 0; sl < n_slabs; sl++) {
         const size_t a = sl == 0 ? 0 : (size_t)members[cut[sl]].in_off;
         const size_t b = sl + 1 == n_slabs ? file_len : (size_t)members[cut[sl + 1]].in_off;
-        if (int rc = copy_pageable_h2d(ctx, ctx->d_file.as<uint8_t>() + a, file + a, b - a, ctx->stream2)) return rc;
+        if (int rc = copy_pageable_h2d(ctx, ctx->d_file.as<uint8_t>() + a, hs, a, b - a, ctx->stream2)) return rc;
         CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         const size_t nm = cut[sl + 1] - cut[sl];
