@@ -55,7 +55,7 @@ MKH_SYMBOLS = ["mkh_pileup_main", "mkh_bam_open", "mkh_bam_close", "mkh_bam_n_re
                "mkh_packed_hdrs", "mkh_packed_heap", "mkh_packed_heap_bytes", "mkh_packed_algorithmic_bytes", "mkh_format_rows",
                "mkh_motif_focus", "mkh_bam_open_device", "mkh_device_chunk", "mkh_bam_ingest_ms", "mkh_bam_total_records",
                "mkh_f32_display", "mkh_bam_partition_key", "mkh_bam_n_ranges", "mkh_pileup_main_sharded", "mkh_shard_plan",
-               "mkh_bam_open_device_pieces", "mkh_bam_fetch", "mkh_summary_main", "mkh_sample_probs_main", "mkh_partition_key_of_cells", "mkh_bam_index_n_mapped"]
+               "mkh_bam_open_device_pieces", "mkh_bam_fetch", "mkh_summary_main", "mkh_sample_probs_main", "mkh_partition_key_of_cells", "mkh_bam_index_n_mapped", "mkh_pct2"]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint64), C.c_size_t, C.c_void_p)
 
@@ -115,6 +115,7 @@ def load_library(build_if_missing=True):
     lib.mkh_bam_ingest_ms.restype = None
     lib.mkh_f32_display.argtypes = [C.c_float, C.c_char_p, C.c_int]
     lib.mkh_bam_partition_key.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int]
+    lib.mkh_pct2.argtypes = [C.c_float, C.c_char_p, C.c_int]
     lib.mkh_bam_index_n_mapped.argtypes = [C.c_char_p, C.c_uint32]
     lib.mkh_bam_index_n_mapped.restype = C.c_int64
     lib.mkh_partition_key_of_cells.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_int]
@@ -219,6 +220,15 @@ def bam_fetch(bam_path, tid, beg, end):
         if n <= cap:
             return offs[:n].copy()
         cap = int(n)
+
+
+def pct2(v):
+    """The bedMethyl writer's two-decimal rendering of an f32 (== printf("%.2f")); CPU only."""
+    buf = C.create_string_buffer(64)
+    n = load_library().mkh_pct2(float(v), buf, 64)
+    if n < 0:
+        raise MkpError("pct2 failed")
+    return buf.value.decode()
 
 
 def bam_index_n_mapped(bam_path, tid):

@@ -305,6 +305,7 @@ public:
         on_device = true;
     }
 
+    void release_host_tables() { std::vector<std::vector<RecRef>>().swap(by_tid); std::vector<Member>().swap(members_); std::vector<uint64_t>().swap(seeds_); run_max_end.clear(); run_max_end.shrink_to_fit(); }
     // virtual offset -> offset in the inflated stream (false: the compressed offset is not a member start)
     bool voff_to_offset(uint64_t v, uint64_t* x) const {
         const uint64_t coff = v >> 16, uoff = v & 0xffff;
@@ -635,9 +636,12 @@ private:
         const size_t flen = (size_t)(members_[m1].in_off + members_[m1].in_len + 8 - fbase);
         size_t n_rec = 0;
         float ms[4] = {0, 0, 0, 0};
-        // (the file bytes are read with pread into the device layer's pinned staging buffers, not through the mapping)
-        if (mkp_bam_load_range_fd(dev, mf.fd, fbase, std::min(flen, mf.size - (size_t)fbase), jobs.data(), jobs.size(), inflated, stop_off - obase,
-                                  seeds.data(), seeds.size(), &n_rec, ms))
+        // the file bytes: copied out of the mapping (default), or - MKH_BAM_PREAD=1 - read with pread into the device layer's pinned
+        // staging buffers (no page of the file mapped; slower per thread on tmpfs)
+        static const bool use_pread = getenv("MKH_BAM_PREAD") && getenv("MKH_BAM_PREAD")[0] == '1';
+        const size_t use_len = std::min(flen, mf.size - (size_t)fbase);
+        if (use_pread ? mkp_bam_load_range_fd(dev, mf.fd, fbase, use_len, jobs.data(), jobs.size(), inflated, stop_off - obase, seeds.data(), seeds.size(), &n_rec, ms)
+                      : mkp_bam_load_range(dev, mf.data + fbase, use_len, jobs.data(), jobs.size(), inflated, stop_off - obase, seeds.data(), seeds.size(), &n_rec, ms))
             throw std::runtime_error(std::string("device ingest: ") + mkp_last_error(dev));
         for (int i = 0; i < 4; i++) ingest_ms[i] += ms[i];
         std::vector<mkp_bam_rec> recs(n_rec);

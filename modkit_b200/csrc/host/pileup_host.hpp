@@ -611,30 +611,56 @@ inline void finish_interval_rows(const RefInterval& iv, const mkp_row* rows, siz
 
 struct BedFormat { bool mixed_delim = false; std::vector<std::string> motif_labels; };
 
-inline char* put_u32(char* p, uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *p++ = t[--n]; return p; }
+inline char* put_u32(char* p, uint32_t v) {
+    if (v < 10) { *p++ = (char)('0' + v); return p; }
+    if (v < 100) { *p++ = (char)('0' + v / 10); *p++ = (char)('0' + v % 10); return p; }
+    char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *p++ = t[--n]; return p;
+}
+
+// printf("%.2f") of a float (writers.rs:140 prints an f32 with {:.2}): the exact binary value rounded to two decimals, ties to even.
+// v * 100 is exact in double (24 + 7 significant bits), so are its integer part and the remainder.
+inline char* put_pct2(char* p, float v) {
+    if (!(v >= 0.0f && v < 1.0e6f)) return p + snprintf(p, 48, "%.2f", (double)v);       // (nan for rows without valid coverage, negatives: never)
+    const double x = (double)v * 100.0;
+    uint64_t k = (uint64_t)x;
+    const double fr = x - (double)k;
+    if (fr > 0.5 || (fr == 0.5 && (k & 1))) k++;
+    p = put_u32(p, (uint32_t)(k / 100));
+    *p++ = '.'; *p++ = (char)('0' + (k / 10) % 10); *p++ = (char)('0' + k % 10);
+    return p;
+}
 
 inline void format_bed_row(const OutRow& o, const std::string& chrom, const BedFormat& fmt, std::string* out) {
     const mkp_row& r = o.r;
     const uint32_t cov = r.n_mod + r.n_canon + r.n_other;
-    char buf[256];
-    char* p = buf;
     const char sp = fmt.mixed_delim ? ' ' : '\t';
-    std::string name = code_text(r.code);
-    if (fmt.motif_labels.size() >= 2 && o.motif_idx >= 0 && (size_t)o.motif_idx < fmt.motif_labels.size()) name += "," + fmt.motif_labels[o.motif_idx];
-    out->append(chrom);
+    // name column: the code (a letter or a ChEBI number), plus the motif label when there are several motifs
+    char name[96];
+    size_t n_name = 0;
+    if (r.code & 0x80000000u) n_name = (size_t)(put_u32(name, r.code & 0x7fffffffu) - name); else name[n_name++] = (char)r.code;
+    const std::string* label = fmt.motif_labels.size() >= 2 && o.motif_idx >= 0 && (size_t)o.motif_idx < fmt.motif_labels.size() ? &fmt.motif_labels[o.motif_idx] : nullptr;
+    // one row, one append: the numeric part needs < 200 bytes
+    char stack_buf[640];
+    std::string big;
+    char* b0 = stack_buf;
+    const size_t need = chrom.size() + n_name + (label ? label->size() + 1 : 0) + 256;
+    if (need > sizeof stack_buf) { big.resize(need); b0 = &big[0]; }
+    char* p = b0;
+    memcpy(p, chrom.data(), chrom.size()); p += chrom.size();
     *p++ = '\t'; p = put_u32(p, r.pos); *p++ = '\t'; p = put_u32(p, r.pos + 1); *p++ = '\t';
-    out->append(buf, p - buf); out->append(name); p = buf;
+    memcpy(p, name, n_name); p += n_name;
+    if (label) { *p++ = ','; memcpy(p, label->data(), label->size()); p += label->size(); }
     *p++ = '\t'; p = put_u32(p, cov); *p++ = '\t'; *p++ = o.strand; *p++ = '\t'; p = put_u32(p, r.pos); *p++ = '\t'; p = put_u32(p, r.pos + 1);
     memcpy(p, "\t255,0,0\t", 9); p += 9;
     p = put_u32(p, cov); *p++ = sp;
     // writers.rs:140: format!("{:.2}", fraction_modified * 100f32) with f32 arithmetic
     const float frac = (float)r.n_mod / (float)cov;
     volatile float pct = frac * 100.0f;
-    p += snprintf(p, 32, "%.2f", (double)pct);
+    p = put_pct2(p, pct);
     *p++ = sp; p = put_u32(p, r.n_mod); *p++ = sp; p = put_u32(p, r.n_canon); *p++ = sp; p = put_u32(p, r.n_other);
     *p++ = sp; p = put_u32(p, r.n_delete); *p++ = sp; p = put_u32(p, r.n_filtered); *p++ = sp; p = put_u32(p, r.n_diff);
     *p++ = sp; p = put_u32(p, r.n_nocall); *p++ = '\n';
-    out->append(buf, p - buf);
+    out->append(b0, (size_t)(p - b0));
 }
 
 // --bedgraph (src/writers.rs:318-381): `chrom start end fraction coverage`, one file per (partition, strand, code[, motif])

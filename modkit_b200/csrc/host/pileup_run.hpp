@@ -1348,6 +1348,12 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                 fclose(jf);
             }
         }
+        if (trace_clock().on) {      // (development: where the release of the run's host objects goes)
+            trace("stats written");
+            std::vector<RefInterval>().swap(ivs); trace("intervals released");
+            part_pool.clear(); part_pool.shrink_to_fit(); shard_parts.clear(); shard_parts.shrink_to_fit(); spare_rows.clear(); spare_rows.shrink_to_fit(); trace("text + row buffers released");
+            bam.release_host_tables(); trace("record tables released");
+        }
         return 0;
     } catch (const std::exception& e) {
         if (error) *error = e.what();

@@ -81,9 +81,10 @@ struct mkp_ctx {
     uint32_t n_hot = 0, state_cap = 4, p_stride = 0;
     bool fused_attr_set = false, focus_ready = false;
     // pinned staging buffers for host -> device copies of pageable memory (the mapped BAM file): one per copy thread
-    static constexpr int N_PIN = 6;
+    static constexpr int N_PIN = 16;                       // staging buffers allocated (MKP_H2D_THREADS of them are used, default 6)
     static constexpr size_t PIN_BYTES = (size_t)16 << 20;
-    void* pin[N_PIN] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* pin[N_PIN] = {};
+    int n_pin = 0;
     cudaEvent_t pin_ev[N_PIN];
     bool pin_ready = false;
     std::vector<mkp_row> h_rows;
@@ -172,7 +173,7 @@ void mkp_destroy(mkp_ctx* ctx) {
                       &ctx->d_need, &ctx->d_totals, &ctx->d_slab_work, &ctx->d_pscr, &ctx->d_inftab, &ctx->d_tiles, &ctx->d_order};
     for (auto* b : bufs) b->release();
     if (ctx->h_rows_pinned) cudaFreeHost(ctx->h_rows_pinned);
-    if (ctx->pin_ready) for (int i = 0; i < mkp_ctx::N_PIN; i++) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_ev[i]); }
+    for (int i = 0; i < ctx->n_pin; i++) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_ev[i]); }
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->stream2);
@@ -743,12 +744,14 @@ static int copy_pageable_h2d(mkp_ctx* ctx, uint8_t* dst, HostSrc hs, size_t src_
         return 0;
     }
     if (!ctx->pin_ready) {
-        for (int i = 0; i < mkp_ctx::N_PIN; i++) { CK(cudaMallocHost(&ctx->pin[i], mkp_ctx::PIN_BYTES)); CK(cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming)); }
+        int want = 6;
+        if (const char* e = getenv("MKP_H2D_THREADS")) want = std::max(1, std::min((int)mkp_ctx::N_PIN, atoi(e)));
+        for (int i = 0; i < want; i++) { CK(cudaMallocHost(&ctx->pin[i], mkp_ctx::PIN_BYTES)); CK(cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming)); ctx->n_pin = i + 1; }
         ctx->pin_ready = true;
     }
     const size_t piece = mkp_ctx::PIN_BYTES;
     const size_t n_piece = (n + piece - 1) / piece;
-    const int nt = (int)std::min<size_t>(mkp_ctx::N_PIN, n_piece);
+    const int nt = (int)std::min<size_t>((size_t)ctx->n_pin, n_piece);
     std::vector<cudaError_t> errs(nt, cudaSuccess);
     std::atomic<bool> read_failed{false};
     auto work = [&](int t) {

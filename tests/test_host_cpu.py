@@ -111,6 +111,24 @@ def test_f32_display_is_shortest_roundtrip_fixed(native_lib):
         assert "e" not in got and np.float32(got) == np.float32(v)
 
 
+def test_percent_column_equals_printf(native_lib):
+    """percent_modified (writers.rs:140, format!("{:.2}", f32)): the writer's own two-decimal formatter == printf("%.2f") of the
+    same f32 for every count pair a pileup can produce up to coverage 400, and for random f32 values (ties included)."""
+    import modkit_b200
+    n = np.arange(0, 401, dtype=np.float32)
+    for cov in range(1, 401):
+        frac = (n[:cov + 1] / np.float32(cov)).astype(np.float32)
+        pct = (frac * np.float32(100.0)).astype(np.float32)
+        for v in pct:
+            assert modkit_b200.pct2(v) == "%.2f" % float(v), float(v)
+    rng = np.random.default_rng(9)
+    vals = list(rng.uniform(0, 100, 20000).astype(np.float32)) + [np.float32(x) for x in (0.125, 0.375, 2.675, 99.995, 100.0, 0.005, 0.015, 0.025, 1e-9, 12345.675)]
+    vals += [np.float32(k / 8 + 0.005) for k in range(64)] + [np.float32((2 * k + 1) / 200.0) for k in range(200)]
+    for v in vals:
+        assert modkit_b200.pct2(v) == "%.2f" % float(v), float(v)
+    assert modkit_b200.pct2(float("nan")) in ("nan", "-nan")
+
+
 def test_partition_keys_of_haplotyped_fixture(native_lib):
     """parse_tags_from_record (src/pileup/mod.rs:629-646): tag values joined by '_', `missing` for absent tags, None when
     no tag is present; RG (Z) and HP (integer) on the reference's haplotyped fixture, cross-checked with the Python reader."""
