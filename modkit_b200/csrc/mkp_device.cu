@@ -821,6 +821,8 @@ static int bam_load_range_impl(mkp_ctx* ctx, HostSrc hs, size_t file_len, const 
     static const bool tab_global = !(getenv("MKP_INFLATE_SMEM") && getenv("MKP_INFLATE_SMEM")[0] == '1');
     int warps_sm = 28;
     if (const char* e = getenv("MKP_INFLATE_WARPS")) warps_sm = std::max(1, std::min(32, atoi(e)));
+    uint32_t hdr_batch = 8;                 // lanes of a warp that run a deflate block header together (k_inflate)
+    if (const char* e = getenv("MKP_INFLATE_HDR_BATCH")) hdr_batch = (uint32_t)std::max(1, std::min(32, atoi(e)));
     const size_t smem = tab_global ? 0 : (size_t)INF_THREADS * INF_STRIDE * 2;
     if (!tab_global && !ctx->inflate_attr_set) {      // per device: the opt-in to > 48 KB of dynamic shared memory
         CK(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -865,7 +867,7 @@ static int bam_load_range_impl(mkp_ctx* ctx, HostSrc hs, size_t file_len, const 
         const size_t nm = cut[sl + 1] - cut[sl];
         const int grid = (int)std::min<size_t>((nm + INF_THREADS - 1) / INF_THREADS, (size_t)ctx->sm_count * per_sm);
         ctx->launches += 1; k_inflate<<<grid, INF_THREADS, smem, st>>>(ctx->d_file.as<uint8_t>(), ctx->d_members.as<mkp_bgzf_member>() + cut[sl], (uint32_t)nm,
-                                                  ctx->d_bam.as<uint8_t>(), u + 10, ctx->d_slab_work.as<uint32_t>() + sl, (uint32_t)cut[sl], gtab);
+                                                  ctx->d_bam.as<uint8_t>(), u + 10, ctx->d_slab_work.as<uint32_t>() + sl, (uint32_t)cut[sl], gtab, hdr_batch);
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream2));
     CK(cudaEventRecord(ctx->ev[2], st));

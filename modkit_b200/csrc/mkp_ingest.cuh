@@ -130,7 +130,7 @@ constexpr int INF_COPY_STEP = 64;
 #define MKP_INF_MINB 28
 #endif
 __global__ void __launch_bounds__(INF_THREADS, MKP_INF_MINB) k_inflate(const uint8_t* __restrict__ in, const mkp_bgzf_member* __restrict__ jobs, uint32_t n_jobs,
-                                                        uint8_t* out, uint32_t* status, uint32_t* work, uint32_t job_base, uint16_t* gtab) {
+                                                        uint8_t* out, uint32_t* status, uint32_t* work, uint32_t job_base, uint16_t* gtab, uint32_t hdr_batch) {
     extern __shared__ uint16_t inf_smem[];
     // decoder tables: shared memory (1.4 KB per decoder: 5 warps of decoders per SM), or - gtab - a per-decoder global scratch that
     // stays in L2: a lookup costs more, but four times as many decoders are resident and the kernel is latency bound
@@ -151,6 +151,12 @@ __global__ void __launch_bounds__(INF_THREADS, MKP_INF_MINB) k_inflate(const uin
     BitReader br;
     br.init(in, in);
     for (;;) {
+        // Block headers are batched: a header (code lengths + two table builds, ~10^4 instructions) run by one lane stalls the 31
+        // others, and with ~4 blocks per member that was half of the warp's instructions. A lane that reaches a header now waits
+        // until hdr_batch lanes stand at one (or nobody is decoding any more); they then run the header code together.
+        const uint32_t at_header = __ballot_sync(0xffffffffu, state == ST_HEADER);
+        const uint32_t decoding = __ballot_sync(0xffffffffu, state == ST_SYMBOL || state == ST_COPY);
+        const bool header_go = (uint32_t)__popc(at_header) >= hdr_batch || decoding == 0;
         if (state == ST_SYMBOL) {
             // up to INF_SYMS_PER_STEP literals per step; the first symbol that is not a literal ends the step
 #pragma unroll 1
@@ -244,6 +250,7 @@ __global__ void __launch_bounds__(INF_THREADS, MKP_INF_MINB) k_inflate(const uin
             o += n; cp_len -= n;
             if (!cp_len) state = ST_SYMBOL;
         } else if (state == ST_HEADER) {
+          if (header_go) {
             last = br.bits(1);
             const uint32_t type = br.bits(2);
             if (type == 0) {
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(INF_THREADS, MKP_INF_MINB) k_inflate(const uin
                 }
                 state = err ? ST_FINISH : ST_SYMBOL;
             }
+          }
         } else if (state == ST_FETCH) {
             j = atomicAdd(work, 1u);
             if (j >= n_jobs) state = ST_DONE;
