@@ -821,7 +821,7 @@ static int bam_load_range_impl(mkp_ctx* ctx, HostSrc hs, size_t file_len, const 
     static const bool tab_global = !(getenv("MKP_INFLATE_SMEM") && getenv("MKP_INFLATE_SMEM")[0] == '1');
     int warps_sm = 28;
     if (const char* e = getenv("MKP_INFLATE_WARPS")) warps_sm = std::max(1, std::min(32, atoi(e)));
-    uint32_t hdr_batch = 8;                 // lanes of a warp that run a deflate block header together (k_inflate)
+    uint32_t hdr_batch = 4;                 // lanes of a warp that run a deflate block header together (k_inflate)
     if (const char* e = getenv("MKP_INFLATE_HDR_BATCH")) hdr_batch = (uint32_t)std::max(1, std::min(32, atoi(e)));
     const size_t smem = tab_global ? 0 : (size_t)INF_THREADS * INF_STRIDE * 2;
     if (!tab_global && !ctx->inflate_attr_set) {      // per device: the opt-in to > 48 KB of dynamic shared memory
