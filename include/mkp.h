@@ -201,10 +201,11 @@ int  mkp_bam_records(mkp_ctx* ctx, mkp_bam_rec* out);
  * the device-side equivalent of slicing them on the host + mkp_upload_chunk. */
 int  mkp_bam_chunk(mkp_ctx* ctx, uint32_t start, uint32_t end, const uint32_t* rec_ids, uint32_t n,
                    const uint32_t* focus_pos, const uint32_t* focus_neg);
-/* --partition-tag on the device front end (src/util.rs:670-688, src/pileup/mod.rs:629-646): the values of n_tags (<= 4) two-letter aux
- * tags (`tags`: 2 * n_tags characters) of the records rec_ids[0..n). out: n * n_tags * 64 bytes, per (record, tag): [0] aux type
- * character (0 = absent or not a stringable type), [1] value length, [2..] the value (Z/H text, or the raw little-endian scalar).
- * A text longer than 61 bytes is an error. */
+/* --partition-tag on the device front end (src/util.rs:670-688, src/pileup/mod.rs:629-646): the values of n_tags (<= 4 per call) two-letter
+ * aux tags (`tags`: 2 * n_tags characters) of the records rec_ids[0..n). out: n * n_tags * MKP_TAG_CELL bytes, per (record, tag): [0] aux
+ * type character (0 = absent or not a stringable type), [1] value length, [2..] the value (Z/H text, or the raw little-endian scalar).
+ * A text longer than MKP_TAG_CELL - 3 bytes is an error. */
+#define MKP_TAG_CELL 256
 int  mkp_bam_tags(mkp_ctx* ctx, const uint32_t* rec_ids, uint32_t n, const char* tags, uint32_t n_tags, uint8_t* out);
 /* Test / debug access: bytes of the inflated stream; headers and heap of the resident chunk
  * (hdrs: n_reads entries or NULL; heap: *heap_bytes capacity in, bytes out; or NULL to query sizes). */

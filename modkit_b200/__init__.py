@@ -535,14 +535,21 @@ class Context:
                                             fn.ctypes.data if fn is not None else None))
         self._n_reads_hint = len(ids)
 
+    TAG_CELL = 256      # MKP_TAG_CELL
+
     def bam_partition_keys(self, rec_ids, tags):
-        """--partition-tag keys of device-resident records (mkp_bam_tags + the host's key rule): list of str | None."""
+        """--partition-tag keys of device-resident records (mkp_bam_tags, four tags per call, + the host's key rule): list of str | None."""
         ids = np.ascontiguousarray(rec_ids, dtype=np.uint32)
-        cells = np.zeros((len(ids), len(tags), 64), dtype=np.uint8)
-        self._check(self._lib.mkp_bam_tags(self._h, ids.ctypes.data, len(ids), "".join(tags).encode(), len(tags), cells.ctypes.data))
-        out, buf = [], C.create_string_buffer(4096)
+        cells = np.zeros((len(ids), len(tags), self.TAG_CELL), dtype=np.uint8)
+        for t0 in range(0, len(tags), 4):
+            sub = tags[t0:t0 + 4]
+            part = np.zeros((len(ids), len(sub), self.TAG_CELL), dtype=np.uint8)
+            self._check(self._lib.mkp_bam_tags(self._h, ids.ctypes.data, len(ids), "".join(sub).encode(), len(sub), part.ctypes.data))
+            cells[:, t0:t0 + len(sub), :] = part
+        out, buf = [], C.create_string_buffer(8192)
         for i in range(len(ids)):
-            rc = self._lib.mkh_partition_key_of_cells(cells[i].ctypes.data, len(tags), buf, 4096)
+            row = np.ascontiguousarray(cells[i])
+            rc = self._lib.mkh_partition_key_of_cells(row.ctypes.data, len(tags), buf, 8192)
             if rc < 0:
                 raise RuntimeError("partition key too long")
             out.append(buf.value.decode() if rc == 1 else None)

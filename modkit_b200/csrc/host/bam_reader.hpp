@@ -858,12 +858,12 @@ inline bool partition_key_of(const uint8_t* r, uint32_t size, const std::vector<
     return any;
 }
 
-// the same key from the 64-byte (type, length, value) cells of mkp_bam_tags (device front end)
+// the same key from the MKP_TAG_CELL-byte (type, length, value) cells of mkp_bam_tags (device front end)
 inline bool partition_key_of_cells(const uint8_t* cells, size_t n_tags, std::string* key) {
     bool any = false;
     std::string k;
     for (size_t i = 0; i < n_tags; i++) {
-        const uint8_t* c = cells + 64 * i;
+        const uint8_t* c = cells + (size_t)MKP_TAG_CELL * i;
         const char ty = (char)c[0];
         const uint8_t* p = c + 2;
         std::string v;

@@ -781,7 +781,6 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
         if (sharded && (to_dir || o.host_ingest)) throw std::runtime_error("multi-GPU runs write one bedMethyl file through the device ingest: --bedgraph / --partition-tag / --host-ingest need a single device");
         if (sharded && (o.out_bed == "-" || o.out_bed == "stdout")) throw std::runtime_error("multi-GPU runs need an output file (ranks write their slices at their offsets)");
         // (partition keys: the tag values come from the device-resident records, mkp_bam_tags; --host-ingest reads them on the host)
-        if (partitioned && o.partition_tags.size() > 4 && !o.host_ingest) throw std::runtime_error("more than 4 partition tags need --host-ingest");
         bool loaded = false;
         if (o.host_ingest) { bam.open(o.in_bam, o.threads); loaded = true; }
         else bam.open_device_index(o.in_bam, dev.ctx);         // header + index; the device load follows once the shard is known
@@ -1125,17 +1124,26 @@ inline int run_pileup(const PileupOptions& o, RunSummary* summary, std::string* 
                             std::vector<RecRef> adm;
                             for (auto& r : all_recs) if (!((r.flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) || r.l_seq == 0)) adm.push_back(r);
                             std::vector<uint8_t> cells;
+                            const size_t n_pt = o.partition_tags.size();
                             if (bam.on_device && !adm.empty()) {
                                 std::vector<uint32_t> ids(adm.size());
                                 for (size_t k = 0; k < adm.size(); k++) ids[k] = adm[k].idx;
-                                std::string tg;
-                                for (auto& t : o.partition_tags) tg += t;
-                                cells.resize(adm.size() * o.partition_tags.size() * 64);
-                                if (mkp_bam_tags(dev.ctx, ids.data(), (uint32_t)ids.size(), tg.c_str(), (uint32_t)o.partition_tags.size(), cells.data())) throw std::runtime_error(mkp_last_error(dev.ctx));
+                                cells.resize(adm.size() * n_pt * MKP_TAG_CELL);
+                                // four tags per call (mkp_bam_tags); the cells of a record are laid side by side in tag order
+                                std::vector<uint8_t> part;
+                                for (size_t t0 = 0; t0 < n_pt; t0 += 4) {
+                                    const size_t nt4 = std::min<size_t>(4, n_pt - t0);
+                                    std::string tg;
+                                    for (size_t t = t0; t < t0 + nt4; t++) tg += o.partition_tags[t];
+                                    part.resize(adm.size() * nt4 * MKP_TAG_CELL);
+                                    if (mkp_bam_tags(dev.ctx, ids.data(), (uint32_t)ids.size(), tg.c_str(), (uint32_t)nt4, part.data())) throw std::runtime_error(mkp_last_error(dev.ctx));
+                                    for (size_t k = 0; k < adm.size(); k++)
+                                        memcpy(cells.data() + (k * n_pt + t0) * MKP_TAG_CELL, part.data() + k * nt4 * MKP_TAG_CELL, nt4 * MKP_TAG_CELL);
+                                }
                             }
                             for (size_t k = 0; k < adm.size(); k++) {
                                 std::string key;
-                                const bool have = bam.on_device ? partition_key_of_cells(cells.data() + k * o.partition_tags.size() * 64, o.partition_tags.size(), &key)
+                                const bool have = bam.on_device ? partition_key_of_cells(cells.data() + k * n_pt * MKP_TAG_CELL, n_pt, &key)
                                                                 : partition_key_of(bam.rec(adm[k]), adm[k].size, o.partition_tags, &key);
                                 groups[have ? key : std::string("\1")].push_back(adm[k]);
                             }

@@ -987,7 +987,7 @@ int mkp_bam_tags(mkp_ctx* ctx, const uint32_t* rec_ids, uint32_t n, const char* 
     cudaStream_t st = ctx->stream;
     for (uint32_t i = 0; i < n; i++) if (rec_ids[i] >= ctx->n_records) return fail(ctx, "record id out of range");
     CK(ctx->d_ids.ensure((size_t)n * 4));
-    CK(ctx->d_plan.ensure(std::max<size_t>(sizeof(SlicePlan), (size_t)n * n_tags * 64)));       // (scratch shared with the slicer)
+    CK(ctx->d_plan.ensure(std::max<size_t>(sizeof(SlicePlan), (size_t)n * n_tags * MKP_TAG_CELL)));       // (scratch shared with the slicer)
     CK(ctx->d_small.ensure(SMALL_BYTES));
     uint32_t* u = (uint32_t*)(ctx->d_small.as<uint8_t>() + 34 * 8);
     uint32_t pk[4] = {0, 0, 0, 0};
@@ -998,11 +998,11 @@ int mkp_bam_tags(mkp_ctx* ctx, const uint32_t* rec_ids, uint32_t n, const char* 
     k_tag_values<<<(n + 7) / 8, 256, 0, st>>>(ctx->d_bam.as<uint8_t>(), ctx->d_recs.as<mkp_bam_rec>(), ctx->d_ids.as<uint32_t>(), n,
                                                  pk[0] | (pk[1] << 16), pk[2] | (pk[3] << 16), n_tags, ctx->d_plan.as<uint8_t>(), u + 14);
     uint32_t ovf = 0;
-    CK(cudaMemcpyAsync(out, ctx->d_plan.p, (size_t)n * n_tags * 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out, ctx->d_plan.p, (size_t)n * n_tags * MKP_TAG_CELL, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&ovf, u + 14, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    if (ovf) return fail(ctx, "a partition tag value is longer than 61 bytes: use --host-ingest for this file");
+    if (ovf) return fail(ctx, "a partition tag value is longer than 253 bytes: use --host-ingest for this file");
     return 0;
 }
 

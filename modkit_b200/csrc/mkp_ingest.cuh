@@ -627,8 +627,8 @@ __global__ void __launch_bounds__(256) k_slice_copy(const uint8_t* __restrict__ 
 }
 
 // ---- --partition-tag on the device front end: the values of up to 4 aux tags of the selected records (src/util.rs:670-688,
-//      src/pileup/mod.rs:629-646). Per (record, tag) 64 bytes: [0] = aux type (0: tag absent or not stringable), [1] = value length,
-//      [2..] = value bytes (Z/H text, or the raw little-endian scalar); a text longer than 61 bytes sets the overflow flag.
+//      src/pileup/mod.rs:629-646). Per (record, tag) MKP_TAG_CELL bytes: [0] = aux type (0: tag absent or not stringable), [1] = value
+//      length, [2..] = value bytes (Z/H text, or the raw little-endian scalar); a text longer than MKP_TAG_CELL - 3 sets the overflow flag.
 __global__ void __launch_bounds__(256) k_tag_values(const uint8_t* __restrict__ bam, const mkp_bam_rec* __restrict__ recs, const uint32_t* __restrict__ ids, uint32_t n,
                                                     uint32_t tags_packed_lo, uint32_t tags_packed_hi, uint32_t n_tags, uint8_t* __restrict__ out, uint32_t* overflow) {
     const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(256) k_tag_values(const uint8_t* __restrict__ 
 #pragma unroll
     for (uint32_t t = 0; t < 4; t++) {
         if (t >= n_tags) break;
-        uint8_t* o = out + ((size_t)i * n_tags + t) * 64;
+        uint8_t* o = out + ((size_t)i * n_tags + t) * MKP_TAG_CELL;
         const AuxHitDev h = hit[t];
         uint32_t len = 0;
         bool have = h.found;
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(256) k_tag_values(const uint8_t* __restrict__ 
             case 'i': case 'I': case 'f': len = 4; break;
             default: have = false;                               // B arrays are not stringable: the tag counts as missing
         }
-        if (len > 61) { if (lane == 0) atomicOr(overflow, 1u); len = 61; }
+        if (len > MKP_TAG_CELL - 3) { if (lane == 0) atomicOr(overflow, 1u); len = MKP_TAG_CELL - 3; }
         if (lane == 0) { o[0] = have ? (uint8_t)h.type : 0; o[1] = have ? (uint8_t)len : 0; }
         for (uint32_t k = lane; have && k < len; k += 32) o[2 + k] = bam[h.p + k];
     }

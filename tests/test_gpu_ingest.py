@@ -288,13 +288,15 @@ def test_device_partition_keys_equal_host(native_lib, synth_exe, tmp_path):
     prefix = str(tmp_path / "pk")
     subprocess.check_call([synth_exe, "--out", prefix, "--contig", "syn1:200000", "--coverage", "15", "--mods", "hm", "--seed", "33",
                            "--partition-tags", "--odd-records"], stdout=subprocess.DEVNULL)
-    for path in (prefix + ".bam", os.path.join(FIX, "bc_anchored_10_reads.haplotyped.sorted.bam")):
+    subprocess.check_call([synth_exe, "--out", prefix + "L", "--contig", "syn1:120000", "--coverage", "10", "--mods", "m", "--seed", "34",
+                           "--partition-tags", "--long-rg"], stdout=subprocess.DEVNULL)           # ONT-style read group ids (~80 characters)
+    for path in (prefix + ".bam", prefix + "L.bam", os.path.join(FIX, "bc_anchored_10_reads.haplotyped.sorted.bam")):
         host = mk.Bam(path, threads=2)
         c = mk.Context(0)
         dev = mk.Bam(path, ctx=c)
         n = host.n_records(0)
         assert n > 0
-        for tags in (["RG", "HP"], ["XF"], ["HP", "XX", "RG", "XF"], ["XX", "YY"]):
+        for tags in (["RG", "HP"], ["XF"], ["HP", "XX", "RG", "XF"], ["XX", "YY"], ["XX", "HP", "YY", "XF", "RG", "MN"]):
             got = c.bam_partition_keys(np.arange(n, dtype=np.uint32), tags)
             exp = [host.partition_key(0, i, tags) for i in range(n)]
             assert got == exp, tags

@@ -259,7 +259,8 @@ def test_gpu_partition_tags_synthetic(native_lib, oracle_exe, synth_exe, tmp_pat
                       "--seed", "21", "--partition-tags", "--odd-records")
     for k, flags in enumerate((["--partition-tag", "RG", "--partition-tag", "HP", "--cpg", "--ref", prefix + ".fa", "--gpu-chunk-bp", "100000"],
                                ["--partition-tag", "XF", "--prefix", "f", "--no-filtering", "-i", "30011"],
-                               ["--partition-tag", "HP", "--bedgraph", "--cpg", "--combine-strands", "--ref", prefix + ".fa"])):
+                               ["--partition-tag", "HP", "--bedgraph", "--cpg", "--combine-strands", "--ref", prefix + ".fa"],
+                               ["--partition-tag", "XX", "--partition-tag", "HP", "--partition-tag", "YY", "--partition-tag", "XF", "--partition-tag", "RG", "--no-filtering", "-i", "50021"])):
         oflags = [f for i, f in enumerate(flags) if f != "--gpu-chunk-bp" and (i == 0 or flags[i - 1] != "--gpu-chunk-bp")]
         gd, od = str(tmp_path / ("g%d" % k)), str(tmp_path / ("o%d" % k))
         assert run_product(flags, prefix + ".bam", gd)[0] == 0
@@ -270,3 +271,11 @@ def test_gpu_partition_tags_synthetic(native_lib, oracle_exe, synth_exe, tmp_pat
             assert "ungrouped.bed" in got and "A_missing.bed" in got and "missing_3.bed" in got and "B_2.bed" in got
         if k == 1:
             assert sorted(got) == ["f_0.1.bed", "f_0.33333334.bed", "f_2.5.bed", "f_ungrouped.bed"]
+    # read-group ids as long as ONT's (run id + model + barcode, ~80 characters): keys come from the device-resident records
+    prefix, _ = synth(synth_exe, tmp_path, "ptl", "--contig", "syn1:150000", "--coverage", "12", "--mods", "m", "--seed", "22", "--partition-tags", "--long-rg")
+    gd, od = str(tmp_path / "gl"), str(tmp_path / "ol")
+    flags = ["--partition-tag", "RG", "--no-filtering"]
+    assert run_product(flags, prefix + ".bam", gd)[0] == 0
+    subprocess.check_call([oracle_exe, "pileup"] + flags + [prefix + ".bam", od], stderr=subprocess.DEVNULL)
+    got, exp = read_dir(gd), read_dir(od)
+    assert sorted(got) == sorted(exp) and got == exp and any(len(name) > 80 for name in got)

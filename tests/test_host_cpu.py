@@ -129,6 +129,36 @@ def test_percent_column_equals_printf(native_lib):
     assert modkit_b200.pct2(float("nan")) in ("nan", "-nan")
 
 
+def test_partition_key_from_device_tag_cells(native_lib):
+    """The key built from the (type, length, value) cells mkp_bam_tags returns (device front end) follows parse_tags_from_record
+    (src/pileup/mod.rs:629-646): values joined by '_', `missing` for absent tags, None when no tag is present."""
+    import ctypes as C
+    import struct
+    import modkit_b200
+    lib = modkit_b200.load_library()
+    cell = modkit_b200.Context.TAG_CELL
+
+    def cells(*vals):
+        out = np.zeros((len(vals), cell), dtype=np.uint8)
+        for i, v in enumerate(vals):
+            if v is None:
+                continue
+            ty, raw = v
+            out[i, 0] = ord(ty); out[i, 1] = len(raw); out[i, 2:2 + len(raw)] = np.frombuffer(raw, dtype=np.uint8)
+        return out
+
+    def key(c):
+        buf = C.create_string_buffer(4096)
+        rc = lib.mkh_partition_key_of_cells(c.ctypes.data, len(c), buf, 4096)
+        return buf.value.decode() if rc == 1 else None
+
+    long_rg = b"4524e8b9-b90e-4ffb-a13a-380266513b64_dna_r10.4.1_e8.2_400bps_hac@v4.2.0_barcode01"
+    assert key(cells(("Z", long_rg), ("C", b"\x02"), None, ("f", struct.pack("<f", 0.1)))) == long_rg.decode() + "_2_missing_0.1"
+    assert key(cells(("i", struct.pack("<i", -7)), ("A", b"q"), ("S", struct.pack("<H", 65535)))) == "-7_q_65535"
+    assert key(cells(None, None)) is None
+    assert key(cells(("Z", b"x" * 253))) == "x" * 253
+
+
 def test_partition_keys_of_haplotyped_fixture(native_lib):
     """parse_tags_from_record (src/pileup/mod.rs:629-646): tag values joined by '_', `missing` for absent tags, None when
     no tag is present; RG (Z) and HP (integer) on the reference's haplotyped fixture, cross-checked with the Python reader."""

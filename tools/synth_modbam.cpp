@@ -4,7 +4,7 @@
 // ever available) the real `modkit` binary.
 //
 //   synth_modbam --out PREFIX [--contig NAME:LEN]... [--coverage 30] [--seed 20260924] [--mods m|hm|hma]
-//                [--mean-len 12000] [--level 1] [--threads 8] [--combined-hm] [--implicit] [--odd-records] [--partition-tags]
+//                [--mean-len 12000] [--level 1] [--threads 8] [--combined-hm] [--implicit] [--odd-records] [--partition-tags [--long-rg]]
 //                [--start-grid G]  (read starts snapped to multiples of G: stacks of reads sharing a start, for --max-depth)
 //                [--region-only START-END]   (only reads overlapping the window; reference still full length)
 // Writes PREFIX.fa, PREFIX.fa.fai, PREFIX.bam, PREFIX.bam.bai and prints a JSON summary (exact algorithmic bytes,
@@ -48,6 +48,7 @@ struct Opts {
     int level = 1, threads = 8;
     bool combined_hm = false, implicit = false, odd = false;
     bool ptags = false;    // --partition-tags: RG:Z (A/B/C or absent), HP (C or i, or absent), XF:f on some reads
+    bool long_rg = false;  // --long-rg: the RG values are long run ids (ONT style, ~80 characters) ending in A/B/C
     int64_t win_start = -1, win_end = -1;
     uint32_t start_grid = 0;   // --start-grid G: read starts snapped down to multiples of G (amplicon-like stacks of reads with one start)
 };
@@ -223,7 +224,11 @@ static void make_read(const Opts& o, const Contig& c, int32_t tid, uint32_t star
     }
     if (o.ptags) {
         const double u1 = rng.uni(), u2 = rng.uni(), u3 = rng.uni();
-        if (u1 < 0.9) { v.push_back('R'); v.push_back('G'); v.push_back('Z'); v.push_back((uint8_t)("ABC"[(int)(u1 * 10) % 3])); v.push_back(0); }
+        if (u1 < 0.9) {
+            v.push_back('R'); v.push_back('G'); v.push_back('Z');
+            if (o.long_rg) { const char* run = "4524e8b9-b90e-4ffb-a13a-380266513b64_dna_r10.4.1_e8.2_400bps_hac@v4.2.0_barcode0"; v.insert(v.end(), run, run + strlen(run)); }
+            v.push_back((uint8_t)("ABC"[(int)(u1 * 10) % 3])); v.push_back(0);
+        }
         if (u2 < 0.7) { v.push_back('H'); v.push_back('P'); v.push_back('C'); v.push_back((uint8_t)(u2 < 0.35 ? 1 : 2)); }
         else if (u2 < 0.8) { v.push_back('H'); v.push_back('P'); v.push_back('i'); put<int32_t>(v, 3); }
         if (u3 < 0.3) { v.push_back('X'); v.push_back('F'); v.push_back('f'); const float f = u3 < 0.1 ? 0.1f : (u3 < 0.2 ? 2.5f : 1.0f / 3.0f); uint32_t b; memcpy(&b, &f, 4); put<uint32_t>(v, b); }
@@ -252,6 +257,7 @@ int main(int argc, char** argv) {
         else if (a == "--implicit") o.implicit = true;
         else if (a == "--odd-records") o.odd = true;
         else if (a == "--partition-tags") o.ptags = true;
+        else if (a == "--long-rg") o.long_rg = true;
         else if (a == "--start-grid") o.start_grid = (uint32_t)std::stoul(val());
         else if (a == "--region-only") { std::string s = val(); auto d = s.find('-'); o.win_start = std::stoll(s.substr(0, d)); o.win_end = std::stoll(s.substr(d + 1)); }
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
